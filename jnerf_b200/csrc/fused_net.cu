@@ -1,0 +1,408 @@
+// NGPNetworks.execute / .density and their backward as ONE kernel each (models/networks/ngp_network.py:77-89):
+//   hash-grid gather (R2) -> density MLP 32->64->16 -> SH(dir) (R4) -> colour MLP 32->64->64->16 (R7) -> (N,4)
+// Encoded features, SH features and all hidden activations stay in shared memory / TMEM; HBM sees only the
+// 28 B coordinate, the 8 B output and (training) a 64 B encoded-feature row kept for backward.
+//
+// Backward reloads the 64 B encoded row, recomputes the MLP forward on the tensor cores (cheaper than storing
+// 448 B of hidden activations per sample), runs the dgrad chain, accumulates all five weight gradients in TMEM
+// across the CTA's tiles, and scatters dL/d(enc) into the hash-grid gradient with f16x2 reductions (R3) without
+// ever materialising dL/d(enc) in HBM.
+//
+// Roofline: forward is bound by the gather (524 B algorithmic per sample, L2-resident table);
+// the tensor work is 20 480 flop/sample forward, 61 440 with dgrad+wgrad.
+#include "mlp_tc.cuh"
+
+int* ngp_err_flag();
+
+namespace {
+using namespace mlp;
+
+// flat weight offsets (halfs) inside the two parameter vectors (OPS/fully_fused_mlp.py:26-40)
+constexpr int WD_W0 = 0, WD_WOUT = 64 * 32, WD_N = 64 * 32 + 16 * 64;
+constexpr int WR_W0 = 0, WR_W1 = 64 * 32, WR_WOUT = 64 * 32 + 64 * 64, WR_N = 64 * 32 + 64 * 64 + 16 * 64;
+
+// ---- shared-memory maps -------------------------------------------------------------------------------
+// activation slab groups
+constexpr uint32_t G_ENC = 0, G_HD = 4, G_RIN = 12, G_H1 = 16, G_H2F = 4 /* fwd: reuses hd */, G_H2B = 24;
+struct SmemFwd {
+    static constexpr uint32_t coords = 0;                         // 128 x 7 f32
+    static constexpr uint32_t act = 4096;                         // 24 groups
+    static constexpr uint32_t w0d = act + 24 * GB;
+    static constexpr uint32_t woutd = w0d + 64 * 32 * 2;
+    static constexpr uint32_t w0r = woutd + 16 * 64 * 2;
+    static constexpr uint32_t w1r = w0r + 64 * 32 * 2;
+    static constexpr uint32_t woutr = w1r + 64 * 64 * 2;
+    static constexpr uint32_t levels = woutr + 16 * 64 * 2;
+    static constexpr uint32_t bar = levels + N_LEVELS * 32;
+    static constexpr uint32_t total = bar + 64;
+};
+// gradient slab groups (backward)
+constexpr uint32_t Q_DYR = 0, Q_GH2 = 2, Q_GH1 = 10, Q_DYD = 18, Q_GHD = 22, Q_DENC = 30, Q_TOTAL = 34;
+struct SmemBwd {
+    static constexpr uint32_t coords = 0;
+    static constexpr uint32_t act = 4096;                         // 32 groups
+    static constexpr uint32_t grd = act + 32 * GB;                // 34 groups
+    static constexpr uint32_t w0d = grd + Q_TOTAL * GB;
+    static constexpr uint32_t woutd = w0d + 64 * 32 * 2;
+    static constexpr uint32_t w0r = woutd + 16 * 64 * 2;
+    static constexpr uint32_t w1r = w0r + 64 * 32 * 2;
+    static constexpr uint32_t woutr = w1r + 64 * 64 * 2;
+    static constexpr uint32_t levels = woutr + 16 * 64 * 2;
+    static constexpr uint32_t bar = levels + N_LEVELS * 32;
+    static constexpr uint32_t total = bar + 64;
+};
+
+template <class S>
+__device__ __forceinline__ void stage_all_weights(uint8_t* smem, const __half* wd, const __half* wr, uint32_t t) {
+    stage_weights(smem + S::w0d, wd + WD_W0, 64, 32, t, 128);
+    stage_weights(smem + S::woutd, wd + WD_WOUT, 16, 64, t, 128);
+    if (wr) {
+        stage_weights(smem + S::w0r, wr + WR_W0, 64, 32, t, 128);
+        stage_weights(smem + S::w1r, wr + WR_W1, 64, 64, t, 128);
+        stage_weights(smem + S::woutr, wr + WR_WOUT, 16, 64, t, 128);
+    }
+}
+
+// Gather phase: thread (level = t&15, sub = t>>4) encodes points sub, sub+8, ... of the tile at its level and writes
+// the half2 feature into the enc slab (and optionally the (N,32) global copy kept for backward).
+template <int STRIDE>
+__device__ __forceinline__ void gather_tile(const float* __restrict__ s_pos /* smem, STRIDE floats per row */, const NgpLevel& lv,
+                                            const __half2* __restrict__ g, uint8_t* act, uint32_t level, uint32_t sub,
+                                            __half* __restrict__ enc_save, uint32_t tile_row0, uint32_t n_live) {
+#pragma unroll 1
+    for (int b = 0; b < 4; ++b) {
+        uint32_t idx[4][8];
+        float w[4][8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t p = sub + 8 * (4 * b + q);
+            hash_corners(lv, s_pos[p * STRIDE], s_pos[p * STRIDE + 1], s_pos[p * STRIDE + 2], idx[q], w[q]);
+        }
+        __half2 v[4][8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[q][c] = __ldg(g + idx[q][c]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t p = sub + 8 * (4 * b + q);
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float2 f = __half22float2(v[q][c]);
+                a0 = fmaf(w[q][c], f.x, a0);
+                a1 = fmaf(w[q][c], f.y, a1);
+            }
+            const __half2 r = __floats2half2_rn(a0, a1);
+            *reinterpret_cast<__half2*>(act + (size_t)(G_ENC + (level >> 2)) * GB + p * 16 + (level & 3) * 4) = r;
+            if (enc_save && tile_row0 + p < n_live)
+                *reinterpret_cast<__half2*>(enc_save + (size_t)(tile_row0 + p) * 32 + 2 * level) = r;
+        }
+    }
+}
+
+// Forward chain up to (and including) the colour net's last hidden layer.  Expects enc in ACT[G_ENC..+4).
+// Returns the fp16 density output h[0] of row t (sigma_raw) and leaves hd / rin / h1 / h2 in the slab.
+template <uint32_t G_H2>
+__device__ __forceinline__ uint32_t forward_chain(uint8_t* smem, uint32_t act_off, uint32_t w0d, uint32_t woutd, uint32_t w0r, uint32_t w1r,
+                                                  const float* s_coords, uint32_t tbase, Pipe& pipe, uint32_t t, uint32_t warp,
+                                                  bool density_only) {
+    const uint32_t smem_s = smem_u32(smem), act_s = smem_s + act_off;
+    uint8_t* act = smem + act_off;
+    const uint32_t D_H = 0, D_S = 64;
+    // density L0: enc(32) -> hd(64)
+    if (t == 0) { issue_fwd(tbase + D_H, act_s, G_ENC, 32, smem_s + w0d, 64); pipe.commit(); }
+    pipe.wait();
+    epi_hidden_relu(tbase, D_H, warp, act, G_HD, t, nullptr);
+    sync_before_issue();
+    // density L1: hd(64) -> h(16)
+    if (t == 0) { issue_fwd(tbase + D_S, act_s, G_HD, 64, smem_s + woutd, 16); pipe.commit(); }
+    pipe.wait();
+    uint32_t sigma_half;
+    {
+        float v[16];
+        tmem_ld16(tmem_addr(tbase, warp, D_S), v);
+        uint4 lo, hi;
+        pack16(v, lo, hi);
+        sigma_half = lo.x & 0xFFFFu;
+        if (density_only) return sigma_half;
+        slab_store16(act, G_RIN, t, lo, hi);
+        float sh[16];
+        sh4(s_coords[t * 7 + 4], s_coords[t * 7 + 5], s_coords[t * 7 + 6], sh);
+        pack16(sh, lo, hi);
+        slab_store16(act, G_RIN + 2, t, lo, hi);
+    }
+    sync_before_issue();
+    // colour L0: [h | sh](32) -> h1(64)
+    if (t == 0) { issue_fwd(tbase + D_H, act_s, G_RIN, 32, smem_s + w0r, 64); pipe.commit(); }
+    pipe.wait();
+    epi_hidden_relu(tbase, D_H, warp, act, G_H1, t, nullptr);
+    sync_before_issue();
+    // colour L1: h1(64) -> h2(64)
+    if (t == 0) { issue_fwd(tbase + D_H, act_s, G_H1, 64, smem_s + w1r, 64); pipe.commit(); }
+    pipe.wait();
+    epi_hidden_relu(tbase, D_H, warp, act, G_H2, t, nullptr);
+    sync_before_issue();
+    return sigma_half;
+}
+
+template <bool DENSITY_ONLY>
+__global__ void __launch_bounds__(128)
+network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const float* __restrict__ coords, const __half* __restrict__ grid,
+                   const NgpLevel* __restrict__ levels, const __half* __restrict__ wd, const __half* __restrict__ wr,
+                   __half* __restrict__ out, __half* __restrict__ enc_save, int* __restrict__ err) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    using S = SmemFwd;
+    constexpr int CS = DENSITY_ONLY ? 3 : 7;
+    const uint32_t t = threadIdx.x, warp = t >> 5;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::bar);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
+    float* s_coords = reinterpret_cast<float*>(smem + S::coords);
+    NgpLevel* s_lv = reinterpret_cast<NgpLevel*>(smem + S::levels);
+
+    stage_all_weights<S>(smem, wd, DENSITY_ONLY ? nullptr : wr, t);
+    if (t < N_LEVELS) s_lv[t] = levels[t];
+    if (t == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc(tmem_ptr, 128);
+    sync_before_issue();
+    const uint32_t tbase = *tmem_ptr;
+    Pipe pipe{bar, 0, err};
+    uint32_t n_live = n_dev ? min(*n_dev, n_max) : n_max;
+    const uint32_t level = t & 15, sub = t >> 4;
+    const NgpLevel lv = s_lv[level];
+    const __half2* g = reinterpret_cast<const __half2*>(grid) + lv.offset;
+
+    const uint32_t ntiles = (n_live + ROWS - 1) / ROWS;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint32_t row0 = tile * ROWS;
+        // stage the coordinate tile (coalesced)
+        for (uint32_t i = t; i < ROWS * CS; i += 128) {
+            const size_t gi = (size_t)row0 * CS + i;
+            s_coords[i] = (row0 + i / CS < n_live) ? __ldg(coords + gi) : 0.f;
+        }
+        __syncthreads();
+        gather_tile<CS>(s_coords, lv, g, smem + S::act, level, sub, DENSITY_ONLY ? nullptr : enc_save, row0, n_live);
+        sync_before_issue();
+        const uint32_t sig = forward_chain<G_H2F>(smem, S::act, S::w0d, S::woutd, S::w0r, S::w1r, s_coords, tbase, pipe, t, warp, DENSITY_ONLY);
+        const uint32_t row = row0 + t;
+        if constexpr (DENSITY_ONLY) {
+            if (row < n_live) reinterpret_cast<uint16_t*>(out)[row] = (uint16_t)sig;
+            // the coords restaging __syncthreads + the next sync_before_issue order TMEM reads before reuse
+        } else {
+            const uint32_t smem_s = smem_u32(smem);
+            if (t == 0) { issue_fwd(tbase + 64, smem_s + S::act, G_H2F, 64, smem_s + S::woutr, 16); pipe.commit(); }
+            pipe.wait();
+            float v[16];
+            tmem_ld16(tmem_addr(tbase, warp, 64), v);
+            if (row < n_live) {
+                uint2 o;
+                o.x = pack_half2(v[0], v[1]);
+                o.y = (pack_half2(v[2], 0.f) & 0xFFFFu) | (sig << 16);
+                reinterpret_cast<uint2*>(out)[row] = o;
+            }
+        }
+        tc_fence_before();
+        __syncthreads();   // coords / slabs are rewritten by the next tile
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_free(tbase, 128);
+}
+
+__global__ void __launch_bounds__(128)
+network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const float* __restrict__ coords, const __half* __restrict__ enc_save,
+                   const NgpLevel* __restrict__ levels, const __half* __restrict__ wd, const __half* __restrict__ wr,
+                   const __half* __restrict__ dout, __half* __restrict__ grid_grad, float* __restrict__ dwd, float* __restrict__ dwr,
+                   int* __restrict__ err) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    using S = SmemBwd;
+    const uint32_t t = threadIdx.x, warp = t >> 5;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::bar);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
+    float* s_coords = reinterpret_cast<float*>(smem + S::coords);
+    NgpLevel* s_lv = reinterpret_cast<NgpLevel*>(smem + S::levels);
+    uint8_t* act = smem + S::act;
+    uint8_t* grd = smem + S::grd;
+
+    stage_all_weights<S>(smem, wd, wr, t);
+    if (t < N_LEVELS) s_lv[t] = levels[t];
+    // dYr columns 4..15, the dYd pad groups: zero once (never rewritten)
+    for (uint32_t i = t; i < Q_TOTAL * GB / 16; i += 128) *reinterpret_cast<uint4*>(grd + i * 16) = make_uint4(0, 0, 0, 0);
+    if (t == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc(tmem_ptr, 512);
+    sync_before_issue();
+    const uint32_t tbase = *tmem_ptr;
+    const uint32_t smem_s = smem_u32(smem), act_s = smem_s + S::act, grd_s = smem_s + S::grd;
+    Pipe pipe{bar, 0, err};
+    const uint32_t n_live = n_dev ? min(*n_dev, n_max) : n_max;
+    const uint32_t level = t & 15, sub = t >> 4;
+    const NgpLevel lv = s_lv[level];
+    __half2* gg = reinterpret_cast<__half2*>(grid_grad) + lv.offset;
+    // TMEM columns
+    const uint32_t D_H = 0, D_S = 64, A_W0D = 96, A_WOUTD = 160, A_W0R = 176, A_W1R = 240, A_WOUTR = 304;
+
+    const uint32_t ntiles = (n_live + ROWS - 1) / ROWS;
+    uint32_t acc = 0;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, acc = 1) {
+        const uint32_t row0 = tile * ROWS, row = row0 + t;
+        const bool valid = row < n_live;
+        for (uint32_t i = t; i < ROWS * 7; i += 128) s_coords[i] = (row0 + i / 7 < n_live) ? __ldg(coords + (size_t)row0 * 7 + i) : 0.f;
+        uint32_t dsig = 0;
+        {
+            const uint4* es = reinterpret_cast<const uint4*>(enc_save + (size_t)row * 32);
+            const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(act + (G_ENC + g) * GB + t * 16) = valid ? __ldg(es + g) : z;
+            uint2 d = valid ? __ldg(reinterpret_cast<const uint2*>(dout) + row) : make_uint2(0, 0);
+            dsig = d.y >> 16;
+            *reinterpret_cast<uint4*>(grd + Q_DYR * GB + t * 16) = make_uint4(d.x, d.y & 0xFFFFu, 0, 0);
+        }
+        sync_before_issue();
+        forward_chain<G_H2B>(smem, S::act, S::w0d, S::woutd, S::w0r, S::w1r, s_coords, tbase, pipe, t, warp, false);
+        // B1: g_h2 = (dYr Woutr) . relu'(h2) ; wgrad Woutr
+        if (t == 0) {
+            issue_dgrad(tbase + D_H, grd_s, Q_DYR, 16, smem_s + S::woutr, 64);
+            issue_wgrad(tbase + A_WOUTR, act_s, G_H2B, grd_s, Q_DYR, 16, acc);
+            pipe.commit();
+        }
+        pipe.wait();
+        epi_dgrad_mask(tbase, D_H, warp, act, G_H2B, grd, Q_GH2, t, nullptr);
+        sync_before_issue();
+        // B2: g_h1 = (g_h2 W1r) . relu'(h1) ; wgrad W1r
+        if (t == 0) {
+            issue_dgrad(tbase + D_H, grd_s, Q_GH2, 64, smem_s + S::w1r, 64);
+            issue_wgrad(tbase + A_W1R, act_s, G_H1, grd_s, Q_GH2, 64, acc);
+            pipe.commit();
+        }
+        pipe.wait();
+        epi_dgrad_mask(tbase, D_H, warp, act, G_H1, grd, Q_GH1, t, nullptr);
+        sync_before_issue();
+        // B3: d_rin = g_h1 W0r (32 cols; the last 16 are dL/dSH, unused) ; wgrad W0r
+        if (t == 0) {
+            issue_dgrad(tbase + D_S, grd_s, Q_GH1, 64, smem_s + S::w0r, 32);
+            issue_wgrad(tbase + A_W0R, act_s, G_RIN, grd_s, Q_GH1, 64, acc);
+            pipe.commit();
+        }
+        pipe.wait();
+        {
+            float v[16];
+            tmem_ld16(tmem_addr(tbase, warp, D_S), v);
+            v[0] += __half2float(__ushort_as_half((unsigned short)dsig));   // + dL/dsigma (ngp_network.py:83)
+            uint4 lo, hi;
+            pack16(v, lo, hi);
+            slab_store16(grd, Q_DYD, t, lo, hi);
+        }
+        sync_before_issue();
+        // B4: g_hd = (dYd Woutd) . relu'(hd) ; wgrad Woutd
+        if (t == 0) {
+            issue_dgrad(tbase + D_H, grd_s, Q_DYD, 16, smem_s + S::woutd, 64);
+            issue_wgrad(tbase + A_WOUTD, act_s, G_HD, grd_s, Q_DYD, 16, acc);
+            pipe.commit();
+        }
+        pipe.wait();
+        epi_dgrad_mask(tbase, D_H, warp, act, G_HD, grd, Q_GHD, t, nullptr);
+        sync_before_issue();
+        // B5: d_enc = g_hd W0d ; wgrad W0d
+        if (t == 0) {
+            issue_dgrad(tbase + D_S, grd_s, Q_GHD, 64, smem_s + S::w0d, 32);
+            issue_wgrad(tbase + A_W0D, act_s, G_ENC, grd_s, Q_GHD, 64, acc);
+            pipe.commit();
+        }
+        pipe.wait();
+        {
+            float v[16];
+            uint4 lo, hi;
+            tmem_ld16(tmem_addr(tbase, warp, D_S), v);
+            pack16(v, lo, hi);
+            slab_store16(grd, Q_DENC, t, lo, hi);
+            tmem_ld16(tmem_addr(tbase, warp, D_S + 16), v);
+            pack16(v, lo, hi);
+            slab_store16(grd, Q_DENC + 2, t, lo, hi);
+        }
+        tc_fence_before();
+        __syncthreads();
+        // scatter: (level, sub) x 16 points -> 8 f16x2 reductions each (HashEncode.h:339-347)
+#pragma unroll 2
+        for (int k = 0; k < 16; ++k) {
+            const uint32_t p = sub + 8 * k;
+            if (row0 + p >= n_live) continue;
+            const __half2 d = *reinterpret_cast<const __half2*>(grd + (size_t)(Q_DENC + (level >> 2)) * GB + p * 16 + (level & 3) * 4);
+            const float2 df = __half22float2(d);
+            if (df.x == 0.f && df.y == 0.f) continue;
+            uint32_t idx[8];
+            float w[8];
+            hash_corners(lv, s_coords[p * 7], s_coords[p * 7 + 1], s_coords[p * 7 + 2], idx, w);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) atomicAdd(gg + idx[c], __floats2half2_rn(df.x * w[c], df.y * w[c]));
+        }
+        __syncthreads();   // slabs / coords are rewritten by the next tile
+    }
+    // flush weight gradients (lane = input feature, column = output feature)
+    if (acc) {
+        float v[16];
+        auto flush = [&](uint32_t col0, uint32_t n_out, uint32_t n_out_valid, uint32_t in_dim, float* dst) {
+            for (uint32_t c = 0; c < n_out / 16; ++c) {
+                tmem_ld16(tmem_addr(tbase, warp, col0 + 16 * c), v);
+                if (t < in_dim) {
+#pragma unroll
+                    for (int o = 0; o < 16; ++o)
+                        if (16 * c + o < n_out_valid) atomicAdd(dst + (size_t)(16 * c + o) * in_dim + t, v[o]);
+                }
+            }
+        };
+        flush(A_W0D, 64, 64, 32, dwd + WD_W0);
+        flush(A_WOUTD, 16, 16, 64, dwd + WD_WOUT);
+        flush(A_W0R, 64, 64, 32, dwr + WR_W0);
+        flush(A_W1R, 64, 64, 64, dwr + WR_W1);
+        flush(A_WOUTR, 16, 3, 64, dwr + WR_WOUT);          // rows >= 3 stay zero (fully_fused_mlp.py:136)
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_free(tbase, 512);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ngp_network_fwd(void* stream, uint32_t n_max, const uint32_t* n_dev, const float* coords, const void* grid, const void* levels_dev,
+                    const void* w_density, const void* w_rgb, void* out, void* enc_save) {
+    if (n_max == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    NGP_CHECK_CUDA(cudaFuncSetAttribute(network_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemFwd::total));
+    const uint32_t ntiles = (n_max + ROWS - 1) / ROWS;
+    const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms() * 3u);
+    network_fwd_kernel<false><<<grid_dim, 128, SmemFwd::total, s>>>(n_max, n_dev, coords, (const __half*)grid, (const NgpLevel*)levels_dev,
+                                                                   (const __half*)w_density, (const __half*)w_rgb, (__half*)out,
+                                                                   (__half*)enc_save, ngp_err_flag());
+    NGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int ngp_density_fwd(void* stream, uint32_t n, const float* pos, const void* grid, const void* levels_dev, const void* w_density, void* sigma_out) {
+    if (n == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    NGP_CHECK_CUDA(cudaFuncSetAttribute(network_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemFwd::total));
+    const uint32_t ntiles = (n + ROWS - 1) / ROWS;
+    const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms() * 3u);
+    network_fwd_kernel<true><<<grid_dim, 128, SmemFwd::total, s>>>(n, nullptr, pos, (const __half*)grid, (const NgpLevel*)levels_dev,
+                                                                  (const __half*)w_density, nullptr, (__half*)sigma_out, nullptr, ngp_err_flag());
+    NGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int ngp_network_bwd(void* stream, uint32_t n_max, const uint32_t* n_dev, const float* coords, const void* enc_save, const void* levels_dev,
+                    const void* w_density, const void* w_rgb, const void* dout, void* grid_grad, float* dw_density, float* dw_rgb) {
+    if (n_max == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd::total));
+    const uint32_t ntiles = (n_max + ROWS - 1) / ROWS;
+    const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms());
+    network_bwd_kernel<<<grid_dim, 128, SmemBwd::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
+                                                            (const __half*)w_density, (const __half*)w_rgb, (const __half*)dout,
+                                                            (__half*)grid_grad, dw_density, dw_rgb, ngp_err_flag());
+    NGP_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

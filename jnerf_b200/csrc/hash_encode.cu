@@ -1,0 +1,212 @@
+// R1-R4: hash-grid level table, standalone hash-grid forward/backward, SH encoder.
+//
+// Replaces the reference's 3-kernel forward (extract_position -> kernel_grid -> transpose_encoded_position,
+// HE/op_header/HashEncode.h:36-50,117-252,254-268) and 3-step backward (transpose_gradients -> memset ->
+// kernel_grid_backward, :270-284,299-396) with one kernel each:
+//   * a warp covers 2 points x 16 levels, so the 32 half2 (or float2) features of a point are written /
+//     read as one fully coalesced 64 B (128 B) row of the AoS (N,32) tensor -- no SoA scratch, no transposes;
+//   * per-level {scale, resolution, offset, size, hashed} records are staged in shared memory once per CTA;
+//   * each thread keeps PPT points in flight (8*PPT independent gathers) to cover L2/HBM latency.
+// Algorithmic bytes: fwd 588 B/point fp16 (512 gather + 12 pos + 64 out), bwd 1100 B/point.
+#include "ngp_common.cuh"
+#include <cmath>
+
+namespace {
+
+__global__ void level_table_kernel(const uint32_t* __restrict__ offsets, int n_levels, uint32_t base_res, float log2_pls,
+                                   NgpLevel* __restrict__ out) {
+    const uint32_t level = threadIdx.x;
+    if ((int)level >= n_levels) return;
+    NgpLevel lv;
+    lv.scale = exp2f(level * log2_pls) * base_res - 1.0f;          // HashEncode.h:149, evaluated on the device
+    lv.resolution = ((uint32_t)ceil(lv.scale) + 1);                // :151
+    lv.offset = offsets[level];
+    lv.size = offsets[level + 1] - offsets[level];
+    uint32_t stride = 1;                                            // grid_index loop, :80-91
+    for (uint32_t dim = 0; dim < 3 && stride <= lv.size; ++dim) stride *= lv.resolution;
+    lv.hashed = lv.size < stride ? 1u : 0u;
+    lv.pad[0] = lv.pad[1] = lv.pad[2] = 0;
+    out[level] = lv;
+}
+
+template <typename T> struct Vec2;
+template <> struct Vec2<float> { using type = float2; };
+template <> struct Vec2<__half> { using type = __half2; };
+
+__device__ __forceinline__ float2 to_f2(float2 v) { return v; }
+__device__ __forceinline__ float2 to_f2(__half2 v) { return __half22float2(v); }
+
+constexpr int HASH_THREADS = 256;
+constexpr int PPT = 4;                                  // points per thread
+constexpr int PTS_PER_BLOCK = (HASH_THREADS / N_LEVELS) * PPT;  // 64
+
+template <typename T>
+__global__ void __launch_bounds__(HASH_THREADS)
+hash_fwd_kernel(uint32_t n, const float* __restrict__ x, const T* __restrict__ grid, const NgpLevel* __restrict__ levels,
+                T* __restrict__ out) {
+    using V = typename Vec2<T>::type;
+    __shared__ NgpLevel s_lv[N_LEVELS];
+    if (threadIdx.x < N_LEVELS) s_lv[threadIdx.x] = levels[threadIdx.x];
+    __syncthreads();
+    const uint32_t level = threadIdx.x & (N_LEVELS - 1), sub = threadIdx.x / N_LEVELS;
+    const NgpLevel lv = s_lv[level];
+    const V* __restrict__ g = reinterpret_cast<const V*>(grid) + lv.offset;
+    const uint32_t base = blockIdx.x * PTS_PER_BLOCK + sub;
+
+    uint32_t idx[PPT][8];
+    float w[PPT][8];
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) {
+        const uint32_t i = base + p * (HASH_THREADS / N_LEVELS);
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (i < n) { px = __ldg(x + 3 * (size_t)i); py = __ldg(x + 3 * (size_t)i + 1); pz = __ldg(x + 3 * (size_t)i + 2); }
+        hash_corners(lv, px, py, pz, idx[p], w[p]);
+    }
+    V v[PPT][8];
+#pragma unroll
+    for (int p = 0; p < PPT; ++p)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[p][c] = __ldg(g + idx[p][c]);
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) {
+        const uint32_t i = base + p * (HASH_THREADS / N_LEVELS);
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {               // corner order and fma chain of HashEncode.h:171-201
+            const float2 f = to_f2(v[p][c]);
+            a0 = fmaf(w[p][c], f.x, a0);
+            a1 = fmaf(w[p][c], f.y, a1);
+        }
+        if (i < n) {
+            V r;
+            if constexpr (sizeof(T) == 2) r = __floats2half2_rn(a0, a1); else r = make_float2(a0, a1);
+            reinterpret_cast<V*>(out)[(size_t)i * N_LEVELS + level] = r;
+        }
+    }
+}
+
+__device__ __forceinline__ void red_add(__half2* addr, float a, float b) { atomicAdd(addr, __floats2half2_rn(a, b)); }
+__device__ __forceinline__ void red_add(float2* addr, float a, float b) { atomicAdd(addr, make_float2(a, b)); }
+
+template <typename T>
+__global__ void __launch_bounds__(HASH_THREADS)
+hash_bwd_kernel(uint32_t n, const float* __restrict__ x, const T* __restrict__ dy, const NgpLevel* __restrict__ levels,
+                T* __restrict__ grid_grad) {
+    using V = typename Vec2<T>::type;
+    __shared__ NgpLevel s_lv[N_LEVELS];
+    if (threadIdx.x < N_LEVELS) s_lv[threadIdx.x] = levels[threadIdx.x];
+    __syncthreads();
+    const uint32_t level = threadIdx.x & (N_LEVELS - 1), sub = threadIdx.x / N_LEVELS;
+    const NgpLevel lv = s_lv[level];
+    V* __restrict__ g = reinterpret_cast<V*>(grid_grad) + lv.offset;
+    const uint32_t base = blockIdx.x * PTS_PER_BLOCK + sub;
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) {
+        const uint32_t i = base + p * (HASH_THREADS / N_LEVELS);
+        if (i >= n) continue;
+        const float px = __ldg(x + 3 * (size_t)i), py = __ldg(x + 3 * (size_t)i + 1), pz = __ldg(x + 3 * (size_t)i + 2);
+        uint32_t idx[8];
+        float w[8];
+        hash_corners(lv, px, py, pz, idx, w);
+        const float2 d = to_f2(reinterpret_cast<const V*>(dy)[(size_t)i * N_LEVELS + level]);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) red_add(g + idx[c], d.x * w[c], d.y * w[c]);   // HashEncode.h:339-356
+    }
+}
+
+template <typename T>
+__global__ void sh_kernel(uint32_t n, const float* __restrict__ dirs, T* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float o[16];
+    sh4(dirs[3 * (size_t)i], dirs[3 * (size_t)i + 1], dirs[3 * (size_t)i + 2], o);
+    if constexpr (sizeof(T) == 2) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            __half2 h = __floats2half2_rn(o[2 * k], o[2 * k + 1]);
+            pk[k] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)i * 16);
+        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    } else {
+        float4* dst = reinterpret_cast<float4*>(out + (size_t)i * 16);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dst[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int ngp_hash_offsets(double aabb_scale, int n_levels, int base_resolution, int log2_hashmap_size, uint32_t* offsets,
+                     double* per_level_scale_out) {
+    NGP_REQUIRE(n_levels >= 2 && n_levels <= 32 && offsets, "ngp_hash_offsets: bad arguments");
+    // HE/grid_encode.py:19-36, python doubles
+    const double pls = std::exp(std::log(2048.0 * aabb_scale / base_resolution) / (n_levels - 1));
+    uint64_t offset = 0;
+    for (int i = 0; i < n_levels; ++i) {
+        const double scale = std::pow(2.0, i * std::log2(pls)) * base_resolution - 1.0;
+        const uint64_t res = (uint64_t)std::ceil(scale) + 1;
+        uint64_t params = res * res * res;
+        params = ((params + 7) / 8) * 8;
+        if (params > (1ull << log2_hashmap_size)) params = 1ull << log2_hashmap_size;
+        offsets[i] = (uint32_t)offset;
+        offset += params;
+    }
+    offsets[n_levels] = (uint32_t)offset;
+    if (per_level_scale_out) *per_level_scale_out = pls;
+    return 0;
+}
+
+int ngp_hash_level_table(void* stream, const uint32_t* offsets_host, int n_levels, uint32_t base_resolution,
+                         float log2_per_level_scale, void* levels_dev) {
+    NGP_REQUIRE(n_levels == N_LEVELS, "ngp_hash_level_table: the encoder is fixed at 16 levels (HE/hash_encoder.py:17-18)");
+    cudaStream_t s = (cudaStream_t)stream;
+    uint32_t* d_off = nullptr;
+    NGP_CHECK_CUDA(cudaMallocAsync(&d_off, sizeof(uint32_t) * (n_levels + 1), s));   // init-time only
+    NGP_CHECK_CUDA(cudaMemcpyAsync(d_off, offsets_host, sizeof(uint32_t) * (n_levels + 1), cudaMemcpyHostToDevice, s));
+    level_table_kernel<<<1, 32, 0, s>>>(d_off, n_levels, base_resolution, log2_per_level_scale, (NgpLevel*)levels_dev);
+    NGP_LAUNCH_CHECK();
+    NGP_CHECK_CUDA(cudaFreeAsync(d_off, s));
+    NGP_CHECK_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int ngp_hash_fwd(void* stream, uint32_t n, const float* x, const void* grid, int dtype, const void* levels_dev, void* out) {
+    if (n == 0) return 0;                                                  // HE/grid_encode.py:78-80
+    const uint32_t blocks = (n + PTS_PER_BLOCK - 1) / PTS_PER_BLOCK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == 1) hash_fwd_kernel<__half><<<blocks, HASH_THREADS, 0, s>>>(n, x, (const __half*)grid, (const NgpLevel*)levels_dev, (__half*)out);
+    else if (dtype == 0) hash_fwd_kernel<float><<<blocks, HASH_THREADS, 0, s>>>(n, x, (const float*)grid, (const NgpLevel*)levels_dev, (float*)out);
+    else NGP_REQUIRE(false, "ngp_hash_fwd: dtype must be 0 (f32) or 1 (f16)");
+    NGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int ngp_hash_bwd(void* stream, uint32_t n, const float* x, const void* dy, int dtype, const void* levels_dev, void* grid_grad,
+                 uint64_t n_params) {
+    NGP_REQUIRE(dtype == 0 || dtype == 1, "ngp_hash_bwd: dtype must be 0 (f32) or 1 (f16)");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) return 0;                                                  // HE/grid_encode.py:142-144 (returns before the memset)
+    NGP_CHECK_CUDA(cudaMemsetAsync(grid_grad, 0, n_params * (dtype == 1 ? 2 : 4), s));   // :153
+    const uint32_t blocks = (n + PTS_PER_BLOCK - 1) / PTS_PER_BLOCK;
+    if (dtype == 1) hash_bwd_kernel<__half><<<blocks, HASH_THREADS, 0, s>>>(n, x, (const __half*)dy, (const NgpLevel*)levels_dev, (__half*)grid_grad);
+    else hash_bwd_kernel<float><<<blocks, HASH_THREADS, 0, s>>>(n, x, (const float*)dy, (const NgpLevel*)levels_dev, (float*)grid_grad);
+    NGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int ngp_sh_fwd(void* stream, uint32_t n, const float* dirs, int dtype, void* out) {
+    if (n == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == 1) sh_kernel<__half><<<(n + 127) / 128, 128, 0, s>>>(n, dirs, (__half*)out);
+    else if (dtype == 0) sh_kernel<float><<<(n + 127) / 128, 128, 0, s>>>(n, dirs, (float*)out);
+    else NGP_REQUIRE(false, "ngp_sh_fwd: dtype must be 0 (f32) or 1 (f16)");
+    NGP_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+// Building blocks of the fully-fused MLP on tcgen05 (used by mlp_tc.cu and fused_net.cu).
+// A tile is 128 rows (samples); thread t of a 128-thread CTA owns row t for every epilogue
+// (TMEM lane t).  Activations and gradients live in shared-memory "slabs" (see tc05.cuh) and never
+// leave the SM between layers.
+#pragma once
+#include "tc05.cuh"
+#include "ngp_common.cuh"
+
+namespace mlp {
+using namespace tc05;
+
+constexpr uint32_t ROWS = 128;
+constexpr uint32_t GB = ROWS * 16;          // bytes of one slab feature-group (8 features x 128 rows)
+
+// ---- weights: global (out=rows, in=K) row-major  ->  smem [K/8][rows][8] (canonical K-major B operand) ----
+__device__ __forceinline__ void stage_weights(uint8_t* dst, const __half* __restrict__ W, int rows, int K, int tid, int nthr) {
+    const int kg = K / 8;
+    for (int i = tid; i < rows * kg; i += nthr) {
+        const int n = i / kg, g = i % kg;
+        *reinterpret_cast<uint4*>(dst + (size_t)g * rows * 16 + n * 16) = __ldg(reinterpret_cast<const uint4*>(W + (size_t)n * K + g * 8));
+    }
+}
+
+// D[128 x N] (+)= ACT[:, 8*g0 .. 8*g0+K) * W^T          (W staged with rows = N)
+__device__ __forceinline__ void issue_fwd(uint32_t d, uint32_t act_s, uint32_t g0, uint32_t K, uint32_t w_s, uint32_t N) {
+    for (uint32_t kb = 0; kb < K / 16; ++kb)
+        mma_f16_ss(d, slab_desc_kmajor(act_s, ROWS, g0, kb), slab_desc_kmajor(w_s, N, 0, kb), idesc_f16(128, N, 0, 0), kb > 0);
+}
+// D[128 x Nin] = GRD[:, 8*g0 .. 8*g0+Kout) * W          (W staged with rows = Kout, K = Nin; read MN-major)
+__device__ __forceinline__ void issue_dgrad(uint32_t d, uint32_t grd_s, uint32_t g0, uint32_t Kout, uint32_t w_s, uint32_t Nin,
+                                            uint32_t accumulate_first = 0) {
+    for (uint32_t kb = 0; kb < Kout / 16; ++kb)
+        mma_f16_ss(d, slab_desc_kmajor(grd_s, ROWS, g0, kb), slab_desc_mnmajor(w_s, Kout, 0, kb), idesc_f16(128, Nin, 0, 1),
+                   (kb > 0) | accumulate_first);
+}
+// D[128 x N] (+)= A^T B : lanes = features [8*ga, 8*ga+128) of slab a, columns = features [8*gb, 8*gb+N) of slab b,
+// contraction over the 128 rows of the tile.  `accumulate` = 0 only for the very first tile of the CTA.
+__device__ __forceinline__ void issue_wgrad(uint32_t d, uint32_t a_s, uint32_t ga, uint32_t b_s, uint32_t gb, uint32_t N, uint32_t accumulate) {
+    for (uint32_t kb = 0; kb < ROWS / 16; ++kb)
+        mma_f16_ss(d, slab_desc_mnmajor(a_s, ROWS, ga, kb), slab_desc_mnmajor(b_s, ROWS, gb, kb), idesc_f16(128, N, 1, 1),
+                   (kb > 0) | accumulate);
+}
+
+// ---- epilogue helpers (thread t = row t) ----------------------------------------------------------
+__device__ __forceinline__ void pack16(const float* v, uint4& lo, uint4& hi) {
+    lo = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
+    hi = make_uint4(pack_half2(v[8], v[9]), pack_half2(v[10], v[11]), pack_half2(v[12], v[13]), pack_half2(v[14], v[15]));
+}
+// store 16 consecutive features (two groups g, g+1) of row t
+__device__ __forceinline__ void slab_store16(uint8_t* slab, uint32_t g, uint32_t t, const uint4& lo, const uint4& hi) {
+    *reinterpret_cast<uint4*>(slab + (size_t)g * GB + t * 16) = lo;
+    *reinterpret_cast<uint4*>(slab + (size_t)(g + 1) * GB + t * 16) = hi;
+}
+__device__ __forceinline__ uint4 slab_load8(const uint8_t* slab, uint32_t g, uint32_t t) {
+    return *reinterpret_cast<const uint4*>(slab + (size_t)g * GB + t * 16);
+}
+// zero the entries of packed half2 `grad` where the matching `act` half is <= 0 (ReLU')
+__device__ __forceinline__ uint32_t relu_mask2(uint32_t grad, uint32_t act) {
+    const __half2 a = *reinterpret_cast<const __half2*>(&act);
+    const __half2 z = __float2half2_rn(0.f);
+    const uint32_t m = __hgt2_mask(a, z);
+    return grad & m;
+}
+__device__ __forceinline__ uint4 relu_mask8(uint4 g, uint4 a) {
+    return make_uint4(relu_mask2(g.x, a.x), relu_mask2(g.y, a.y), relu_mask2(g.z, a.z), relu_mask2(g.w, a.w));
+}
+
+// Hidden-layer epilogue: D[:, 0..64) -> ReLU -> fp16 -> slab groups [g0, g0+8); optionally also to global (row-major 64).
+__device__ __forceinline__ void epi_hidden_relu(uint32_t tbase, uint32_t dcol, uint32_t warp, uint8_t* slab, uint32_t g0, uint32_t t,
+                                                __half* gdst /* row pointer or nullptr */) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float v[16];
+        tmem_ld16(tmem_addr(tbase, warp & 3, dcol + 16 * c), v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+        uint4 lo, hi;
+        pack16(v, lo, hi);
+        slab_store16(slab, g0 + 2 * c, t, lo, hi);
+        if (gdst) {
+            reinterpret_cast<uint4*>(gdst)[2 * c] = lo;
+            reinterpret_cast<uint4*>(gdst)[2 * c + 1] = hi;
+        }
+    }
+}
+// dgrad epilogue: D[:, 0..64) -> fp16 -> masked by ReLU'(act) -> grad slab groups [g0,g0+8); optional global copy.
+__device__ __forceinline__ void epi_dgrad_mask(uint32_t tbase, uint32_t dcol, uint32_t warp, const uint8_t* act_slab, uint32_t ga,
+                                               uint8_t* grd_slab, uint32_t g0, uint32_t t, __half* gdst) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float v[16];
+        tmem_ld16(tmem_addr(tbase, warp & 3, dcol + 16 * c), v);
+        uint4 lo, hi;
+        pack16(v, lo, hi);
+        lo = relu_mask8(lo, slab_load8(act_slab, ga + 2 * c, t));
+        hi = relu_mask8(hi, slab_load8(act_slab, ga + 2 * c + 1, t));
+        slab_store16(grd_slab, g0 + 2 * c, t, lo, hi);
+        if (gdst) {
+            reinterpret_cast<uint4*>(gdst)[2 * c] = lo;
+            reinterpret_cast<uint4*>(gdst)[2 * c + 1] = hi;
+        }
+    }
+}
+
+// Sync point between "all threads wrote smem operands / finished reading TMEM" and "thread 0 issues MMAs".
+__device__ __forceinline__ void sync_before_issue() {
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncthreads();
+    tc_fence_after();
+}
+
+struct Pipe {
+    uint64_t* bar;
+    uint32_t phase;
+    int* err;
+    __device__ __forceinline__ void commit() { mma_commit(bar); }
+    __device__ __forceinline__ void wait() {
+        if (!mbar_wait(bar, phase)) { if (err) atomicExch(err, 1); }
+        phase ^= 1;
+        tc_fence_after();
+    }
+};
+
+}  // namespace mlp

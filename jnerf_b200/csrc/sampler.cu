@@ -1,0 +1,489 @@
+// R5/R6/R8/R9: occupancy-grid ray march, compaction and volume-render composite (forward / backward /
+// inference / fused training tail).  Compiled with -fmad=false: every multiply-add that the reference's GPU build
+// contracts is written as an explicit __fmaf_rn so the sample sequence is reproducible op-for-op by the oracle
+// (oracle/ngp_oracle.c, fma_mode 1) and sample indices stay bit-exact.
+//
+// March (replaces DGS/op_header/ray_sampler.h:4-114): pass 1 counts steps per ray, a single-CTA scan turns the
+// counts into ray-ordered bases (deterministic; the reference claims ranges with atomicAdd), pass 2 emits the
+// NerfCoordinate rows.  No 117 MB memset (DGS/ray_sampler.py:50), no host sync (:65,70).
+#include "ngp_common.cuh"
+#include <cfloat>
+
+namespace {
+
+struct MarchCfg {
+    uint32_t cascades;
+    int const_dt;
+    float min_cone, max_cone;
+};
+__host__ __device__ inline MarchCfg make_cfg(uint32_t cascades, int const_dt) {
+    MarchCfg c;
+    c.cascades = cascades;
+    c.const_dt = const_dt;
+    c.min_cone = 1.73205080757f / 1024.0f;                                   // STEPSIZE(), density_grid_sampler.py:102-104
+    c.max_cone = c.min_cone * (float)(1u << (cascades - 1)) * 1024.0f / 128.0f;  // :105 (all factors are powers of two)
+    return c;
+}
+__device__ __forceinline__ float calc_dt(const MarchCfg& c, float t, float cone) {
+    if (c.const_dt) return c.min_cone * 0.5f;                                // density_grid_sampler.py:107-110
+    const float v = t * cone;                                                // :112-115
+    return v < c.min_cone ? c.min_cone : (c.max_cone < v ? c.max_cone : v);
+}
+__device__ __forceinline__ int mip_from_pos(const MarchCfg& c, float px, float py, float pz) {
+    int e;
+    const float m = fmaxf(fmaxf(fabsf(px - 0.5f), fabsf(py - 0.5f)), fabsf(pz - 0.5f));
+    frexpf(m, &e);
+    return min((int)c.cascades - 1, max(0, e + 1));                          // ray_sampler_header.h:60-66
+}
+__device__ __forceinline__ int mip_from_dt(const MarchCfg& c, float dt, float px, float py, float pz) {
+    const int mip = mip_from_pos(c, px, py, pz);
+    dt *= 2 * NERF_GRIDSIZE;
+    if (dt < 1.f) return mip;
+    int e;
+    frexpf(dt, &e);
+    return min((int)c.cascades - 1, max(e, mip));                            // :68-77
+}
+__device__ __forceinline__ uint32_t grid_idx_at(float px, float py, float pz, uint32_t mip) {
+    const float s = scalbnf(1.0f, -(int)mip);                                // :755-770
+    float q[3] = {px, py, pz};
+    int ix[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        float v = q[d] - 0.5f;
+        v *= s;
+        v += 0.5f;
+        const int i = (int)(v * NERF_GRIDSIZE);
+        ix[d] = min(max(i, 0), (int)NERF_GRIDSIZE - 1);
+    }
+    return morton3D(ix[0], ix[1], ix[2]);
+}
+__device__ __forceinline__ bool occupied_at(float px, float py, float pz, const uint8_t* __restrict__ bits, uint32_t mip) {
+    const uint32_t idx = grid_idx_at(px, py, pz, mip);
+    return __ldg(bits + idx / 8 + (NERF_GRID_N / 8) * mip) & (1 << (idx % 8));   // :772-776
+}
+__device__ __forceinline__ float sgn(float x) { return copysignf(1.0f, x); }
+__device__ __forceinline__ float advance_to_next_voxel(const MarchCfg& c, float t, float cone, const float p_[3], const float d[3],
+                                                       const float id[3], uint32_t res) {
+    const float r = (float)res;                                              // :728-753
+    const float p[3] = {r * p_[0], r * p_[1], r * p_[2]};
+    const float tx = (floorf(p[0] + 0.5f + 0.5f * sgn(d[0])) - p[0]) * id[0];
+    const float ty = (floorf(p[1] + 0.5f + 0.5f * sgn(d[1])) - p[1]) * id[1];
+    const float tz = (floorf(p[2] + 0.5f + 0.5f * sgn(d[2])) - p[2]) * id[2];
+    const float tt = fminf(fminf(tx, ty), tz);
+    const float t_target = t + fmaxf(tt / r, 0.0f);
+    do { t += calc_dt(c, t, cone); } while (t < t_target);
+    return t;
+}
+__device__ __forceinline__ bool contains(float lo, float hi, const float p[3]) {
+    return p[0] >= lo && p[0] <= hi && p[1] >= lo && p[1] <= hi && p[2] >= lo && p[2] <= hi;
+}
+__device__ __forceinline__ float ray_tmin(float lo, float hi, const float o[3], const float d[3]) {
+    float tmin = (lo - o[0]) / d[0], tmax = (hi - o[0]) / d[0], t;           // :408-465
+    if (tmin > tmax) { t = tmin; tmin = tmax; tmax = t; }
+    float tymin = (lo - o[1]) / d[1], tymax = (hi - o[1]) / d[1];
+    if (tymin > tymax) { t = tymin; tymin = tymax; tymax = t; }
+    if (tmin > tymax || tymin > tmax) return FLT_MAX;
+    if (tymin > tmin) tmin = tymin;
+    if (tymax < tmax) tmax = tymax;
+    float tzmin = (lo - o[2]) / d[2], tzmax = (hi - o[2]) / d[2];
+    if (tzmin > tzmax) { t = tzmin; tzmin = tzmax; tzmax = t; }
+    if (tmin > tzmax || tzmin > tmax) return FLT_MAX;
+    if (tzmin > tmin) tmin = tzmin;
+    return tmin;
+}
+
+struct RayState {
+    float o[3], d[3], id[3], startt;
+};
+__device__ __forceinline__ RayState ray_setup(uint32_t i, const float* __restrict__ rays_o, const float* __restrict__ rays_d, float lo,
+                                              float hi, float near_distance, float cone, const MarchCfg& c, uint64_t rng_state,
+                                              uint64_t rng_inc) {
+    RayState r;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { r.o[k] = rays_o[3 * (size_t)i + k]; r.d[k] = rays_d[3 * (size_t)i + k]; r.id[k] = 1.0f / r.d[k]; }
+    Pcg32 rng{rng_state, rng_inc};
+    rng.advance((int64_t)(uint32_t)(i * 8u));                                // ray_sampler.h:30, N_MAX_RANDOM_SAMPLES_PER_RAY = 8
+    float tmin = fmaxf(ray_tmin(lo, hi, r.o, r.d), near_distance);           // :41-44
+    r.startt = __fmaf_rn(calc_dt(c, tmin, cone), rng.next_float(), tmin);    // :48
+    return r;
+}
+
+// one marching pass; EMIT=false counts, EMIT=true writes rows
+template <bool EMIT>
+__device__ __forceinline__ uint32_t march_ray(const RayState& r, float lo, float hi, float cone, const MarchCfg& c,
+                                              const uint8_t* __restrict__ bits, uint32_t limit, float* __restrict__ out) {
+    uint32_t j = 0;
+    float t = r.startt;
+    float wd[3], diag = hi - lo;
+    if (EMIT) { wd[0] = (r.d[0] + 1.0f) * 0.5f; wd[1] = (r.d[1] + 1.0f) * 0.5f; wd[2] = (r.d[2] + 1.0f) * 0.5f; }
+    for (;;) {
+        const float p[3] = {__fmaf_rn(t, r.d[0], r.o[0]), __fmaf_rn(t, r.d[1], r.o[1]), __fmaf_rn(t, r.d[2], r.o[2])};
+        if (!(contains(lo, hi, p) && j < limit)) break;
+        const float dt = calc_dt(c, t, cone);
+        const uint32_t mip = (uint32_t)mip_from_dt(c, dt, p[0], p[1], p[2]);
+        if (occupied_at(p[0], p[1], p[2], bits, mip)) {
+            if (EMIT) {
+                float* q = out + (size_t)j * 7;
+                q[0] = (p[0] - lo) / diag; q[1] = (p[1] - lo) / diag; q[2] = (p[2] - lo) / diag;   // warp_position
+                q[3] = nerf_warp_dt(dt, c.cascades);
+                q[4] = wd[0]; q[5] = wd[1]; q[6] = wd[2];
+            }
+            ++j;
+            t += dt;
+        } else {
+            t = advance_to_next_voxel(c, t, cone, p, r.d, r.id, NERF_GRIDSIZE >> mip);
+        }
+    }
+    return j;
+}
+
+__global__ void march_count_kernel(uint32_t n_rays, float lo, float hi, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                   const uint8_t* __restrict__ bits, float cone, float near_distance, MarchCfg c, uint64_t rng_state,
+                                   uint64_t rng_inc, uint32_t* __restrict__ counts) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rays) return;
+    const RayState r = ray_setup(i, rays_o, rays_d, lo, hi, near_distance, cone, c, rng_state, rng_inc);
+    counts[i] = march_ray<false>(r, lo, hi, cone, c, bits, NERF_STEPS, nullptr);
+}
+
+// Single-CTA exclusive scan over ray counts (R <= a few 100k): numsteps[i] = {count or 0, base}, ray index of accepted rays.
+__global__ void __launch_bounds__(1024) march_scan_kernel(uint32_t n_rays, uint32_t max_samples, const uint32_t* __restrict__ counts,
+                                                          uint32_t* __restrict__ numsteps, uint32_t* __restrict__ ray_indices,
+                                                          uint32_t* __restrict__ counters) {
+    __shared__ uint32_t s_sum[1024], s_acc[1024];
+    const uint32_t t = threadIdx.x;
+    const uint32_t per = (n_rays + 1023) / 1024;
+    const uint32_t b = t * per, e = min(b + per, n_rays);
+    uint32_t sum = 0;
+    for (uint32_t i = b; i < e; ++i) sum += counts[i];
+    s_sum[t] = sum;
+    __syncthreads();
+    for (uint32_t off = 1; off < 1024; off <<= 1) {           // Hillis-Steele inclusive scan
+        uint32_t v = (t >= off) ? s_sum[t - off] : 0;
+        __syncthreads();
+        s_sum[t] += v;
+        __syncthreads();
+    }
+    uint32_t base = s_sum[t] - sum, acc = 0;
+    for (uint32_t i = b; i < e; ++i) {
+        const uint32_t n = counts[i];
+        const bool ok = base + n <= max_samples;                 // ray_sampler.h:74-80
+        numsteps[2 * i] = ok ? n : 0;
+        numsteps[2 * i + 1] = base;
+        acc += ok ? 1 : 0;
+        base += n;
+    }
+    s_acc[t] = acc;
+    __syncthreads();
+    for (uint32_t off = 1; off < 1024; off <<= 1) {
+        uint32_t v = (t >= off) ? s_acc[t - off] : 0;
+        __syncthreads();
+        s_acc[t] += v;
+        __syncthreads();
+    }
+    uint32_t ridx = s_acc[t] - acc;
+    base = s_sum[t] - sum;
+    for (uint32_t i = b; i < e; ++i) {
+        const uint32_t n = counts[i];
+        const bool ok = base + n <= max_samples;
+        if (ok) ray_indices[i] = (n == 0) ? 0xFFFFFFFFu : ridx;  // :84-93
+        ridx += ok ? 1 : 0;
+        base += n;
+    }
+    if (t == 1023) { counters[0] = s_acc[1023]; counters[1] = s_sum[1023]; }
+}
+
+__global__ void march_emit_kernel(uint32_t n_rays, float lo, float hi, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                  const uint8_t* __restrict__ bits, float cone, float near_distance, MarchCfg c, uint64_t rng_state,
+                                  uint64_t rng_inc, const uint32_t* __restrict__ numsteps, float* __restrict__ coords) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rays) return;
+    const uint32_t n = numsteps[2 * i], base = numsteps[2 * i + 1];
+    if (n == 0) return;
+    const RayState r = ray_setup(i, rays_o, rays_d, lo, hi, near_distance, cone, c, rng_state, rng_inc);
+    march_ray<true>(r, lo, hi, cone, c, bits, n, coords + (size_t)base * 7);
+}
+
+// Compaction bases: exclusive scan of the per-ray counts in ray order (single CTA), with the reference's truncation rule.
+__global__ void __launch_bounds__(1024) compact_scan_kernel(uint32_t n_rays, uint32_t max_compacted, const uint32_t* __restrict__ numsteps_in,
+                                                            uint32_t* __restrict__ numsteps_out, uint32_t* __restrict__ counters) {
+    __shared__ uint32_t s_sum[1024], s_acc[1024];
+    const uint32_t t = threadIdx.x;
+    const uint32_t per = (n_rays + 1023) / 1024;
+    const uint32_t b = min(t * per, n_rays), e = min(b + per, n_rays);
+    uint32_t sum = 0;
+    for (uint32_t i = b; i < e; ++i) sum += numsteps_in[2 * i];
+    s_sum[t] = sum;
+    __syncthreads();
+    for (uint32_t off = 1; off < 1024; off <<= 1) {
+        uint32_t v = (t >= off) ? s_sum[t - off] : 0;
+        __syncthreads();
+        s_sum[t] += v;
+        __syncthreads();
+    }
+    uint32_t base = s_sum[t] - sum, acc = 0;
+    for (uint32_t i = b; i < e; ++i) {
+        const uint32_t n = numsteps_in[2 * i];
+        const uint32_t cn = min(max_compacted - min(max_compacted, base), n);      // compacted_coord.h:62-63
+        numsteps_out[2 * i] = cn;
+        numsteps_out[2 * i + 1] = base;
+        acc += cn ? 1 : 0;
+        base += n;
+    }
+    s_acc[t] = acc;
+    __syncthreads();
+    if (t == 0) {
+        uint32_t rays = 0;
+        for (int k = 0; k < 1024; ++k) rays += s_acc[k];
+        counters[0] = s_sum[1023];
+        counters[1] = rays;
+    }
+}
+// one warp per ray copies its rows from the raw base to the compacted base
+__global__ void compact_copy_kernel(uint32_t n_rays, const float* __restrict__ coords_in, const uint32_t* __restrict__ numsteps_in,
+                                    float* __restrict__ coords_out, const uint32_t* __restrict__ numsteps_out) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_rays) return;
+    const uint32_t base = numsteps_in[2 * warp + 1], cn = numsteps_out[2 * warp], cbase = numsteps_out[2 * warp + 1];
+    for (uint32_t k = lane; k < cn * 7; k += 32) coords_out[(size_t)cbase * 7 + k] = coords_in[(size_t)base * 7 + k];
+}
+__global__ void zero_tail_kernel(float* __restrict__ coords_out, const uint32_t* __restrict__ counters, uint32_t max_compacted) {
+    const uint32_t total = min(counters[0], max_compacted);
+    const size_t b = (size_t)total * 7, e = (size_t)max_compacted * 7;
+    for (size_t k = b + blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < e; k += (size_t)gridDim.x * blockDim.x) coords_out[k] = 0.f;
+}
+
+// ---- composite -------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float4 load_net(const T* net, size_t k);
+template <> __device__ __forceinline__ float4 load_net<float>(const float* net, size_t k) { return __ldg(reinterpret_cast<const float4*>(net) + k); }
+template <> __device__ __forceinline__ float4 load_net<__half>(const __half* net, size_t k) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(net) + k);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T> __device__ __forceinline__ void store_net(T* dst, size_t k, float4 v);
+template <> __device__ __forceinline__ void store_net<float>(float* dst, size_t k, float4 v) { reinterpret_cast<float4*>(dst)[k] = v; }
+template <> __device__ __forceinline__ void store_net<__half>(__half* dst, size_t k, float4 v) {
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    reinterpret_cast<uint2*>(dst)[k] = u;
+}
+
+struct Sample {
+    float rgb[3], alpha, dt, sigma_raw;
+};
+template <typename T>
+__device__ __forceinline__ Sample eval_sample(const T* __restrict__ net, const float* __restrict__ coords, size_t k, uint32_t cascades,
+                                              float4* raw) {
+    const float4 o = load_net<T>(net, k);
+    *raw = o;
+    Sample s;
+    s.rgb[0] = logistic_f(o.x); s.rgb[1] = logistic_f(o.y); s.rgb[2] = logistic_f(o.z);   // network_to_rgb, Logistic
+    s.dt = nerf_unwarp_dt(__ldg(coords + k * 7 + 3), cascades);
+    const float density = __expf(o.w);                                                     // network_to_density, Exponential
+    s.alpha = 1.f - __expf(-density * s.dt);
+    s.sigma_raw = o.w;
+    return s;
+}
+
+template <typename T, bool INFER>
+__global__ void composite_fwd_kernel(uint32_t n_rays, const T* __restrict__ net, const float* __restrict__ coords,
+                                     const uint32_t* __restrict__ numsteps_in, const uint32_t* __restrict__ numsteps_c,
+                                     const float* __restrict__ bg, uint32_t cascades, float* __restrict__ rgb_out, float* __restrict__ alpha_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rays) return;
+    const uint32_t n = numsteps_c[2 * i], base = numsteps_c[2 * i + 1];
+    if (n == 0) {
+        if (INFER) { rgb_out[3 * i] = rgb_out[3 * i + 1] = rgb_out[3 * i + 2] = 0.f; alpha_out[i] = 0.f; }
+        else { rgb_out[3 * i] = bg[3 * i]; rgb_out[3 * i + 1] = bg[3 * i + 1]; rgb_out[3 * i + 2] = bg[3 * i + 2]; }   // calc_rgb.h:35-39
+        return;
+    }
+    float T_ = 1.f, r[3] = {0.f, 0.f, 0.f};
+    for (uint32_t j = 0; j < n; ++j) {
+        float4 raw;
+        const Sample s = eval_sample<T>(net, coords, (size_t)base + j, cascades, &raw);
+        const float w = s.alpha * T_;
+        r[0] = __fmaf_rn(w, s.rgb[0], r[0]); r[1] = __fmaf_rn(w, s.rgb[1], r[1]); r[2] = __fmaf_rn(w, s.rgb[2], r[2]);
+        T_ *= (1.f - s.alpha);
+    }
+    if (!INFER && n == numsteps_in[2 * i]) {                                                // :68-71
+        r[0] = __fmaf_rn(T_, bg[3 * i], r[0]); r[1] = __fmaf_rn(T_, bg[3 * i + 1], r[1]); r[2] = __fmaf_rn(T_, bg[3 * i + 2], r[2]);
+    }
+    rgb_out[3 * i] = r[0]; rgb_out[3 * i + 1] = r[1]; rgb_out[3 * i + 2] = r[2];
+    if (INFER) alpha_out[i] = 1 - T_;
+}
+
+template <typename T>
+__device__ __forceinline__ void composite_bwd_ray(uint32_t n, uint32_t base, const T* __restrict__ net, const float* __restrict__ coords,
+                                                  const float lg[3], const float rr[3], float loss_scale, float l1, uint32_t cascades,
+                                                  T* __restrict__ dnet) {
+    float T_ = 1.f, r2[3] = {0.f, 0.f, 0.f};
+    for (uint32_t j = 0; j < n; ++j) {
+        float4 raw;
+        const Sample s = eval_sample<T>(net, coords, (size_t)base + j, cascades, &raw);
+        const float w = s.alpha * T_;
+        r2[0] = __fmaf_rn(w, s.rgb[0], r2[0]); r2[1] = __fmaf_rn(w, s.rgb[1], r2[1]); r2[2] = __fmaf_rn(w, s.rgb[2], r2[2]);
+        T_ *= (1.f - s.alpha);
+        const float suffix[3] = {rr[0] - r2[0], rr[1] - r2[1], rr[2] - r2[2]};
+        float4 dl;
+        dl.x = loss_scale * ((w * lg[0]) * (s.rgb[0] * (1 - s.rgb[0])));                    // calc_rgb.h:133-135 (l2 reg is 0 for Logistic)
+        dl.y = loss_scale * ((w * lg[1]) * (s.rgb[1] * (1 - s.rgb[1])));
+        dl.z = loss_scale * ((w * lg[2]) * (s.rgb[2] * (1 - s.rgb[2])));
+        const float dd = __expf(fminf(fmaxf(raw.w, -15.0f), 15.0f));                        // network_to_density_derivative
+        const float dot = lg[0] * (T_ * s.rgb[0] - suffix[0]) + (lg[1] * (T_ * s.rgb[1] - suffix[1]) + lg[2] * (T_ * s.rgb[2] - suffix[2]));
+        dl.w = loss_scale * (dd * (s.dt * dot)) + (raw.w < 0 ? -l1 : 0.0f);                 // :137-139
+        store_net<T>(dnet, (size_t)base + j, dl);
+    }
+}
+
+template <typename T>
+__global__ void composite_bwd_kernel(uint32_t n_rays, const T* __restrict__ net, const float* __restrict__ coords,
+                                     const uint32_t* __restrict__ numsteps_c, const float* __restrict__ loss_grad,
+                                     const float* __restrict__ rgb_ray, const float* __restrict__ mean, uint32_t cascades, T* __restrict__ dnet) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rays) return;
+    float loss_scale = 128;
+    loss_scale /= n_rays;                                                                   // :100-101
+    const float l1 = *mean < 0.01f ? 1e-4f : 0.0f;                                          // :112
+    const float lg[3] = {loss_grad[3 * i], loss_grad[3 * i + 1], loss_grad[3 * i + 2]};
+    const float rr[3] = {rgb_ray[3 * i], rgb_ray[3 * i + 1], rgb_ray[3 * i + 2]};
+    composite_bwd_ray<T>(numsteps_c[2 * i], numsteps_c[2 * i + 1], net, coords, lg, rr, loss_scale, l1, cascades, dnet);
+}
+
+// Fused training tail: composite forward, Huber gradient, composite backward -- one thread per ray.
+__global__ void composite_loss_bwd_kernel(uint32_t n_rays, const __half* __restrict__ net, const float* __restrict__ coords,
+                                          const uint32_t* __restrict__ numsteps_in, const uint32_t* __restrict__ numsteps_c,
+                                          const float* __restrict__ bg, const float* __restrict__ target, float delta,
+                                          const float* __restrict__ mean, uint32_t cascades, float* __restrict__ rgb_out,
+                                          float* __restrict__ loss_out, __half* __restrict__ dnet) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rays) return;
+    const uint32_t n = numsteps_c[2 * i], base = numsteps_c[2 * i + 1];
+    float T_ = 1.f, r[3] = {0.f, 0.f, 0.f};
+    if (n == 0) { r[0] = bg[3 * i]; r[1] = bg[3 * i + 1]; r[2] = bg[3 * i + 2]; }
+    else {
+        for (uint32_t j = 0; j < n; ++j) {
+            float4 raw;
+            const Sample s = eval_sample<__half>(net, coords, (size_t)base + j, cascades, &raw);
+            const float w = s.alpha * T_;
+            r[0] = __fmaf_rn(w, s.rgb[0], r[0]); r[1] = __fmaf_rn(w, s.rgb[1], r[1]); r[2] = __fmaf_rn(w, s.rgb[2], r[2]);
+            T_ *= (1.f - s.alpha);
+        }
+        if (n == numsteps_in[2 * i]) {
+            r[0] = __fmaf_rn(T_, bg[3 * i], r[0]); r[1] = __fmaf_rn(T_, bg[3 * i + 1], r[1]); r[2] = __fmaf_rn(T_, bg[3 * i + 2], r[2]);
+        }
+    }
+    float lg[3], loss = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {                                                           // huber_loss.py:11-14
+        const float diff = r[k] - target[3 * i + k], rel = fabsf(diff);
+        loss += rel > delta ? rel - 0.5f * delta : 0.5f / delta * rel * rel;
+        lg[k] = rel > delta ? (diff > 0 ? 1.0f : -1.0f) : diff / delta;
+        rgb_out[3 * i + k] = r[k];
+    }
+    if (loss_out) loss_out[i] = loss;
+    float loss_scale = 128;
+    loss_scale /= n_rays;
+    const float l1 = *mean < 0.01f ? 1e-4f : 0.0f;
+    composite_bwd_ray<__half>(n, base, net, coords, lg, r, loss_scale, l1, cascades, dnet);
+}
+
+}  // namespace
+
+extern "C" {
+
+uint64_t ngp_march_workspace_bytes(uint32_t n_rays) { return (uint64_t)n_rays * 4 + 256; }
+
+int ngp_march(void* stream, uint32_t n_rays, float aabb_lo, float aabb_hi, uint32_t max_samples, const float* rays_o, const float* rays_d,
+              const uint8_t* bitfield, float cone_angle, float near_distance, uint32_t cascades, int const_dt, uint64_t rng_state,
+              uint64_t rng_inc, uint32_t* counters, uint32_t* ray_indices, uint32_t* numsteps, float* coords, void* workspace) {
+    cudaStream_t s = (cudaStream_t)stream;
+    NGP_REQUIRE(cascades >= 1 && cascades <= 8, "ngp_march: cascades out of range");
+    NGP_CHECK_CUDA(cudaMemsetAsync(counters, 0, 8, s));                                     // ray_sampler.py:29
+    if (n_rays == 0) return 0;
+    const MarchCfg c = make_cfg(cascades, const_dt);
+    uint32_t* counts = (uint32_t*)workspace;
+    const uint32_t blocks = (n_rays + 127) / 128;
+    march_count_kernel<<<blocks, 128, 0, s>>>(n_rays, aabb_lo, aabb_hi, rays_o, rays_d, bitfield, cone_angle, near_distance, c, rng_state,
+                                              rng_inc, counts);
+    NGP_LAUNCH_CHECK();
+    march_scan_kernel<<<1, 1024, 0, s>>>(n_rays, max_samples, counts, numsteps, ray_indices, counters);
+    NGP_LAUNCH_CHECK();
+    march_emit_kernel<<<blocks, 128, 0, s>>>(n_rays, aabb_lo, aabb_hi, rays_o, rays_d, bitfield, cone_angle, near_distance, c, rng_state,
+                                             rng_inc, numsteps, coords);
+    NGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int ngp_compact(void* stream, uint32_t n_rays, uint32_t max_compacted, const float* coords_in, const uint32_t* numsteps_in, float* coords_out,
+                uint32_t* numsteps_out, uint32_t* counters, int zero_fill) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_rays == 0) { NGP_CHECK_CUDA(cudaMemsetAsync(counters, 0, 8, s)); return 0; }
+    const int copy = coords_out != coords_in;   // aliased call: bookkeeping only (ray-ordered march output is already compact)
+    compact_scan_kernel<<<1, 1024, 0, s>>>(n_rays, max_compacted, numsteps_in, numsteps_out, counters);
+    NGP_LAUNCH_CHECK();
+    if (copy) {
+        compact_copy_kernel<<<(n_rays * 32 + 255) / 256, 256, 0, s>>>(n_rays, coords_in, numsteps_in, coords_out, numsteps_out);
+        NGP_LAUNCH_CHECK();
+    }
+    if (zero_fill && copy) {
+        zero_tail_kernel<<<ngp_num_sms(), 256, 0, s>>>(coords_out, counters, max_compacted);
+        NGP_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+int ngp_composite_fwd(void* stream, uint32_t n_rays, const void* net_out, int dtype, const float* coords, const uint32_t* numsteps_in,
+                      const uint32_t* numsteps_compacted, const float* bg, uint32_t cascades, float* rgb_out) {
+    if (n_rays == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t blocks = (n_rays + 127) / 128;
+    if (dtype == 1) composite_fwd_kernel<__half, false><<<blocks, 128, 0, s>>>(n_rays, (const __half*)net_out, coords, numsteps_in, numsteps_compacted, bg, cascades, rgb_out, nullptr);
+    else if (dtype == 0) composite_fwd_kernel<float, false><<<blocks, 128, 0, s>>>(n_rays, (const float*)net_out, coords, numsteps_in, numsteps_compacted, bg, cascades, rgb_out, nullptr);
+    else NGP_REQUIRE(false, "ngp_composite_fwd: bad dtype");
+    NGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int ngp_composite_infer(void* stream, uint32_t n_rays, const void* net_out, int dtype, const float* coords, const uint32_t* numsteps,
+                        uint32_t cascades, float* rgb_out, float* alpha_out) {
+    if (n_rays == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t blocks = (n_rays + 127) / 128;
+    if (dtype == 1) composite_fwd_kernel<__half, true><<<blocks, 128, 0, s>>>(n_rays, (const __half*)net_out, coords, numsteps, numsteps, nullptr, cascades, rgb_out, alpha_out);
+    else if (dtype == 0) composite_fwd_kernel<float, true><<<blocks, 128, 0, s>>>(n_rays, (const float*)net_out, coords, numsteps, numsteps, nullptr, cascades, rgb_out, alpha_out);
+    else NGP_REQUIRE(false, "ngp_composite_infer: bad dtype");
+    NGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int ngp_composite_bwd(void* stream, uint32_t n_rays, uint32_t n_elements, const void* net_out, int dtype, const float* coords,
+                      const uint32_t* numsteps_compacted, const float* loss_grad, const float* rgb_ray, const float* density_grid_mean,
+                      uint32_t cascades, void* dnet_out) {
+    NGP_REQUIRE(dtype == 0 || dtype == 1, "ngp_composite_bwd: bad dtype");
+    cudaStream_t s = (cudaStream_t)stream;
+    NGP_CHECK_CUDA(cudaMemsetAsync(dnet_out, 0, (size_t)n_elements * 4 * (dtype == 1 ? 2 : 4), s));   // DGS/calc_rgb.py:93
+    if (n_rays == 0) return 0;
+    const uint32_t blocks = (n_rays + 127) / 128;
+    if (dtype == 1) composite_bwd_kernel<__half><<<blocks, 128, 0, s>>>(n_rays, (const __half*)net_out, coords, numsteps_compacted, loss_grad, rgb_ray, density_grid_mean, cascades, (__half*)dnet_out);
+    else composite_bwd_kernel<float><<<blocks, 128, 0, s>>>(n_rays, (const float*)net_out, coords, numsteps_compacted, loss_grad, rgb_ray, density_grid_mean, cascades, (float*)dnet_out);
+    NGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int ngp_composite_loss_bwd(void* stream, uint32_t n_rays, uint32_t n_elements, const void* net_out, const float* coords,
+                           const uint32_t* numsteps_in, const uint32_t* numsteps_compacted, const float* bg, const float* target,
+                           float huber_delta, const float* density_grid_mean, uint32_t cascades, float* rgb_out, float* loss_out, void* dnet_out) {
+    (void)n_elements;   // rows not covered by a ray are never read downstream (the network backward is count-limited)
+    if (n_rays == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    composite_loss_bwd_kernel<<<(n_rays + 127) / 128, 128, 0, s>>>(n_rays, (const __half*)net_out, coords, numsteps_in, numsteps_compacted, bg,
+                                                                  target, huber_delta, density_grid_mean, cascades, rgb_out, loss_out,
+                                                                  (__half*)dnet_out);
+    NGP_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -108,8 +108,13 @@ static inline uint32_t grid_index(uint32_t hashmap_size, uint32_t res, const uin
     if (hashmap_size < stride) index = g[0] ^ g[1] * 19349663u ^ g[2] * 83492791u; /* cfg hash_func, ngp_base.py:66 */
     return (index % hashmap_size) * 2;
 }
+/* The reference evaluates exp2f on the GPU (MUFU.EX2, <= 2 ulp), libm's exp2f is correctly rounded: the two can
+ * differ in the last bits, and the finest levels amplify a 1e-7 relative scale error by the resolution (2048).
+ * Tests that compare against a GPU run install the device-computed scales here (NULL = compute with libm). */
+static const float* g_level_scales = 0;
+void orc_set_level_scales(const float* scales) { g_level_scales = scales; }
 static inline void level_setup(uint32_t level, uint32_t base_res, float log2_pls, float* scale, uint32_t* res) {
-    *scale = exp2f(level * log2_pls) * base_res - 1.0f;       /* HashEncode.h:149 */
+    *scale = g_level_scales ? g_level_scales[level] : exp2f(level * log2_pls) * base_res - 1.0f;  /* HashEncode.h:149 */
     *res = (uint32_t)ceil(*scale) + 1;                        /* :151 */
 }
 static inline void pos_fract(float in, float scale, float* pos, uint32_t* g) {
@@ -552,7 +557,7 @@ static inline float warp_dt(const march_cfg* c, float dt) {
 }
 static inline float unwarp_dt(const march_cfg* c, float dt) {
     float max_stepsize = c->min_cone * (1 << (c->cascades - 1));
-    return dt * (max_stepsize - c->min_cone) + c->min_cone;
+    return mad(dt, max_stepsize - c->min_cone, c->min_cone);
 }
 
 /* counters[0] = rays with base in range (ray_counter), counters[1] = total numsteps (incl. overflowing rays).

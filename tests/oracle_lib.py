@@ -42,6 +42,7 @@ def oracle():
         _oracle.orc_grid_mean.restype = _f32
         _oracle.orc_morton3D.restype = _u32
         _oracle.orc_morton3D_invert.restype = _u32
+        _oracle.orc_set_level_scales.argtypes = [_p]
     return _oracle
 
 
