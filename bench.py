@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- Instant-NGP lego training throughput on N B200s (BASELINE.json metric: NGP lego iters/s & rays/s).
+
+  python bench.py --gpus N --steps K --warmup W            our arm   (torchrun for N>1: one rank per GPU, NCCL)
+  python bench.py --impl reference --gpus N --steps K ...  reference arm: the path's CPU implementation (oracle port)
+
+A step = one full training iteration of projects/ngp/configs/ngp_base.py + fp16 (BASELINE config #2):
+[density-grid update every 16] -> ray gen -> march -> fused hash+MLP forward -> composite + Huber + composite
+backward -> fused MLP/hash backward -> [grad all-reduce] -> fused Adam+EMA over all 12.2 M parameters.
+Data is synthetic (lego is downloaded at run time by the reference and is not available offline): 100 procedurally
+ray-traced 800x800 RGBA views with lego's intrinsics; weights are random-init.  Before the W warm-up steps the model is
+trained for --pretrain steps (untimed) so that the occupancy grid and the adaptive ray batch are in steady state, which
+is also the state the reference's published tqdm reading (133 it/s) refers to.
+
+value  = rays/s over all ranks, inputs resident in HBM (pixels shuffled and rays generated on the device, as the
+         reference does);  e2e = the same metric with every step's ray batch (origins, directions, RGBA targets)
+         copied from pinned host memory and the loss read back, through Runner.train_step(batch).
+Prints ONE JSON line on rank 0."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+ALGO = {   # algorithmic bytes / flops per sample
+    "network_fwd": dict(bytes=524 + 28 + 8 + 64, flops=20480),
+    "network_bwd": dict(bytes=64 + 28 + 8 + 128 * 8, flops=61440),
+}
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return p["hbm_gbs"], p["bf16_tflops"], "measured"
+    except Exception:
+        return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------- CPU arm
+def cpu_train_iteration(n_rays, seed=0):
+    """One training iteration's ray-proportional work with the oracle (CPU port of the reference path): march, compaction,
+    hash encode + MLPs forward, composite + Huber + composite backward, MLP backward, hash scatter.  Returns seconds, rays, samples."""
+    import numpy as np
+    import oracle_lib as ol
+    cfg = ol.HashCfg(1)
+    rng = np.random.default_rng(seed)
+    st = cpu_train_iteration.__dict__
+    if "grid" not in st:
+        st["grid"] = rng.uniform(-1e-4, 1e-4, cfg.n_params).astype(np.float16)
+        st["wd"] = rng.uniform(-0.3, 0.3, 3072).astype(np.float16)
+        st["wr"] = rng.uniform(-0.3, 0.3, 7168).astype(np.float16)
+        st["bits"], _ = ol.sphere_bitfield(0.3, shell=0.02)      # thin shell: ~60-90 samples per hit ray, like a trained scene
+    grid, wd, wr, bits = st["grid"], st["wd"], st["wr"], st["bits"]
+    o, d = ol.random_rays(n_rays, seed=seed)
+    bg = rng.random((n_rays, 3), dtype=np.float32)
+    target = rng.random((n_rays, 3), dtype=np.float32)
+    t0 = time.perf_counter()
+    coords, _, numsteps, cnt = ol.march(o, d, bits, max_samples=n_rays * 1024)
+    S = int(cnt[1])
+    cc, ns_c, _ = ol.compact(coords, numsteps, max(S, 1))
+    pos, dirs = np.ascontiguousarray(cc[:S, :3]), np.ascontiguousarray(cc[:S, 4:])
+    out, enc, h = ol.network_fwd(cfg, pos, dirs, grid, wd, wr, acc32=False)
+    rgb = ol.composite_fwd(out, cc, numsteps, ns_c, bg)
+    g, _ = ol.huber_grad(rgb, target)
+    dnet = ol.composite_bwd(out, cc, ns_c, g.reshape(n_rays, 3), rgb, 0.001)
+    _, inter_d = ol.mlp_fwd(wd, enc, 0)
+    rin = np.concatenate([h, ol.sh(dirs, np.float16)], 1)
+    _, inter_r = ol.mlp_fwd(wr, rin, 1)
+    dYr = np.zeros((S, 16), np.float16)
+    dYr[:, :3] = dnet[:, :3]
+    d_rin, _, _ = ol.mlp_bwd(wr, rin, inter_r, dYr, 1, 3)
+    dYd = d_rin[:, :16].astype(np.float32)
+    dYd[:, 0] += dnet[:, 3].astype(np.float32)
+    d_enc, _, _ = ol.mlp_bwd(wd, enc, inter_d, dYd.astype(np.float16), 0, 16)
+    ol.hash_bwd(cfg, pos, d_enc)
+    return time.perf_counter() - t0, n_rays, S
+
+
+def cpu_baseline(n_rays=256, iters=4):
+    cpu_train_iteration(64)                                 # warm up (builds the oracle, touches the table)
+    t, r, s = 0.0, 0, 0
+    for k in range(iters):
+        dt, rr, ss = cpu_train_iteration(n_rays, seed=k + 1)
+        t, r, s = t + dt, r + rr, s + ss
+    cores = len(os.sched_getaffinity(0))
+    return {"value": r / t, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": f"{iters} training iterations of {n_rays} rays ({s // iters} samples each): march, hash+MLP fwd, composite+loss+bwd, "
+                      f"MLP bwd, hash scatter with the oracle (OpenMP where the loop is parallel); dense Adam sweep excluded",
+            "samples_per_s": s / t}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_rays = max(16, min(256, 4096 // max(args.steps, 1)))     # bounded sample: the whole run stays within minutes
+    for _ in range(max(args.warmup, 1)):
+        cpu_train_iteration(64)
+    t, r, s = 0.0, 0, 0
+    for k in range(args.steps):
+        dt, rr, ss = cpu_train_iteration(n_rays, seed=k + 1)
+        t, r, s = t + dt, r + rr, s + ss
+    cores = len(os.sched_getaffinity(0))
+    v = r / t
+    print(json.dumps({
+        "impl": "reference", "metric": "ngp_lego_train_rays_per_s", "value": v, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16", "data": "synthetic", "config": {"workload": "Instant-NGP lego (ngp_base.py + fp16), synthetic stand-in scene; "
+                                                        f"bounded sample of {n_rays} rays per step on the host CPU"},
+        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} iterations x {n_rays} rays (~{s // max(args.steps, 1)} samples each), oracle port of the reference path"},
+        "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+# ---------------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from jnerf_b200 import lib, ops, plugin  # noqa: F401
+    from jnerf_b200.runner import Runner, lego_cfg
+    from jnerf_b200.utils.config import get_cfg, update_cfg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        pg = dist.group.WORLD
+    lib.load()
+    get_cfg().clear()
+    update_cfg(**lego_cfg(fp16=True, synthetic=True, seed=1))
+    n_img = args.images
+    cfg = get_cfg()
+    cfg.dataset.train.n_images = n_img
+    cfg.dataset.train.H = cfg.dataset.train.W = args.res
+    cfg.dataset.val = None
+    cfg.dataset.train.pop("root_dir", None)
+    runner = Runner(rank=rank, world_size=world, process_group=pg)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # steady state: occupancy grid carved, ray batch adapted (untimed)
+    for _ in range(args.pretrain):
+        runner.train_step()
+    for _ in range(args.warmup):
+        runner.train_step()
+    sync()
+
+    # ---- timed region: K steps, device-resident inputs ----
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = lib.launch_count
+    rays = 0
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        rays += runner.sampler.n_rays_per_batch
+        runner.train_step()
+    e1.record()
+    sync()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    launches = lib.launch_count - launches0
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    clk = clocks.stop() if rank == 0 else None
+    total_rays = rays * world
+    value = total_rays / (ms * 1e-3)
+
+    # ---- e2e: every step's ray batch comes from pinned host memory; loss goes back to the host ----
+    ds = runner.dataset["train"]
+    host_batches = []
+    for _ in range(min(args.steps, 64) + 1):
+        b = runner.next_batch()
+        host_batches.append(tuple(t.cpu().pin_memory() for t in b))
+    h2d = sum(t.numel() * t.element_size() for t in host_batches[0])
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def host_step(k):
+        hb = host_batches[k % len(host_batches)]
+        dev = tuple(t.cuda(non_blocking=True) for t in hb)
+        loss = runner.train_step(dev)
+        loss_host.copy_(loss.mean().reshape(1), non_blocking=True)
+        return hb[1].shape[0]
+
+    for k in range(max(args.warmup, 3)):
+        host_step(k)
+    sync()
+    rays_e = 0
+    e0.record()
+    for k in range(args.steps):
+        rays_e += host_step(k)
+    e1.record()
+    sync()
+    ms_e = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
+    ms_e = float(ms_e.item())
+    e2e = {"value": rays_e * world / (ms_e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+           "iters_per_s": args.steps / (ms_e * 1e-3)}
+
+    # ---- per-kernel times on the launching stream (CUDA events), for the roofline of the dominant kernel ----
+    stage = stage_times(runner, 16)
+    n_samples = stage.pop("_samples")
+    hbm, tfl, src = peaks()
+    dom = max(("network_fwd", "network_bwd"), key=lambda k: stage[k])
+    algo = ALGO[dom]
+    t_dom = stage[dom] * 1e-3
+    gbs = n_samples * algo["bytes"] / t_dom / 1e9
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": None,
+                "peak_source": f"{src} (MEASURED_PEAKS.json hbm_gbs)", "launch_ms": stage[dom], "samples_per_launch": n_samples,
+                "algorithmic_bytes_per_sample": algo["bytes"],
+                "tensor": {"achieved_tflops": n_samples * algo["flops"] / t_dom / 1e12, "peak_tflops": tfl,
+                           "frac": n_samples * algo["flops"] / t_dom / 1e12 / tfl},
+                "stage_ms": stage}
+    out = {
+        "metric": "ngp_lego_train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "iters_per_s": args.steps / (ms * 1e-3), "published_iters_per_s_rtx3090": 133.0, "samples_per_s": None,
+        "config": {"workload": "Instant-NGP lego: projects/ngp/configs/ngp_base.py + fp16 fully-fused MLP (BASELINE config #2), "
+                               f"{n_img} synthetic {args.res}x{args.res} views, target_batch_size 2^18 samples/iter/GPU, adaptive ray batch "
+                               f"({runner.sampler.n_rays_per_batch} rays/iter/GPU at measurement), pretrain {args.pretrain} steps",
+                   "parallelism": f"dp{world}", "l2": "per-step working set (24 MB table + 171 MB optimizer state + 7 MB samples) exceeds the 126 MB L2; no explicit flush"},
+        "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline,
+    }
+    if rank == 0:
+        out["samples_per_s"] = n_samples * world * out["iters_per_s"]
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def stage_times(runner, iters):
+    """Average per-stage device time (ms) of the training step, CUDA events on the current stream."""
+    import torch
+    from jnerf_b200 import ops
+    s, m = runner.sampler, runner.model
+    names = ["raygen+target", "march", "network_fwd", "composite_loss_bwd", "network_bwd", "adam_ema"]
+    acc = {k: 0.0 for k in names}
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+    nsamp = 0
+    for it in range(iters):
+        runner.cfg.m_training_step += 1 if runner.cfg.m_training_step % 16 == 0 else 0      # keep grid updates out of the per-stage split
+        ev[0].record()
+        img_ids, rays_o, rays_d, rgba = runner.next_batch()
+        R = rays_o.shape[0]
+        bg = torch.rand((R, 3), device="cuda")
+        target = (rgba[:, :3] * rgba[:, 3:] + bg * (1 - rgba[:, 3:])).contiguous()
+        ev[1].record()
+        s.sample(img_ids, rays_o, rays_d, is_training=True)
+        ev[2].record()
+        coords, n_dev = s.coords_compacted, s.n_samples_dev
+        ops.network_fwd(coords, m.pos_encoder.m_grid, m.pos_encoder.levels, m.density_mlp.con_weights, m.rgb_mlp.con_weights, n_dev=n_dev,
+                        out=runner.net_out, enc=runner.enc)
+        ev[3].record()
+        ops.composite_loss_bwd(runner.net_out, coords, s._rays_numsteps, s._rays_numsteps_compacted, bg, target, s.density_grid_mean,
+                               delta=0.1, cascades=s.NERF_CASCADES, dnet=runner.dnet)
+        ev[4].record()
+        ops.network_bwd(coords, runner.enc, m.pos_encoder.levels, m.density_mlp.con_weights, m.rgb_mlp.con_weights, runner.dnet, runner.grid_grad,
+                        runner.dwd, runner.dwr, n_dev=n_dev)
+        ev[5].record()
+        adam = runner.optimizer._nested_optimizer
+        for p, g in ((m.pos_encoder.m_grid, runner.grid_grad), (m.density_mlp.con_weights, runner.dwd), (m.rgb_mlp.con_weights, runner.dwr)):
+            st = runner._st[id(p)]
+            ops.adam_ema(p.data, g, st.m, st.v, st.master, 0.0, max(adam.n_step, 1), zero_grad=True)   # lr 0: timing only, parameters barely move
+        ev[6].record()
+        torch.cuda.synchronize()
+        for k, name in enumerate(names):
+            acc[name] += ev[k].elapsed_time(ev[k + 1])
+        nsamp = min(int(n_dev.item()), s.target_batch_size)
+        runner.cfg.m_training_step += 1
+    out = {k: v / iters for k, v in acc.items()}
+    out["_samples"] = nsamp
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pretrain", type=int, default=256)
+    ap.add_argument("--images", type=int, default=100)
+    ap.add_argument("--res", type=int, default=800)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

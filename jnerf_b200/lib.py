@@ -43,6 +43,14 @@ SIGNATURES = {
     "ngp_pcg32_advance": (None, [_vp, _i64]),
 }
 
+# kernels launched by each entry point (our own __global__ functions; memsets not counted) -- bench.py's gpu_launches
+KERNELS_PER_CALL = {
+    "ngp_hash_level_table": 1, "ngp_hash_fwd": 1, "ngp_hash_bwd": 1, "ngp_sh_fwd": 1, "ngp_mlp_fwd": 1, "ngp_mlp_bwd": 1,
+    "ngp_network_fwd": 1, "ngp_network_bwd": 1, "ngp_density_fwd": 1, "ngp_march": 3, "ngp_compact": 1, "ngp_composite_fwd": 1,
+    "ngp_composite_bwd": 1, "ngp_composite_infer": 1, "ngp_composite_loss_bwd": 1, "ngp_grid_mark_untrained": 1,
+    "ngp_grid_generate_samples": 1, "ngp_grid_splat": 1, "ngp_grid_ema": 1, "ngp_grid_update_bitfield": 7, "ngp_adam_ema": 1, "ngp_raygen": 1,
+}
+launch_count = 0
 _lib = None
 
 
@@ -68,7 +76,9 @@ def load():
 
 def call(name, *args):
     """Call an int-returning entry point and raise NgpError(ngp_last_error()) on a non-zero status."""
+    global launch_count
     lib = load()
+    launch_count += KERNELS_PER_CALL.get(name, 0)
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise NgpError(f"{name} failed ({rc}): {lib.ngp_last_error().decode()}")

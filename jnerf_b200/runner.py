@@ -1,0 +1,223 @@
+"""Thin training / evaluation driver: the caller of the hot path, mirroring runner/runner.py:14-264 step for step
+(SURVEY.md section 3.1).  `train_step` is the B200 fast path: no autograd graph, no host sync (except the
+reference's own batch-size adaptation every 16 steps), one C-ABI call per stage:
+
+    [grid update /16] -> raygen -> march -> (compaction bookkeeping) -> fused network fwd ->
+    fused composite + Huber + composite bwd -> fused network bwd -> [NCCL all-reduce] -> fused Adam+EMA
+
+`train_step_autograd` runs the same step through the per-operator plugin classes and torch autograd, exactly as
+JNeRF's Runner.train does with Jittor; tests check that both give the same parameters."""
+import os
+
+import numpy as np
+import torch
+
+from . import ops
+from .plugin import losses as L
+from .utils.config import get_cfg
+from .utils.registry import DATASETS, LOSSES, NETWORKS, OPTIMS, SAMPLERS, build_from_cfg
+
+
+class Runner:
+    def __init__(self, rank=0, world_size=1, process_group=None):
+        self.cfg = get_cfg()
+        cfg = self.cfg
+        self.rank, self.world_size, self.pg = rank, world_size, process_group
+        self.dataset = {"train": build_from_cfg(cfg.dataset.train, DATASETS)}
+        cfg.dataset_obj = self.dataset["train"]
+        self.dataset["val"] = build_from_cfg(cfg.dataset.val, DATASETS) if cfg.dataset.val else self.dataset["train"]
+        self.dataset["test"] = None
+        self.model = build_from_cfg(cfg.model, NETWORKS)
+        cfg.model_obj = self.model
+        self.sampler = build_from_cfg(cfg.sampler, SAMPLERS)
+        cfg.sampler_obj = self.sampler
+        if world_size > 1:
+            self.sampler.dp_group = (process_group, world_size)
+        params = list(self.model.parameters())
+        self.optimizer = build_from_cfg(cfg.optim, OPTIMS, params=params)
+        self.optimizer = build_from_cfg(cfg.expdecay, OPTIMS, nested_optimizer=self.optimizer)
+        self.ema_optimizer = build_from_cfg(cfg.ema, OPTIMS, params=params)
+        self.ema_optimizer.attach(self.optimizer)
+        self.loss_func = build_from_cfg(cfg.loss, LOSSES)
+        self.background_color = cfg.background_color
+        self.tot_train_steps = cfg.tot_train_steps
+        self.n_rays_per_batch = cfg.n_rays_per_batch
+        self.W, self.H = self.dataset["train"].resolution
+        self.start = 0
+        cfg.m_training_step = 0
+        self.val_freq = 4096
+        self.fast = bool(getattr(self.model, "fused", False))
+        if self.fast:
+            self._init_fast_path()
+        self._bg_gen = torch.Generator(device="cuda").manual_seed(int(cfg.seed or 1) + 7)
+
+    # ------------------------------------------------------------------------------------------ fast path
+    def _init_fast_path(self):
+        dev = "cuda"
+        m = self.model
+        cap = self.sampler.target_batch_size
+        self.grid_grad = torch.zeros(m.pos_encoder.m_grid.numel(), dtype=torch.float16, device=dev)
+        n_w = m.density_mlp.con_weights.numel() + m.rgb_mlp.con_weights.numel()
+        # [dW density | dW colour | measured-sample counter]: one flat fp32 buffer = one small all-reduce
+        self.w_grad = torch.zeros(n_w + 8, dtype=torch.float32, device=dev)
+        self.dwd = self.w_grad[:m.density_mlp.con_weights.numel()]
+        self.dwr = self.w_grad[m.density_mlp.con_weights.numel():n_w]
+        self.net_out = torch.zeros((cap, 4), dtype=torch.float16, device=dev)
+        self.enc = torch.empty((cap, 32), dtype=torch.float16, device=dev)
+        self.dnet = torch.zeros((cap, 4), dtype=torch.float16, device=dev)
+        adam = self.optimizer._nested_optimizer
+        self._st = {id(s.p): s for s in adam.state}
+        self.last_loss = None
+        self.last_rgb = None
+
+    def next_batch(self):
+        """Global pixel batch of this step (identical on every rank), sharded contiguously by rank."""
+        ds = self.dataset["train"]
+        n = self.sampler.n_rays_per_batch                       # per-rank rays; the global batch is world_size x n (weak scaling)
+        pix = ds.next_pixels(n * self.world_size)
+        if self.world_size > 1:
+            pix = pix[self.rank * n:(self.rank + 1) * n]
+        img_ids, rays_o, rays_d = ds.rays_for(pix)
+        return img_ids, rays_o, rays_d, ds.rgba_for(pix)
+
+    def train_step(self, batch=None):
+        cfg, s, m = self.cfg, self.sampler, self.model
+        i = cfg.m_training_step
+        img_ids, rays_o, rays_d, rgba = self.next_batch() if batch is None else batch
+        R = rays_o.shape[0]
+        bg = torch.rand((R * self.world_size, 3), device="cuda", generator=self._bg_gen)    # runner.py:66 (global batch, then this rank's rows)
+        if self.world_size > 1:
+            bg = bg[self.rank * R:(self.rank + 1) * R].contiguous()
+        target = rgba[:, :3] * rgba[:, 3:] + bg * (1 - rgba[:, 3:])                         # runner.py:68
+        s.sample(img_ids, rays_o, rays_d, is_training=True, ray_index_offset=self.rank * R)  # grid update /16, march, bookkeeping
+        coords, n_dev = s.coords_compacted, s.n_samples_dev
+        ops.network_fwd(coords, m.pos_encoder.m_grid, m.pos_encoder.levels, m.density_mlp.con_weights, m.rgb_mlp.con_weights,
+                        n_dev=n_dev, out=self.net_out, enc=self.enc)
+        rgb, loss, _ = ops.composite_loss_bwd(self.net_out, coords, s._rays_numsteps, s._rays_numsteps_compacted, bg, target.contiguous(),
+                                              s.density_grid_mean, delta=self.loss_func.delta, cascades=s.NERF_CASCADES, dnet=self.dnet)
+        ops.network_bwd(coords, self.enc, m.pos_encoder.levels, m.density_mlp.con_weights, m.rgb_mlp.con_weights, self.dnet,
+                        self.grid_grad, self.dwd, self.dwr, n_dev=n_dev)
+        scale = 1.0
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.grid_grad, group=self.pg)
+            dist.all_reduce(self.w_grad, group=self.pg)
+            scale = 1.0 / self.world_size          # local loss_scale is 128/R_local (calc_rgb.h:100-101): the sum is W x the global-batch gradient
+        lr = self.optimizer.advance_lr()
+        adam = self.optimizer._nested_optimizer
+        adam.n_step += 1
+        self.ema_optimizer.steps += 1
+        for p, g in ((m.pos_encoder.m_grid, self.grid_grad), (m.density_mlp.con_weights, self.dwd), (m.rgb_mlp.con_weights, self.dwr)):
+            st = self._st[id(p)]
+            ops.adam_ema(p.data, g, st.m, st.v, st.master, lr, adam.n_step, adam.betas[0], adam.betas[1], adam.eps, self.ema_optimizer.decay,
+                         grad_scale=scale, zero_grad=True)
+        self.last_loss, self.last_rgb = loss, rgb
+        cfg.m_training_step = i + 1
+        return loss
+
+    # --------------------------------------------------------------------- per-operator path (as the reference wires it)
+    def train_step_autograd(self, batch=None):
+        cfg = self.cfg
+        i = cfg.m_training_step
+        img_ids, rays_o, rays_d, rgba = self.next_batch() if batch is None else batch
+        bg = torch.rand((rays_o.shape[0], 3), device="cuda", generator=self._bg_gen)
+        target = (rgba[:, :3] * rgba[:, 3:] + bg * (1 - rgba[:, 3:])).detach()
+        pos, dir_ = self.sampler.sample(img_ids, rays_o, rays_d, is_training=True)
+        network_outputs = self.model(pos, dir_)
+        rgb = self.sampler.rays2rgb(network_outputs, bg)
+        loss = self.loss_func(rgb, target)
+        self.optimizer.step(loss)
+        self.ema_optimizer.ema_step()
+        cfg.m_training_step = i + 1
+        return loss.sum(-1)
+
+    def train(self, steps=None, log_every=0):
+        end = self.tot_train_steps if steps is None else self.cfg.m_training_step + steps
+        step_fn = self.train_step if self.fast else self.train_step_autograd
+        while self.cfg.m_training_step < end:
+            loss = step_fn()
+            i = self.cfg.m_training_step
+            if log_every and i % log_every == 0 and self.rank == 0:
+                print(f"STEP={i} | LOSS={loss.mean().item():.6f} | rays/batch={self.sampler.n_rays_per_batch}", flush=True)
+
+    # ------------------------------------------------------------------------------------------ evaluation
+    @torch.no_grad()
+    def render_img(self, dataset_mode="train", img_id=0):
+        """runner.py:197-236: tile the image in n_rays_per_batch chunks; returns (img HxWx3, target HxWx3)."""
+        ds = self.dataset[dataset_mode]
+        W, H = ds.resolution
+        rays_o, rays_d = ds.generate_rays_total_test(img_id)
+        tile = self.cfg.n_rays_per_batch
+        img = torch.empty((H * W, 3), device="cuda")
+        alpha = torch.empty((H * W, 1), device="cuda")
+        ids = torch.zeros(tile, dtype=torch.int32, device="cuda")
+        s, m = self.sampler, self.model
+        for p in range(0, H * W, tile):
+            e = min(p + tile, H * W)
+            o, d = rays_o[p:e], rays_d[p:e]
+            if e - p < tile:
+                o = torch.cat([o, torch.ones((tile - (e - p), 3), device="cuda")])
+                d = torch.cat([d, torch.ones((tile - (e - p), 3), device="cuda")])
+            s.sample(ids, o.contiguous(), d.contiguous())
+            coords = s._coords
+            if self.fast:
+                out, _ = ops.network_fwd(coords.contiguous(), m.pos_encoder.m_grid, m.pos_encoder.levels, m.density_mlp.con_weights,
+                                         m.rgb_mlp.con_weights, save_enc=False) if coords.shape[0] else (torch.empty((0, 4), dtype=torch.float16, device="cuda"), None)
+            else:
+                out = m(coords[:, :3], coords[:, 4:])
+            rgb, a = s.rays2rgb(out, inference=True)
+            img[p:e], alpha[p:e] = rgb[:e - p], a[:e - p]
+        bgc = torch.tensor(self.background_color, dtype=torch.float32, device="cuda")
+        img = img + bgc * (1 - alpha)
+        tar = ds.rgba_for(torch.arange(H * W, device="cuda", dtype=torch.int32) + int(img_id) * H * W)
+        tar = tar[:, :3] * tar[:, 3:] + bgc * (1 - tar[:, 3:])
+        return img.reshape(H, W, 3), tar.reshape(H, W, 3)
+
+    @torch.no_grad()
+    def psnr(self, dataset_mode="val", max_images=None):
+        """mean over images of -10 log10(mse) (runner.py:86-99, mse_loss.py:6-7)."""
+        ds = self.dataset[dataset_mode]
+        n = ds.n_images if max_images is None else min(max_images, ds.n_images)
+        tot = 0.0
+        for k in range(n):
+            img, tar = self.render_img(dataset_mode, k)
+            tot += float(L.mse2psnr(L.img2mse(img, tar)).item())
+        return tot / n
+
+    # ------------------------------------------------------------------------------------------ checkpoint (N4)
+    def save_ckpt(self, path):
+        adam = self.optimizer._nested_optimizer
+        torch.save({"global_step": self.cfg.m_training_step, "model": self.model.state_dict(), "sampler": self.sampler.state_dict(),
+                    "optimizer": self.optimizer.state_dict(), "nested_optimizer": adam.state_dict(),
+                    "ema_optimizer": self.ema_optimizer.state_dict()}, path)
+
+    def load_ckpt(self, path):
+        ck = torch.load(path, map_location="cuda", weights_only=False)
+        self.cfg.m_training_step = self.start = ck["global_step"]
+        self.model.load_state_dict(ck["model"])
+        self.sampler.load_state_dict(ck["sampler"])
+        self.optimizer.load_state_dict(ck["optimizer"])
+        self.optimizer._nested_optimizer.load_state_dict(ck["nested_optimizer"])
+        self.ema_optimizer.load_state_dict(ck["ema_optimizer"])
+
+
+def lego_cfg(fp16=True, synthetic=True, **over):
+    """projects/ngp/configs/ngp_base.py key for key, + fp16 (BASELINE config #2) and the synthetic stand-in dataset."""
+    ds_type = "SyntheticNerfDataset" if synthetic else "NerfDataset"
+    c = dict(
+        sampler=dict(type="DensityGridSampler", update_den_freq=16),
+        encoder=dict(pos_encoder=dict(type="HashEncoder"), dir_encoder=dict(type="SHEncoder")),
+        model=dict(type="NGPNetworks", use_fully=True),
+        loss=dict(type="HuberLoss", delta=0.1),
+        optim=dict(type="Adam", lr=1e-1, eps=1e-15, betas=(0.9, 0.99)),
+        ema=dict(type="EMA", decay=0.95),
+        expdecay=dict(type="ExpDecay", decay_start=20_000, decay_interval=10_000, decay_base=0.33, decay_end=None),
+        dataset=dict(train=dict(type=ds_type, root_dir="data/lego", batch_size=4096, mode="train"),
+                     val=dict(type=ds_type, root_dir="data/lego", batch_size=4096, mode="val", preload_shuffle=False),
+                     test=dict(type=ds_type, root_dir="data/lego", batch_size=4096, mode="test", preload_shuffle=False)),
+        exp_name="lego", log_dir="./logs", tot_train_steps=40000, background_color=[0, 0, 0],
+        hash_func="p0 ^ p1 * 19349663 ^ p2 * 83492791", cone_angle_constant=0.00390625, near_distance=0.2, n_rays_per_batch=4096,
+        n_training_steps=16, target_batch_size=1 << 18, const_dt=True, load_ckpt=False, ckpt_path=None, alpha_image=False, fp16=fp16,
+    )
+    c.update(over)
+    return c

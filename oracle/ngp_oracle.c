@@ -386,8 +386,13 @@ void orc_mlp_bwd(uint32_t n, uint32_t in_dim, uint32_t width, uint32_t out_pad, 
     const half_t* Wh = W + (size_t)width * in_dim;
     const half_t* Wo = Wh + (size_t)n_hidden_matmuls * width * width;
     double* acc = (double*)calloc(nW, sizeof(double));
+#pragma omp parallel
+    {
+    double* acc_t = (double*)calloc(nW, sizeof(double));       /* per-thread partial sums, reduced in thread order below */
     float* g = (float*)malloc(sizeof(float) * 2 * width);
-    for (uint32_t s = 0; s < n; ++s) {
+#pragma omp for schedule(static)
+    for (int64_t ss = 0; ss < (int64_t)n; ++ss) {
+        const uint32_t s = (uint32_t)ss;
         float* gc = g; float* gn = g + width;
         /* last hidden layer */
         const half_t* hl = inter + ((size_t)(nh - 1) * n + s) * width;
@@ -397,14 +402,14 @@ void orc_mlp_bwd(uint32_t n, uint32_t in_dim, uint32_t width, uint32_t out_pad, 
             gc[k] = h2f(f2h(h2f(hl[k]) > 0 ? a : 0));
         }
         /* wgrad of the output layer */
-        double* aWo = acc + (size_t)width * in_dim + (size_t)n_hidden_matmuls * width * width;
+        double* aWo = acc_t + (size_t)width * in_dim + (size_t)n_hidden_matmuls * width * width;
         for (uint32_t o = 0; o < n_out_valid; ++o)
             for (uint32_t k = 0; k < width; ++k) aWo[o * width + k] += (double)h2f(dY[(size_t)s * out_pad + o]) * h2f(hl[k]);
         if (temps) for (uint32_t k = 0; k < width; ++k) temps[((size_t)0 * n + s) * width + k] = f2h(gc[k]);
         for (int l = (int)nh - 1; l >= 1; --l) { /* hidden matmul l maps hidden l-1 -> hidden l */
             const half_t* Wl = Wh + (size_t)(l - 1) * width * width;
             const half_t* hp = inter + ((size_t)(l - 1) * n + s) * width;
-            double* aW = acc + (size_t)width * in_dim + (size_t)(l - 1) * width * width;
+            double* aW = acc_t + (size_t)width * in_dim + (size_t)(l - 1) * width * width;
             for (uint32_t o = 0; o < width; ++o)
                 for (uint32_t k = 0; k < width; ++k) aW[o * width + k] += (double)gc[o] * h2f(hp[k]);
             for (uint32_t k = 0; k < width; ++k) {
@@ -416,7 +421,7 @@ void orc_mlp_bwd(uint32_t n, uint32_t in_dim, uint32_t width, uint32_t out_pad, 
             if (temps) for (uint32_t k = 0; k < width; ++k) temps[((size_t)(nh - l) * n + s) * width + k] = f2h(gc[k]);
         }
         for (uint32_t o = 0; o < width; ++o)
-            for (uint32_t k = 0; k < in_dim; ++k) acc[o * in_dim + k] += (double)gc[o] * h2f(X[(size_t)s * in_dim + k]);
+            for (uint32_t k = 0; k < in_dim; ++k) acc_t[o * in_dim + k] += (double)gc[o] * h2f(X[(size_t)s * in_dim + k]);
         if (dX)
             for (uint32_t k = 0; k < in_dim; ++k) {
                 float a = 0;
@@ -424,8 +429,12 @@ void orc_mlp_bwd(uint32_t n, uint32_t in_dim, uint32_t width, uint32_t out_pad, 
                 dX[(size_t)s * in_dim + k] = f2h(a);
             }
     }
+#pragma omp critical
+    for (size_t i = 0; i < nW; ++i) acc[i] += acc_t[i];
+    free(acc_t); free(g);
+    }
     for (size_t i = 0; i < nW; ++i) dW[i] = (float)acc[i];
-    free(acc); free(g);
+    free(acc);
 }
 
 /* ------------------------------------------------------------------------------------------------

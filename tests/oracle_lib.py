@@ -381,8 +381,9 @@ def raygen(pix, W, H, xforms, focal, principal):
 # ----------------------------------------------------------------------------------------------------
 # synthetic scene helpers shared by tests / bench (not reference semantics)
 # ----------------------------------------------------------------------------------------------------
-def sphere_bitfield(radius=0.3, center=(0.5, 0.5, 0.5), cascades=5):
-    """Occupancy bitfield of an analytic solid sphere in the unit cube, built through the oracle's grid path."""
+def sphere_bitfield(radius=0.3, center=(0.5, 0.5, 0.5), cascades=5, shell=None):
+    """Occupancy bitfield of an analytic solid sphere (or, with `shell`, a spherical shell of that half-thickness) in the
+    unit cube, built through the oracle's grid path."""
     grid = np.zeros(G3 * 5, np.float32)
     ids = np.arange(G3, dtype=np.uint32)
     def minv(x):
@@ -399,7 +400,8 @@ def sphere_bitfield(radius=0.3, center=(0.5, 0.5, 0.5), cascades=5):
         py = ((y + 0.5) / 128 - 0.5) * sc + 0.5
         pz = ((z + 0.5) / 128 - 0.5) * sc + 0.5
         d2 = (px - center[0]) ** 2 + (py - center[1]) ** 2 + (pz - center[2]) ** 2
-        grid[lvl * G3:(lvl + 1) * G3] = np.where(d2 < radius * radius, 1.0, 0.0)
+        inside = d2 < radius * radius if shell is None else np.abs(np.sqrt(d2) - radius) < shell
+        grid[lvl * G3:(lvl + 1) * G3] = np.where(inside, 1.0, 0.0)
     return update_bitfield(grid, 1.0, cascades), grid
 
 
