@@ -108,42 +108,93 @@ __device__ __forceinline__ RayState ray_setup(uint32_t i, const float* __restric
     return r;
 }
 
-// one marching pass; EMIT=false counts, EMIT=true writes rows
+// One marching pass by a whole warp per ray; EMIT=false counts, EMIT=true writes rows.
+//
+// The reference's loop visits a fixed sequence t_{k+1} = t_k + calc_dt(t_k) that does not depend on the occupancy
+// (both its branches advance by calc_dt; the empty-space branch just advances several steps without testing).  The warp
+// therefore materialises 32 consecutive t_k (same float additions, same order), evaluates position, mip level, occupancy
+// bit and the distance to the next voxel of all 32 in parallel, and then replays the reference's sequential control flow
+// on two ballot masks -- identical arithmetic per visited step, 32 occupancy lookups in flight instead of one.
 template <bool EMIT>
-__device__ __forceinline__ uint32_t march_ray(const RayState& r, float lo, float hi, float cone, const MarchCfg& c,
-                                              const uint8_t* __restrict__ bits, uint32_t limit, float* __restrict__ out) {
+__device__ __forceinline__ uint32_t march_ray_warp(const RayState& r, float lo, float hi, float cone, const MarchCfg& c,
+                                                   const uint8_t* __restrict__ bits, uint32_t limit, float* __restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
     uint32_t j = 0;
-    float t = r.startt;
+    float t0 = r.startt;          // t of lane 0 of the current chunk
+    bool pending = false;         // an empty-space skip that did not finish inside the previous chunk
+    float pending_tt = 0.f;
     float wd[3], diag = hi - lo;
     if (EMIT) { wd[0] = (r.d[0] + 1.0f) * 0.5f; wd[1] = (r.d[1] + 1.0f) * 0.5f; wd[2] = (r.d[2] + 1.0f) * 0.5f; }
-    for (;;) {
-        const float p[3] = {__fmaf_rn(t, r.d[0], r.o[0]), __fmaf_rn(t, r.d[1], r.o[1]), __fmaf_rn(t, r.d[2], r.o[2])};
-        if (!(contains(lo, hi, p) && j < limit)) break;
+    for (uint32_t guard = 0; guard < (1u << 20); ++guard) {   // a degenerate ray (d == 0) would spin forever in the reference
+        float t = t0;
+        for (uint32_t i = 0; i < lane; ++i) t += calc_dt(c, t, cone);          // t_k .. t_{k+31}, sequential float adds
         const float dt = calc_dt(c, t, cone);
-        const uint32_t mip = (uint32_t)mip_from_dt(c, dt, p[0], p[1], p[2]);
-        if (occupied_at(p[0], p[1], p[2], bits, mip)) {
-            if (EMIT) {
-                float* q = out + (size_t)j * 7;
-                q[0] = (p[0] - lo) / diag; q[1] = (p[1] - lo) / diag; q[2] = (p[2] - lo) / diag;   // warp_position
-                q[3] = nerf_warp_dt(dt, c.cascades);
-                q[4] = wd[0]; q[5] = wd[1]; q[6] = wd[2];
-            }
-            ++j;
-            t += dt;
-        } else {
-            t = advance_to_next_voxel(c, t, cone, p, r.d, r.id, NERF_GRIDSIZE >> mip);
+        const float t_next_chunk = __shfl_sync(FULL, t + dt, 31);
+        int cur = 0;
+        if (pending) {
+            const uint32_t ge = __ballot_sync(FULL, !(t < pending_tt));
+            if (ge == 0) { t0 = t_next_chunk; continue; }                       // the whole chunk lies inside the skipped span
+            cur = __ffs(ge) - 1;
+            pending = false;
         }
+        const float p[3] = {__fmaf_rn(t, r.d[0], r.o[0]), __fmaf_rn(t, r.d[1], r.o[1]), __fmaf_rn(t, r.d[2], r.o[2])};
+        const bool inside = contains(lo, hi, p);
+        uint32_t mip = 0;
+        bool occ = false;
+        float t_target = 0.f;
+        if (inside) {
+            mip = (uint32_t)mip_from_dt(c, dt, p[0], p[1], p[2]);
+            occ = occupied_at(p[0], p[1], p[2], bits, mip);
+            if (!occ) {                                                          // distance_to_next_voxel, ray_sampler_header.h:728-739
+                const float rs = (float)(NERF_GRIDSIZE >> mip);
+                const float q[3] = {rs * p[0], rs * p[1], rs * p[2]};
+                const float tx = (floorf(q[0] + 0.5f + 0.5f * sgn(r.d[0])) - q[0]) * r.id[0];
+                const float ty = (floorf(q[1] + 0.5f + 0.5f * sgn(r.d[1])) - q[1]) * r.id[1];
+                const float tz = (floorf(q[2] + 0.5f + 0.5f * sgn(r.d[2])) - q[2]) * r.id[2];
+                t_target = t + fmaxf(fminf(fminf(tx, ty), tz) / rs, 0.0f);
+            }
+        }
+        const uint32_t inside_m = __ballot_sync(FULL, inside), occ_m = __ballot_sync(FULL, occ);
+        bool done = false;
+        while (cur < 32) {
+            if (!((inside_m >> cur) & 1u) || j >= limit) { done = true; break; }   // while (aabb.contains(pos) && j < limit)
+            if ((occ_m >> cur) & 1u) {
+                const uint32_t run_m = (occ_m & inside_m) >> cur;                 // consecutive occupied steps are taken one by one
+                uint32_t n_run = (run_m == 0xffffffffu) ? 32u : (uint32_t)__ffs(~run_m) - 1u;
+                n_run = min(n_run, limit - j);
+                if (EMIT && (int)lane >= cur && lane < cur + n_run) {
+                    float* q = out + (size_t)(j + lane - cur) * 7;
+                    q[0] = (p[0] - lo) / diag; q[1] = (p[1] - lo) / diag; q[2] = (p[2] - lo) / diag;   // warp_position
+                    q[3] = nerf_warp_dt(dt, c.cascades);
+                    q[4] = wd[0]; q[5] = wd[1]; q[6] = wd[2];
+                }
+                j += n_run;
+                cur += n_run;
+            } else {
+                // advance_to_next_voxel: do { t += dt } while (t < t_target)  -> first later step with !(t < t_target)
+                const float tt = __shfl_sync(FULL, t_target, cur);
+                uint32_t ge = __ballot_sync(FULL, !(t < tt));
+                ge &= (cur >= 31) ? 0u : ~((2u << cur) - 1u);
+                if (ge) cur = __ffs(ge) - 1;
+                else { pending = true; pending_tt = tt; cur = 32; }
+            }
+        }
+        if (done) break;
+        t0 = t_next_chunk;
     }
     return j;
 }
 
-__global__ void march_count_kernel(uint32_t n_rays, float lo, float hi, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                                   const uint8_t* __restrict__ bits, float cone, float near_distance, MarchCfg c, uint64_t rng_state,
-                                   uint64_t rng_inc, uint32_t* __restrict__ counts) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) march_count_kernel(uint32_t n_rays, float lo, float hi, const float* __restrict__ rays_o,
+                                                          const float* __restrict__ rays_d, const uint8_t* __restrict__ bits, float cone,
+                                                          float near_distance, MarchCfg c, uint64_t rng_state, uint64_t rng_inc,
+                                                          uint32_t* __restrict__ counts) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per ray
     if (i >= n_rays) return;
     const RayState r = ray_setup(i, rays_o, rays_d, lo, hi, near_distance, cone, c, rng_state, rng_inc);
-    counts[i] = march_ray<false>(r, lo, hi, cone, c, bits, NERF_STEPS, nullptr);
+    const uint32_t n = march_ray_warp<false>(r, lo, hi, cone, c, bits, NERF_STEPS, nullptr);
+    if ((threadIdx.x & 31) == 0) counts[i] = n;
 }
 
 // Single-CTA exclusive scan over ray counts (R <= a few 100k): numsteps[i] = {count or 0, base}, ray index of accepted rays.
@@ -193,15 +244,16 @@ __global__ void __launch_bounds__(1024) march_scan_kernel(uint32_t n_rays, uint3
     if (t == 1023) { counters[0] = s_acc[1023]; counters[1] = s_sum[1023]; }
 }
 
-__global__ void march_emit_kernel(uint32_t n_rays, float lo, float hi, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                                  const uint8_t* __restrict__ bits, float cone, float near_distance, MarchCfg c, uint64_t rng_state,
-                                  uint64_t rng_inc, const uint32_t* __restrict__ numsteps, float* __restrict__ coords) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) march_emit_kernel(uint32_t n_rays, float lo, float hi, const float* __restrict__ rays_o,
+                                                         const float* __restrict__ rays_d, const uint8_t* __restrict__ bits, float cone,
+                                                         float near_distance, MarchCfg c, uint64_t rng_state, uint64_t rng_inc,
+                                                         const uint32_t* __restrict__ numsteps, float* __restrict__ coords) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= n_rays) return;
     const uint32_t n = numsteps[2 * i], base = numsteps[2 * i + 1];
     if (n == 0) return;
     const RayState r = ray_setup(i, rays_o, rays_d, lo, hi, near_distance, cone, c, rng_state, rng_inc);
-    march_ray<true>(r, lo, hi, cone, c, bits, n, coords + (size_t)base * 7);
+    march_ray_warp<true>(r, lo, hi, cone, c, bits, n, coords + (size_t)base * 7);
 }
 
 // Compaction bases: exclusive scan of the per-ray counts in ray order (single CTA), with the reference's truncation rule.
@@ -288,89 +340,136 @@ __device__ __forceinline__ Sample eval_sample(const T* __restrict__ net, const f
     return s;
 }
 
+// ---- warp-per-ray composite -----------------------------------------------------------------------------------
+// Lane l handles samples l, l+32, ... of its ray.  Transmittance T_j = prod_{k<j}(1-alpha_k) and the running colour are
+// warp scans (the reference accumulates them serially per thread, calc_rgb.h:45-65): same formulae, reassociated sums.
+__device__ __forceinline__ float warp_incl_prod(float v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_up_sync(0xffffffffu, v, o); if ((int)lane >= o) v *= u; }
+    return v;
+}
+__device__ __forceinline__ float warp_incl_sum(float v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_up_sync(0xffffffffu, v, o); if ((int)lane >= o) v += u; }
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// forward over one ray: returns (all lanes) the composited colour WITHOUT background and the final transmittance
+template <typename T>
+__device__ __forceinline__ void composite_ray_fwd(uint32_t n, uint32_t base, const T* __restrict__ net, const float* __restrict__ coords,
+                                                  uint32_t cascades, uint32_t lane, float rgb[3], float* T_final) {
+    float carry = 1.f, acc[3] = {0.f, 0.f, 0.f};
+    for (uint32_t j0 = 0; j0 < n; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        float a = 0.f, c[3] = {0.f, 0.f, 0.f};
+        if (j < n) {
+            float4 raw;
+            const Sample s = eval_sample<T>(net, coords, (size_t)base + j, cascades, &raw);
+            a = s.alpha; c[0] = s.rgb[0]; c[1] = s.rgb[1]; c[2] = s.rgb[2];
+        }
+        const float incl = warp_incl_prod(1.f - a, lane);
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.f;
+        const float w = a * (carry * excl);
+        acc[0] = __fmaf_rn(w, c[0], acc[0]); acc[1] = __fmaf_rn(w, c[1], acc[1]); acc[2] = __fmaf_rn(w, c[2], acc[2]);
+        carry *= __shfl_sync(0xffffffffu, incl, 31);
+    }
+    rgb[0] = warp_sum(acc[0]); rgb[1] = warp_sum(acc[1]); rgb[2] = warp_sum(acc[2]);
+    *T_final = carry;
+}
+
+template <typename T>
+__device__ __forceinline__ void composite_ray_bwd(uint32_t n, uint32_t base, const T* __restrict__ net, const float* __restrict__ coords,
+                                                  const float lg[3], const float rr[3], float loss_scale, float l1, uint32_t cascades,
+                                                  uint32_t lane, T* __restrict__ dnet) {
+    float carry_T = 1.f, carry_S[3] = {0.f, 0.f, 0.f};
+    for (uint32_t j0 = 0; j0 < n; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        float a = 0.f, c[3] = {0.f, 0.f, 0.f}, dt = 0.f;
+        float4 raw = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < n) {
+            const Sample s = eval_sample<T>(net, coords, (size_t)base + j, cascades, &raw);
+            a = s.alpha; c[0] = s.rgb[0]; c[1] = s.rgb[1]; c[2] = s.rgb[2]; dt = s.dt;
+        }
+        const float incl = warp_incl_prod(1.f - a, lane);
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.f;
+        const float w = a * (carry_T * excl);
+        const float T_after = carry_T * incl;                                 // T after this sample (calc_rgb.h:125)
+        float S[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) S[q] = carry_S[q] + warp_incl_sum(w * c[q], lane);   // rgb_ray2 including this sample
+        if (j < n) {
+            const float suffix[3] = {rr[0] - S[0], rr[1] - S[1], rr[2] - S[2]};
+            float4 dl;
+            dl.x = loss_scale * ((w * lg[0]) * (c[0] * (1 - c[0])));                        // calc_rgb.h:133-135 (l2 reg is 0 for Logistic)
+            dl.y = loss_scale * ((w * lg[1]) * (c[1] * (1 - c[1])));
+            dl.z = loss_scale * ((w * lg[2]) * (c[2] * (1 - c[2])));
+            const float dd = __expf(fminf(fmaxf(raw.w, -15.0f), 15.0f));                    // network_to_density_derivative
+            const float dot = lg[0] * (T_after * c[0] - suffix[0]) + (lg[1] * (T_after * c[1] - suffix[1]) + lg[2] * (T_after * c[2] - suffix[2]));
+            dl.w = loss_scale * (dd * (dt * dot)) + (raw.w < 0 ? -l1 : 0.0f);               // :137-139
+            store_net<T>(dnet, (size_t)base + j, dl);
+        }
+        carry_T *= __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) carry_S[q] = __shfl_sync(0xffffffffu, S[q], 31);
+    }
+}
+
 template <typename T, bool INFER>
-__global__ void composite_fwd_kernel(uint32_t n_rays, const T* __restrict__ net, const float* __restrict__ coords,
-                                     const uint32_t* __restrict__ numsteps_in, const uint32_t* __restrict__ numsteps_c,
-                                     const float* __restrict__ bg, uint32_t cascades, float* __restrict__ rgb_out, float* __restrict__ alpha_out) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) composite_fwd_kernel(uint32_t n_rays, const T* __restrict__ net, const float* __restrict__ coords,
+                                                            const uint32_t* __restrict__ numsteps_in, const uint32_t* __restrict__ numsteps_c,
+                                                            const float* __restrict__ bg, uint32_t cascades, float* __restrict__ rgb_out,
+                                                            float* __restrict__ alpha_out) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= n_rays) return;
     const uint32_t n = numsteps_c[2 * i], base = numsteps_c[2 * i + 1];
+    float r[3] = {0.f, 0.f, 0.f}, T_ = 1.f;
     if (n == 0) {
-        if (INFER) { rgb_out[3 * i] = rgb_out[3 * i + 1] = rgb_out[3 * i + 2] = 0.f; alpha_out[i] = 0.f; }
-        else { rgb_out[3 * i] = bg[3 * i]; rgb_out[3 * i + 1] = bg[3 * i + 1]; rgb_out[3 * i + 2] = bg[3 * i + 2]; }   // calc_rgb.h:35-39
-        return;
+        if (!INFER) { r[0] = bg[3 * i]; r[1] = bg[3 * i + 1]; r[2] = bg[3 * i + 2]; }                // calc_rgb.h:35-39
+    } else {
+        composite_ray_fwd<T>(n, base, net, coords, cascades, lane, r, &T_);
+        if (!INFER && n == numsteps_in[2 * i]) {                                                     // :68-71
+            r[0] = __fmaf_rn(T_, bg[3 * i], r[0]); r[1] = __fmaf_rn(T_, bg[3 * i + 1], r[1]); r[2] = __fmaf_rn(T_, bg[3 * i + 2], r[2]);
+        }
     }
-    float T_ = 1.f, r[3] = {0.f, 0.f, 0.f};
-    for (uint32_t j = 0; j < n; ++j) {
-        float4 raw;
-        const Sample s = eval_sample<T>(net, coords, (size_t)base + j, cascades, &raw);
-        const float w = s.alpha * T_;
-        r[0] = __fmaf_rn(w, s.rgb[0], r[0]); r[1] = __fmaf_rn(w, s.rgb[1], r[1]); r[2] = __fmaf_rn(w, s.rgb[2], r[2]);
-        T_ *= (1.f - s.alpha);
-    }
-    if (!INFER && n == numsteps_in[2 * i]) {                                                // :68-71
-        r[0] = __fmaf_rn(T_, bg[3 * i], r[0]); r[1] = __fmaf_rn(T_, bg[3 * i + 1], r[1]); r[2] = __fmaf_rn(T_, bg[3 * i + 2], r[2]);
-    }
-    rgb_out[3 * i] = r[0]; rgb_out[3 * i + 1] = r[1]; rgb_out[3 * i + 2] = r[2];
-    if (INFER) alpha_out[i] = 1 - T_;
+    if (lane < 3) rgb_out[3 * i + lane] = r[lane];
+    if (INFER && lane == 0) alpha_out[i] = (n == 0) ? 0.f : 1 - T_;
 }
 
 template <typename T>
-__device__ __forceinline__ void composite_bwd_ray(uint32_t n, uint32_t base, const T* __restrict__ net, const float* __restrict__ coords,
-                                                  const float lg[3], const float rr[3], float loss_scale, float l1, uint32_t cascades,
-                                                  T* __restrict__ dnet) {
-    float T_ = 1.f, r2[3] = {0.f, 0.f, 0.f};
-    for (uint32_t j = 0; j < n; ++j) {
-        float4 raw;
-        const Sample s = eval_sample<T>(net, coords, (size_t)base + j, cascades, &raw);
-        const float w = s.alpha * T_;
-        r2[0] = __fmaf_rn(w, s.rgb[0], r2[0]); r2[1] = __fmaf_rn(w, s.rgb[1], r2[1]); r2[2] = __fmaf_rn(w, s.rgb[2], r2[2]);
-        T_ *= (1.f - s.alpha);
-        const float suffix[3] = {rr[0] - r2[0], rr[1] - r2[1], rr[2] - r2[2]};
-        float4 dl;
-        dl.x = loss_scale * ((w * lg[0]) * (s.rgb[0] * (1 - s.rgb[0])));                    // calc_rgb.h:133-135 (l2 reg is 0 for Logistic)
-        dl.y = loss_scale * ((w * lg[1]) * (s.rgb[1] * (1 - s.rgb[1])));
-        dl.z = loss_scale * ((w * lg[2]) * (s.rgb[2] * (1 - s.rgb[2])));
-        const float dd = __expf(fminf(fmaxf(raw.w, -15.0f), 15.0f));                        // network_to_density_derivative
-        const float dot = lg[0] * (T_ * s.rgb[0] - suffix[0]) + (lg[1] * (T_ * s.rgb[1] - suffix[1]) + lg[2] * (T_ * s.rgb[2] - suffix[2]));
-        dl.w = loss_scale * (dd * (s.dt * dot)) + (raw.w < 0 ? -l1 : 0.0f);                 // :137-139
-        store_net<T>(dnet, (size_t)base + j, dl);
-    }
-}
-
-template <typename T>
-__global__ void composite_bwd_kernel(uint32_t n_rays, const T* __restrict__ net, const float* __restrict__ coords,
-                                     const uint32_t* __restrict__ numsteps_c, const float* __restrict__ loss_grad,
-                                     const float* __restrict__ rgb_ray, const float* __restrict__ mean, uint32_t cascades, T* __restrict__ dnet) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) composite_bwd_kernel(uint32_t n_rays, const T* __restrict__ net, const float* __restrict__ coords,
+                                                            const uint32_t* __restrict__ numsteps_c, const float* __restrict__ loss_grad,
+                                                            const float* __restrict__ rgb_ray, const float* __restrict__ mean, uint32_t cascades,
+                                                            T* __restrict__ dnet) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= n_rays) return;
     float loss_scale = 128;
     loss_scale /= n_rays;                                                                   // :100-101
     const float l1 = *mean < 0.01f ? 1e-4f : 0.0f;                                          // :112
     const float lg[3] = {loss_grad[3 * i], loss_grad[3 * i + 1], loss_grad[3 * i + 2]};
     const float rr[3] = {rgb_ray[3 * i], rgb_ray[3 * i + 1], rgb_ray[3 * i + 2]};
-    composite_bwd_ray<T>(numsteps_c[2 * i], numsteps_c[2 * i + 1], net, coords, lg, rr, loss_scale, l1, cascades, dnet);
+    composite_ray_bwd<T>(numsteps_c[2 * i], numsteps_c[2 * i + 1], net, coords, lg, rr, loss_scale, l1, cascades, lane, dnet);
 }
 
-// Fused training tail: composite forward, Huber gradient, composite backward -- one thread per ray.
-__global__ void composite_loss_bwd_kernel(uint32_t n_rays, const __half* __restrict__ net, const float* __restrict__ coords,
-                                          const uint32_t* __restrict__ numsteps_in, const uint32_t* __restrict__ numsteps_c,
-                                          const float* __restrict__ bg, const float* __restrict__ target, float delta,
-                                          const float* __restrict__ mean, uint32_t cascades, float* __restrict__ rgb_out,
-                                          float* __restrict__ loss_out, __half* __restrict__ dnet) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// Fused training tail: composite forward, Huber gradient, composite backward -- one warp per ray.
+__global__ void __launch_bounds__(256) composite_loss_bwd_kernel(uint32_t n_rays, const __half* __restrict__ net, const float* __restrict__ coords,
+                                                                 const uint32_t* __restrict__ numsteps_in, const uint32_t* __restrict__ numsteps_c,
+                                                                 const float* __restrict__ bg, const float* __restrict__ target, float delta,
+                                                                 const float* __restrict__ mean, uint32_t cascades, float* __restrict__ rgb_out,
+                                                                 float* __restrict__ loss_out, __half* __restrict__ dnet) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= n_rays) return;
     const uint32_t n = numsteps_c[2 * i], base = numsteps_c[2 * i + 1];
     float T_ = 1.f, r[3] = {0.f, 0.f, 0.f};
     if (n == 0) { r[0] = bg[3 * i]; r[1] = bg[3 * i + 1]; r[2] = bg[3 * i + 2]; }
     else {
-        for (uint32_t j = 0; j < n; ++j) {
-            float4 raw;
-            const Sample s = eval_sample<__half>(net, coords, (size_t)base + j, cascades, &raw);
-            const float w = s.alpha * T_;
-            r[0] = __fmaf_rn(w, s.rgb[0], r[0]); r[1] = __fmaf_rn(w, s.rgb[1], r[1]); r[2] = __fmaf_rn(w, s.rgb[2], r[2]);
-            T_ *= (1.f - s.alpha);
-        }
+        composite_ray_fwd<__half>(n, base, net, coords, cascades, lane, r, &T_);
         if (n == numsteps_in[2 * i]) {
             r[0] = __fmaf_rn(T_, bg[3 * i], r[0]); r[1] = __fmaf_rn(T_, bg[3 * i + 1], r[1]); r[2] = __fmaf_rn(T_, bg[3 * i + 2], r[2]);
         }
@@ -381,13 +480,13 @@ __global__ void composite_loss_bwd_kernel(uint32_t n_rays, const __half* __restr
         const float diff = r[k] - target[3 * i + k], rel = fabsf(diff);
         loss += rel > delta ? rel - 0.5f * delta : 0.5f / delta * rel * rel;
         lg[k] = rel > delta ? (diff > 0 ? 1.0f : -1.0f) : diff / delta;
-        rgb_out[3 * i + k] = r[k];
     }
-    if (loss_out) loss_out[i] = loss;
+    if (lane < 3) rgb_out[3 * i + lane] = r[lane];
+    if (loss_out && lane == 0) loss_out[i] = loss;
     float loss_scale = 128;
     loss_scale /= n_rays;
     const float l1 = *mean < 0.01f ? 1e-4f : 0.0f;
-    composite_bwd_ray<__half>(n, base, net, coords, lg, r, loss_scale, l1, cascades, dnet);
+    composite_ray_bwd<__half>(n, base, net, coords, lg, r, loss_scale, l1, cascades, lane, dnet);
 }
 
 }  // namespace
@@ -405,7 +504,7 @@ int ngp_march(void* stream, uint32_t n_rays, float aabb_lo, float aabb_hi, uint3
     if (n_rays == 0) return 0;
     const MarchCfg c = make_cfg(cascades, const_dt);
     uint32_t* counts = (uint32_t*)workspace;
-    const uint32_t blocks = (n_rays + 127) / 128;
+    const uint32_t blocks = (n_rays + 3) / 4;             // one warp per ray, 4 rays per CTA
     march_count_kernel<<<blocks, 128, 0, s>>>(n_rays, aabb_lo, aabb_hi, rays_o, rays_d, bitfield, cone_angle, near_distance, c, rng_state,
                                               rng_inc, counts);
     NGP_LAUNCH_CHECK();
@@ -439,9 +538,9 @@ int ngp_composite_fwd(void* stream, uint32_t n_rays, const void* net_out, int dt
                       const uint32_t* numsteps_compacted, const float* bg, uint32_t cascades, float* rgb_out) {
     if (n_rays == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    const uint32_t blocks = (n_rays + 127) / 128;
-    if (dtype == 1) composite_fwd_kernel<__half, false><<<blocks, 128, 0, s>>>(n_rays, (const __half*)net_out, coords, numsteps_in, numsteps_compacted, bg, cascades, rgb_out, nullptr);
-    else if (dtype == 0) composite_fwd_kernel<float, false><<<blocks, 128, 0, s>>>(n_rays, (const float*)net_out, coords, numsteps_in, numsteps_compacted, bg, cascades, rgb_out, nullptr);
+    const uint32_t blocks = (n_rays + 7) / 8;
+    if (dtype == 1) composite_fwd_kernel<__half, false><<<blocks, 256, 0, s>>>(n_rays, (const __half*)net_out, coords, numsteps_in, numsteps_compacted, bg, cascades, rgb_out, nullptr);
+    else if (dtype == 0) composite_fwd_kernel<float, false><<<blocks, 256, 0, s>>>(n_rays, (const float*)net_out, coords, numsteps_in, numsteps_compacted, bg, cascades, rgb_out, nullptr);
     else NGP_REQUIRE(false, "ngp_composite_fwd: bad dtype");
     NGP_LAUNCH_CHECK();
     return 0;
@@ -451,9 +550,9 @@ int ngp_composite_infer(void* stream, uint32_t n_rays, const void* net_out, int 
                         uint32_t cascades, float* rgb_out, float* alpha_out) {
     if (n_rays == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    const uint32_t blocks = (n_rays + 127) / 128;
-    if (dtype == 1) composite_fwd_kernel<__half, true><<<blocks, 128, 0, s>>>(n_rays, (const __half*)net_out, coords, numsteps, numsteps, nullptr, cascades, rgb_out, alpha_out);
-    else if (dtype == 0) composite_fwd_kernel<float, true><<<blocks, 128, 0, s>>>(n_rays, (const float*)net_out, coords, numsteps, numsteps, nullptr, cascades, rgb_out, alpha_out);
+    const uint32_t blocks = (n_rays + 7) / 8;
+    if (dtype == 1) composite_fwd_kernel<__half, true><<<blocks, 256, 0, s>>>(n_rays, (const __half*)net_out, coords, numsteps, numsteps, nullptr, cascades, rgb_out, alpha_out);
+    else if (dtype == 0) composite_fwd_kernel<float, true><<<blocks, 256, 0, s>>>(n_rays, (const float*)net_out, coords, numsteps, numsteps, nullptr, cascades, rgb_out, alpha_out);
     else NGP_REQUIRE(false, "ngp_composite_infer: bad dtype");
     NGP_LAUNCH_CHECK();
     return 0;
@@ -466,9 +565,9 @@ int ngp_composite_bwd(void* stream, uint32_t n_rays, uint32_t n_elements, const 
     cudaStream_t s = (cudaStream_t)stream;
     NGP_CHECK_CUDA(cudaMemsetAsync(dnet_out, 0, (size_t)n_elements * 4 * (dtype == 1 ? 2 : 4), s));   // DGS/calc_rgb.py:93
     if (n_rays == 0) return 0;
-    const uint32_t blocks = (n_rays + 127) / 128;
-    if (dtype == 1) composite_bwd_kernel<__half><<<blocks, 128, 0, s>>>(n_rays, (const __half*)net_out, coords, numsteps_compacted, loss_grad, rgb_ray, density_grid_mean, cascades, (__half*)dnet_out);
-    else composite_bwd_kernel<float><<<blocks, 128, 0, s>>>(n_rays, (const float*)net_out, coords, numsteps_compacted, loss_grad, rgb_ray, density_grid_mean, cascades, (float*)dnet_out);
+    const uint32_t blocks = (n_rays + 7) / 8;
+    if (dtype == 1) composite_bwd_kernel<__half><<<blocks, 256, 0, s>>>(n_rays, (const __half*)net_out, coords, numsteps_compacted, loss_grad, rgb_ray, density_grid_mean, cascades, (__half*)dnet_out);
+    else composite_bwd_kernel<float><<<blocks, 256, 0, s>>>(n_rays, (const float*)net_out, coords, numsteps_compacted, loss_grad, rgb_ray, density_grid_mean, cascades, (float*)dnet_out);
     NGP_LAUNCH_CHECK();
     return 0;
 }
@@ -479,7 +578,7 @@ int ngp_composite_loss_bwd(void* stream, uint32_t n_rays, uint32_t n_elements, c
     (void)n_elements;   // rows not covered by a ray are never read downstream (the network backward is count-limited)
     if (n_rays == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    composite_loss_bwd_kernel<<<(n_rays + 127) / 128, 128, 0, s>>>(n_rays, (const __half*)net_out, coords, numsteps_in, numsteps_compacted, bg,
+    composite_loss_bwd_kernel<<<(n_rays + 7) / 8, 256, 0, s>>>(n_rays, (const __half*)net_out, coords, numsteps_in, numsteps_compacted, bg,
                                                                   target, huber_delta, density_grid_mean, cascades, rgb_out, loss_out,
                                                                   (__half*)dnet_out);
     NGP_LAUNCH_CHECK();
