@@ -69,23 +69,24 @@ template <int STRIDE>
 __device__ __forceinline__ void gather_tile(const float* __restrict__ s_pos /* smem, STRIDE floats per row */, const NgpLevel& lv,
                                             const __half2* __restrict__ g, uint8_t* act, uint32_t level, uint32_t sub,
                                             __half* __restrict__ enc_save, uint32_t tile_row0, uint32_t n_live) {
+    constexpr int Q = 2;                         // points in flight per thread (16 independent gathers); rolled to keep the code small
 #pragma unroll 1
-    for (int b = 0; b < 4; ++b) {
-        uint32_t idx[4][8];
-        float w[4][8];
+    for (int b = 0; b < 16 / Q; ++b) {
+        uint32_t idx[Q][8];
+        float w[Q][8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t p = sub + 8 * (4 * b + q);
+        for (int q = 0; q < Q; ++q) {
+            const uint32_t p = sub + 8 * (Q * b + q);
             hash_corners(lv, s_pos[p * STRIDE], s_pos[p * STRIDE + 1], s_pos[p * STRIDE + 2], idx[q], w[q]);
         }
-        __half2 v[4][8];
+        __half2 v[Q][8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int q = 0; q < Q; ++q)
 #pragma unroll
             for (int c = 0; c < 8; ++c) v[q][c] = __ldg(g + idx[q][c]);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t p = sub + 8 * (4 * b + q);
+        for (int q = 0; q < Q; ++q) {
+            const uint32_t p = sub + 8 * (Q * b + q);
             float a0 = 0.f, a1 = 0.f;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
@@ -322,7 +323,7 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
         tc_fence_before();
         __syncthreads();
         // scatter: (level, sub) x 16 points -> 8 f16x2 reductions each (HashEncode.h:339-347)
-#pragma unroll 2
+#pragma unroll 1
         for (int k = 0; k < 16; ++k) {
             const uint32_t p = sub + 8 * k;
             if (row0 + p >= n_live) continue;
@@ -340,21 +341,22 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
     // flush weight gradients (lane = input feature, column = output feature)
     if (acc) {
         float v[16];
-        auto flush = [&](uint32_t col0, uint32_t n_out, uint32_t n_out_valid, uint32_t in_dim, float* dst) {
-            for (uint32_t c = 0; c < n_out / 16; ++c) {
-                tmem_ld16(tmem_addr(tbase, warp, col0 + 16 * c), v);
-                if (t < in_dim) {
+        const uint32_t f_col[5] = {A_W0D, A_WOUTD, A_W0R, A_W1R, A_WOUTR};
+        const uint32_t f_nout[5] = {64, 16, 64, 64, 16}, f_valid[5] = {64, 16, 64, 64, 3};   // colour Wout rows >= 3 stay zero (fully_fused_mlp.py:136)
+        const uint32_t f_in[5] = {32, 64, 32, 64, 64};
+        float* const f_dst[5] = {dwd + WD_W0, dwd + WD_WOUT, dwr + WR_W0, dwr + WR_W1, dwr + WR_WOUT};
+#pragma unroll 1
+        for (int m = 0; m < 5; ++m) {
+#pragma unroll 1
+            for (uint32_t c = 0; c < f_nout[m] / 16; ++c) {
+                tmem_ld16(tmem_addr(tbase, warp, f_col[m] + 16 * c), v);
+                if (t < f_in[m]) {
 #pragma unroll
                     for (int o = 0; o < 16; ++o)
-                        if (16 * c + o < n_out_valid) atomicAdd(dst + (size_t)(16 * c + o) * in_dim + t, v[o]);
+                        if (16 * c + o < f_valid[m]) atomicAdd(f_dst[m] + (size_t)(16 * c + o) * f_in[m] + t, v[o]);
                 }
             }
-        };
-        flush(A_W0D, 64, 64, 32, dwd + WD_W0);
-        flush(A_WOUTD, 16, 16, 64, dwd + WD_WOUT);
-        flush(A_W0R, 64, 64, 32, dwr + WR_W0);
-        flush(A_W1R, 64, 64, 64, dwr + WR_W1);
-        flush(A_WOUTR, 16, 3, 64, dwr + WR_WOUT);          // rows >= 3 stay zero (fully_fused_mlp.py:136)
+        }
     }
     tc_fence_before();
     __syncthreads();

@@ -13,7 +13,7 @@ constexpr uint32_t ROWS = 128;
 constexpr uint32_t GB = ROWS * 16;          // bytes of one slab feature-group (8 features x 128 rows)
 
 // ---- weights: global (out=rows, in=K) row-major  ->  smem [K/8][rows][8] (canonical K-major B operand) ----
-__device__ __forceinline__ void stage_weights(uint8_t* dst, const __half* __restrict__ W, int rows, int K, int tid, int nthr) {
+static __device__ __noinline__ void stage_weights(uint8_t* dst, const __half* __restrict__ W, int rows, int K, int tid, int nthr) {
     const int kg = K / 8;
     for (int i = tid; i < rows * kg; i += nthr) {
         const int n = i / kg, g = i % kg;
@@ -21,21 +21,27 @@ __device__ __forceinline__ void stage_weights(uint8_t* dst, const __half* __rest
     }
 }
 
+// NOTE on code size: these helpers are deliberately __noinline__ with rolled loops.  With everything inlined and unrolled the
+// per-tile body of the fused backward kernel was 77 KB of SASS -- larger than the SM's 32 KB L1.5 instruction cache -- and the
+// 4 warps of a CTA spent most of their time waiting for instruction fetches from L2 (measured: ~44k cycles per tile).
 // D[128 x N] (+)= ACT[:, 8*g0 .. 8*g0+K) * W^T          (W staged with rows = N)
-__device__ __forceinline__ void issue_fwd(uint32_t d, uint32_t act_s, uint32_t g0, uint32_t K, uint32_t w_s, uint32_t N) {
+static __device__ __noinline__ void issue_fwd(uint32_t d, uint32_t act_s, uint32_t g0, uint32_t K, uint32_t w_s, uint32_t N) {
+#pragma unroll 1
     for (uint32_t kb = 0; kb < K / 16; ++kb)
         mma_f16_ss(d, slab_desc_kmajor(act_s, ROWS, g0, kb), slab_desc_kmajor(w_s, N, 0, kb), idesc_f16(128, N, 0, 0), kb > 0);
 }
 // D[128 x Nin] = GRD[:, 8*g0 .. 8*g0+Kout) * W          (W staged with rows = Kout, K = Nin; read MN-major)
-__device__ __forceinline__ void issue_dgrad(uint32_t d, uint32_t grd_s, uint32_t g0, uint32_t Kout, uint32_t w_s, uint32_t Nin,
+static __device__ __noinline__ void issue_dgrad(uint32_t d, uint32_t grd_s, uint32_t g0, uint32_t Kout, uint32_t w_s, uint32_t Nin,
                                             uint32_t accumulate_first = 0) {
+#pragma unroll 1
     for (uint32_t kb = 0; kb < Kout / 16; ++kb)
         mma_f16_ss(d, slab_desc_kmajor(grd_s, ROWS, g0, kb), slab_desc_mnmajor(w_s, Kout, 0, kb), idesc_f16(128, Nin, 0, 1),
                    (kb > 0) | accumulate_first);
 }
 // D[128 x N] (+)= A^T B : lanes = features [8*ga, 8*ga+128) of slab a, columns = features [8*gb, 8*gb+N) of slab b,
 // contraction over the 128 rows of the tile.  `accumulate` = 0 only for the very first tile of the CTA.
-__device__ __forceinline__ void issue_wgrad(uint32_t d, uint32_t a_s, uint32_t ga, uint32_t b_s, uint32_t gb, uint32_t N, uint32_t accumulate) {
+static __device__ __noinline__ void issue_wgrad(uint32_t d, uint32_t a_s, uint32_t ga, uint32_t b_s, uint32_t gb, uint32_t N, uint32_t accumulate) {
+#pragma unroll 1
     for (uint32_t kb = 0; kb < ROWS / 16; ++kb)
         mma_f16_ss(d, slab_desc_mnmajor(a_s, ROWS, ga, kb), slab_desc_mnmajor(b_s, ROWS, gb, kb), idesc_f16(128, N, 1, 1),
                    (kb > 0) | accumulate);
@@ -66,14 +72,17 @@ __device__ __forceinline__ uint4 relu_mask8(uint4 g, uint4 a) {
 }
 
 // Hidden-layer epilogue: D[:, 0..64) -> ReLU -> fp16 -> slab groups [g0, g0+8); optionally also to global (row-major 64).
-__device__ __forceinline__ void epi_hidden_relu(uint32_t tbase, uint32_t dcol, uint32_t warp, uint8_t* slab, uint32_t g0, uint32_t t,
+static __device__ __noinline__ void epi_hidden_relu(uint32_t tbase, uint32_t dcol, uint32_t warp, uint8_t* slab, uint32_t g0, uint32_t t,
                                                 __half* gdst /* row pointer or nullptr */) {
+    uint32_t r[4][16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tmem_ld16_nowait(tmem_addr(tbase, warp & 3, dcol + 16 * c), r[c]);   // 64 columns in flight
+    tmem_ld_wait();
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         float v[16];
-        tmem_ld16(tmem_addr(tbase, warp & 3, dcol + 16 * c), v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(__uint_as_float(r[c][i]), 0.f);
         uint4 lo, hi;
         pack16(v, lo, hi);
         slab_store16(slab, g0 + 2 * c, t, lo, hi);
@@ -84,12 +93,17 @@ __device__ __forceinline__ void epi_hidden_relu(uint32_t tbase, uint32_t dcol, u
     }
 }
 // dgrad epilogue: D[:, 0..64) -> fp16 -> masked by ReLU'(act) -> grad slab groups [g0,g0+8); optional global copy.
-__device__ __forceinline__ void epi_dgrad_mask(uint32_t tbase, uint32_t dcol, uint32_t warp, const uint8_t* act_slab, uint32_t ga,
+static __device__ __noinline__ void epi_dgrad_mask(uint32_t tbase, uint32_t dcol, uint32_t warp, const uint8_t* act_slab, uint32_t ga,
                                                uint8_t* grd_slab, uint32_t g0, uint32_t t, __half* gdst) {
+    uint32_t r[4][16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tmem_ld16_nowait(tmem_addr(tbase, warp & 3, dcol + 16 * c), r[c]);
+    tmem_ld_wait();
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         float v[16];
-        tmem_ld16(tmem_addr(tbase, warp & 3, dcol + 16 * c), v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[c][i]);
         uint4 lo, hi;
         pack16(v, lo, hi);
         lo = relu_mask8(lo, slab_load8(act_slab, ga + 2 * c, t));

@@ -24,62 +24,68 @@ __device__ __forceinline__ float adam_one(float g, float& m, float& v, float& ma
     return master;
 }
 
-// 8 parameters per thread-iteration
+// Each thread handles 4 consecutive parameters per slot, so that every 16-byte (fp32) / 8-byte (fp16) access of a warp is one
+// fully coalesced 512 B / 256 B request; UNROLL slots are issued back to back to keep ~100 B per thread in flight.
+// (The first version let a thread own 8 consecutive parameters = 32 B-strided float4 accesses: only 17 of 32 bytes per sector
+//  were used per request and the kernel stalled on the LSU queue at 1.9 TB/s, profiles/r01_step_ncu.md.)
 template <typename PT, typename GT>
 __global__ void __launch_bounds__(256) adam_ema_kernel(uint64_t n, PT* __restrict__ param, GT* __restrict__ grad, float* __restrict__ m,
                                                        float* __restrict__ v, float* __restrict__ master, AdamArgs a, int zero_grad) {
-    const uint64_t n8 = n / 8;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n8; i += (uint64_t)gridDim.x * blockDim.x) {
-        float g[8], mm[8], vv[8], ms[8];
-        if constexpr (sizeof(GT) == 2) {
-            const uint4 u = reinterpret_cast<const uint4*>(grad)[i];
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    constexpr int UNROLL = 2;
+    const uint64_t n4 = n / 4, T = (uint64_t)gridDim.x * blockDim.x, g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    for (uint64_t i0 = g; i0 < n4; i0 += UNROLL * T) {
+        float4 gr[UNROLL], mm[UNROLL], vv[UNROLL], ms[UNROLL];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
-                g[2 * k] = f.x; g[2 * k + 1] = f.y;
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint64_t i = i0 + u * T;
+            if (i < n4) {
+                if constexpr (sizeof(GT) == 2) {
+                    const uint2 w = reinterpret_cast<const uint2*>(grad)[i];
+                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&w.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+                    gr[u] = make_float4(f0.x, f0.y, f1.x, f1.y);
+                } else {
+                    gr[u] = reinterpret_cast<const float4*>(grad)[i];
+                }
+                mm[u] = reinterpret_cast<const float4*>(m)[i];
+                vv[u] = reinterpret_cast<const float4*>(v)[i];
+                ms[u] = reinterpret_cast<const float4*>(master)[i];
             }
-            if (zero_grad) reinterpret_cast<uint4*>(grad)[i] = make_uint4(0, 0, 0, 0);
-        } else {
-            const float4 a0 = reinterpret_cast<const float4*>(grad)[2 * i], a1 = reinterpret_cast<const float4*>(grad)[2 * i + 1];
-            g[0] = a0.x; g[1] = a0.y; g[2] = a0.z; g[3] = a0.w; g[4] = a1.x; g[5] = a1.y; g[6] = a1.z; g[7] = a1.w;
-            if (zero_grad) { reinterpret_cast<float4*>(grad)[2 * i] = make_float4(0, 0, 0, 0); reinterpret_cast<float4*>(grad)[2 * i + 1] = make_float4(0, 0, 0, 0); }
         }
-        *reinterpret_cast<float4*>(mm) = reinterpret_cast<const float4*>(m)[2 * i];
-        *reinterpret_cast<float4*>(mm + 4) = reinterpret_cast<const float4*>(m)[2 * i + 1];
-        *reinterpret_cast<float4*>(vv) = reinterpret_cast<const float4*>(v)[2 * i];
-        *reinterpret_cast<float4*>(vv + 4) = reinterpret_cast<const float4*>(v)[2 * i + 1];
-        *reinterpret_cast<float4*>(ms) = reinterpret_cast<const float4*>(master)[2 * i];
-        *reinterpret_cast<float4*>(ms + 4) = reinterpret_cast<const float4*>(master)[2 * i + 1];
-        float p[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) p[k] = adam_one(g[k], mm[k], vv[k], ms[k], a);
-        reinterpret_cast<float4*>(m)[2 * i] = *reinterpret_cast<float4*>(mm);
-        reinterpret_cast<float4*>(m)[2 * i + 1] = *reinterpret_cast<float4*>(mm + 4);
-        reinterpret_cast<float4*>(v)[2 * i] = *reinterpret_cast<float4*>(vv);
-        reinterpret_cast<float4*>(v)[2 * i + 1] = *reinterpret_cast<float4*>(vv + 4);
-        reinterpret_cast<float4*>(master)[2 * i] = *reinterpret_cast<float4*>(ms);
-        reinterpret_cast<float4*>(master)[2 * i + 1] = *reinterpret_cast<float4*>(ms + 4);
-        if constexpr (sizeof(PT) == 2) {
-            uint4 o;
-            __half2 h;
-            h = __floats2half2_rn(p[0], p[1]); o.x = *reinterpret_cast<uint32_t*>(&h);
-            h = __floats2half2_rn(p[2], p[3]); o.y = *reinterpret_cast<uint32_t*>(&h);
-            h = __floats2half2_rn(p[4], p[5]); o.z = *reinterpret_cast<uint32_t*>(&h);
-            h = __floats2half2_rn(p[6], p[7]); o.w = *reinterpret_cast<uint32_t*>(&h);
-            reinterpret_cast<uint4*>(param)[i] = o;
-        } else {
-            reinterpret_cast<float4*>(param)[2 * i] = make_float4(p[0], p[1], p[2], p[3]);
-            reinterpret_cast<float4*>(param)[2 * i + 1] = make_float4(p[4], p[5], p[6], p[7]);
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint64_t i = i0 + u * T;
+            if (i < n4) {
+                float4 p;
+                p.x = adam_one(gr[u].x, mm[u].x, vv[u].x, ms[u].x, a);
+                p.y = adam_one(gr[u].y, mm[u].y, vv[u].y, ms[u].y, a);
+                p.z = adam_one(gr[u].z, mm[u].z, vv[u].z, ms[u].z, a);
+                p.w = adam_one(gr[u].w, mm[u].w, vv[u].w, ms[u].w, a);
+                reinterpret_cast<float4*>(m)[i] = mm[u];
+                reinterpret_cast<float4*>(v)[i] = vv[u];
+                reinterpret_cast<float4*>(master)[i] = ms[u];
+                if constexpr (sizeof(PT) == 2) {
+                    __half2 h0 = __floats2half2_rn(p.x, p.y), h1 = __floats2half2_rn(p.z, p.w);
+                    uint2 o;
+                    o.x = *reinterpret_cast<uint32_t*>(&h0);
+                    o.y = *reinterpret_cast<uint32_t*>(&h1);
+                    reinterpret_cast<uint2*>(param)[i] = o;
+                } else {
+                    reinterpret_cast<float4*>(param)[i] = p;
+                }
+                if (zero_grad) {
+                    if constexpr (sizeof(GT) == 2) reinterpret_cast<uint2*>(grad)[i] = make_uint2(0, 0);
+                    else reinterpret_cast<float4*>(grad)[i] = make_float4(0, 0, 0, 0);
+                }
+            }
         }
     }
-    // tail (n % 8)
-    if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
-        const uint64_t i = n8 * 8 + threadIdx.x;
-        float g = (float)grad[i], mm = m[i], vv = v[i], ms = master[i];
+    // tail (n % 4)
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const uint64_t i = n4 * 4 + threadIdx.x;
+        float g1 = (float)grad[i], m1 = m[i], v1 = v[i], s1 = master[i];
         if (zero_grad) grad[i] = (GT)0.f;
-        const float p = adam_one(g, mm, vv, ms, a);
-        m[i] = mm; v[i] = vv; master[i] = ms; param[i] = (PT)p;
+        const float p = adam_one(g1, m1, v1, s1, a);
+        m[i] = m1; v[i] = v1; master[i] = s1; param[i] = (PT)p;
     }
 }
 
@@ -114,8 +120,8 @@ int ngp_adam_ema(void* stream, uint64_t n, void* param, int param_dtype, void* g
     a.debias_old = (float)(1.0 - std::pow((double)ema_decay, (double)step - 1.0));
     a.debias_new = (float)(1.0 / (1.0 - std::pow((double)ema_decay, (double)step)));
     cudaStream_t s = (cudaStream_t)stream;
-    const uint64_t n8 = (n + 7) / 8;
-    const uint32_t blocks = (uint32_t)std::min<uint64_t>((n8 + 255) / 256, (uint64_t)ngp_num_sms() * 16);
+    const uint64_t n4 = (n + 3) / 4;
+    const uint32_t blocks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((n4 + 511) / 512, (uint64_t)ngp_num_sms() * 32));
     if (param_dtype == 1 && grad_dtype == 1) adam_ema_kernel<__half, __half><<<blocks, 256, 0, s>>>(n, (__half*)param, (__half*)grad, m, v, master, a, zero_grad);
     else if (param_dtype == 1 && grad_dtype == 0) adam_ema_kernel<__half, float><<<blocks, 256, 0, s>>>(n, (__half*)param, (float*)grad, m, v, master, a, zero_grad);
     else if (param_dtype == 0 && grad_dtype == 0) adam_ema_kernel<float, float><<<blocks, 256, 0, s>>>(n, (float*)param, (float*)grad, m, v, master, a, zero_grad);

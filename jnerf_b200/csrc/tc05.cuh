@@ -41,6 +41,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a descriptor mistake must not hang the GPU box.  Returns false on timeout.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1   // the compiler otherwise unrolls this spin loop dozens of times (it made the fused kernels I-cache bound)
     for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
         if (mbar_try_wait(bar, parity)) return true;
     }

@@ -170,13 +170,11 @@ class DensityGridSampler(Module):
             self.update_density_grid_nerf(self.density_grid_decay, G3 * n_cascades // 4, G3 * n_cascades // 4)
 
     def update_batch_rays(self):
+        from .. import dp
         if self.dp_group is not None:                                  # data parallel: every rank adapts to the global mean
-            import torch.distributed as dist
-            dist.all_reduce(self.measured_batch_size, group=self.dp_group[0])
-            self.measured_batch_size //= self.dp_group[1]
-        measured = max(self.measured_batch_size.item() / 16, 1)        # the one host sync per 16 steps (density_grid_sampler.py:266-271)
-        rays_per_batch = int(self.n_rays_per_batch * self.target_batch_size / measured)
-        self.n_rays_per_batch = int(min(((int(rays_per_batch) + 127) // 128) * 128, self.target_batch_size))
+            dp.global_mean_count(self.measured_batch_size, self.dp_group[0], self.dp_group[1])
+        measured = self.measured_batch_size.item() / 16                # the one host sync per 16 steps (density_grid_sampler.py:266-271)
+        self.n_rays_per_batch = dp.adapt_rays_per_batch(self.n_rays_per_batch, measured, self.target_batch_size)
         self.measured_batch_size.zero_()
         self.dataset.batch_size = self.n_rays_per_batch
 
@@ -189,4 +187,4 @@ class DensityGridSampler(Module):
         for k in ("density_grid", "density_grid_bitfield", "density_grid_mean", "density_grid_ema_step"):
             getattr(self, k).copy_(sd[k])
         self.n_rays_per_batch = int(sd["n_rays_per_batch"])
-        self.rng = sd["rng"].numpy().astype(np.uint64)
+        self.rng = sd["rng"].cpu().numpy().astype(np.uint64)

@@ -12,7 +12,7 @@ import os
 import numpy as np
 import torch
 
-from . import ops
+from . import dp, ops
 from .plugin import losses as L
 from .utils.config import get_cfg
 from .utils.registry import DATASETS, LOSSES, NETWORKS, OPTIMS, SAMPLERS, build_from_cfg
@@ -89,7 +89,7 @@ class Runner:
         if self.world_size > 1:
             bg = bg[self.rank * R:(self.rank + 1) * R].contiguous()
         target = rgba[:, :3] * rgba[:, 3:] + bg * (1 - rgba[:, 3:])                         # runner.py:68
-        s.sample(img_ids, rays_o, rays_d, is_training=True, ray_index_offset=self.rank * R)  # grid update /16, march, bookkeeping
+        s.sample(img_ids, rays_o, rays_d, is_training=True, ray_index_offset=dp.shard_range(R, self.rank)[0])  # grid update /16, march, bookkeeping
         coords, n_dev = s.coords_compacted, s.n_samples_dev
         ops.network_fwd(coords, m.pos_encoder.m_grid, m.pos_encoder.levels, m.density_mlp.con_weights, m.rgb_mlp.con_weights,
                         n_dev=n_dev, out=self.net_out, enc=self.enc)
@@ -97,12 +97,8 @@ class Runner:
                                               s.density_grid_mean, delta=self.loss_func.delta, cascades=s.NERF_CASCADES, dnet=self.dnet)
         ops.network_bwd(coords, self.enc, m.pos_encoder.levels, m.density_mlp.con_weights, m.rgb_mlp.con_weights, self.dnet,
                         self.grid_grad, self.dwd, self.dwr, n_dev=n_dev)
-        scale = 1.0
-        if self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.grid_grad, group=self.pg)
-            dist.all_reduce(self.w_grad, group=self.pg)
-            scale = 1.0 / self.world_size          # local loss_scale is 128/R_local (calc_rgb.h:100-101): the sum is W x the global-batch gradient
+        # local loss_scale is 128/R_local (calc_rgb.h:100-101): the all-reduced sum is W x the global-batch gradient
+        scale = dp.allreduce_grads((self.grid_grad, self.w_grad), self.pg, self.world_size)
         lr = self.optimizer.advance_lr()
         adam = self.optimizer._nested_optimizer
         adam.n_step += 1
