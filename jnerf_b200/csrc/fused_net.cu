@@ -14,6 +14,13 @@
 
 int* ngp_err_flag();
 
+#ifdef NGP_TIMELINE
+__device__ long long g_dbg_bwd[64];
+#define DBGB(i) do { if (blockIdx.x == 0 && t == 0 && tile == blockIdx.x + gridDim.x) g_dbg_bwd[i] = clock64(); } while (0)
+#else
+#define DBGB(i) do { } while (0)
+#endif
+
 namespace {
 using namespace mlp;
 
@@ -33,7 +40,8 @@ struct SmemFwd {
     static constexpr uint32_t w1r = w0r + 64 * 32 * 2;
     static constexpr uint32_t woutr = w1r + 64 * 64 * 2;
     static constexpr uint32_t levels = woutr + 16 * 64 * 2;
-    static constexpr uint32_t bar = levels + N_LEVELS * 32;
+    static constexpr uint32_t ops = levels + N_LEVELS * 32;          // MMA program (<= 72 ops)
+    static constexpr uint32_t bar = ops + 72 * 32;
     static constexpr uint32_t total = bar + 64;
 };
 // gradient slab groups (backward)
@@ -48,9 +56,13 @@ struct SmemBwd {
     static constexpr uint32_t w1r = w0r + 64 * 32 * 2;
     static constexpr uint32_t woutr = w1r + 64 * 64 * 2;
     static constexpr uint32_t levels = woutr + 16 * 64 * 2;
-    static constexpr uint32_t bar = levels + N_LEVELS * 32;
+    static constexpr uint32_t ops = levels + N_LEVELS * 32;
+    static constexpr uint32_t bar = ops + 72 * 32;
     static constexpr uint32_t total = bar + 64;
 };
+
+// MMA program layout (op indices) shared by the forward chain of both kernels
+constexpr uint32_t OP_L0D = 0, OP_L1D = 2, OP_L0R = 6, OP_L1R = 8, OP_L2R = 12, OP_FWD_END = 16;
 
 template <class S>
 __device__ __forceinline__ void stage_all_weights(uint8_t* smem, const __half* wd, const __half* wr, uint32_t t) {
@@ -63,61 +75,73 @@ __device__ __forceinline__ void stage_all_weights(uint8_t* smem, const __half* w
     }
 }
 
-// Gather phase: thread (level = t&15, sub = t>>4) encodes points sub, sub+8, ... of the tile at its level and writes
-// the half2 feature into the enc slab (and optionally the (N,32) global copy kept for backward).
+// Gather phase: thread (level = t&15, sub = t>>4) encodes the 16 CONSECUTIVE points 16*sub .. 16*sub+15 of the tile at its
+// level.  Samples arrive ray-ordered, so consecutive points usually stay in the same grid cell at the coarser levels: the 8
+// corner values are re-fetched only when the cell changes (run-length reuse).  The arithmetic per point is unchanged; the
+// number of L1/L2 requests drops by the average run length (the gather is bound by request rate, not by bytes).
 template <int STRIDE>
 __device__ __forceinline__ void gather_tile(const float* __restrict__ s_pos /* smem, STRIDE floats per row */, const NgpLevel& lv,
                                             const __half2* __restrict__ g, uint8_t* act, uint32_t level, uint32_t sub,
                                             __half* __restrict__ enc_save, uint32_t tile_row0, uint32_t n_live) {
-    constexpr int Q = 2;                         // points in flight per thread (16 independent gathers); rolled to keep the code small
+    uint32_t cgx = 0xffffffffu, cgy = 0, cgz = 0;
+    __half2 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = __float2half2_rn(0.f);
 #pragma unroll 1
-    for (int b = 0; b < 16 / Q; ++b) {
-        uint32_t idx[Q][8];
-        float w[Q][8];
+    for (int k = 0; k < 16; ++k) {
+        const uint32_t p = 16 * sub + k;
+        const HashCell hc = hash_cell(lv, s_pos[p * STRIDE], s_pos[p * STRIDE + 1], s_pos[p * STRIDE + 2]);
+        if (hc.gx != cgx || hc.gy != cgy || hc.gz != cgz) {
+            cgx = hc.gx; cgy = hc.gy; cgz = hc.gz;
+            uint32_t idx[8];
+            hash_cell_indices(lv, cgx, cgy, cgz, idx);
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            const uint32_t p = sub + 8 * (Q * b + q);
-            hash_corners(lv, s_pos[p * STRIDE], s_pos[p * STRIDE + 1], s_pos[p * STRIDE + 2], idx[q], w[q]);
+            for (int c = 0; c < 8; ++c) v[c] = __ldg(g + idx[c]);
         }
-        __half2 v[Q][8];
+        float w[8];
+        hash_cell_weights(hc, w);
+        float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-        for (int q = 0; q < Q; ++q)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) v[q][c] = __ldg(g + idx[q][c]);
-#pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            const uint32_t p = sub + 8 * (Q * b + q);
-            float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float2 f = __half22float2(v[q][c]);
-                a0 = fmaf(w[q][c], f.x, a0);
-                a1 = fmaf(w[q][c], f.y, a1);
-            }
-            const __half2 r = __floats2half2_rn(a0, a1);
-            *reinterpret_cast<__half2*>(act + (size_t)(G_ENC + (level >> 2)) * GB + p * 16 + (level & 3) * 4) = r;
-            if (enc_save && tile_row0 + p < n_live)
-                *reinterpret_cast<__half2*>(enc_save + (size_t)(tile_row0 + p) * 32 + 2 * level) = r;
+        for (int c = 0; c < 8; ++c) {
+            const float2 f = __half22float2(v[c]);
+            a0 = fmaf(w[c], f.x, a0);
+            a1 = fmaf(w[c], f.y, a1);
         }
+        const __half2 r = __floats2half2_rn(a0, a1);
+        *reinterpret_cast<__half2*>(act + (size_t)(G_ENC + (level >> 2)) * GB + p * 16 + (level & 3) * 4) = r;
+        if (enc_save && tile_row0 + p < n_live)
+            *reinterpret_cast<__half2*>(enc_save + (size_t)(tile_row0 + p) * 32 + 2 * level) = r;
     }
+}
+
+// Forward MMA program (ops [0,16)): built once per kernel by warp 0's lanes.
+template <class S, uint32_t G_H2>
+__device__ __forceinline__ void build_forward_program(uint8_t* smem, uint32_t tbase, uint32_t lane) {
+    MmaOp* ops = reinterpret_cast<MmaOp*>(smem + S::ops);
+    const uint32_t smem_s = smem_u32(smem), act_s = smem_s + S::act;
+    const uint32_t D_H = 0, D_S = 64;
+    build_fwd(ops + OP_L0D, lane, tbase + D_H, act_s, G_ENC, 32, smem_s + S::w0d, 64);
+    build_fwd(ops + OP_L1D, lane, tbase + D_S, act_s, G_HD, 64, smem_s + S::woutd, 16);
+    build_fwd(ops + OP_L0R, lane, tbase + D_H, act_s, G_RIN, 32, smem_s + S::w0r, 64);
+    build_fwd(ops + OP_L1R, lane, tbase + D_H, act_s, G_H1, 64, smem_s + S::w1r, 64);
+    build_fwd(ops + OP_L2R, lane, tbase + D_S, act_s, G_H2, 64, smem_s + S::woutr, 16);
 }
 
 // Forward chain up to (and including) the colour net's last hidden layer.  Expects enc in ACT[G_ENC..+4).
 // Returns the fp16 density output h[0] of row t (sigma_raw) and leaves hd / rin / h1 / h2 in the slab.
 template <uint32_t G_H2>
-__device__ __forceinline__ uint32_t forward_chain(uint8_t* smem, uint32_t act_off, uint32_t w0d, uint32_t woutd, uint32_t w0r, uint32_t w1r,
+__device__ __forceinline__ uint32_t forward_chain(uint8_t* smem, uint32_t act_off, const MmaOp* ops,
                                                   const float* s_coords, uint32_t tbase, Pipe& pipe, uint32_t t, uint32_t warp,
                                                   bool density_only) {
-    const uint32_t smem_s = smem_u32(smem), act_s = smem_s + act_off;
     uint8_t* act = smem + act_off;
     const uint32_t D_H = 0, D_S = 64;
     // density L0: enc(32) -> hd(64)
-    if (t == 0) { issue_fwd(tbase + D_H, act_s, G_ENC, 32, smem_s + w0d, 64); pipe.commit(); }
+    if (t == 0) { run_ops(ops, OP_L0D, 2, 0); pipe.commit(); }
     pipe.wait();
     epi_hidden_relu(tbase, D_H, warp, act, G_HD, t, nullptr);
     sync_before_issue();
     // density L1: hd(64) -> h(16)
-    if (t == 0) { issue_fwd(tbase + D_S, act_s, G_HD, 64, smem_s + woutd, 16); pipe.commit(); }
+    if (t == 0) { run_ops(ops, OP_L1D, 4, 0); pipe.commit(); }
     pipe.wait();
     uint32_t sigma_half;
     {
@@ -135,12 +159,12 @@ __device__ __forceinline__ uint32_t forward_chain(uint8_t* smem, uint32_t act_of
     }
     sync_before_issue();
     // colour L0: [h | sh](32) -> h1(64)
-    if (t == 0) { issue_fwd(tbase + D_H, act_s, G_RIN, 32, smem_s + w0r, 64); pipe.commit(); }
+    if (t == 0) { run_ops(ops, OP_L0R, 2, 0); pipe.commit(); }
     pipe.wait();
     epi_hidden_relu(tbase, D_H, warp, act, G_H1, t, nullptr);
     sync_before_issue();
     // colour L1: h1(64) -> h2(64)
-    if (t == 0) { issue_fwd(tbase + D_H, act_s, G_H1, 64, smem_s + w1r, 64); pipe.commit(); }
+    if (t == 0) { run_ops(ops, OP_L1R, 4, 0); pipe.commit(); }
     pipe.wait();
     epi_hidden_relu(tbase, D_H, warp, act, G_H2, t, nullptr);
     sync_before_issue();
@@ -167,6 +191,9 @@ network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
     if (warp == 0) tmem_alloc(tmem_ptr, 128);
     sync_before_issue();
     const uint32_t tbase = *tmem_ptr;
+    if (warp == 0) build_forward_program<S, G_H2F>(smem, tbase, t);
+    __syncthreads();
+    const MmaOp* ops = reinterpret_cast<const MmaOp*>(smem + S::ops);
     Pipe pipe{bar, 0, err};
     uint32_t n_live = n_dev ? min(*n_dev, n_max) : n_max;
     const uint32_t level = t & 15, sub = t >> 4;
@@ -184,14 +211,13 @@ network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
         __syncthreads();
         gather_tile<CS>(s_coords, lv, g, smem + S::act, level, sub, DENSITY_ONLY ? nullptr : enc_save, row0, n_live);
         sync_before_issue();
-        const uint32_t sig = forward_chain<G_H2F>(smem, S::act, S::w0d, S::woutd, S::w0r, S::w1r, s_coords, tbase, pipe, t, warp, DENSITY_ONLY);
+        const uint32_t sig = forward_chain<G_H2F>(smem, S::act, ops, s_coords, tbase, pipe, t, warp, DENSITY_ONLY);
         const uint32_t row = row0 + t;
         if constexpr (DENSITY_ONLY) {
             if (row < n_live) reinterpret_cast<uint16_t*>(out)[row] = (uint16_t)sig;
             // the coords restaging __syncthreads + the next sync_before_issue order TMEM reads before reuse
         } else {
-            const uint32_t smem_s = smem_u32(smem);
-            if (t == 0) { issue_fwd(tbase + 64, smem_s + S::act, G_H2F, 64, smem_s + S::woutr, 16); pipe.commit(); }
+            if (t == 0) { run_ops(ops, OP_L2R, 4, 0); pipe.commit(); }
             pipe.wait();
             float v[16];
             tmem_ld16(tmem_addr(tbase, warp, 64), v);
@@ -234,19 +260,44 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
     sync_before_issue();
     const uint32_t tbase = *tmem_ptr;
     const uint32_t smem_s = smem_u32(smem), act_s = smem_s + S::act, grd_s = smem_s + S::grd;
+    // TMEM columns
+    const uint32_t D_H = 0, D_S = 64, A_W0D = 96, A_WOUTD = 160, A_W0R = 176, A_W1R = 240, A_WOUTR = 304;
+    // backward MMA program: each stage = dgrad ops followed by the wgrad ops that become ready with it
+    constexpr uint32_t OP_B1 = 16, OP_B2 = OP_B1 + 1 + 8, OP_B3 = OP_B2 + 4 + 8, OP_B4 = OP_B3 + 4 + 8, OP_B5 = OP_B4 + 1 + 8, OP_END = OP_B5 + 4 + 8;
+    static_assert(OP_END <= 72, "MMA program does not fit");
+    {
+        MmaOp* w = reinterpret_cast<MmaOp*>(smem + S::ops);
+        if (warp == 0) build_forward_program<S, G_H2B>(smem, tbase, t);
+        if (warp == 1) {
+            const uint32_t l = t & 31;
+            build_dgrad(w + OP_B1, l, tbase + D_H, grd_s, Q_DYR, 16, smem_s + S::woutr, 64);
+            build_wgrad(w + OP_B1 + 1, l, tbase + A_WOUTR, act_s, G_H2B, grd_s, Q_DYR, 16);
+            build_dgrad(w + OP_B2, l, tbase + D_H, grd_s, Q_GH2, 64, smem_s + S::w1r, 64);
+            build_wgrad(w + OP_B2 + 4, l, tbase + A_W1R, act_s, G_H1, grd_s, Q_GH2, 64);
+            build_dgrad(w + OP_B3, l, tbase + D_S, grd_s, Q_GH1, 64, smem_s + S::w0r, 32);
+            build_wgrad(w + OP_B3 + 4, l, tbase + A_W0R, act_s, G_RIN, grd_s, Q_GH1, 64);
+        }
+        if (warp == 2) {
+            const uint32_t l = t & 31;
+            build_dgrad(w + OP_B4, l, tbase + D_H, grd_s, Q_DYD, 16, smem_s + S::woutd, 64);
+            build_wgrad(w + OP_B4 + 1, l, tbase + A_WOUTD, act_s, G_HD, grd_s, Q_DYD, 16);
+            build_dgrad(w + OP_B5, l, tbase + D_S, grd_s, Q_GHD, 64, smem_s + S::w0d, 32);
+            build_wgrad(w + OP_B5 + 4, l, tbase + A_W0D, act_s, G_ENC, grd_s, Q_GHD, 64);
+        }
+        __syncthreads();
+    }
+    const MmaOp* ops = reinterpret_cast<const MmaOp*>(smem + S::ops);
     Pipe pipe{bar, 0, err};
     const uint32_t n_live = n_dev ? min(*n_dev, n_max) : n_max;
     const uint32_t level = t & 15, sub = t >> 4;
     const NgpLevel lv = s_lv[level];
     __half2* gg = reinterpret_cast<__half2*>(grid_grad) + lv.offset;
-    // TMEM columns
-    const uint32_t D_H = 0, D_S = 64, A_W0D = 96, A_WOUTD = 160, A_W0R = 176, A_W1R = 240, A_WOUTR = 304;
-
     const uint32_t ntiles = (n_live + ROWS - 1) / ROWS;
     uint32_t acc = 0;
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, acc = 1) {
         const uint32_t row0 = tile * ROWS, row = row0 + t;
         const bool valid = row < n_live;
+        DBGB(0);
         for (uint32_t i = t; i < ROWS * 7; i += 128) s_coords[i] = (row0 + i / 7 < n_live) ? __ldg(coords + (size_t)row0 * 7 + i) : 0.f;
         uint32_t dsig = 0;
         {
@@ -258,32 +309,28 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             dsig = d.y >> 16;
             *reinterpret_cast<uint4*>(grd + Q_DYR * GB + t * 16) = make_uint4(d.x, d.y & 0xFFFFu, 0, 0);
         }
+        DBGB(1);
         sync_before_issue();
-        forward_chain<G_H2B>(smem, S::act, S::w0d, S::woutd, S::w0r, S::w1r, s_coords, tbase, pipe, t, warp, false);
+        DBGB(2);
+        forward_chain<G_H2B>(smem, S::act, ops, s_coords, tbase, pipe, t, warp, false);
+        DBGB(3);
         // B1: g_h2 = (dYr Woutr) . relu'(h2) ; wgrad Woutr
-        if (t == 0) {
-            issue_dgrad(tbase + D_H, grd_s, Q_DYR, 16, smem_s + S::woutr, 64);
-            issue_wgrad(tbase + A_WOUTR, act_s, G_H2B, grd_s, Q_DYR, 16, acc);
-            pipe.commit();
-        }
+        if (t == 0) { run_ops(ops, OP_B1, 1 + 8, acc); DBGB(4); pipe.commit(); }
         pipe.wait();
+        DBGB(5);
         epi_dgrad_mask(tbase, D_H, warp, act, G_H2B, grd, Q_GH2, t, nullptr);
+        DBGB(6);
         sync_before_issue();
+        DBGB(7);
         // B2: g_h1 = (g_h2 W1r) . relu'(h1) ; wgrad W1r
-        if (t == 0) {
-            issue_dgrad(tbase + D_H, grd_s, Q_GH2, 64, smem_s + S::w1r, 64);
-            issue_wgrad(tbase + A_W1R, act_s, G_H1, grd_s, Q_GH2, 64, acc);
-            pipe.commit();
-        }
+        if (t == 0) { run_ops(ops, OP_B2, 4 + 8, acc); DBGB(8); pipe.commit(); }
         pipe.wait();
+        DBGB(9);
         epi_dgrad_mask(tbase, D_H, warp, act, G_H1, grd, Q_GH1, t, nullptr);
         sync_before_issue();
+        DBGB(10);
         // B3: d_rin = g_h1 W0r (32 cols; the last 16 are dL/dSH, unused) ; wgrad W0r
-        if (t == 0) {
-            issue_dgrad(tbase + D_S, grd_s, Q_GH1, 64, smem_s + S::w0r, 32);
-            issue_wgrad(tbase + A_W0R, act_s, G_RIN, grd_s, Q_GH1, 64, acc);
-            pipe.commit();
-        }
+        if (t == 0) { run_ops(ops, OP_B3, 4 + 8, acc); pipe.commit(); }
         pipe.wait();
         {
             float v[16];
@@ -295,20 +342,12 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
         }
         sync_before_issue();
         // B4: g_hd = (dYd Woutd) . relu'(hd) ; wgrad Woutd
-        if (t == 0) {
-            issue_dgrad(tbase + D_H, grd_s, Q_DYD, 16, smem_s + S::woutd, 64);
-            issue_wgrad(tbase + A_WOUTD, act_s, G_HD, grd_s, Q_DYD, 16, acc);
-            pipe.commit();
-        }
+        if (t == 0) { run_ops(ops, OP_B4, 1 + 8, acc); pipe.commit(); }
         pipe.wait();
         epi_dgrad_mask(tbase, D_H, warp, act, G_HD, grd, Q_GHD, t, nullptr);
         sync_before_issue();
         // B5: d_enc = g_hd W0d ; wgrad W0d
-        if (t == 0) {
-            issue_dgrad(tbase + D_S, grd_s, Q_GHD, 64, smem_s + S::w0d, 32);
-            issue_wgrad(tbase + A_W0D, act_s, G_ENC, grd_s, Q_GHD, 64, acc);
-            pipe.commit();
-        }
+        if (t == 0) { run_ops(ops, OP_B5, 4 + 8, acc); pipe.commit(); }
         pipe.wait();
         {
             float v[16];
@@ -322,21 +361,45 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
         }
         tc_fence_before();
         __syncthreads();
-        // scatter: (level, sub) x 16 points -> 8 f16x2 reductions each (HashEncode.h:339-347)
+        DBGB(11);
+        // scatter (HashEncode.h:339-347): thread (level, sub) walks its 16 consecutive samples, accumulates the 8 corner
+        // contributions in fp32 registers while the grid cell stays the same and issues the f16x2 reductions only when the
+        // cell changes -- the atomic count (the bound of this phase) drops by the average run length.
+        {
+            uint32_t cgx = 0xffffffffu, cgy = 0, cgz = 0, idx[8];
+            float2 accv[8];
+            bool dirty = false;
 #pragma unroll 1
-        for (int k = 0; k < 16; ++k) {
-            const uint32_t p = sub + 8 * k;
-            if (row0 + p >= n_live) continue;
-            const __half2 d = *reinterpret_cast<const __half2*>(grd + (size_t)(Q_DENC + (level >> 2)) * GB + p * 16 + (level & 3) * 4);
-            const float2 df = __half22float2(d);
-            if (df.x == 0.f && df.y == 0.f) continue;
-            uint32_t idx[8];
-            float w[8];
-            hash_corners(lv, s_coords[p * 7], s_coords[p * 7 + 1], s_coords[p * 7 + 2], idx, w);
+            for (int k = 0; k < 16; ++k) {
+                const uint32_t p = 16 * sub + k;
+                if (row0 + p >= n_live) break;
+                const __half2 d = *reinterpret_cast<const __half2*>(grd + (size_t)(Q_DENC + (level >> 2)) * GB + p * 16 + (level & 3) * 4);
+                const float2 df = __half22float2(d);
+                if (df.x == 0.f && df.y == 0.f) continue;
+                const HashCell hc = hash_cell(lv, s_coords[p * 7], s_coords[p * 7 + 1], s_coords[p * 7 + 2]);
+                if (hc.gx != cgx || hc.gy != cgy || hc.gz != cgz) {
+                    if (dirty) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) atomicAdd(gg + idx[c], __floats2half2_rn(df.x * w[c], df.y * w[c]));
+                        for (int c = 0; c < 8; ++c) atomicAdd(gg + idx[c], __floats2half2_rn(accv[c].x, accv[c].y));
+                    }
+                    cgx = hc.gx; cgy = hc.gy; cgz = hc.gz;
+                    hash_cell_indices(lv, cgx, cgy, cgz, idx);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) accv[c] = make_float2(0.f, 0.f);
+                    dirty = true;
+                }
+                float w[8];
+                hash_cell_weights(hc, w);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { accv[c].x = fmaf(df.x, w[c], accv[c].x); accv[c].y = fmaf(df.y, w[c], accv[c].y); }
+            }
+            if (dirty) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) atomicAdd(gg + idx[c], __floats2half2_rn(accv[c].x, accv[c].y));
+            }
         }
         __syncthreads();   // slabs / coords are rewritten by the next tile
+        DBGB(12);
     }
     // flush weight gradients (lane = input feature, column = output feature)
     if (acc) {
@@ -366,6 +429,10 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
 }  // namespace
 
 extern "C" {
+
+#ifdef NGP_TIMELINE
+int ngp_debug_read_timeline_bwd(long long* host64) { return (int)cudaMemcpyFromSymbol(host64, g_dbg_bwd, sizeof(long long) * 64); }
+#endif
 
 int ngp_network_fwd(void* stream, uint32_t n_max, const uint32_t* n_dev, const float* coords, const void* grid, const void* levels_dev,
                     const void* w_density, const void* w_rgb, void* out, void* enc_save) {

@@ -11,6 +11,7 @@
 //   kernel_mlp_fused_backward + 5 cuBLAS GEMMs with K = batch (fully_fused_mlp.py:123-143).
 // Roofline: tensor: 20 480 flop/sample fwd for the two NGP nets, 61 440 fwd+dgrad+wgrad.
 #include "mlp_tc.cuh"
+#include <cstdlib>
 
 namespace {
 using namespace mlp;
@@ -290,7 +291,9 @@ int ngp_mlp_fwd(void* stream, const void* weights, const void* input, void* inte
     const uint32_t smem = FwdSmem::total(nhm);
     NGP_CHECK_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t ntiles = (n + ROWS - 1) / ROWS;
-    const uint32_t grid = min(ntiles, (uint32_t)ngp_num_sms() * 4u);
+    uint32_t per_sm = 4u;
+    if (const char* e = getenv("NGP_MLP_CTAS_PER_SM")) per_sm = (uint32_t)atoi(e);   // experiment knob
+    const uint32_t grid = min(ntiles, (uint32_t)ngp_num_sms() * per_sm);
     mlp_fwd_kernel<<<grid, 128, smem, s>>>((const __half*)weights, (const __half*)input, (__half*)inter, (__half*)output, nhm, n, err_flag());
     NGP_LAUNCH_CHECK();
     return 0;

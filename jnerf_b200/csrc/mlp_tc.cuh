@@ -47,6 +47,44 @@ static __device__ __noinline__ void issue_wgrad(uint32_t d, uint32_t a_s, uint32
                    (kb > 0) | accumulate);
 }
 
+// ---- precomputed MMA programs ---------------------------------------------------------------------------
+// All operand addresses are compile-time-constant offsets inside the CTA's shared memory, so every descriptor is built ONCE
+// per kernel (by as many threads as there are MMAs) and the issuing thread only streams 32-byte records.  Building the
+// two 64-bit descriptors inline cost ~200 cycles per MMA of single-thread latency (tools/dbg_timeline.py), which dominated
+// stages with 9-12 MMAs (dgrad + wgrad).
+struct __align__(16) MmaOp {
+    uint64_t a, b;
+    uint32_t d, idesc, acc, flags;      // flags bit0: wgrad op (accumulate across tiles: acc |= tile_acc)
+};
+static_assert(sizeof(MmaOp) == 32, "MmaOp must be 32 bytes");
+
+// op builders (any thread): write `n` ops starting at ops[0]; return n
+__device__ __forceinline__ uint32_t build_fwd(MmaOp* ops, uint32_t lane, uint32_t d, uint32_t act_s, uint32_t g0, uint32_t K, uint32_t w_s, uint32_t N) {
+    const uint32_t n = K / 16;
+    if (lane < n) ops[lane] = MmaOp{slab_desc_kmajor(act_s, ROWS, g0, lane), slab_desc_kmajor(w_s, N, 0, lane), d, idesc_f16(128, N, 0, 0), lane > 0, 0};
+    return n;
+}
+__device__ __forceinline__ uint32_t build_dgrad(MmaOp* ops, uint32_t lane, uint32_t d, uint32_t grd_s, uint32_t g0, uint32_t Kout, uint32_t w_s, uint32_t Nin) {
+    const uint32_t n = Kout / 16;
+    if (lane < n) ops[lane] = MmaOp{slab_desc_kmajor(grd_s, ROWS, g0, lane), slab_desc_mnmajor(w_s, Kout, 0, lane), d, idesc_f16(128, Nin, 0, 1), lane > 0, 0};
+    return n;
+}
+__device__ __forceinline__ uint32_t build_wgrad(MmaOp* ops, uint32_t lane, uint32_t d, uint32_t a_s, uint32_t ga, uint32_t b_s, uint32_t gb, uint32_t N) {
+    const uint32_t n = ROWS / 16;
+    if (lane < n) ops[lane] = MmaOp{slab_desc_mnmajor(a_s, ROWS, ga, lane), slab_desc_mnmajor(b_s, ROWS, gb, lane), d, idesc_f16(128, N, 1, 1), lane > 0, 1};
+    return n;
+}
+// issue ops[first, first+count) (one thread); tile_acc = 1 once the CTA's wgrad accumulators hold a previous tile
+static __device__ __noinline__ void run_ops(const MmaOp* ops, uint32_t first, uint32_t count, uint32_t tile_acc) {
+#pragma unroll 1
+    for (uint32_t i = first; i < first + count; ++i) {
+        const uint4 lo = *reinterpret_cast<const uint4*>(&ops[i]);
+        const uint4 hi = *(reinterpret_cast<const uint4*>(&ops[i]) + 1);
+        const uint64_t a = ((uint64_t)lo.y << 32) | lo.x, b = ((uint64_t)lo.w << 32) | lo.z;
+        mma_f16_ss(hi.x, a, b, hi.y, hi.z | (hi.w & tile_acc));
+    }
+}
+
 // ---- epilogue helpers (thread t = row t) ----------------------------------------------------------
 __device__ __forceinline__ void pack16(const float* v, uint4& lo, uint4& hi) {
     lo = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));

@@ -72,6 +72,43 @@ __device__ __forceinline__ void hash_corners(const NgpLevel& lv, float x, float 
     for (int c = 0; c < 8; ++c) w[c] = (1.0f * wx[c & 1]) * wy[(c >> 1) & 1] * wz[(c >> 2) & 1];
 }
 
+// Split form used by the run-length kernels: cell coordinates + fractions, then indices of a cell, then weights.
+struct HashCell {
+    uint32_t gx, gy, gz;
+    float fx, fy, fz;
+};
+__device__ __forceinline__ HashCell hash_cell(const NgpLevel& lv, float x, float y, float z) {
+    HashCell c;
+    float px = fmaf(x, lv.scale, 0.5f), py = fmaf(y, lv.scale, 0.5f), pz = fmaf(z, lv.scale, 0.5f);
+    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    c.gx = (uint32_t)(int)fx; c.gy = (uint32_t)(int)fy; c.gz = (uint32_t)(int)fz;
+    c.fx = px - fx; c.fy = py - fy; c.fz = pz - fz;
+    return c;
+}
+__device__ __forceinline__ void hash_cell_indices(const NgpLevel& lv, uint32_t gx, uint32_t gy, uint32_t gz, uint32_t idx[8]) {
+    if (lv.hashed) {
+        const uint32_t mask = lv.size - 1;
+        const uint32_t hy0 = gy * 19349663u, hy1 = (gy + 1) * 19349663u;
+        const uint32_t hz0 = gz * 83492791u, hz1 = (gz + 1) * 83492791u;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) idx[c] = ((gx + (c & 1)) ^ ((c & 2) ? hy1 : hy0) ^ ((c & 4) ? hz1 : hz0)) & mask;
+    } else {
+        const uint32_t res = lv.resolution, res2 = res * res;
+        const uint32_t b = (gx + gy * res + gz * res2) % lv.size;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            uint32_t v = b + (c & 1) + ((c & 2) ? res : 0u) + ((c & 4) ? res2 : 0u);
+            v -= (v >= lv.size) ? lv.size : 0u;
+            idx[c] = v;
+        }
+    }
+}
+__device__ __forceinline__ void hash_cell_weights(const HashCell& c, float w[8]) {
+    const float wx[2] = {1.0f - c.fx, c.fx}, wy[2] = {1.0f - c.fy, c.fy}, wz[2] = {1.0f - c.fz, c.fz};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = (1.0f * wx[k & 1]) * wy[(k >> 1) & 1] * wz[(k >> 2) & 1];
+}
+
 // ---- SH degree 4 (SphericalEncode.h:65-95) ---------------------------------------------------------
 __device__ __forceinline__ void sh4(float dx, float dy, float dz, float* o) {
     const float x = dx * 2.f - 1.f, y = dy * 2.f - 1.f, z = dz * 2.f - 1.f;
