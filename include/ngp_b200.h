@@ -143,6 +143,11 @@ int ngp_adam_ema(void* stream, uint64_t n, void* param, int param_dtype, void* g
 int ngp_raygen(void* stream, uint32_t n, const uint32_t* pix_index, uint32_t W, uint32_t H, const float* xforms,
                const float* focal, const float* principal, uint32_t* img_id_out, float* rays_o, float* rays_d);
 
+/* ray generation + RGBA gather (uint8/255 or f32 images, (n_img*H*W,4)) + target = rgb*a + bg*(1-a) in one launch */
+int ngp_prepare_batch(void* stream, uint32_t n, const uint32_t* pix_index, uint32_t W, uint32_t H, const float* xforms,
+                      const float* focal, const float* principal, const void* images_rgba, int image_is_u8, const float* bg,
+                      uint32_t* img_id_out, float* rays_o, float* rays_d, float* target);
+
 /* pcg32 helpers (ops/op_include/pcg32/pcg32.h): host-side, pure integer */
 void ngp_pcg32_seed(uint64_t initstate, uint64_t initseq, uint64_t* state_inc);
 void ngp_pcg32_advance(uint64_t* state_inc, int64_t delta);

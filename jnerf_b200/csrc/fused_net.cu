@@ -294,21 +294,34 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
     __half2* gg = reinterpret_cast<__half2*>(grid_grad) + lv.offset;
     const uint32_t ntiles = (n_live + ROWS - 1) / ROWS;
     uint32_t acc = 0;
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, acc = 1) {
-        const uint32_t row0 = tile * ROWS, row = row0 + t;
-        const bool valid = row < n_live;
-        DBGB(0);
-        for (uint32_t i = t; i < ROWS * 7; i += 128) s_coords[i] = (row0 + i / 7 < n_live) ? __ldg(coords + (size_t)row0 * 7 + i) : 0.f;
-        uint32_t dsig = 0;
-        {
-            const uint4* es = reinterpret_cast<const uint4*>(enc_save + (size_t)row * 32);
-            const uint4 z = make_uint4(0, 0, 0, 0);
+    // software prefetch: the next tile's inputs (7 coordinate words, the 64 B encoded row, the 8 B output gradient) are loaded into
+    // registers before the scatter phase of the current tile, so their HBM latency (~2 us with one CTA per SM) is hidden.
+    float pf_c[7];
+    uint4 pf_e[4];
+    uint2 pf_d;
+    auto prefetch = [&](uint32_t tile_) {
+        const uint32_t r0 = tile_ * ROWS, r = r0 + t;
+        const bool ok = r < n_live;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(act + (G_ENC + g) * GB + t * 16) = valid ? __ldg(es + g) : z;
-            uint2 d = valid ? __ldg(reinterpret_cast<const uint2*>(dout) + row) : make_uint2(0, 0);
-            dsig = d.y >> 16;
-            *reinterpret_cast<uint4*>(grd + Q_DYR * GB + t * 16) = make_uint4(d.x, d.y & 0xFFFFu, 0, 0);
+        for (int j = 0; j < 7; ++j) {
+            const uint32_t i = t + 128 * j;
+            pf_c[j] = (r0 + i / 7 < n_live) ? __ldg(coords + (size_t)r0 * 7 + i) : 0.f;
         }
+        const uint4* es = reinterpret_cast<const uint4*>(enc_save + (size_t)r * 32);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) pf_e[g] = ok ? __ldg(es + g) : make_uint4(0, 0, 0, 0);
+        pf_d = ok ? __ldg(reinterpret_cast<const uint2*>(dout) + r) : make_uint2(0, 0);
+    };
+    if (blockIdx.x < ntiles) prefetch(blockIdx.x);
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, acc = 1) {
+        const uint32_t row0 = tile * ROWS;
+        DBGB(0);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) s_coords[t + 128 * j] = pf_c[j];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(act + (G_ENC + g) * GB + t * 16) = pf_e[g];
+        const uint32_t dsig = pf_d.y >> 16;
+        *reinterpret_cast<uint4*>(grd + Q_DYR * GB + t * 16) = make_uint4(pf_d.x, pf_d.y & 0xFFFFu, 0, 0);
         DBGB(1);
         sync_before_issue();
         DBGB(2);
@@ -362,6 +375,7 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
         tc_fence_before();
         __syncthreads();
         DBGB(11);
+        if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x);
         // scatter (HashEncode.h:339-347): thread (level, sub) walks its 16 consecutive samples, accumulates the 8 corner
         // contributions in fp32 registers while the grid cell stays the same and issues the f16x2 reductions only when the
         // cell changes -- the atomic count (the bound of this phase) drops by the average run length.

@@ -105,6 +105,37 @@ __global__ void raygen_kernel(uint32_t n, const uint32_t* __restrict__ pix, uint
     rays_d[3 * (size_t)i] = d0 / nrm; rays_d[3 * (size_t)i + 1] = d1 / nrm; rays_d[3 * (size_t)i + 2] = d2 / nrm;
 }
 
+// N2 fused: ray generation + RGBA gather + target = rgb*a + bg*(1-a)  (dataset.py:172-188, runner.py:66-68) in one launch.
+template <typename IMG>
+__global__ void prepare_batch_kernel(uint32_t n, const uint32_t* __restrict__ pix, uint32_t W, uint32_t H, const float* __restrict__ xforms,
+                                     const float* __restrict__ focal, const float* __restrict__ principal, const IMG* __restrict__ images,
+                                     const float* __restrict__ bg, uint32_t* __restrict__ img_id, float* __restrict__ rays_o,
+                                     float* __restrict__ rays_d, float* __restrict__ target) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t px = pix[i];
+    const uint32_t id = px / (H * W), off = px % (H * W);
+    const float* m = xforms + 12 * (size_t)id;
+    const float x = ((off % W) + 0.5f) / W, y = ((off / W) + 0.5f) / H;
+    const float dx = (x - principal[2 * id]) * W / focal[2 * id], dy = (y - principal[2 * id + 1]) * H / focal[2 * id + 1];
+    const float d0 = m[0] * dx + m[3] * dy + m[6], d1 = m[1] * dx + m[4] * dy + m[7], d2 = m[2] * dx + m[5] * dy + m[8];
+    const float nrm = fmaxf(sqrtf(d0 * d0 + d1 * d1 + d2 * d2), 1e-12f);
+    img_id[i] = id;
+    rays_o[3 * (size_t)i] = m[9]; rays_o[3 * (size_t)i + 1] = m[10]; rays_o[3 * (size_t)i + 2] = m[11];
+    rays_d[3 * (size_t)i] = d0 / nrm; rays_d[3 * (size_t)i + 1] = d1 / nrm; rays_d[3 * (size_t)i + 2] = d2 / nrm;
+    float4 c;
+    if constexpr (sizeof(IMG) == 1) {
+        const uchar4 u = reinterpret_cast<const uchar4*>(images)[px];
+        c = make_float4(u.x / 255.0f, u.y / 255.0f, u.z / 255.0f, u.w / 255.0f);      // read_image: uint8 / 255
+    } else {
+        c = reinterpret_cast<const float4*>(images)[px];
+    }
+    const float ia = 1.0f - c.w;
+    target[3 * (size_t)i] = c.x * c.w + bg[3 * (size_t)i] * ia;
+    target[3 * (size_t)i + 1] = c.y * c.w + bg[3 * (size_t)i + 1] * ia;
+    target[3 * (size_t)i + 2] = c.z * c.w + bg[3 * (size_t)i + 2] * ia;
+}
+
 }  // namespace
 
 extern "C" {
@@ -126,6 +157,17 @@ int ngp_adam_ema(void* stream, uint64_t n, void* param, int param_dtype, void* g
     else if (param_dtype == 1 && grad_dtype == 0) adam_ema_kernel<__half, float><<<blocks, 256, 0, s>>>(n, (__half*)param, (float*)grad, m, v, master, a, zero_grad);
     else if (param_dtype == 0 && grad_dtype == 0) adam_ema_kernel<float, float><<<blocks, 256, 0, s>>>(n, (float*)param, (float*)grad, m, v, master, a, zero_grad);
     else NGP_REQUIRE(false, "ngp_adam_ema: unsupported dtype combination");
+    NGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int ngp_prepare_batch(void* stream, uint32_t n, const uint32_t* pix_index, uint32_t W, uint32_t H, const float* xforms, const float* focal,
+                      const float* principal, const void* images_rgba, int image_is_u8, const float* bg, uint32_t* img_id_out, float* rays_o,
+                      float* rays_d, float* target) {
+    if (n == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (image_is_u8) prepare_batch_kernel<uint8_t><<<(n + 127) / 128, 128, 0, s>>>(n, pix_index, W, H, xforms, focal, principal, (const uint8_t*)images_rgba, bg, img_id_out, rays_o, rays_d, target);
+    else prepare_batch_kernel<float><<<(n + 127) / 128, 128, 0, s>>>(n, pix_index, W, H, xforms, focal, principal, (const float*)images_rgba, bg, img_id_out, rays_o, rays_d, target);
     NGP_LAUNCH_CHECK();
     return 0;
 }

@@ -202,6 +202,18 @@ def raygen(pix, W, H, xforms, focal, principal):
     return img, o, d
 
 
+def prepare_batch(pix, W, H, xforms, focal, principal, images, bg):
+    n = pix.numel()
+    dev = pix.device
+    img = torch.empty(n, dtype=torch.int32, device=dev)
+    o = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    d = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    target = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    lib.call("ngp_prepare_batch", _stream(), n, _p(pix), W, H, _p(xforms), _p(focal), _p(principal), _p(images), int(images.dtype == torch.uint8),
+             _p(bg), _p(img), _p(o), _p(d), _p(target))
+    return img, o, d, target
+
+
 def pcg32_seed(seed=1337, seq=1):
     si = np.zeros(2, np.uint64)
     lib.load().ngp_pcg32_seed(seed, seq, si.ctypes.data)

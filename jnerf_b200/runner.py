@@ -83,12 +83,23 @@ class Runner:
     def train_step(self, batch=None):
         cfg, s, m = self.cfg, self.sampler, self.model
         i = cfg.m_training_step
-        img_ids, rays_o, rays_d, rgba = self.next_batch() if batch is None else batch
-        R = rays_o.shape[0]
-        bg = torch.rand((R * self.world_size, 3), device="cuda", generator=self._bg_gen)    # runner.py:66 (global batch, then this rank's rows)
-        if self.world_size > 1:
-            bg = bg[self.rank * R:(self.rank + 1) * R].contiguous()
-        target = rgba[:, :3] * rgba[:, 3:] + bg * (1 - rgba[:, 3:])                         # runner.py:68
+        if batch is None:
+            ds = self.dataset["train"]
+            R = s.n_rays_per_batch                                   # per-rank rays; the global batch is world_size x R (weak scaling)
+            pix = ds.next_pixels(R * self.world_size)
+            bg = torch.rand((R * self.world_size, 3), device="cuda", generator=self._bg_gen)    # runner.py:66 (global batch, then this rank's rows)
+            if self.world_size > 1:
+                lo, hi = dp.shard_range(R, self.rank)
+                pix, bg = pix[lo:hi], bg[lo:hi]
+            img_ids, rays_o, rays_d, target = ops.prepare_batch(pix.contiguous(), ds.W, ds.H, ds.transforms_gpu, ds.focal_lengths, ds.principal,
+                                                                ds.image_data, bg.contiguous())          # dataset.py:172-188 + runner.py:68
+        else:
+            img_ids, rays_o, rays_d, rgba = batch
+            R = rays_o.shape[0]
+            bg = torch.rand((R * self.world_size, 3), device="cuda", generator=self._bg_gen)
+            if self.world_size > 1:
+                bg = bg[self.rank * R:(self.rank + 1) * R].contiguous()
+            target = rgba[:, :3] * rgba[:, 3:] + bg * (1 - rgba[:, 3:])                     # runner.py:68
         s.sample(img_ids, rays_o, rays_d, is_training=True, ray_index_offset=dp.shard_range(R, self.rank)[0])  # grid update /16, march, bookkeeping
         coords, n_dev = s.coords_compacted, s.n_samples_dev
         ops.network_fwd(coords, m.pos_encoder.m_grid, m.pos_encoder.levels, m.density_mlp.con_weights, m.rgb_mlp.con_weights,

@@ -376,3 +376,23 @@ def test_raygen(ops):
     ir, orr, dr = ol.raygen(pix.view(np.uint32), W, H, xf, focal, pp)
     assert np.array_equal(npy(img).view(np.uint32), ir) and np.array_equal(npy(o), orr)
     assert np.abs(npy(d) - dr).max() <= 1e-6
+
+
+def test_prepare_batch(ops):
+    rng = np.random.default_rng(6)
+    n_img, W, H = 3, 32, 24
+    xf = rng.standard_normal((n_img, 12)).astype(np.float32)
+    focal = np.full((n_img, 2), 40.0, np.float32)
+    pp = np.full((n_img, 2), 0.5, np.float32)
+    pix = rng.integers(0, n_img * W * H, 1000).astype(np.int32)
+    bg = rng.random((1000, 3), dtype=np.float32)
+    for dt in (np.uint8, np.float32):
+        img = rng.integers(0, 256, (n_img * W * H, 4)).astype(np.uint8)
+        imgf = img.astype(np.float32) / 255.0
+        images = img if dt == np.uint8 else imgf
+        ids, o, d, target = ops.prepare_batch(cu(pix), W, H, cu(xf), cu(focal), cu(pp), cu(images), cu(bg))
+        ir, orr, dr = ol.raygen(pix.view(np.uint32), W, H, xf, focal, pp)
+        c = imgf[pix]
+        tref = c[:, :3] * c[:, 3:] + bg * (1 - c[:, 3:])                                   # runner/runner.py:68
+        assert np.array_equal(npy(ids).view(np.uint32), ir) and np.array_equal(npy(o), orr) and np.abs(npy(d) - dr).max() <= 1e-6
+        assert np.abs(npy(target) - tref).max() <= 1e-6
