@@ -204,6 +204,9 @@ def run_ours(args):
     launches0 = lib.launch_count
     rays = 0
     sync()
+    profiling = bool(os.environ.get("NGP_PROFILE"))          # ncu --profile-from-start off: capture exactly the timed region
+    if profiling:
+        torch.cuda.profiler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -211,6 +214,8 @@ def run_ours(args):
         runner.train_step()
     e1.record()
     sync()
+    if profiling:
+        torch.cuda.profiler.stop()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
     launches = lib.launch_count - launches0
     if world > 1:
@@ -290,17 +295,19 @@ def stage_times(runner, iters):
     import torch
     from jnerf_b200 import ops
     s, m = runner.sampler, runner.model
-    names = ["raygen+target", "march", "network_fwd", "composite_loss_bwd", "network_bwd", "adam_ema"]
+    names = ["prepare_batch", "march", "network_fwd", "composite_loss_bwd", "network_bwd", "adam_ema"]
     acc = {k: 0.0 for k in names}
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
     nsamp = 0
     for it in range(iters):
         runner.cfg.m_training_step += 1 if runner.cfg.m_training_step % 16 == 0 else 0      # keep grid updates out of the per-stage split
         ev[0].record()
-        img_ids, rays_o, rays_d, rgba = runner.next_batch()
-        R = rays_o.shape[0]
+        ds = runner.dataset["train"]
+        R = s.n_rays_per_batch
+        pix = ds.next_pixels(R)
         bg = torch.rand((R, 3), device="cuda")
-        target = (rgba[:, :3] * rgba[:, 3:] + bg * (1 - rgba[:, 3:])).contiguous()
+        img_ids, rays_o, rays_d, target = ops.prepare_batch(pix.contiguous(), ds.W, ds.H, ds.transforms_gpu, ds.focal_lengths, ds.principal,
+                                                            ds.image_data, bg)
         ev[1].record()
         s.sample(img_ids, rays_o, rays_d, is_training=True)
         ev[2].record()
