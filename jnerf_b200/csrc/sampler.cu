@@ -115,9 +115,13 @@ __device__ __forceinline__ RayState ray_setup(uint32_t i, const float* __restric
 // therefore materialises 32 consecutive t_k (same float additions, same order), evaluates position, mip level, occupancy
 // bit and the distance to the next voxel of all 32 in parallel, and then replays the reference's sequential control flow
 // on two ballot masks -- identical arithmetic per visited step, 32 occupancy lookups in flight instead of one.
+constexpr uint32_t MARCH_MAXC = 80;      // chunks (of 32 steps) recorded per ray by the count pass: 2560 steps >= sqrt(3)/min_dt
+struct ChunkRec { float t0; uint32_t mask; };
+
 template <bool EMIT>
 __device__ __forceinline__ uint32_t march_ray_warp(const RayState& r, float lo, float hi, float cone, const MarchCfg& c,
-                                                   const uint8_t* __restrict__ bits, uint32_t limit, float* __restrict__ out) {
+                                                   const uint8_t* __restrict__ bits, uint32_t limit, float* __restrict__ out,
+                                                   ChunkRec* __restrict__ rec = nullptr, uint32_t* __restrict__ n_chunks = nullptr) {
     const uint32_t lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     uint32_t j = 0;
@@ -126,6 +130,7 @@ __device__ __forceinline__ uint32_t march_ray_warp(const RayState& r, float lo, 
     float pending_tt = 0.f;
     float wd[3], diag = hi - lo;
     if (EMIT) { wd[0] = (r.d[0] + 1.0f) * 0.5f; wd[1] = (r.d[1] + 1.0f) * 0.5f; wd[2] = (r.d[2] + 1.0f) * 0.5f; }
+    uint32_t chunk = 0;
     for (uint32_t guard = 0; guard < (1u << 20); ++guard) {   // a degenerate ray (d == 0) would spin forever in the reference
         float t = t0;
         for (uint32_t i = 0; i < lane; ++i) t += calc_dt(c, t, cone);          // t_k .. t_{k+31}, sequential float adds
@@ -134,7 +139,12 @@ __device__ __forceinline__ uint32_t march_ray_warp(const RayState& r, float lo, 
         int cur = 0;
         if (pending) {
             const uint32_t ge = __ballot_sync(FULL, !(t < pending_tt));
-            if (ge == 0) { t0 = t_next_chunk; continue; }                       // the whole chunk lies inside the skipped span
+            if (ge == 0) {                                                      // the whole chunk lies inside the skipped span
+                if (!EMIT && rec && chunk < MARCH_MAXC && lane == 0) rec[chunk] = ChunkRec{t0, 0u};
+                ++chunk;
+                t0 = t_next_chunk;
+                continue;
+            }
             cur = __ffs(ge) - 1;
             pending = false;
         }
@@ -157,12 +167,14 @@ __device__ __forceinline__ uint32_t march_ray_warp(const RayState& r, float lo, 
         }
         const uint32_t inside_m = __ballot_sync(FULL, inside), occ_m = __ballot_sync(FULL, occ);
         bool done = false;
+        uint32_t emit_m = 0;
         while (cur < 32) {
             if (!((inside_m >> cur) & 1u) || j >= limit) { done = true; break; }   // while (aabb.contains(pos) && j < limit)
             if ((occ_m >> cur) & 1u) {
                 const uint32_t run_m = (occ_m & inside_m) >> cur;                 // consecutive occupied steps are taken one by one
                 uint32_t n_run = (run_m == 0xffffffffu) ? 32u : (uint32_t)__ffs(~run_m) - 1u;
                 n_run = min(n_run, limit - j);
+                emit_m |= (n_run >= 32u ? 0xffffffffu : ((1u << n_run) - 1u)) << cur;
                 if (EMIT && (int)lane >= cur && lane < cur + n_run) {
                     float* q = out + (size_t)(j + lane - cur) * 7;
                     q[0] = (p[0] - lo) / diag; q[1] = (p[1] - lo) / diag; q[2] = (p[2] - lo) / diag;   // warp_position
@@ -180,20 +192,24 @@ __device__ __forceinline__ uint32_t march_ray_warp(const RayState& r, float lo, 
                 else { pending = true; pending_tt = tt; cur = 32; }
             }
         }
+        if (!EMIT && rec && chunk < MARCH_MAXC && lane == 0) rec[chunk] = ChunkRec{t0, emit_m};
+        ++chunk;
         if (done) break;
         t0 = t_next_chunk;
     }
+    if (!EMIT && n_chunks && lane == 0) *n_chunks = chunk;
     return j;
 }
 
 __global__ void __launch_bounds__(128) march_count_kernel(uint32_t n_rays, float lo, float hi, const float* __restrict__ rays_o,
                                                           const float* __restrict__ rays_d, const uint8_t* __restrict__ bits, float cone,
                                                           float near_distance, MarchCfg c, uint64_t rng_state, uint64_t rng_inc,
-                                                          uint32_t* __restrict__ counts) {
+                                                          uint32_t* __restrict__ counts, ChunkRec* __restrict__ recs,
+                                                          uint32_t* __restrict__ n_chunks) {
     const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per ray
     if (i >= n_rays) return;
     const RayState r = ray_setup(i, rays_o, rays_d, lo, hi, near_distance, cone, c, rng_state, rng_inc);
-    const uint32_t n = march_ray_warp<false>(r, lo, hi, cone, c, bits, NERF_STEPS, nullptr);
+    const uint32_t n = march_ray_warp<false>(r, lo, hi, cone, c, bits, NERF_STEPS, nullptr, recs + (size_t)i * MARCH_MAXC, n_chunks + i);
     if ((threadIdx.x & 31) == 0) counts[i] = n;
 }
 
@@ -244,16 +260,52 @@ __global__ void __launch_bounds__(1024) march_scan_kernel(uint32_t n_rays, uint3
     if (t == 1023) { counters[0] = s_acc[1023]; counters[1] = s_sum[1023]; }
 }
 
+// Emit pass.  The count pass left, per ray, the start t and the emit mask of each 32-step chunk; only chunks that emit samples
+// are revisited (typically 4-5 of ~36), each by re-deriving its 32 t values with the same sequential float additions.  Rays with
+// more than MARCH_MAXC chunks (long cone-stepped rays) fall back to a full re-march.
 __global__ void __launch_bounds__(128) march_emit_kernel(uint32_t n_rays, float lo, float hi, const float* __restrict__ rays_o,
                                                          const float* __restrict__ rays_d, const uint8_t* __restrict__ bits, float cone,
                                                          float near_distance, MarchCfg c, uint64_t rng_state, uint64_t rng_inc,
-                                                         const uint32_t* __restrict__ numsteps, float* __restrict__ coords) {
-    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                                                         const uint32_t* __restrict__ numsteps, float* __restrict__ coords,
+                                                         const ChunkRec* __restrict__ recs, const uint32_t* __restrict__ n_chunks) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= n_rays) return;
     const uint32_t n = numsteps[2 * i], base = numsteps[2 * i + 1];
     if (n == 0) return;
-    const RayState r = ray_setup(i, rays_o, rays_d, lo, hi, near_distance, cone, c, rng_state, rng_inc);
-    march_ray_warp<true>(r, lo, hi, cone, c, bits, n, coords + (size_t)base * 7);
+    const uint32_t nc = n_chunks[i];
+    float* out = coords + (size_t)base * 7;
+    if (nc > MARCH_MAXC) {
+        const RayState r = ray_setup(i, rays_o, rays_d, lo, hi, near_distance, cone, c, rng_state, rng_inc);
+        march_ray_warp<true>(r, lo, hi, cone, c, bits, n, out);
+        return;
+    }
+    float o[3], d[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { o[k] = rays_o[3 * (size_t)i + k]; d[k] = rays_d[3 * (size_t)i + k]; }
+    const float wd[3] = {(d[0] + 1.0f) * 0.5f, (d[1] + 1.0f) * 0.5f, (d[2] + 1.0f) * 0.5f}, diag = hi - lo;
+    const ChunkRec* rec = recs + (size_t)i * MARCH_MAXC;
+    uint32_t j = 0;
+    for (uint32_t g0 = 0; g0 < nc; g0 += 32) {               // 32 chunk records per coalesced load, then visit the non-empty ones in order
+        ChunkRec mine = ChunkRec{0.f, 0u};
+        if (g0 + lane < nc) mine = rec[g0 + lane];
+        uint32_t nz = __ballot_sync(0xffffffffu, mine.mask != 0);
+        while (nz) {
+            const int ch = __ffs(nz) - 1;
+            nz &= nz - 1;
+            const uint32_t mask = __shfl_sync(0xffffffffu, mine.mask, ch);
+            float t = __shfl_sync(0xffffffffu, mine.t0, ch);
+            for (uint32_t k = 0; k < lane; ++k) t += calc_dt(c, t, cone);
+            if ((mask >> lane) & 1u) {
+                const float dt = calc_dt(c, t, cone);
+                const float p[3] = {__fmaf_rn(t, d[0], o[0]), __fmaf_rn(t, d[1], o[1]), __fmaf_rn(t, d[2], o[2])};
+                float* q = out + (size_t)(j + __popc(mask & ((1u << lane) - 1u))) * 7;
+                q[0] = (p[0] - lo) / diag; q[1] = (p[1] - lo) / diag; q[2] = (p[2] - lo) / diag;   // warp_position
+                q[3] = nerf_warp_dt(dt, c.cascades);
+                q[4] = wd[0]; q[5] = wd[1]; q[6] = wd[2];
+            }
+            j += __popc(mask);
+        }
+    }
 }
 
 // Compaction bases: exclusive scan of the per-ray counts in ray order (single CTA), with the reference's truncation rule.
@@ -493,7 +545,10 @@ __global__ void __launch_bounds__(256) composite_loss_bwd_kernel(uint32_t n_rays
 
 extern "C" {
 
-uint64_t ngp_march_workspace_bytes(uint32_t n_rays) { return (uint64_t)n_rays * 4 + 256; }
+uint64_t ngp_march_workspace_bytes(uint32_t n_rays) {
+    // counts[n] | n_chunks[n] | ChunkRec[n][MARCH_MAXC]
+    return (uint64_t)n_rays * (4 + 4 + MARCH_MAXC * sizeof(ChunkRec)) + 512;
+}
 
 int ngp_march(void* stream, uint32_t n_rays, float aabb_lo, float aabb_hi, uint32_t max_samples, const float* rays_o, const float* rays_d,
               const uint8_t* bitfield, float cone_angle, float near_distance, uint32_t cascades, int const_dt, uint64_t rng_state,
@@ -504,14 +559,16 @@ int ngp_march(void* stream, uint32_t n_rays, float aabb_lo, float aabb_hi, uint3
     if (n_rays == 0) return 0;
     const MarchCfg c = make_cfg(cascades, const_dt);
     uint32_t* counts = (uint32_t*)workspace;
+    uint32_t* n_chunks = counts + n_rays;
+    ChunkRec* recs = reinterpret_cast<ChunkRec*>((reinterpret_cast<uintptr_t>(n_chunks + n_rays) + 15) & ~(uintptr_t)15);
     const uint32_t blocks = (n_rays + 3) / 4;             // one warp per ray, 4 rays per CTA
     march_count_kernel<<<blocks, 128, 0, s>>>(n_rays, aabb_lo, aabb_hi, rays_o, rays_d, bitfield, cone_angle, near_distance, c, rng_state,
-                                              rng_inc, counts);
+                                              rng_inc, counts, recs, n_chunks);
     NGP_LAUNCH_CHECK();
     march_scan_kernel<<<1, 1024, 0, s>>>(n_rays, max_samples, counts, numsteps, ray_indices, counters);
     NGP_LAUNCH_CHECK();
     march_emit_kernel<<<blocks, 128, 0, s>>>(n_rays, aabb_lo, aabb_hi, rays_o, rays_d, bitfield, cone_angle, near_distance, c, rng_state,
-                                             rng_inc, numsteps, coords);
+                                             rng_inc, numsteps, coords, recs, n_chunks);
     NGP_LAUNCH_CHECK();
     return 0;
 }
