@@ -45,10 +45,10 @@ struct SmemFwd {
     static constexpr uint32_t total = bar + 64;
 };
 // gradient slab groups (backward)
-constexpr uint32_t Q_DYR = 0, Q_GH2 = 2, Q_GH1 = 10, Q_DYD = 18, Q_GHD = 22, Q_DENC = 30, Q_TOTAL = 34;
+constexpr uint32_t Q_DYR = 0, Q_GH2 = 2, Q_GH1 = 10, Q_DYD = 18, Q_GHD = 22, Q_DENC = 30 /* two buffers of 4 groups */, Q_TOTAL = 38;
 struct SmemBwd {
-    static constexpr uint32_t coords = 0;
-    static constexpr uint32_t act = 4096;                         // 32 groups
+    static constexpr uint32_t coords = 0;                         // two buffers of 128 x 7 f32 (3584 B each)
+    static constexpr uint32_t act = 8192;                         // 32 groups
     static constexpr uint32_t grd = act + 32 * GB;                // 34 groups
     static constexpr uint32_t w0d = grd + Q_TOTAL * GB;
     static constexpr uint32_t woutd = w0d + 64 * 32 * 2;
@@ -129,7 +129,7 @@ __device__ __forceinline__ void build_forward_program(uint8_t* smem, uint32_t tb
 
 // Forward chain up to (and including) the colour net's last hidden layer.  Expects enc in ACT[G_ENC..+4).
 // Returns the fp16 density output h[0] of row t (sigma_raw) and leaves hd / rin / h1 / h2 in the slab.
-template <uint32_t G_H2>
+template <uint32_t G_H2, bool CHAIN128 = false>
 __device__ __forceinline__ uint32_t forward_chain(uint8_t* smem, uint32_t act_off, const MmaOp* ops,
                                                   const float* s_coords, uint32_t tbase, Pipe& pipe, uint32_t t, uint32_t warp,
                                                   bool density_only) {
@@ -139,7 +139,7 @@ __device__ __forceinline__ uint32_t forward_chain(uint8_t* smem, uint32_t act_of
     if (t == 0) { run_ops(ops, OP_L0D, 2, 0); pipe.commit(); }
     pipe.wait();
     epi_hidden_relu(tbase, D_H, warp, act, G_HD, t, nullptr);
-    sync_before_issue();
+    sync_before_issue<CHAIN128>();
     // density L1: hd(64) -> h(16)
     if (t == 0) { run_ops(ops, OP_L1D, 4, 0); pipe.commit(); }
     pipe.wait();
@@ -157,17 +157,17 @@ __device__ __forceinline__ uint32_t forward_chain(uint8_t* smem, uint32_t act_of
         pack16(sh, lo, hi);
         slab_store16(act, G_RIN + 2, t, lo, hi);
     }
-    sync_before_issue();
+    sync_before_issue<CHAIN128>();
     // colour L0: [h | sh](32) -> h1(64)
     if (t == 0) { run_ops(ops, OP_L0R, 2, 0); pipe.commit(); }
     pipe.wait();
     epi_hidden_relu(tbase, D_H, warp, act, G_H1, t, nullptr);
-    sync_before_issue();
+    sync_before_issue<CHAIN128>();
     // colour L1: h1(64) -> h2(64)
     if (t == 0) { run_ops(ops, OP_L1R, 4, 0); pipe.commit(); }
     pipe.wait();
     epi_hidden_relu(tbase, D_H, warp, act, G_H2, t, nullptr);
-    sync_before_issue();
+    sync_before_issue<CHAIN128>();
     return sigma_half;
 }
 
@@ -236,7 +236,11 @@ network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
     if (warp == 0) tmem_free(tbase, 128);
 }
 
-__global__ void __launch_bounds__(128)
+// Warp-specialised backward: warps 0-3 ("chain") run the tensor-core MLP chain of tile i while warps 4-7 ("scatter") push the
+// hash-grid gradient of tile i-1 from a double-buffered dL/d(enc) slab.  The scatter is bound by the L2 atomic rate, the chain
+// by its serial stage latency; neither keeps an SM busy alone (tools/dbg_timeline_bwd.py: 19 k vs 32 k cycles per tile), so
+// they overlap.  Hand-off through named barriers FULL[b] / EMPTY[b] (ids 2+b / 4+b, 256 threads: 128 arrive + 128 sync).
+__global__ void __launch_bounds__(256)
 network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const float* __restrict__ coords, const __half* __restrict__ enc_save,
                    const NgpLevel* __restrict__ levels, const __half* __restrict__ wd, const __half* __restrict__ wr,
                    const __half* __restrict__ dout, __half* __restrict__ grid_grad, float* __restrict__ dwd, float* __restrict__ dwr,
@@ -244,17 +248,21 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
     extern __shared__ __align__(1024) uint8_t smem[];
     using S = SmemBwd;
     const uint32_t t = threadIdx.x, warp = t >> 5;
+    const bool is_chain = warp < 4;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::bar);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
-    float* s_coords = reinterpret_cast<float*>(smem + S::coords);
     NgpLevel* s_lv = reinterpret_cast<NgpLevel*>(smem + S::levels);
     uint8_t* act = smem + S::act;
     uint8_t* grd = smem + S::grd;
 
-    stage_all_weights<S>(smem, wd, wr, t);
+    stage_weights(smem + S::w0d, wd + WD_W0, 64, 32, t, 256);
+    stage_weights(smem + S::woutd, wd + WD_WOUT, 16, 64, t, 256);
+    stage_weights(smem + S::w0r, wr + WR_W0, 64, 32, t, 256);
+    stage_weights(smem + S::w1r, wr + WR_W1, 64, 64, t, 256);
+    stage_weights(smem + S::woutr, wr + WR_WOUT, 16, 64, t, 256);
     if (t < N_LEVELS) s_lv[t] = levels[t];
     // dYr columns 4..15, the dYd pad groups: zero once (never rewritten)
-    for (uint32_t i = t; i < Q_TOTAL * GB / 16; i += 128) *reinterpret_cast<uint4*>(grd + i * 16) = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = t; i < Q_TOTAL * GB / 16; i += 256) *reinterpret_cast<uint4*>(grd + i * 16) = make_uint4(0, 0, 0, 0);
     if (t == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(tmem_ptr, 512);
     sync_before_issue();
@@ -287,99 +295,130 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
         __syncthreads();
     }
     const MmaOp* ops = reinterpret_cast<const MmaOp*>(smem + S::ops);
-    Pipe pipe{bar, 0, err};
     const uint32_t n_live = n_dev ? min(*n_dev, n_max) : n_max;
-    const uint32_t level = t & 15, sub = t >> 4;
-    const NgpLevel lv = s_lv[level];
-    __half2* gg = reinterpret_cast<__half2*>(grid_grad) + lv.offset;
     const uint32_t ntiles = (n_live + ROWS - 1) / ROWS;
     uint32_t acc = 0;
-    // software prefetch: the next tile's inputs (7 coordinate words, the 64 B encoded row, the 8 B output gradient) are loaded into
-    // registers before the scatter phase of the current tile, so their HBM latency (~2 us with one CTA per SM) is hidden.
-    float pf_c[7];
-    uint4 pf_e[4];
-    uint2 pf_d;
-    auto prefetch = [&](uint32_t tile_) {
-        const uint32_t r0 = tile_ * ROWS, r = r0 + t;
-        const bool ok = r < n_live;
+
+    if (is_chain) {
+        // ------------------------------------------------------------------ MLP chain (threads 0..127, thread t = row t)
+        Pipe pipe{bar, 0, err};
+        // software prefetch of the next tile's inputs (7 coordinate words, the 64 B encoded row, the 8 B output gradient)
+        float pf_c[7];
+        uint4 pf_e[4];
+        uint2 pf_d;
+        auto prefetch = [&](uint32_t tile_) {
+            const uint32_t r0 = tile_ * ROWS, r = r0 + t;
+            const bool ok = r < n_live;
 #pragma unroll
-        for (int j = 0; j < 7; ++j) {
-            const uint32_t i = t + 128 * j;
-            pf_c[j] = (r0 + i / 7 < n_live) ? __ldg(coords + (size_t)r0 * 7 + i) : 0.f;
+            for (int j = 0; j < 7; ++j) {
+                const uint32_t i = t + 128 * j;
+                pf_c[j] = (r0 + i / 7 < n_live) ? __ldg(coords + (size_t)r0 * 7 + i) : 0.f;
+            }
+            const uint4* es = reinterpret_cast<const uint4*>(enc_save + (size_t)r * 32);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) pf_e[g] = ok ? __ldg(es + g) : make_uint4(0, 0, 0, 0);
+            pf_d = ok ? __ldg(reinterpret_cast<const uint2*>(dout) + r) : make_uint2(0, 0);
+        };
+        if (blockIdx.x < ntiles) prefetch(blockIdx.x);
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, acc = 1, ++it) {
+            const uint32_t buf = it & 1;
+            float* s_coords = reinterpret_cast<float*>(smem + S::coords + buf * 3584);
+            if (it >= 2) named_bar_sync(4 + buf, 256);          // the scatter of tile it-2 has released coords[buf] / d_enc[buf]
+            DBGB(0);
+#pragma unroll
+            for (int j = 0; j < 7; ++j) s_coords[t + 128 * j] = pf_c[j];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(act + (G_ENC + g) * GB + t * 16) = pf_e[g];
+            const uint32_t dsig = pf_d.y >> 16;
+            *reinterpret_cast<uint4*>(grd + Q_DYR * GB + t * 16) = make_uint4(pf_d.x, pf_d.y & 0xFFFFu, 0, 0);
+            if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x);   // in flight during the whole chain
+            DBGB(1);
+            sync_before_issue<true>();
+            DBGB(2);
+            forward_chain<G_H2B, true>(smem, S::act, ops, s_coords, tbase, pipe, t, warp, false);
+            DBGB(3);
+            // B1: g_h2 = (dYr Woutr) . relu'(h2) ; wgrad Woutr
+            if (t == 0) { run_ops(ops, OP_B1, 1 + 8, acc); DBGB(4); pipe.commit(); }
+            pipe.wait();
+            DBGB(5);
+            epi_dgrad_mask(tbase, D_H, warp, act, G_H2B, grd, Q_GH2, t, nullptr);
+            DBGB(6);
+            sync_before_issue<true>();
+            DBGB(7);
+            // B2: g_h1 = (g_h2 W1r) . relu'(h1) ; wgrad W1r
+            if (t == 0) { run_ops(ops, OP_B2, 4 + 8, acc); DBGB(8); pipe.commit(); }
+            pipe.wait();
+            DBGB(9);
+            epi_dgrad_mask(tbase, D_H, warp, act, G_H1, grd, Q_GH1, t, nullptr);
+            sync_before_issue<true>();
+            DBGB(10);
+            // B3: d_rin = g_h1 W0r (32 cols; the last 16 are dL/dSH, unused) ; wgrad W0r
+            if (t == 0) { run_ops(ops, OP_B3, 4 + 8, acc); pipe.commit(); }
+            pipe.wait();
+            {
+                float v[16];
+                tmem_ld16(tmem_addr(tbase, warp, D_S), v);
+                v[0] += __half2float(__ushort_as_half((unsigned short)dsig));   // + dL/dsigma (ngp_network.py:83)
+                uint4 lo, hi;
+                pack16(v, lo, hi);
+                slab_store16(grd, Q_DYD, t, lo, hi);
+            }
+            sync_before_issue<true>();
+            // B4: g_hd = (dYd Woutd) . relu'(hd) ; wgrad Woutd
+            if (t == 0) { run_ops(ops, OP_B4, 1 + 8, acc); pipe.commit(); }
+            pipe.wait();
+            epi_dgrad_mask(tbase, D_H, warp, act, G_HD, grd, Q_GHD, t, nullptr);
+            sync_before_issue<true>();
+            // B5: d_enc = g_hd W0d ; wgrad W0d
+            if (t == 0) { run_ops(ops, OP_B5, 4 + 8, acc); pipe.commit(); }
+            pipe.wait();
+            {
+                float v[16];
+                uint4 lo, hi;
+                tmem_ld16(tmem_addr(tbase, warp, D_S), v);
+                pack16(v, lo, hi);
+                slab_store16(grd, Q_DENC + 4 * buf, t, lo, hi);
+                tmem_ld16(tmem_addr(tbase, warp, D_S + 16), v);
+                pack16(v, lo, hi);
+                slab_store16(grd, Q_DENC + 4 * buf + 2, t, lo, hi);
+            }
+            tc_fence_before();
+            named_bar_arrive(2 + buf, 256);                      // FULL[buf]: dL/d(enc) and coords of this tile are ready
+            DBGB(11);
         }
-        const uint4* es = reinterpret_cast<const uint4*>(enc_save + (size_t)r * 32);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) pf_e[g] = ok ? __ldg(es + g) : make_uint4(0, 0, 0, 0);
-        pf_d = ok ? __ldg(reinterpret_cast<const uint2*>(dout) + r) : make_uint2(0, 0);
-    };
-    if (blockIdx.x < ntiles) prefetch(blockIdx.x);
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, acc = 1) {
-        const uint32_t row0 = tile * ROWS;
-        DBGB(0);
-#pragma unroll
-        for (int j = 0; j < 7; ++j) s_coords[t + 128 * j] = pf_c[j];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(act + (G_ENC + g) * GB + t * 16) = pf_e[g];
-        const uint32_t dsig = pf_d.y >> 16;
-        *reinterpret_cast<uint4*>(grd + Q_DYR * GB + t * 16) = make_uint4(pf_d.x, pf_d.y & 0xFFFFu, 0, 0);
-        DBGB(1);
-        sync_before_issue();
-        DBGB(2);
-        forward_chain<G_H2B>(smem, S::act, ops, s_coords, tbase, pipe, t, warp, false);
-        DBGB(3);
-        // B1: g_h2 = (dYr Woutr) . relu'(h2) ; wgrad Woutr
-        if (t == 0) { run_ops(ops, OP_B1, 1 + 8, acc); DBGB(4); pipe.commit(); }
-        pipe.wait();
-        DBGB(5);
-        epi_dgrad_mask(tbase, D_H, warp, act, G_H2B, grd, Q_GH2, t, nullptr);
-        DBGB(6);
-        sync_before_issue();
-        DBGB(7);
-        // B2: g_h1 = (g_h2 W1r) . relu'(h1) ; wgrad W1r
-        if (t == 0) { run_ops(ops, OP_B2, 4 + 8, acc); DBGB(8); pipe.commit(); }
-        pipe.wait();
-        DBGB(9);
-        epi_dgrad_mask(tbase, D_H, warp, act, G_H1, grd, Q_GH1, t, nullptr);
-        sync_before_issue();
-        DBGB(10);
-        // B3: d_rin = g_h1 W0r (32 cols; the last 16 are dL/dSH, unused) ; wgrad W0r
-        if (t == 0) { run_ops(ops, OP_B3, 4 + 8, acc); pipe.commit(); }
-        pipe.wait();
-        {
+        // flush weight gradients (lane = input feature, column = output feature)
+        if (acc) {
             float v[16];
-            tmem_ld16(tmem_addr(tbase, warp, D_S), v);
-            v[0] += __half2float(__ushort_as_half((unsigned short)dsig));   // + dL/dsigma (ngp_network.py:83)
-            uint4 lo, hi;
-            pack16(v, lo, hi);
-            slab_store16(grd, Q_DYD, t, lo, hi);
+            const uint32_t f_col[5] = {A_W0D, A_WOUTD, A_W0R, A_W1R, A_WOUTR};
+            const uint32_t f_nout[5] = {64, 16, 64, 64, 16}, f_valid[5] = {64, 16, 64, 64, 3};   // colour Wout rows >= 3 stay zero (fully_fused_mlp.py:136)
+            const uint32_t f_in[5] = {32, 64, 32, 64, 64};
+            float* const f_dst[5] = {dwd + WD_W0, dwd + WD_WOUT, dwr + WR_W0, dwr + WR_W1, dwr + WR_WOUT};
+#pragma unroll 1
+            for (int m = 0; m < 5; ++m) {
+#pragma unroll 1
+                for (uint32_t c = 0; c < f_nout[m] / 16; ++c) {
+                    tmem_ld16(tmem_addr(tbase, warp, f_col[m] + 16 * c), v);
+                    if (t < f_in[m]) {
+#pragma unroll
+                        for (int o = 0; o < 16; ++o)
+                            if (16 * c + o < f_valid[m]) atomicAdd(f_dst[m] + (size_t)(16 * c + o) * f_in[m] + t, v[o]);
+                    }
+                }
+            }
         }
-        sync_before_issue();
-        // B4: g_hd = (dYd Woutd) . relu'(hd) ; wgrad Woutd
-        if (t == 0) { run_ops(ops, OP_B4, 1 + 8, acc); pipe.commit(); }
-        pipe.wait();
-        epi_dgrad_mask(tbase, D_H, warp, act, G_HD, grd, Q_GHD, t, nullptr);
-        sync_before_issue();
-        // B5: d_enc = g_hd W0d ; wgrad W0d
-        if (t == 0) { run_ops(ops, OP_B5, 4 + 8, acc); pipe.commit(); }
-        pipe.wait();
-        {
-            float v[16];
-            uint4 lo, hi;
-            tmem_ld16(tmem_addr(tbase, warp, D_S), v);
-            pack16(v, lo, hi);
-            slab_store16(grd, Q_DENC, t, lo, hi);
-            tmem_ld16(tmem_addr(tbase, warp, D_S + 16), v);
-            pack16(v, lo, hi);
-            slab_store16(grd, Q_DENC + 2, t, lo, hi);
-        }
-        tc_fence_before();
-        __syncthreads();
-        DBGB(11);
-        if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x);
-        // scatter (HashEncode.h:339-347): thread (level, sub) walks its 16 consecutive samples, accumulates the 8 corner
-        // contributions in fp32 registers while the grid cell stays the same and issues the f16x2 reductions only when the
-        // cell changes -- the atomic count (the bound of this phase) drops by the average run length.
-        {
+    } else {
+        // ------------------------------------------------------------------ scatter (threads 128..255)
+        // HashEncode.h:339-347.  Thread (level, sub) walks its 16 consecutive samples, accumulates the 8 corner contributions in
+        // fp32 registers while the grid cell stays the same and issues the f16x2 reductions only when the cell changes.
+        const uint32_t ts = t - 128, level = ts & 15, sub = ts >> 4;
+        const NgpLevel lv = s_lv[level];
+        __half2* gg = reinterpret_cast<__half2*>(grid_grad) + lv.offset;
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const uint32_t buf = it & 1, row0 = tile * ROWS;
+            const float* s_coords = reinterpret_cast<const float*>(smem + S::coords + buf * 3584);
+            named_bar_sync(2 + buf, 256);                        // FULL[buf]
             uint32_t cgx = 0xffffffffu, cgy = 0, cgz = 0, idx[8];
             float2 accv[8];
             bool dirty = false;
@@ -387,7 +426,7 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             for (int k = 0; k < 16; ++k) {
                 const uint32_t p = 16 * sub + k;
                 if (row0 + p >= n_live) break;
-                const __half2 d = *reinterpret_cast<const __half2*>(grd + (size_t)(Q_DENC + (level >> 2)) * GB + p * 16 + (level & 3) * 4);
+                const __half2 d = *reinterpret_cast<const __half2*>(grd + (size_t)(Q_DENC + 4 * buf + (level >> 2)) * GB + p * 16 + (level & 3) * 4);
                 const float2 df = __half22float2(d);
                 if (df.x == 0.f && df.y == 0.f) continue;
                 const HashCell hc = hash_cell(lv, s_coords[p * 7], s_coords[p * 7 + 1], s_coords[p * 7 + 2]);
@@ -411,28 +450,7 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
 #pragma unroll
                 for (int c = 0; c < 8; ++c) atomicAdd(gg + idx[c], __floats2half2_rn(accv[c].x, accv[c].y));
             }
-        }
-        __syncthreads();   // slabs / coords are rewritten by the next tile
-        DBGB(12);
-    }
-    // flush weight gradients (lane = input feature, column = output feature)
-    if (acc) {
-        float v[16];
-        const uint32_t f_col[5] = {A_W0D, A_WOUTD, A_W0R, A_W1R, A_WOUTR};
-        const uint32_t f_nout[5] = {64, 16, 64, 64, 16}, f_valid[5] = {64, 16, 64, 64, 3};   // colour Wout rows >= 3 stay zero (fully_fused_mlp.py:136)
-        const uint32_t f_in[5] = {32, 64, 32, 64, 64};
-        float* const f_dst[5] = {dwd + WD_W0, dwd + WD_WOUT, dwr + WR_W0, dwr + WR_W1, dwr + WR_WOUT};
-#pragma unroll 1
-        for (int m = 0; m < 5; ++m) {
-#pragma unroll 1
-            for (uint32_t c = 0; c < f_nout[m] / 16; ++c) {
-                tmem_ld16(tmem_addr(tbase, warp, f_col[m] + 16 * c), v);
-                if (t < f_in[m]) {
-#pragma unroll
-                    for (int o = 0; o < 16; ++o)
-                        if (16 * c + o < f_valid[m]) atomicAdd(f_dst[m] + (size_t)(16 * c + o) * f_in[m] + t, v[o]);
-                }
-            }
+            if (tile + 2 * gridDim.x < ntiles) named_bar_arrive(4 + buf, 256);   // EMPTY[buf] for the chain's tile it+2
         }
     }
     tc_fence_before();
@@ -481,7 +499,7 @@ int ngp_network_bwd(void* stream, uint32_t n_max, const uint32_t* n_dev, const f
     NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd::total));
     const uint32_t ntiles = (n_max + ROWS - 1) / ROWS;
     const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms());
-    network_bwd_kernel<<<grid_dim, 128, SmemBwd::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
+    network_bwd_kernel<<<grid_dim, 256, SmemBwd::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
                                                             (const __half*)w_density, (const __half*)w_rgb, (const __half*)dout,
                                                             (__half*)grid_grad, dw_density, dw_rgb, ngp_err_flag());
     NGP_LAUNCH_CHECK();

@@ -154,11 +154,17 @@ static __device__ __noinline__ void epi_dgrad_mask(uint32_t tbase, uint32_t dcol
     }
 }
 
+// named barriers (bar.sync / bar.arrive) for warp-specialised kernels; id 0 is __syncthreads
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 // Sync point between "all threads wrote smem operands / finished reading TMEM" and "thread 0 issues MMAs".
+// CHAIN128 = true: only the 128 MLP-chain threads (warps 0-3) of a warp-specialised CTA take part (named barrier 1).
+template <bool CHAIN128 = false>
 __device__ __forceinline__ void sync_before_issue() {
     tc_fence_before();
     fence_proxy_async_smem();
-    __syncthreads();
+    if (CHAIN128) named_bar_sync(1, 128); else __syncthreads();
     tc_fence_after();
 }
 
