@@ -31,10 +31,11 @@ constexpr int WR_W0 = 0, WR_W1 = 64 * 32, WR_WOUT = 64 * 32 + 64 * 64, WR_N = 64
 // ---- shared-memory maps -------------------------------------------------------------------------------
 // activation slab groups
 constexpr uint32_t G_ENC = 0, G_HD = 4, G_RIN = 12, G_H1 = 16, G_H2F = 4 /* fwd: reuses hd */, G_H2B = 24;
+constexpr uint32_t G_ENC1 = 24;   // forward kernel only: second (double-buffered) encoded-feature slab
 struct SmemFwd {
-    static constexpr uint32_t coords = 0;                         // 128 x 7 f32
-    static constexpr uint32_t act = 4096;                         // 24 groups
-    static constexpr uint32_t w0d = act + 24 * GB;
+    static constexpr uint32_t coords = 0;                         // two buffers of 128 x 7 f32 (3584 B each)
+    static constexpr uint32_t act = 8192;                         // 28 groups: enc0 | hd/h2 | rin | h1 | enc1
+    static constexpr uint32_t w0d = act + 28 * GB;
     static constexpr uint32_t woutd = w0d + 64 * 32 * 2;
     static constexpr uint32_t w0r = woutd + 16 * 64 * 2;
     static constexpr uint32_t w1r = w0r + 64 * 32 * 2;
@@ -63,6 +64,7 @@ struct SmemBwd {
 
 // MMA program layout (op indices) shared by the forward chain of both kernels
 constexpr uint32_t OP_L0D = 0, OP_L1D = 2, OP_L0R = 6, OP_L1R = 8, OP_L2R = 12, OP_FWD_END = 16;
+constexpr uint32_t OP_L0D_B1 = 16;   // forward kernel only: density layer 0 reading the second enc buffer
 
 template <class S>
 __device__ __forceinline__ void stage_all_weights(uint8_t* smem, const __half* wd, const __half* wr, uint32_t t) {
@@ -81,7 +83,7 @@ __device__ __forceinline__ void stage_all_weights(uint8_t* smem, const __half* w
 // number of L1/L2 requests drops by the average run length (the gather is bound by request rate, not by bytes).
 template <int STRIDE>
 __device__ __forceinline__ void gather_tile(const float* __restrict__ s_pos /* smem, STRIDE floats per row */, const NgpLevel& lv,
-                                            const __half2* __restrict__ g, uint8_t* act, uint32_t level, uint32_t sub,
+                                            const __half2* __restrict__ g, uint8_t* act, uint32_t g_enc, uint32_t level, uint32_t sub,
                                             __half* __restrict__ enc_save, uint32_t tile_row0, uint32_t n_live) {
     uint32_t cgx = 0xffffffffu, cgy = 0, cgz = 0;
     __half2 v[8];
@@ -108,7 +110,7 @@ __device__ __forceinline__ void gather_tile(const float* __restrict__ s_pos /* s
             a1 = fmaf(w[c], f.y, a1);
         }
         const __half2 r = __floats2half2_rn(a0, a1);
-        *reinterpret_cast<__half2*>(act + (size_t)(G_ENC + (level >> 2)) * GB + p * 16 + (level & 3) * 4) = r;
+        *reinterpret_cast<__half2*>(act + (size_t)(g_enc + (level >> 2)) * GB + p * 16 + (level & 3) * 4) = r;
         if (enc_save && tile_row0 + p < n_live)
             *reinterpret_cast<__half2*>(enc_save + (size_t)(tile_row0 + p) * 32 + 2 * level) = r;
     }
@@ -130,13 +132,13 @@ __device__ __forceinline__ void build_forward_program(uint8_t* smem, uint32_t tb
 // Forward chain up to (and including) the colour net's last hidden layer.  Expects enc in ACT[G_ENC..+4).
 // Returns the fp16 density output h[0] of row t (sigma_raw) and leaves hd / rin / h1 / h2 in the slab.
 template <uint32_t G_H2, bool CHAIN128 = false>
-__device__ __forceinline__ uint32_t forward_chain(uint8_t* smem, uint32_t act_off, const MmaOp* ops,
+__device__ __forceinline__ uint32_t forward_chain(uint8_t* smem, uint32_t act_off, const MmaOp* ops, uint32_t op_l0d,
                                                   const float* s_coords, uint32_t tbase, Pipe& pipe, uint32_t t, uint32_t warp,
                                                   bool density_only) {
     uint8_t* act = smem + act_off;
     const uint32_t D_H = 0, D_S = 64;
     // density L0: enc(32) -> hd(64)
-    if (t == 0) { run_ops(ops, OP_L0D, 2, 0); pipe.commit(); }
+    if (t == 0) { run_ops(ops, op_l0d, 2, 0); pipe.commit(); }
     pipe.wait();
     epi_hidden_relu(tbase, D_H, warp, act, G_HD, t, nullptr);
     sync_before_issue<CHAIN128>();
@@ -171,8 +173,12 @@ __device__ __forceinline__ uint32_t forward_chain(uint8_t* smem, uint32_t act_of
     return sigma_half;
 }
 
+// Warp-specialised forward: warps 4-7 ("gather") stage the coordinates of tile i+1 and encode them into one of two enc slabs while
+// warps 0-3 ("chain") run the tensor-core MLP chain of tile i.  The gather is bound by the L1/L2 request rate, the chain by its
+// serial stage latency; with both resident on the SM they overlap.  Hand-off through named barriers FULL[b] / EMPTY[b]
+// (ids 2+b / 4+b, 256 threads: 128 arrive + 128 sync); the gather warps synchronise among themselves on barrier 6.
 template <bool DENSITY_ONLY>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const float* __restrict__ coords, const __half* __restrict__ grid,
                    const NgpLevel* __restrict__ levels, const __half* __restrict__ wd, const __half* __restrict__ wr,
                    __half* __restrict__ out, __half* __restrict__ enc_save, int* __restrict__ err) {
@@ -180,56 +186,77 @@ network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
     using S = SmemFwd;
     constexpr int CS = DENSITY_ONLY ? 3 : 7;
     const uint32_t t = threadIdx.x, warp = t >> 5;
+    const bool is_chain = warp < 4;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::bar);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
-    float* s_coords = reinterpret_cast<float*>(smem + S::coords);
     NgpLevel* s_lv = reinterpret_cast<NgpLevel*>(smem + S::levels);
 
-    stage_all_weights<S>(smem, wd, DENSITY_ONLY ? nullptr : wr, t);
+    stage_weights(smem + S::w0d, wd + WD_W0, 64, 32, t, 256);
+    stage_weights(smem + S::woutd, wd + WD_WOUT, 16, 64, t, 256);
+    if (!DENSITY_ONLY) {
+        stage_weights(smem + S::w0r, wr + WR_W0, 64, 32, t, 256);
+        stage_weights(smem + S::w1r, wr + WR_W1, 64, 64, t, 256);
+        stage_weights(smem + S::woutr, wr + WR_WOUT, 16, 64, t, 256);
+    }
     if (t < N_LEVELS) s_lv[t] = levels[t];
     if (t == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(tmem_ptr, 128);
     sync_before_issue();
     const uint32_t tbase = *tmem_ptr;
-    if (warp == 0) build_forward_program<S, G_H2F>(smem, tbase, t);
+    if (warp == 0) {
+        build_forward_program<S, G_H2F>(smem, tbase, t);
+        build_fwd(reinterpret_cast<MmaOp*>(smem + S::ops) + OP_L0D_B1, t, tbase + 0, smem_u32(smem) + S::act, G_ENC1, 32, smem_u32(smem) + S::w0d, 64);
+    }
     __syncthreads();
     const MmaOp* ops = reinterpret_cast<const MmaOp*>(smem + S::ops);
-    Pipe pipe{bar, 0, err};
-    uint32_t n_live = n_dev ? min(*n_dev, n_max) : n_max;
-    const uint32_t level = t & 15, sub = t >> 4;
-    const NgpLevel lv = s_lv[level];
-    const __half2* g = reinterpret_cast<const __half2*>(grid) + lv.offset;
-
+    const uint32_t n_live = n_dev ? min(*n_dev, n_max) : n_max;
     const uint32_t ntiles = (n_live + ROWS - 1) / ROWS;
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint32_t row0 = tile * ROWS;
-        // stage the coordinate tile (coalesced)
-        for (uint32_t i = t; i < ROWS * CS; i += 128) {
-            const size_t gi = (size_t)row0 * CS + i;
-            s_coords[i] = (row0 + i / CS < n_live) ? __ldg(coords + gi) : 0.f;
-        }
-        __syncthreads();
-        gather_tile<CS>(s_coords, lv, g, smem + S::act, level, sub, DENSITY_ONLY ? nullptr : enc_save, row0, n_live);
-        sync_before_issue();
-        const uint32_t sig = forward_chain<G_H2F>(smem, S::act, ops, s_coords, tbase, pipe, t, warp, DENSITY_ONLY);
-        const uint32_t row = row0 + t;
-        if constexpr (DENSITY_ONLY) {
-            if (row < n_live) reinterpret_cast<uint16_t*>(out)[row] = (uint16_t)sig;
-            // the coords restaging __syncthreads + the next sync_before_issue order TMEM reads before reuse
-        } else {
-            if (t == 0) { run_ops(ops, OP_L2R, 4, 0); pipe.commit(); }
-            pipe.wait();
-            float v[16];
-            tmem_ld16(tmem_addr(tbase, warp, 64), v);
-            if (row < n_live) {
-                uint2 o;
-                o.x = pack_half2(v[0], v[1]);
-                o.y = (pack_half2(v[2], 0.f) & 0xFFFFu) | (sig << 16);
-                reinterpret_cast<uint2*>(out)[row] = o;
+
+    if (is_chain) {
+        Pipe pipe{bar, 0, err};
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const uint32_t buf = it & 1, row = tile * ROWS + t;
+            const float* s_coords = reinterpret_cast<const float*>(smem + S::coords + buf * 3584);
+            named_bar_sync(2 + buf, 256);                       // FULL[buf]: enc slab + coordinates of this tile are in smem
+            tc_fence_after();
+            // forward_chain releases nothing itself: the enc slab is dead after layer 0, the coordinates after the SH epilogue;
+            // both are handed back together right after the chain (the gather runs a full tile ahead, so this is not on its path)
+            const uint32_t sig = forward_chain<G_H2F, true>(smem, S::act, ops, buf ? OP_L0D_B1 : OP_L0D, s_coords, tbase, pipe, t, warp, DENSITY_ONLY);
+            if (tile + 2 * gridDim.x < ntiles) named_bar_arrive(4 + buf, 256);   // EMPTY[buf]
+            if constexpr (DENSITY_ONLY) {
+                if (row < n_live) reinterpret_cast<uint16_t*>(out)[row] = (uint16_t)sig;
+                sync_before_issue<true>();                      // TMEM reads of this tile precede the next tile's MMAs
+            } else {
+                if (t == 0) { run_ops(ops, OP_L2R, 4, 0); pipe.commit(); }
+                pipe.wait();
+                float v[16];
+                tmem_ld16(tmem_addr(tbase, warp, 64), v);
+                if (row < n_live) {
+                    uint2 o;
+                    o.x = pack_half2(v[0], v[1]);
+                    o.y = (pack_half2(v[2], 0.f) & 0xFFFFu) | (sig << 16);
+                    reinterpret_cast<uint2*>(out)[row] = o;
+                }
+                sync_before_issue<true>();
             }
         }
-        tc_fence_before();
-        __syncthreads();   // coords / slabs are rewritten by the next tile
+    } else {
+        const uint32_t tg = t - 128, level = tg & 15, sub = tg >> 4;
+        const NgpLevel lv = s_lv[level];
+        const __half2* g = reinterpret_cast<const __half2*>(grid) + lv.offset;
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const uint32_t buf = it & 1, row0 = tile * ROWS;
+            float* s_coords = reinterpret_cast<float*>(smem + S::coords + buf * 3584);
+            if (it >= 2) named_bar_sync(4 + buf, 256);          // EMPTY[buf]: the chain of tile it-2 is done with this buffer
+            for (uint32_t i = tg; i < ROWS * CS; i += 128)       // stage the coordinate tile (coalesced)
+                s_coords[i] = (row0 + i / CS < n_live) ? __ldg(coords + (size_t)row0 * CS + i) : 0.f;
+            named_bar_sync(6, 128);
+            gather_tile<CS>(s_coords, lv, g, smem + S::act, buf ? G_ENC1 : G_ENC, level, sub, DENSITY_ONLY ? nullptr : enc_save, row0, n_live);
+            fence_proxy_async_smem();                           // the enc slab is read by the tensor core (async proxy)
+            named_bar_arrive(2 + buf, 256);                     // FULL[buf]
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -336,7 +363,7 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             DBGB(1);
             sync_before_issue<true>();
             DBGB(2);
-            forward_chain<G_H2B, true>(smem, S::act, ops, s_coords, tbase, pipe, t, warp, false);
+            forward_chain<G_H2B, true>(smem, S::act, ops, OP_L0D, s_coords, tbase, pipe, t, warp, false);
             DBGB(3);
             // B1: g_h2 = (dYr Woutr) . relu'(h2) ; wgrad Woutr
             if (t == 0) { run_ops(ops, OP_B1, 1 + 8, acc); DBGB(4); pipe.commit(); }
@@ -472,8 +499,8 @@ int ngp_network_fwd(void* stream, uint32_t n_max, const uint32_t* n_dev, const f
     cudaStream_t s = (cudaStream_t)stream;
     NGP_CHECK_CUDA(cudaFuncSetAttribute(network_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemFwd::total));
     const uint32_t ntiles = (n_max + ROWS - 1) / ROWS;
-    const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms() * 3u);
-    network_fwd_kernel<false><<<grid_dim, 128, SmemFwd::total, s>>>(n_max, n_dev, coords, (const __half*)grid, (const NgpLevel*)levels_dev,
+    const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms() * 2u);
+    network_fwd_kernel<false><<<grid_dim, 256, SmemFwd::total, s>>>(n_max, n_dev, coords, (const __half*)grid, (const NgpLevel*)levels_dev,
                                                                    (const __half*)w_density, (const __half*)w_rgb, (__half*)out,
                                                                    (__half*)enc_save, ngp_err_flag());
     NGP_LAUNCH_CHECK();
@@ -485,8 +512,8 @@ int ngp_density_fwd(void* stream, uint32_t n, const float* pos, const void* grid
     cudaStream_t s = (cudaStream_t)stream;
     NGP_CHECK_CUDA(cudaFuncSetAttribute(network_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemFwd::total));
     const uint32_t ntiles = (n + ROWS - 1) / ROWS;
-    const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms() * 3u);
-    network_fwd_kernel<true><<<grid_dim, 128, SmemFwd::total, s>>>(n, nullptr, pos, (const __half*)grid, (const NgpLevel*)levels_dev,
+    const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms() * 2u);
+    network_fwd_kernel<true><<<grid_dim, 256, SmemFwd::total, s>>>(n, nullptr, pos, (const __half*)grid, (const NgpLevel*)levels_dev,
                                                                   (const __half*)w_density, nullptr, (__half*)sigma_out, nullptr, ngp_err_flag());
     NGP_LAUNCH_CHECK();
     return 0;
