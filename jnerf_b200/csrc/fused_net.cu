@@ -81,7 +81,7 @@ __device__ __forceinline__ void stage_all_weights(uint8_t* smem, const __half* w
 // level.  Samples arrive ray-ordered, so consecutive points usually stay in the same grid cell at the coarser levels: the 8
 // corner values are re-fetched only when the cell changes (run-length reuse).  The arithmetic per point is unchanged; the
 // number of L1/L2 requests drops by the average run length (the gather is bound by request rate, not by bytes).
-template <int STRIDE>
+template <int STRIDE, int PTS>
 __device__ __forceinline__ void gather_tile(const float* __restrict__ s_pos /* smem, STRIDE floats per row */, const NgpLevel& lv,
                                             const __half2* __restrict__ g, uint8_t* act, uint32_t g_enc, uint32_t level, uint32_t sub,
                                             __half* __restrict__ enc_save, uint32_t tile_row0, uint32_t n_live) {
@@ -90,8 +90,8 @@ __device__ __forceinline__ void gather_tile(const float* __restrict__ s_pos /* s
 #pragma unroll
     for (int c = 0; c < 8; ++c) v[c] = __float2half2_rn(0.f);
 #pragma unroll 1
-    for (int k = 0; k < 16; ++k) {
-        const uint32_t p = 16 * sub + k;
+    for (int k = 0; k < PTS; ++k) {
+        const uint32_t p = PTS * sub + k;
         const HashCell hc = hash_cell(lv, s_pos[p * STRIDE], s_pos[p * STRIDE + 1], s_pos[p * STRIDE + 2]);
         if (hc.gx != cgx || hc.gy != cgy || hc.gz != cgz) {
             cgx = hc.gx; cgy = hc.gy; cgz = hc.gz;
@@ -177,8 +177,13 @@ __device__ __forceinline__ uint32_t forward_chain(uint8_t* smem, uint32_t act_of
 // warps 0-3 ("chain") run the tensor-core MLP chain of tile i.  The gather is bound by the L1/L2 request rate, the chain by its
 // serial stage latency; with both resident on the SM they overlap.  Hand-off through named barriers FULL[b] / EMPTY[b]
 // (ids 2+b / 4+b, 256 threads: 128 arrive + 128 sync); the gather warps synchronise among themselves on barrier 6.
+// Gather warps per CTA.  Measured on the lego stand-in: 4 warps x 16-point runs 104 us, 8 warps x 8-point runs 76 us per forward
+// (the gather is instruction-latency bound with few warps; shorter runs cost a few more requests).
+constexpr int FWD_GW = 8;
+constexpr int FWD_THREADS = 128 + 32 * FWD_GW;
+
 template <bool DENSITY_ONLY>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(FWD_THREADS)
 network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const float* __restrict__ coords, const __half* __restrict__ grid,
                    const NgpLevel* __restrict__ levels, const __half* __restrict__ wd, const __half* __restrict__ wr,
                    __half* __restrict__ out, __half* __restrict__ enc_save, int* __restrict__ err) {
@@ -191,12 +196,12 @@ network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
     NgpLevel* s_lv = reinterpret_cast<NgpLevel*>(smem + S::levels);
 
-    stage_weights(smem + S::w0d, wd + WD_W0, 64, 32, t, 256);
-    stage_weights(smem + S::woutd, wd + WD_WOUT, 16, 64, t, 256);
+    stage_weights(smem + S::w0d, wd + WD_W0, 64, 32, t, FWD_THREADS);
+    stage_weights(smem + S::woutd, wd + WD_WOUT, 16, 64, t, FWD_THREADS);
     if (!DENSITY_ONLY) {
-        stage_weights(smem + S::w0r, wr + WR_W0, 64, 32, t, 256);
-        stage_weights(smem + S::w1r, wr + WR_W1, 64, 64, t, 256);
-        stage_weights(smem + S::woutr, wr + WR_WOUT, 16, 64, t, 256);
+        stage_weights(smem + S::w0r, wr + WR_W0, 64, 32, t, FWD_THREADS);
+        stage_weights(smem + S::w1r, wr + WR_W1, 64, 64, t, FWD_THREADS);
+        stage_weights(smem + S::woutr, wr + WR_WOUT, 16, 64, t, FWD_THREADS);
     }
     if (t < N_LEVELS) s_lv[t] = levels[t];
     if (t == 0) { mbar_init(bar, 1); fence_mbar_init(); }
@@ -218,12 +223,12 @@ network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
         for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const uint32_t buf = it & 1, row = tile * ROWS + t;
             const float* s_coords = reinterpret_cast<const float*>(smem + S::coords + buf * 3584);
-            named_bar_sync(2 + buf, 256);                       // FULL[buf]: enc slab + coordinates of this tile are in smem
+            named_bar_sync(2 + buf, FWD_THREADS);                       // FULL[buf]: enc slab + coordinates of this tile are in smem
             tc_fence_after();
             // forward_chain releases nothing itself: the enc slab is dead after layer 0, the coordinates after the SH epilogue;
             // both are handed back together right after the chain (the gather runs a full tile ahead, so this is not on its path)
             const uint32_t sig = forward_chain<G_H2F, true>(smem, S::act, ops, buf ? OP_L0D_B1 : OP_L0D, s_coords, tbase, pipe, t, warp, DENSITY_ONLY);
-            if (tile + 2 * gridDim.x < ntiles) named_bar_arrive(4 + buf, 256);   // EMPTY[buf]
+            if (tile + 2 * gridDim.x < ntiles) named_bar_arrive(4 + buf, FWD_THREADS);   // EMPTY[buf]
             if constexpr (DENSITY_ONLY) {
                 if (row < n_live) reinterpret_cast<uint16_t*>(out)[row] = (uint16_t)sig;
                 sync_before_issue<true>();                      // TMEM reads of this tile precede the next tile's MMAs
@@ -249,13 +254,13 @@ network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
         for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const uint32_t buf = it & 1, row0 = tile * ROWS;
             float* s_coords = reinterpret_cast<float*>(smem + S::coords + buf * 3584);
-            if (it >= 2) named_bar_sync(4 + buf, 256);          // EMPTY[buf]: the chain of tile it-2 is done with this buffer
-            for (uint32_t i = tg; i < ROWS * CS; i += 128)       // stage the coordinate tile (coalesced)
+            if (it >= 2) named_bar_sync(4 + buf, FWD_THREADS);          // EMPTY[buf]: the chain of tile it-2 is done with this buffer
+            for (uint32_t i = tg; i < ROWS * CS; i += 32 * FWD_GW)       // stage the coordinate tile (coalesced)
                 s_coords[i] = (row0 + i / CS < n_live) ? __ldg(coords + (size_t)row0 * CS + i) : 0.f;
-            named_bar_sync(6, 128);
-            gather_tile<CS>(s_coords, lv, g, smem + S::act, buf ? G_ENC1 : G_ENC, level, sub, DENSITY_ONLY ? nullptr : enc_save, row0, n_live);
+            named_bar_sync(6, 32 * FWD_GW);
+            gather_tile<CS, 64 / FWD_GW>(s_coords, lv, g, smem + S::act, buf ? G_ENC1 : G_ENC, level, sub, DENSITY_ONLY ? nullptr : enc_save, row0, n_live);
             fence_proxy_async_smem();                           // the enc slab is read by the tensor core (async proxy)
-            named_bar_arrive(2 + buf, 256);                     // FULL[buf]
+            named_bar_arrive(2 + buf, FWD_THREADS);                     // FULL[buf]
         }
     }
     tc_fence_before();
@@ -267,6 +272,9 @@ network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
 // hash-grid gradient of tile i-1 from a double-buffered dL/d(enc) slab.  The scatter is bound by the L2 atomic rate, the chain
 // by its serial stage latency; neither keeps an SM busy alone (tools/dbg_timeline_bwd.py: 19 k vs 32 k cycles per tile), so
 // they overlap.  Hand-off through named barriers FULL[b] / EMPTY[b] (ids 2+b / 4+b, 256 threads: 128 arrive + 128 sync).
+// Scatter warps: 4 (16-sample runs).  Measured on the lego stand-in, us per backward: 2 warps x 32-sample runs 294, 4 x 16 177,
+// 8 x 8 209, 8 warps x 16-sample runs with the cell's corners split over two threads 250 -- longer runs save atomics, but more
+// scatter warps starve the MLP chain, which is the critical path of this kernel.
 __global__ void __launch_bounds__(256)
 network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const float* __restrict__ coords, const __half* __restrict__ enc_save,
                    const NgpLevel* __restrict__ levels, const __half* __restrict__ wd, const __half* __restrict__ wr,
@@ -290,7 +298,8 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
     if (t < N_LEVELS) s_lv[t] = levels[t];
     // dYr columns 4..15, the dYd pad groups: zero once (never rewritten)
     for (uint32_t i = t; i < Q_TOTAL * GB / 16; i += 256) *reinterpret_cast<uint4*>(grd + i * 16) = make_uint4(0, 0, 0, 0);
-    if (t == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    uint64_t* bar_w = bar + 2;                                   // completes when the 5 wgrad batches of a tile are done
+    if (t == 0) { mbar_init(bar, 1); mbar_init(bar_w, 5); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(tmem_ptr, 512);
     sync_before_issue();
     const uint32_t tbase = *tmem_ptr;
@@ -352,6 +361,7 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             const uint32_t buf = it & 1;
             float* s_coords = reinterpret_cast<float*>(smem + S::coords + buf * 3584);
             if (it >= 2) named_bar_sync(4 + buf, 256);          // the scatter of tile it-2 has released coords[buf] / d_enc[buf]
+            if (it >= 1) { if (!mbar_wait(bar_w, (it - 1) & 1)) atomicExch(err, 2); }   // the previous tile's wgrad MMAs have read their slabs
             DBGB(0);
 #pragma unroll
             for (int j = 0; j < 7; ++j) s_coords[t + 128 * j] = pf_c[j];
@@ -366,7 +376,8 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             forward_chain<G_H2B, true>(smem, S::act, ops, OP_L0D, s_coords, tbase, pipe, t, warp, false);
             DBGB(3);
             // B1: g_h2 = (dYr Woutr) . relu'(h2) ; wgrad Woutr
-            if (t == 0) { run_ops(ops, OP_B1, 1 + 8, acc); DBGB(4); pipe.commit(); }
+            if (t == 0) { run_ops(ops, OP_B1, 1, acc); DBGB(4); pipe.commit(); }
+            if (t == 32) { run_ops(ops, OP_B1 + 1, 8, acc); mma_commit(bar_w); }   // weight gradient: issued by a second thread, off the critical path
             pipe.wait();
             DBGB(5);
             epi_dgrad_mask(tbase, D_H, warp, act, G_H2B, grd, Q_GH2, t, nullptr);
@@ -374,14 +385,16 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             sync_before_issue<true>();
             DBGB(7);
             // B2: g_h1 = (g_h2 W1r) . relu'(h1) ; wgrad W1r
-            if (t == 0) { run_ops(ops, OP_B2, 4 + 8, acc); DBGB(8); pipe.commit(); }
+            if (t == 0) { run_ops(ops, OP_B2, 4, acc); DBGB(8); pipe.commit(); }
+            if (t == 32) { run_ops(ops, OP_B2 + 4, 8, acc); mma_commit(bar_w); }   // weight gradient: issued by a second thread, off the critical path
             pipe.wait();
             DBGB(9);
             epi_dgrad_mask(tbase, D_H, warp, act, G_H1, grd, Q_GH1, t, nullptr);
             sync_before_issue<true>();
             DBGB(10);
             // B3: d_rin = g_h1 W0r (32 cols; the last 16 are dL/dSH, unused) ; wgrad W0r
-            if (t == 0) { run_ops(ops, OP_B3, 4 + 8, acc); pipe.commit(); }
+            if (t == 0) { run_ops(ops, OP_B3, 4, acc); pipe.commit(); }
+            if (t == 32) { run_ops(ops, OP_B3 + 4, 8, acc); mma_commit(bar_w); }   // weight gradient: issued by a second thread, off the critical path
             pipe.wait();
             {
                 float v[16];
@@ -393,12 +406,14 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             }
             sync_before_issue<true>();
             // B4: g_hd = (dYd Woutd) . relu'(hd) ; wgrad Woutd
-            if (t == 0) { run_ops(ops, OP_B4, 1 + 8, acc); pipe.commit(); }
+            if (t == 0) { run_ops(ops, OP_B4, 1, acc); pipe.commit(); }
+            if (t == 32) { run_ops(ops, OP_B4 + 1, 8, acc); mma_commit(bar_w); }   // weight gradient: issued by a second thread, off the critical path
             pipe.wait();
             epi_dgrad_mask(tbase, D_H, warp, act, G_HD, grd, Q_GHD, t, nullptr);
             sync_before_issue<true>();
             // B5: d_enc = g_hd W0d ; wgrad W0d
-            if (t == 0) { run_ops(ops, OP_B5, 4 + 8, acc); pipe.commit(); }
+            if (t == 0) { run_ops(ops, OP_B5, 4, acc); pipe.commit(); }
+            if (t == 32) { run_ops(ops, OP_B5 + 4, 8, acc); mma_commit(bar_w); }   // weight gradient: issued by a second thread, off the critical path
             pipe.wait();
             {
                 float v[16];
@@ -416,6 +431,8 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
         }
         // flush weight gradients (lane = input feature, column = output feature)
         if (acc) {
+            if (!mbar_wait(bar_w, (it - 1) & 1)) atomicExch(err, 2);
+            tc_fence_after();
             float v[16];
             const uint32_t f_col[5] = {A_W0D, A_WOUTD, A_W0R, A_W1R, A_WOUTR};
             const uint32_t f_nout[5] = {64, 16, 64, 64, 16}, f_valid[5] = {64, 16, 64, 64, 3};   // colour Wout rows >= 3 stay zero (fully_fused_mlp.py:136)
@@ -500,7 +517,7 @@ int ngp_network_fwd(void* stream, uint32_t n_max, const uint32_t* n_dev, const f
     NGP_CHECK_CUDA(cudaFuncSetAttribute(network_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemFwd::total));
     const uint32_t ntiles = (n_max + ROWS - 1) / ROWS;
     const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms() * 2u);
-    network_fwd_kernel<false><<<grid_dim, 256, SmemFwd::total, s>>>(n_max, n_dev, coords, (const __half*)grid, (const NgpLevel*)levels_dev,
+    network_fwd_kernel<false><<<grid_dim, FWD_THREADS, SmemFwd::total, s>>>(n_max, n_dev, coords, (const __half*)grid, (const NgpLevel*)levels_dev,
                                                                    (const __half*)w_density, (const __half*)w_rgb, (__half*)out,
                                                                    (__half*)enc_save, ngp_err_flag());
     NGP_LAUNCH_CHECK();
@@ -513,7 +530,7 @@ int ngp_density_fwd(void* stream, uint32_t n, const float* pos, const void* grid
     NGP_CHECK_CUDA(cudaFuncSetAttribute(network_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemFwd::total));
     const uint32_t ntiles = (n + ROWS - 1) / ROWS;
     const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms() * 2u);
-    network_fwd_kernel<true><<<grid_dim, 256, SmemFwd::total, s>>>(n, nullptr, pos, (const __half*)grid, (const NgpLevel*)levels_dev,
+    network_fwd_kernel<true><<<grid_dim, FWD_THREADS, SmemFwd::total, s>>>(n, nullptr, pos, (const __half*)grid, (const NgpLevel*)levels_dev,
                                                                   (const __half*)w_density, nullptr, (__half*)sigma_out, nullptr, ngp_err_flag());
     NGP_LAUNCH_CHECK();
     return 0;
