@@ -44,7 +44,7 @@ def peaks():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md recipe)."""
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
@@ -52,33 +52,48 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def mark(self):
+        """Host time stamp (same clock nvidia-smi prints) -- used to pick the samples that fall inside the timed region."""
+        return time.time()
+
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.05)
         self.proc.terminate()
         self.t.join(timeout=2)
-        sm, mx, reasons = [], [], set()
+        import datetime
+        rows = []
         for l in self.lines:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), f[5:9]))
             except ValueError:
                 continue
+        inside = [r for r in rows if t0 is not None and t0 <= r[0] <= t1]
+        window = "timed region"
+        if len(inside) < 3:                       # nvidia-smi samples slower than asked on some boxes: fall back to everything under load
+            inside, window = rows, "warm-up + timed region"
+        sm, mx, reasons = [], [], set()
+        for _, a, b, flags in inside:
+            sm.append(a); mx.append(b)
+            f = [None] * 5 + list(flags)
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm),
+                "window": window}
 
 
 # ---------------------------------------------------------------------------------------------------- CPU arm
@@ -138,7 +153,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_rays = max(16, min(256, 4096 // max(args.steps, 1)))     # bounded sample: the whole run stays within minutes
+    n_rays = max(64, min(256, 16384 // max(args.steps, 1)))    # bounded sample: the whole run stays within minutes
     for _ in range(max(args.warmup, 1)):
         cpu_train_iteration(64)
     t, r, s = 0.0, 0, 0
@@ -190,6 +205,9 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()                    # started early: nvidia-smi needs a few hundred ms before its first sample
     # steady state: occupancy grid carved, ray batch adapted (untimed)
     for _ in range(args.pretrain):
         runner.train_step()
@@ -198,9 +216,6 @@ def run_ours(args):
     sync()
 
     # ---- timed region: K steps, device-resident inputs ----
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     launches0 = lib.launch_count
     rays = 0
     sync()
@@ -208,12 +223,15 @@ def run_ours(args):
     if profiling:
         torch.cuda.profiler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = clocks.mark()
     e0.record()
     for _ in range(args.steps):
         rays += runner.sampler.n_rays_per_batch
         runner.train_step()
+    runner._table_ready()                 # N>1: the last step's all-gather belongs to the timed region
     e1.record()
     sync()
+    t_host1 = clocks.mark()
     if profiling:
         torch.cuda.profiler.stop()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -221,7 +239,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop(t_host0, t_host1) if rank == 0 else None
     total_rays = rays * world
     value = total_rays / (ms * 1e-3)
 
@@ -248,6 +266,7 @@ def run_ours(args):
     e0.record()
     for k in range(args.steps):
         rays_e += host_step(k)
+    runner._table_ready()
     e1.record()
     sync()
     ms_e = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -304,6 +323,7 @@ def stage_times(runner, iters):
         ev[0].record()
         ds = runner.dataset["train"]
         R = s.n_rays_per_batch
+        runner._table_ready()
         pix = ds.next_pixels(R)
         bg = torch.rand((R, 3), device="cuda")
         img_ids, rays_o, rays_d, target = ops.prepare_batch(pix.contiguous(), ds.W, ds.H, ds.transforms_gpu, ds.focal_lengths, ds.principal,
@@ -322,9 +342,8 @@ def stage_times(runner, iters):
                         runner.dwd, runner.dwr, n_dev=n_dev)
         ev[5].record()
         adam = runner.optimizer._nested_optimizer
-        for p, g in ((m.pos_encoder.m_grid, runner.grid_grad), (m.density_mlp.con_weights, runner.dwd), (m.rgb_mlp.con_weights, runner.dwr)):
-            st = runner._st[id(p)]
-            ops.adam_ema(p.data, g, st.m, st.v, st.master, 0.0, max(adam.n_step, 1), zero_grad=True)   # lr 0: timing only, parameters barely move
+        runner._optimizer_step(0.0, max(adam.n_step, 1))     # lr 0: timing only, parameters barely move; N>1: + reduce-scatter / all-gather
+        runner._table_ready()
         ev[6].record()
         torch.cuda.synchronize()
         for k, name in enumerate(names):
@@ -339,7 +358,7 @@ def stage_times(runner, iters):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 1000; 32 for --impl reference)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pretrain", type=int, default=256)
@@ -347,6 +366,8 @@ def main():
     ap.add_argument("--res", type=int, default=800)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 32 if args.impl == "reference" else 1000
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -139,6 +139,27 @@ int ngp_adam_ema(void* stream, uint64_t n, void* param, int param_dtype, void* g
                  float* m, float* v, float* master, float lr, float beta1, float beta2, float eps, uint32_t step,
                  float ema_decay, int zero_grad);
 
+/* ---- 8e  data-parallel exchange fused with the optimizer, over NVLink peer memory ------------------------------------
+ * The reference has no multi-GPU path for NGP (its only exchange is jt.mpi all-reduce inside nn optimizers,
+ * python/jnerf/optims/adam.py:8-16 via jt.nn.Adam).  One launch per step replaces gradient all-reduce + Adam + EMA:
+ * reduce-scatter by pulling the peers' gradient slices, Adam+EMA on this rank's slice of the padded hash table, all-gather
+ * by pushing the fp16 slice into every peer's table, all-reduce + update of the MLP weights; flag hand-shake in peer memory.
+ * peer_* are HOST arrays of `world` DEVICE pointers (own rank = local buffers, others = ngp_ipc_open mappings):
+ *   peer_table / peer_table_grad: fp16, world*slice_len elements; peer_w_grad: fp32 n_w; peer_flags: 64 zero-initialised words.
+ * m/v/master: this rank's slice state (slice_len fp32 each); w_*: local MLP weights (fp16) and their fp32 state (n_w).
+ * epoch: 1,2,3,... identical on all ranks.  Gradients are NOT zeroed: call ngp_dp_exchange_wait(epoch) first, then clear them. */
+int ngp_dp_exchange_step(void* stream, int world, int rank, uint64_t slice_len, uint32_t n_w, void* const* peer_table,
+                         void* const* peer_table_grad, float* const* peer_w_grad, uint32_t* const* peer_flags, uint32_t epoch, float* m,
+                         float* v, float* master, void* w_param, float* w_m, float* w_v, float* w_master, float grad_scale, float lr,
+                         float beta1, float beta2, float eps, uint32_t step, float ema_decay);
+/* Stream-ordered wait until every peer finished epoch `epoch` (their stores into this rank's table are visible and they no
+ * longer read this rank's gradients).  Traps after 20 s instead of hanging. */
+int ngp_dp_exchange_wait(void* stream, int world, const uint32_t* my_flags, uint32_t epoch);
+/* CUDA IPC plumbing: export the allocation containing dev_ptr (64-byte handle + byte offset), map a peer's export. */
+int ngp_ipc_export(const void* dev_ptr, uint8_t* handle64, uint64_t* offset);
+int ngp_ipc_open(const uint8_t* handle64, uint64_t offset, void** dev_ptr);
+int ngp_ipc_close(void* dev_ptr, uint64_t offset);
+
 /* ---- N2  ray generation + target blend (dataset/dataset.py:172-188, runner/runner.py:65-68) ------------ */
 int ngp_raygen(void* stream, uint32_t n, const uint32_t* pix_index, uint32_t W, uint32_t H, const float* xforms,
                const float* focal, const float* principal, uint32_t* img_id_out, float* rays_o, float* rays_d);

@@ -8,6 +8,7 @@
 // `values` buffer and doubles as the fp32 master copy of fp16 parameters (documented deviation).
 #include "ngp_common.cuh"
 #include <cmath>
+#include <cstring>
 
 namespace {
 
@@ -15,12 +16,14 @@ struct AdamArgs {
     float step_size, b1, b2, eps, decay, debias_old, debias_new, grad_scale;
 };
 
+// Every operation is spelled out (no compiler-chosen FMA contraction) so that all kernels that inline this -- the single-GPU
+// sweep, its scalar tail and the data-parallel exchange kernel -- produce bit-identical parameters from identical inputs.
 __device__ __forceinline__ float adam_one(float g, float& m, float& v, float& master, const AdamArgs& a) {
-    g *= a.grad_scale;
-    m = a.b1 * m + (1.f - a.b1) * g;
-    v = a.b2 * v + (1.f - a.b2) * g * g;
-    const float p = master - m * a.step_size / (sqrtf(v) + a.eps);                       // jt.nn.Adam.step
-    master = ((1.f - a.decay) * p + a.decay * master * a.debias_old) * a.debias_new;     // ema.py:33-36
+    g = __fmul_rn(g, a.grad_scale);
+    m = __fmaf_rn(a.b1, m, __fmul_rn(1.f - a.b1, g));
+    v = __fmaf_rn(a.b2, v, __fmul_rn(__fmul_rn(1.f - a.b2, g), g));
+    const float p = __fsub_rn(master, __fdiv_rn(__fmul_rn(m, a.step_size), __fadd_rn(sqrtf(v), a.eps)));          // jt.nn.Adam.step
+    master = __fmul_rn(__fmaf_rn(1.f - a.decay, p, __fmul_rn(__fmul_rn(a.decay, master), a.debias_old)), a.debias_new);   // ema.py:33-36
     return master;
 }
 
@@ -136,6 +139,142 @@ __global__ void prepare_batch_kernel(uint32_t n, const uint32_t* __restrict__ pi
     target[3 * (size_t)i + 2] = c.z * c.w + bg[3 * (size_t)i + 2] * ia;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 8e: data-parallel gradient exchange + optimizer in ONE kernel over NVLink peer memory.
+//
+// Every rank maps every other rank's gradient buffers, parameter table and flag block (CUDA IPC, dp.py).  Rank k owns the
+// slice [k*slice_len, (k+1)*slice_len) of the padded hash table:
+//   1. block 0 tells every peer "my gradients of this step are complete" (release store of `epoch` into the peer's flag block;
+//      the kernel is stream-ordered behind the backward kernel), then every block waits until all peers have said so;
+//   2. reduce-scatter by pulling: g = sum over ranks of table_grad[r][slice] (128-bit loads over NVLink), fused Adam + EMA
+//      on the slice (optimizer state exists only for the slice: 1/W of the 171 MB state traffic per GPU);
+//   3. all-gather by pushing: the updated fp16 slice is stored into every rank's table (128-bit stores over NVLink);
+//   4. the two small MLP weight tensors (10 240 values) are all-reduced by every rank reading every rank's copy -- same order
+//      of summation everywhere, so the replicas stay bit-identical -- and updated locally;
+//   5. the last block to finish tells every peer "my stores into your table are complete and I no longer read your
+//      gradients"; ngp_dp_exchange_wait() consumes those flags before the next forward pass / gradient zeroing.
+// Replaces reduce-scatter + all-reduce + 3 Adam launches + all-gather (NCCL path, dp.py) with one launch.
+constexpr int DP_MAX_WORLD = 16;
+constexpr int DP_FLAG_GRADS = 0, DP_FLAG_DONE = 16, DP_FLAG_COUNTER = 32, DP_FLAG_WORDS = 64;
+
+struct DpPeers {
+    __half* table[DP_MAX_WORLD];
+    __half* table_grad[DP_MAX_WORLD];
+    float* w_grad[DP_MAX_WORLD];
+    uint32_t* flags[DP_MAX_WORLD];
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Bounded spin (a dead peer must not hang the GPU): traps after 20 s.
+__device__ __forceinline__ void wait_flag(const uint32_t* p, uint32_t epoch) {
+    const uint64_t t0 = global_timer_ns();
+#pragma unroll 1
+    while ((int32_t)(ld_acquire_sys(p) - epoch) < 0) {
+        if (global_timer_ns() - t0 > 20ull * 1000000000ull) __trap();
+    }
+}
+
+__global__ void __launch_bounds__(256, 2) dp_exchange_kernel(DpPeers P, int W, int rank, uint64_t slice_len, uint32_t n_w, uint32_t epoch,
+                                                          float* m, float* v, float* master, __half* w_param, float* w_m, float* w_v,
+                                                          float* w_master, AdamArgs a) {
+    if (blockIdx.x == 0 && threadIdx.x < W) {
+        __threadfence_system();
+        st_release_sys(P.flags[threadIdx.x] + DP_FLAG_GRADS + rank, epoch);
+    }
+    if (threadIdx.x < W) wait_flag(P.flags[rank] + DP_FLAG_GRADS + threadIdx.x, epoch);
+    __syncthreads();
+
+    const uint64_t lo = (uint64_t)rank * slice_len, n8 = slice_len / 8;
+    const uint64_t T = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n8; i += T) {
+        float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        uint4 w[DP_MAX_WORLD];
+#pragma unroll
+        for (int r = 0; r < DP_MAX_WORLD; ++r)
+            if (r < W) w[r] = *reinterpret_cast<uint4*>(P.table_grad[r] + lo + 8 * i);       // W independent 16 B loads in flight
+        float4 mm[2], vv[2], ms[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            mm[h] = reinterpret_cast<const float4*>(m)[2 * i + h];
+            vv[h] = reinterpret_cast<const float4*>(v)[2 * i + h];
+            ms[h] = reinterpret_cast<const float4*>(master)[2 * i + h];
+        }
+#pragma unroll
+        for (int r = 0; r < DP_MAX_WORLD; ++r) {
+            if (r < W) {
+                const uint32_t u[4] = {w[r].x, w[r].y, w[r].z, w[r].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[k]));
+                    g[2 * k] += f.x;
+                    g[2 * k + 1] += f.y;
+                }
+            }
+        }
+        float p[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            p[4 * h + 0] = adam_one(g[4 * h + 0], mm[h].x, vv[h].x, ms[h].x, a);
+            p[4 * h + 1] = adam_one(g[4 * h + 1], mm[h].y, vv[h].y, ms[h].y, a);
+            p[4 * h + 2] = adam_one(g[4 * h + 2], mm[h].z, vv[h].z, ms[h].z, a);
+            p[4 * h + 3] = adam_one(g[4 * h + 3], mm[h].w, vv[h].w, ms[h].w, a);
+            reinterpret_cast<float4*>(m)[2 * i + h] = mm[h];
+            reinterpret_cast<float4*>(v)[2 * i + h] = vv[h];
+            reinterpret_cast<float4*>(master)[2 * i + h] = ms[h];
+        }
+        uint4 o;
+        {
+            __half2 h0 = __floats2half2_rn(p[0], p[1]), h1 = __floats2half2_rn(p[2], p[3]), h2 = __floats2half2_rn(p[4], p[5]),
+                    h3 = __floats2half2_rn(p[6], p[7]);
+            o.x = *reinterpret_cast<uint32_t*>(&h0);
+            o.y = *reinterpret_cast<uint32_t*>(&h1);
+            o.z = *reinterpret_cast<uint32_t*>(&h2);
+            o.w = *reinterpret_cast<uint32_t*>(&h3);
+        }
+#pragma unroll
+        for (int r = 0; r < DP_MAX_WORLD; ++r)
+            if (r < W) *reinterpret_cast<uint4*>(P.table[r] + lo + 8 * i) = o;
+    }
+    // MLP weights: identical all-reduce + update on every rank
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_w; j += (uint32_t)T) {
+        float g = 0.f;
+        for (int r = 0; r < W; ++r) g += P.w_grad[r][j];
+        float m1 = w_m[j], v1 = w_v[j], s1 = w_master[j];
+        const float p = adam_one(g, m1, v1, s1, a);
+        w_m[j] = m1; w_v[j] = v1; w_master[j] = s1;
+        w_param[j] = __float2half_rn(p);
+    }
+    // completion: all of this rank's peer stores are performed before any peer sees the flag
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    uint32_t* mine = P.flags[rank];
+    if (threadIdx.x == 0) last = atomicAdd(mine + DP_FLAG_COUNTER, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        if (threadIdx.x < W) st_release_sys(P.flags[threadIdx.x] + DP_FLAG_DONE + rank, epoch);
+        if (threadIdx.x == 0) mine[DP_FLAG_COUNTER] = 0;
+    }
+}
+
+__global__ void dp_wait_kernel(const uint32_t* my_flags, int W, uint32_t epoch) {
+    if (threadIdx.x < W) wait_flag(my_flags + DP_FLAG_DONE + threadIdx.x, epoch);
+}
+
 }  // namespace
 
 extern "C" {
@@ -158,6 +297,81 @@ int ngp_adam_ema(void* stream, uint64_t n, void* param, int param_dtype, void* g
     else if (param_dtype == 0 && grad_dtype == 0) adam_ema_kernel<float, float><<<blocks, 256, 0, s>>>(n, (float*)param, (float*)grad, m, v, master, a, zero_grad);
     else NGP_REQUIRE(false, "ngp_adam_ema: unsupported dtype combination");
     NGP_LAUNCH_CHECK();
+    return 0;
+}
+
+static AdamArgs make_adam_args(float lr, float beta1, float beta2, float eps, uint32_t step, float ema_decay, float grad_scale) {
+    AdamArgs a;
+    const double n1 = 1.0 - std::pow((double)beta1, (double)step), n2 = 1.0 - std::pow((double)beta2, (double)step);
+    a.step_size = (float)(lr * std::sqrt(n2) / n1);
+    a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.decay = ema_decay; a.grad_scale = grad_scale;
+    a.debias_old = (float)(1.0 - std::pow((double)ema_decay, (double)step - 1.0));
+    a.debias_new = (float)(1.0 / (1.0 - std::pow((double)ema_decay, (double)step)));
+    return a;
+}
+
+int ngp_dp_exchange_step(void* stream, int world, int rank, uint64_t slice_len, uint32_t n_w, void* const* peer_table,
+                         void* const* peer_table_grad, float* const* peer_w_grad, uint32_t* const* peer_flags, uint32_t epoch, float* m,
+                         float* v, float* master, void* w_param, float* w_m, float* w_v, float* w_master, float grad_scale, float lr,
+                         float beta1, float beta2, float eps, uint32_t step, float ema_decay) {
+    NGP_REQUIRE(world >= 1 && world <= DP_MAX_WORLD && rank >= 0 && rank < world, "ngp_dp_exchange_step: world must be 1..16 and rank < world");
+    NGP_REQUIRE(slice_len % 256 == 0, "ngp_dp_exchange_step: slice_len must be a multiple of 256 (dp.padded_len)");
+    NGP_REQUIRE(step >= 1 && epoch >= 1, "ngp_dp_exchange_step: step and epoch are 1-based");
+    DpPeers P;
+    for (int r = 0; r < DP_MAX_WORLD; ++r) {
+        const int q = r < world ? r : rank;
+        P.table[r] = (__half*)peer_table[q];
+        P.table_grad[r] = (__half*)peer_table_grad[q];
+        P.w_grad[r] = peer_w_grad[q];
+        P.flags[r] = peer_flags[q];
+    }
+    const AdamArgs a = make_adam_args(lr, beta1, beta2, eps, step, ema_decay, grad_scale);
+    // every block spins on peer flags before it starts: keep the grid co-resident (2 CTAs/SM, enforced by __launch_bounds__)
+    const uint64_t n8 = slice_len / 8;
+    const uint32_t blocks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((n8 + 255) / 256, (uint64_t)ngp_num_sms() * 2));
+    dp_exchange_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(P, world, rank, slice_len, n_w, epoch, m, v, master, (__half*)w_param, w_m, w_v,
+                                                                 w_master, a);
+    NGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int ngp_dp_exchange_wait(void* stream, int world, const uint32_t* my_flags, uint32_t epoch) {
+    NGP_REQUIRE(world >= 1 && world <= DP_MAX_WORLD, "ngp_dp_exchange_wait: world must be 1..16");
+    dp_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(my_flags, world, epoch);
+    NGP_LAUNCH_CHECK();
+    return 0;
+}
+
+// CUDA IPC plumbing for the peer mapping (runtime API only; the base of the allocation comes from the driver entry point so that
+// the library keeps no link-time dependency on libcuda and still loads on a machine without a GPU).
+int ngp_ipc_export(const void* dev_ptr, uint8_t* handle64, uint64_t* offset) {
+    typedef int (*GetRange)(unsigned long long*, size_t*, unsigned long long);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    NGP_CHECK_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr));
+    NGP_REQUIRE(fn != nullptr && qr == cudaDriverEntryPointSuccess, "ngp_ipc_export: cuMemGetAddressRange not available");
+    unsigned long long base = 0;
+    size_t size = 0;
+    NGP_REQUIRE(((GetRange)fn)(&base, &size, (unsigned long long)(uintptr_t)dev_ptr) == 0, "ngp_ipc_export: not a device allocation");
+    cudaIpcMemHandle_t h;
+    NGP_CHECK_CUDA(cudaIpcGetMemHandle(&h, (void*)(uintptr_t)base));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+    *offset = (uint64_t)((uintptr_t)dev_ptr - (uintptr_t)base);
+    return 0;
+}
+
+int ngp_ipc_open(const uint8_t* handle64, uint64_t offset, void** dev_ptr) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* base = nullptr;
+    NGP_CHECK_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    *dev_ptr = (void*)((uintptr_t)base + offset);
+    return 0;
+}
+
+int ngp_ipc_close(void* dev_ptr, uint64_t offset) {
+    NGP_CHECK_CUDA(cudaIpcCloseMemHandle((void*)((uintptr_t)dev_ptr - offset)));
     return 0;
 }
 

@@ -38,6 +38,12 @@ SIGNATURES = {
     "ngp_grid_ema": (_i32, [_vp, _u32, _f32, _vp, _vp]),
     "ngp_grid_update_bitfield": (_i32, [_vp, _vp, _vp, _vp, _u32]),
     "ngp_adam_ema": (_i32, [_vp, _u64, _vp, _i32, _vp, _i32, _f32, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _u32, _f32, _i32]),
+    "ngp_dp_exchange_step": (_i32, [_vp, _i32, _i32, _u64, _u32, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32,
+                                    _f32, _f32, _u32, _f32]),
+    "ngp_dp_exchange_wait": (_i32, [_vp, _i32, _vp, _u32]),
+    "ngp_ipc_export": (_i32, [_vp, _vp, _vp]),
+    "ngp_ipc_open": (_i32, [_vp, _u64, _vp]),
+    "ngp_ipc_close": (_i32, [_vp, _u64]),
     "ngp_raygen": (_i32, [_vp, _u32, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ngp_prepare_batch": (_i32, [_vp, _u32, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "ngp_pcg32_seed": (None, [_u64, _u64, _vp]),
@@ -49,7 +55,7 @@ KERNELS_PER_CALL = {
     "ngp_hash_level_table": 1, "ngp_hash_fwd": 1, "ngp_hash_bwd": 1, "ngp_sh_fwd": 1, "ngp_mlp_fwd": 1, "ngp_mlp_bwd": 1,
     "ngp_network_fwd": 1, "ngp_network_bwd": 1, "ngp_density_fwd": 1, "ngp_march": 3, "ngp_compact": 1, "ngp_composite_fwd": 1,
     "ngp_composite_bwd": 1, "ngp_composite_infer": 1, "ngp_composite_loss_bwd": 1, "ngp_grid_mark_untrained": 1,
-    "ngp_grid_generate_samples": 1, "ngp_grid_splat": 1, "ngp_grid_ema": 1, "ngp_grid_update_bitfield": 7, "ngp_adam_ema": 1, "ngp_raygen": 1, "ngp_prepare_batch": 1,
+    "ngp_grid_generate_samples": 1, "ngp_grid_splat": 1, "ngp_grid_ema": 1, "ngp_grid_update_bitfield": 7, "ngp_adam_ema": 1, "ngp_dp_exchange_step": 1, "ngp_dp_exchange_wait": 1, "ngp_raygen": 1, "ngp_prepare_batch": 1,
 }
 launch_count = 0
 _lib = None

@@ -223,3 +223,19 @@ def pcg32_seed(seed=1337, seq=1):
 def pcg32_advance(si, delta=1 << 32):
     lib.load().ngp_pcg32_advance(si.ctypes.data, delta)
     return si
+
+
+def dp_exchange_step(world, rank, slice_len, n_w, peer_table, peer_table_grad, peer_w_grad, peer_flags, epoch, m, v, master, w_param, w_m, w_v,
+                     w_master, lr, step, beta1=0.9, beta2=0.99, eps=1e-15, ema_decay=0.95, grad_scale=1.0):
+    """8e: gradient reduce-scatter + Adam/EMA on this rank's table slice + all-gather + MLP-weight all-reduce/update in ONE
+    launch over NVLink peer memory.  peer_* are ctypes arrays of `world` device pointers (dp.PeerArena.peers)."""
+    import ctypes
+    assert m.numel() == slice_len and v.numel() == slice_len and master.numel() == slice_len and w_param.numel() == n_w
+    lib.call("ngp_dp_exchange_step", _stream(), int(world), int(rank), int(slice_len), int(n_w), ctypes.addressof(peer_table),
+             ctypes.addressof(peer_table_grad), ctypes.addressof(peer_w_grad), ctypes.addressof(peer_flags), int(epoch), _p(m), _p(v), _p(master),
+             _p(w_param), _p(w_m), _p(w_v), _p(w_master), float(grad_scale), float(lr), float(beta1), float(beta2), float(eps), int(step),
+             float(ema_decay))
+
+
+def dp_exchange_wait(world, my_flags, epoch):
+    lib.call("ngp_dp_exchange_wait", _stream(), int(world), _p(my_flags), int(epoch))

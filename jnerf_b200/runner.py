@@ -69,6 +69,85 @@ class Runner:
         self._st = {id(s.p): s for s in adam.state}
         self.last_loss = None
         self.last_rgb = None
+        self._table_work = None
+        if self.world_size > 1:
+            self._init_sharded_table()
+
+    def _init_sharded_table(self):
+        """Sharded optimizer for the hash table (dp.py header): this rank owns slice [lo, hi) of the padded table.
+        Exchange mode (env NGP_DP_EXCHANGE = auto | p2p | nccl):
+          p2p  -- ONE kernel per step over NVLink peer memory (ngp_dp_exchange_step): pull-reduce the peers' gradient slices,
+                  Adam+EMA on the slice, push the fp16 slice into every peer's table, all-reduce + update the MLP weights;
+          nccl -- reduce-scatter -> Adam+EMA on the slice -> async all-gather, + all-reduce of the MLP weight gradients.
+        Either way the table of the next step is awaited only after the march (which does not read it)."""
+        import os
+        g = self.model.pos_encoder.m_grid
+        m = self.model
+        n, W = g.numel(), self.world_size
+        mode = os.environ.get("NGP_DP_EXCHANGE", "auto")
+        assert mode in ("auto", "p2p", "nccl")
+        self.dp_mode = "p2p" if mode == "p2p" or (mode == "auto" and dp.peer_exchange_available(W)) else "nccl"
+        P = dp.padded_len(n, W)
+        nd, nr = m.density_mlp.con_weights.numel(), m.rgb_mlp.con_weights.numel()
+        if self.dp_mode == "p2p":
+            self._arena = dp.PeerArena(n, nd + nr, W, self.rank, self.pg)
+            self._table, self._table_grad, self.w_grad = self._arena.table, self._arena.table_grad, self._arena.w_grad
+            self.dwd, self.dwr = self.w_grad[:nd], self.w_grad[nd:nd + nr]
+            self._peers = {k: self._arena.peers(k) for k in ("table", "table_grad", "w_grad", "flags")}
+            # the two MLP weight tensors and their optimizer state become views of flat buffers (one sweep inside the kernel)
+            self._w_param = torch.cat([m.density_mlp.con_weights.data.reshape(-1), m.rgb_mlp.con_weights.data.reshape(-1)]).contiguous()
+            m.density_mlp.con_weights.data = self._w_param[:nd].view_as(m.density_mlp.con_weights.data)
+            m.rgb_mlp.con_weights.data = self._w_param[nd:].view_as(m.rgb_mlp.con_weights.data)
+            std, str_ = self._st[id(m.density_mlp.con_weights)], self._st[id(m.rgb_mlp.con_weights)]
+            self._w_m, self._w_v = torch.cat([std.m, str_.m]), torch.cat([std.v, str_.v])
+            self._w_master = torch.cat([std.master, str_.master])
+            for st, lo_, hi_ in ((std, 0, nd), (str_, nd, nd + nr)):
+                st.m, st.v, st.master = self._w_m[lo_:hi_], self._w_v[lo_:hi_], self._w_master[lo_:hi_]
+            self._epoch, self._pending_epoch = 0, None
+        else:
+            self._table = torch.zeros(P, dtype=g.dtype, device=g.device)
+            self._table_grad = torch.zeros(P, dtype=self.grid_grad.dtype, device=g.device)
+        self._table[:n].copy_(g.data.reshape(-1))
+        g.data = self._table[:n]                                   # the live parameter is a view of the padded table
+        self.grid_grad = self._table_grad[:n]
+        self._lo, self._hi = dp.slice_bounds(P, W, self.rank)
+        self._slice_grad = torch.empty(self._hi - self._lo, dtype=self.grid_grad.dtype, device=g.device)
+        self._slice_param = self._table[self._lo:self._hi].clone()
+        st = self._st[id(g)]
+        master = torch.zeros(P, dtype=torch.float32, device=g.device)
+        master[:n].copy_(st.master)
+        st.master = master[self._lo:self._hi].clone()
+        st.m = torch.zeros(self._hi - self._lo, dtype=torch.float32, device=g.device)
+        st.v = torch.zeros_like(st.m)
+
+    def _table_ready(self):
+        """Make the current stream wait for the in-flight all-gather of the updated table (no-op on one GPU)."""
+        if self._table_work is not None:
+            self._table_work.wait()
+            self._table_work = None
+        if getattr(self, "_pending_epoch", None) is not None:
+            ops.dp_exchange_wait(self.world_size, self._arena.flags, self._pending_epoch)
+            self._arena.grads.zero_()                                # peers no longer read them: clear table + MLP gradients in one memset
+            self._pending_epoch = None
+
+    def _gather_table_state(self):
+        """Full-length (m, v, master) of the hash table for checkpoints: all-gather of the per-rank slices."""
+        g = self.model.pos_encoder.m_grid
+        st, n = self._st[id(g)], g.numel()
+        out = []
+        for t in (st.m, st.v, st.master):
+            full = torch.empty(self._table.numel(), dtype=torch.float32, device=g.device)
+            dp.all_gather_slices(full, t, self.pg, self.world_size)
+            out.append(full[:n].clone())
+        return out
+
+    def _scatter_table_state(self, m, v, master):
+        g = self.model.pos_encoder.m_grid
+        st, n = self._st[id(g)], g.numel()
+        for dst, src in ((st.m, m), (st.v, v), (st.master, master)):
+            full = torch.zeros(self._table.numel(), dtype=torch.float32, device=g.device)
+            full[:n].copy_(src.reshape(-1))
+            dst.copy_(full[self._lo:self._hi])
 
     def next_batch(self):
         """Global pixel batch of this step (identical on every rank), sharded contiguously by rank."""
@@ -100,7 +179,10 @@ class Runner:
             if self.world_size > 1:
                 bg = bg[self.rank * R:(self.rank + 1) * R].contiguous()
             target = rgba[:, :3] * rgba[:, 3:] + bg * (1 - rgba[:, 3:])                     # runner.py:68
+        if i % s.update_den_freq == 0:
+            self._table_ready()                                      # the occupancy-grid update evaluates the density network
         s.sample(img_ids, rays_o, rays_d, is_training=True, ray_index_offset=dp.shard_range(R, self.rank)[0])  # grid update /16, march, bookkeeping
+        self._table_ready()
         coords, n_dev = s.coords_compacted, s.n_samples_dev
         ops.network_fwd(coords, m.pos_encoder.m_grid, m.pos_encoder.levels, m.density_mlp.con_weights, m.rgb_mlp.con_weights,
                         n_dev=n_dev, out=self.net_out, enc=self.enc)
@@ -109,18 +191,43 @@ class Runner:
         ops.network_bwd(coords, self.enc, m.pos_encoder.levels, m.density_mlp.con_weights, m.rgb_mlp.con_weights, self.dnet,
                         self.grid_grad, self.dwd, self.dwr, n_dev=n_dev)
         # local loss_scale is 128/R_local (calc_rgb.h:100-101): the all-reduced sum is W x the global-batch gradient
-        scale = dp.allreduce_grads((self.grid_grad, self.w_grad), self.pg, self.world_size)
         lr = self.optimizer.advance_lr()
         adam = self.optimizer._nested_optimizer
         adam.n_step += 1
         self.ema_optimizer.steps += 1
-        for p, g in ((m.pos_encoder.m_grid, self.grid_grad), (m.density_mlp.con_weights, self.dwd), (m.rgb_mlp.con_weights, self.dwr)):
-            st = self._st[id(p)]
-            ops.adam_ema(p.data, g, st.m, st.v, st.master, lr, adam.n_step, adam.betas[0], adam.betas[1], adam.eps, self.ema_optimizer.decay,
-                         grad_scale=scale, zero_grad=True)
+        self._optimizer_step(lr, adam.n_step)
         self.last_loss, self.last_rgb = loss, rgb
         cfg.m_training_step = i + 1
         return loss
+
+    def _optimizer_step(self, lr, n_step):
+        """Gradient exchange + fused Adam/EMA sweep(s) (optims/adam.py + ema.py; runner.py:75-76)."""
+        m = self.model
+        adam = self.optimizer._nested_optimizer
+        hyper = (lr, n_step, adam.betas[0], adam.betas[1], adam.eps, self.ema_optimizer.decay)
+        if self.world_size > 1 and self.dp_mode == "p2p":
+            st = self._st[id(m.pos_encoder.m_grid)]
+            self._epoch += 1
+            ops.dp_exchange_step(self.world_size, self.rank, self._hi - self._lo, self._w_param.numel(), self._peers["table"],
+                                 self._peers["table_grad"], self._peers["w_grad"], self._peers["flags"], self._epoch, st.m, st.v, st.master,
+                                 self._w_param, self._w_m, self._w_v, self._w_master, *hyper, grad_scale=1.0 / self.world_size)
+            self._pending_epoch = self._epoch
+            return
+        if self.world_size > 1:
+            # hash table: reduce-scatter -> Adam+EMA on this rank's slice -> async all-gather (waited for in the NEXT step, after the march)
+            dp.reduce_scatter_sum(self._slice_grad, self._table_grad, self.pg, self.world_size, self.rank)
+            scale = dp.allreduce_grads((self.w_grad,), self.pg, self.world_size)
+            st = self._st[id(m.pos_encoder.m_grid)]
+            ops.adam_ema(self._slice_param, self._slice_grad, st.m, st.v, st.master, *hyper, grad_scale=scale, zero_grad=False)
+            self._table_work = dp.all_gather_slices(self._table, self._slice_param, self.pg, self.world_size, async_op=True)
+            self._table_grad.zero_()
+            tensors = ((m.density_mlp.con_weights, self.dwd), (m.rgb_mlp.con_weights, self.dwr))
+        else:
+            scale = 1.0
+            tensors = ((m.pos_encoder.m_grid, self.grid_grad), (m.density_mlp.con_weights, self.dwd), (m.rgb_mlp.con_weights, self.dwr))
+        for p, g in tensors:
+            st = self._st[id(p)]
+            ops.adam_ema(p.data, g, st.m, st.v, st.master, *hyper, grad_scale=scale, zero_grad=True)
 
     # --------------------------------------------------------------------- per-operator path (as the reference wires it)
     def train_step_autograd(self, batch=None):
@@ -151,6 +258,7 @@ class Runner:
     @torch.no_grad()
     def render_img(self, dataset_mode="train", img_id=0):
         """runner.py:197-236: tile the image in n_rays_per_batch chunks; returns (img HxWx3, target HxWx3)."""
+        self._table_ready()
         ds = self.dataset[dataset_mode]
         W, H = ds.resolution
         rays_o, rays_d = ds.generate_rays_total_test(img_id)
@@ -193,9 +301,20 @@ class Runner:
 
     # ------------------------------------------------------------------------------------------ checkpoint (N4)
     def save_ckpt(self, path):
+        """Every rank must call this when world_size > 1 (the table's optimizer state is gathered); rank 0 writes the file."""
         adam = self.optimizer._nested_optimizer
+        self._table_ready()
+        nested = adam.state_dict()
+        if self.world_size > 1:
+            k = [id(s.p) for s in adam.state].index(id(self.model.pos_encoder.m_grid))
+            full = self._gather_table_state()
+            for key, t in zip(("m", "v", "master"), full):
+                nested[key] = list(nested[key])
+                nested[key][k] = t
+            if self.rank != 0:
+                return
         torch.save({"global_step": self.cfg.m_training_step, "model": self.model.state_dict(), "sampler": self.sampler.state_dict(),
-                    "optimizer": self.optimizer.state_dict(), "nested_optimizer": adam.state_dict(),
+                    "optimizer": self.optimizer.state_dict(), "nested_optimizer": nested,
                     "ema_optimizer": self.ema_optimizer.state_dict()}, path)
 
     def load_ckpt(self, path):
@@ -204,7 +323,15 @@ class Runner:
         self.model.load_state_dict(ck["model"])
         self.sampler.load_state_dict(ck["sampler"])
         self.optimizer.load_state_dict(ck["optimizer"])
-        self.optimizer._nested_optimizer.load_state_dict(ck["nested_optimizer"])
+        nested = ck["nested_optimizer"]
+        if self.world_size > 1:
+            adam = self.optimizer._nested_optimizer
+            k = [id(s.p) for s in adam.state].index(id(self.model.pos_encoder.m_grid))
+            self._scatter_table_state(nested["m"][k], nested["v"][k], nested["master"][k])
+            st = self._st[id(self.model.pos_encoder.m_grid)]
+            nested = dict(nested, **{key: [t if j != k else getattr(st, key) for j, t in enumerate(nested[key])] for key in ("m", "v", "master")})
+            self._slice_param.copy_(self._table[self._lo:self._hi])
+        self.optimizer._nested_optimizer.load_state_dict(nested)
         self.ema_optimizer.load_state_dict(ck["ema_optimizer"])
 
 

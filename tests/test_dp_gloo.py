@@ -79,3 +79,40 @@ def test_adapt_rays_per_batch_matches_reference_formula():
         m = max(measured, 1)
         ref = int(min(((int(R * target / m)) + 127) // 128 * 128, target))
         assert dp.adapt_rays_per_batch(R, measured, target) == ref
+
+
+def _sharded_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from jnerf_b200 import dp
+    torch.set_num_threads(1)
+    n = 6_098_120 // 64 * 2 + 6                                    # not a multiple of world*256: exercises the padding
+    P = dp.padded_len(n, world)
+    lo, hi = dp.slice_bounds(P, world, rank)
+    g = torch.Generator().manual_seed(100 + rank)
+    grad = torch.zeros(P)
+    grad[:n] = torch.randn(n, generator=g)
+    table = torch.zeros(P)
+    table[:n] = torch.arange(n, dtype=torch.float32) * 1e-3       # identical on every rank
+    # reduce-scatter -> "optimizer" on the slice (plain SGD stands in for ngp_adam_ema) -> all-gather
+    my_grad = torch.empty(hi - lo)
+    dp.reduce_scatter_sum(my_grad, grad, None, world, rank)
+    my_slice = table[lo:hi] - 0.1 * my_grad / world
+    work = dp.all_gather_slices(table, my_slice.contiguous(), None, world, async_op=True)
+    work.wait()
+    ret[rank] = dict(table=table[:n].numpy().copy(), P=P, lo=lo, hi=hi, tail=float(table[n:].abs().sum()))
+    dist.destroy_process_group()
+
+
+def test_sharded_table_optimizer_equals_allreduce_update():
+    """dp.py sharded optimizer plumbing: reduce-scatter + per-slice update + all-gather == all-reduce + full update, on every rank."""
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_sharded_worker, args=(world, 30511 + os.getpid() % 1000, ret), nprocs=world, join=True)
+    n = 6_098_120 // 64 * 2 + 6
+    assert ret[0]["P"] % (world * 256) == 0 and ret[0]["P"] >= n and ret[0]["hi"] == ret[1]["lo"] and ret[1]["hi"] == ret[0]["P"]
+    gsum = sum(torch.randn(n, generator=torch.Generator().manual_seed(100 + r)) for r in range(world))
+    want = torch.arange(n, dtype=torch.float32) * 1e-3 - 0.1 * gsum / world
+    for r in range(world):
+        assert np.array_equal(ret[r]["table"], want.numpy()) and ret[r]["tail"] == 0.0

@@ -396,3 +396,53 @@ def test_prepare_batch(ops):
         tref = c[:, :3] * c[:, 3:] + bg * (1 - c[:, 3:])                                   # runner/runner.py:68
         assert np.array_equal(npy(ids).view(np.uint32), ir) and np.array_equal(npy(o), orr) and np.abs(npy(d) - dr).max() <= 1e-6
         assert np.abs(npy(target) - tref).max() <= 1e-6
+
+
+@pytest.mark.gpu
+def test_dp_exchange_kernel_two_ranks_on_one_device(ops):
+    """ngp_dp_exchange_step with two emulated ranks (two arenas, two streams, one GPU): the flag hand-shake completes, every
+    rank ends with the same table == ngp_adam_ema applied to the summed gradients, for two consecutive epochs."""
+    from jnerf_b200 import dp
+    W, n, n_w = 2, 400_003, 10240
+    arenas = [dp.PeerArena(n, n_w, W, r, None, ipc=False) for r in range(W)]
+    for a in arenas:
+        a.base = [b.buf.data_ptr() for b in arenas]
+    P = arenas[0].P
+    sl = P // W
+    g = torch.Generator(device="cuda").manual_seed(5)
+    table0 = torch.zeros(P, device="cuda")
+    table0[:n] = torch.rand(n, device="cuda", generator=g) * 2e-4 - 1e-4
+    w0 = (torch.randn(n_w, device="cuda", generator=g) * 0.1)
+    state = []
+    for r, a in enumerate(arenas):
+        a.table.copy_(table0.half())
+        state.append(dict(m=torch.zeros(sl, device="cuda"), v=torch.zeros(sl, device="cuda"), master=table0.half().float()[r * sl:(r + 1) * sl].clone(),
+                          w=w0.half().clone(), wm=torch.zeros(n_w, device="cuda"), wv=torch.zeros(n_w, device="cuda"), wmaster=w0.half().float().clone()))
+    # reference: one plain Adam+EMA over the whole table / weight vector with the summed gradient
+    ref = dict(p=table0.half().clone(), m=torch.zeros(P, device="cuda"), v=torch.zeros(P, device="cuda"), master=table0.half().float().clone(),
+               w=w0.half().clone(), wm=torch.zeros(n_w, device="cuda"), wv=torch.zeros(n_w, device="cuda"), wmaster=w0.half().float().clone())
+    streams = [torch.cuda.Stream() for _ in range(W)]
+    for epoch in (1, 2):
+        gsum, wsum = torch.zeros(P, device="cuda"), torch.zeros(n_w, device="cuda")
+        for a in arenas:
+            a.table_grad[:n].copy_((torch.randn(n, device="cuda", generator=g) * 1e-3).half())
+            a.w_grad[:n_w].copy_(torch.randn(n_w, device="cuda", generator=g) * 1e-2)
+            gsum += a.table_grad.float()
+            wsum += a.w_grad[:n_w]
+        torch.cuda.synchronize()
+        for r, a in enumerate(arenas):
+            st = state[r]
+            with torch.cuda.stream(streams[r]):
+                ops.dp_exchange_step(W, r, sl, n_w, a.peers("table"), a.peers("table_grad"), a.peers("w_grad"), a.peers("flags"), epoch,
+                                     st["m"], st["v"], st["master"], st["w"], st["wm"], st["wv"], st["wmaster"], 0.1, epoch, grad_scale=0.5)
+                ops.dp_exchange_wait(W, a.flags, epoch)
+                a.grads.zero_()
+        torch.cuda.synchronize()
+        ops.adam_ema(ref["p"], gsum, ref["m"], ref["v"], ref["master"], 0.1, epoch, grad_scale=0.5, zero_grad=False)
+        ops.adam_ema(ref["w"], wsum, ref["wm"], ref["wv"], ref["wmaster"], 0.1, epoch, grad_scale=0.5, zero_grad=False)
+        torch.cuda.synchronize()
+        for r, a in enumerate(arenas):
+            assert torch.equal(a.table, ref["p"]), f"epoch {epoch}: table of rank {r} differs"
+            assert torch.equal(state[r]["w"], ref["w"]), f"epoch {epoch}: MLP weights of rank {r} differ"
+            assert torch.equal(state[r]["master"], ref["master"][r * sl:(r + 1) * sl])
+            assert int(a.table_grad.abs().sum()) == 0 and int(a.flags[32]) == 0
