@@ -120,21 +120,35 @@ class PeerArena:
         if world_size > 1 and ipc:                                               # ipc=False: the caller fills self.base (single-process tests)
             import ctypes
             import numpy as np
+            err = None
             h = np.zeros(64, np.uint8)
             off = ctypes.c_uint64(0)
-            lib.call("ngp_ipc_export", self.buf.data_ptr(), h.ctypes.data, ctypes.addressof(off))
-            mine = (h.tobytes(), int(off.value), int(torch.cuda.current_device()))
+            try:
+                lib.call("ngp_ipc_export", self.buf.data_ptr(), h.ctypes.data, ctypes.addressof(off))
+            except lib.NgpError as e:
+                err = e
+            mine = (h.tobytes(), int(off.value), err is None)
             everyone = [None] * world_size
             dist.all_gather_object(everyone, mine, group=group)
-            for r, (hb, o, _dev) in enumerate(everyone):
-                if r == rank:
+            for r, (hb, o, good) in enumerate(everyone):
+                if r == rank or err is not None or not good:
                     continue
                 hr = np.frombuffer(hb, np.uint8).copy()
                 out = ctypes.c_void_p(0)
-                lib.call("ngp_ipc_open", hr.ctypes.data, o, ctypes.addressof(out))
+                try:
+                    lib.call("ngp_ipc_open", hr.ctypes.data, o, ctypes.addressof(out))
+                except lib.NgpError as e:
+                    err = e
+                    continue
                 self.base[r] = int(out.value)
                 self._opened.append((int(out.value), o))
-            dist.barrier(group=group)                                           # every arena is zeroed and mapped before the first epoch
+            # every rank learns whether EVERY mapping succeeded (so that all ranks fall back together); also: every arena is
+            # zeroed and mapped before the first epoch
+            good = torch.tensor([int(err is None and all(g for _, _, g in everyone))], device=device)
+            dist.all_reduce(good, op=dist.ReduceOp.MIN, group=group)
+            if not bool(good.item()):
+                self.close()
+                raise RuntimeError(f"peer mapping failed on at least one rank ({err})")
 
     def peers(self, name):
         import ctypes

@@ -90,7 +90,15 @@ class Runner:
         P = dp.padded_len(n, W)
         nd, nr = m.density_mlp.con_weights.numel(), m.rgb_mlp.con_weights.numel()
         if self.dp_mode == "p2p":
-            self._arena = dp.PeerArena(n, nd + nr, W, self.rank, self.pg)
+            try:
+                self._arena = dp.PeerArena(n, nd + nr, W, self.rank, self.pg)
+            except RuntimeError as e:                                  # raised on EVERY rank when any mapping failed
+                if mode == "p2p":
+                    raise
+                if self.rank == 0:
+                    print(f"[jnerf_b200] peer-memory exchange unavailable ({e}); using the NCCL exchange", flush=True)
+                self.dp_mode = "nccl"
+        if self.dp_mode == "p2p":
             self._table, self._table_grad, self.w_grad = self._arena.table, self._arena.table_grad, self._arena.w_grad
             self.dwd, self.dwr = self.w_grad[:nd], self.w_grad[nd:nd + nr]
             self._peers = {k: self._arena.peers(k) for k in ("table", "table_grad", "w_grad", "flags")}
