@@ -42,6 +42,16 @@ def peaks():
         return 6650.0, 1590.0, "fallback"
 
 
+def measured_traffic(stage):
+    """DRAM bytes per launch (read + write) of the stage's kernel from the committed ncu --set full capture, or None."""
+    try:
+        k = json.load(open(os.path.join(ROOT, "profiles", "r01b_traffic.json")))["kernels"]
+        e = k[{"network_bwd": "network_bwd_kernel", "network_fwd": "network_fwd_kernel<0>"}[stage]]
+        return e["dram_bytes_read"] + e["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md recipe)."""
     Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
@@ -284,7 +294,9 @@ def run_ours(args):
     algo = ALGO[dom]
     t_dom = stage[dom] * 1e-3
     gbs = n_samples * algo["bytes"] / t_dom / 1e9
-    roofline = {"kernel": dom, "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": None,
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": measured_traffic(dom),
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01b_traffic.json (gradient atomics resolve in L2, "
+                                "so DRAM traffic is well below the algorithmic bytes)",
                 "peak_source": f"{src} (MEASURED_PEAKS.json hbm_gbs)", "launch_ms": stage[dom], "samples_per_launch": n_samples,
                 "algorithmic_bytes_per_sample": algo["bytes"],
                 "tensor": {"achieved_tflops": n_samples * algo["flops"] / t_dom / 1e12, "peak_tflops": tfl,

@@ -155,8 +155,44 @@ static __device__ __noinline__ void epi_dgrad_mask(uint32_t tbase, uint32_t dcol
 }
 
 // named barriers (bar.sync / bar.arrive) for warp-specialised kernels; id 0 is __syncthreads
-__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// The barrier id is always emitted as an IMMEDIATE: with a register operand ptxas must reserve all 16 hardware barriers for the
+// CTA ("used 16 barriers"), and barriers are an occupancy limiter (ncu: "Block Limit Barriers") -- two CTAs per SM need <= 8 each.
+template <uint32_t ID>
+__device__ __forceinline__ void bar_sync_imm(uint32_t nthreads) { asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(nthreads) : "memory"); }
+template <uint32_t ID>
+__device__ __forceinline__ void bar_arrive_imm(uint32_t nthreads) { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+    switch (id) {
+        case 1: bar_sync_imm<1>(nthreads); break;
+        case 2: bar_sync_imm<2>(nthreads); break;
+        case 3: bar_sync_imm<3>(nthreads); break;
+        case 4: bar_sync_imm<4>(nthreads); break;
+        case 5: bar_sync_imm<5>(nthreads); break;
+        case 6: bar_sync_imm<6>(nthreads); break;
+        case 7: bar_sync_imm<7>(nthreads); break;
+        case 8: bar_sync_imm<8>(nthreads); break;
+        case 9: bar_sync_imm<9>(nthreads); break;
+        case 10: bar_sync_imm<10>(nthreads); break;
+        case 11: bar_sync_imm<11>(nthreads); break;
+        default: __trap();
+    }
+}
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+    switch (id) {
+        case 1: bar_arrive_imm<1>(nthreads); break;
+        case 2: bar_arrive_imm<2>(nthreads); break;
+        case 3: bar_arrive_imm<3>(nthreads); break;
+        case 4: bar_arrive_imm<4>(nthreads); break;
+        case 5: bar_arrive_imm<5>(nthreads); break;
+        case 6: bar_arrive_imm<6>(nthreads); break;
+        case 7: bar_arrive_imm<7>(nthreads); break;
+        case 8: bar_arrive_imm<8>(nthreads); break;
+        case 9: bar_arrive_imm<9>(nthreads); break;
+        case 10: bar_arrive_imm<10>(nthreads); break;
+        case 11: bar_arrive_imm<11>(nthreads); break;
+        default: __trap();
+    }
+}
 
 // Sync point between "all threads wrote smem operands / finished reading TMEM" and "thread 0 issues MMAs".
 // CHAIN128 = true: only the 128 MLP-chain threads (warps 0-3) of a warp-specialised CTA take part (named barrier 1).
@@ -168,13 +204,30 @@ __device__ __forceinline__ void sync_before_issue() {
     tc_fence_after();
 }
 
+// chain-group variant: `bar_id` is the named barrier of the 128 threads that form one MLP chain
+__device__ __forceinline__ void sync_chain(uint32_t bar_id) {
+    tc_fence_before();
+    fence_proxy_async_smem();
+    named_bar_sync(bar_id, 128);
+    tc_fence_after();
+}
+
 struct Pipe {
     uint64_t* bar;
     uint32_t phase;
     int* err;
     __device__ __forceinline__ void commit() { mma_commit(bar); }
     __device__ __forceinline__ void wait() {
+        // The issuing thread's warp-mates must not start polling while it is still issuing: a blocking mbarrier.try_wait on the
+        // divergent path stalls the whole warp, and the single-thread MMA issue took ~570 cycles instead of ~50 per stage
+        // (tools/dbg_timeline_bwd.py).  Reconverge first.
+        __syncwarp();
+#ifdef NGP_POLL_LANE0
+        if ((threadIdx.x & 31) == 0) { if (!mbar_wait(bar, phase)) { if (err) atomicExch(err, 1); } }
+        __syncwarp();
+#else
         if (!mbar_wait(bar, phase)) { if (err) atomicExch(err, 1); }
+#endif
         phase ^= 1;
         tc_fence_after();
     }

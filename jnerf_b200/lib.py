@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libngp_b200.so")
+LIB_PATH = os.environ.get("NGP_B200_LIB") or os.path.join(HERE, "libngp_b200.so")   # override: A/B timing of experimental builds
 
 _vp, _u32, _u64, _i64, _f32, _i32, _f64 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int64, C.c_float, C.c_int, C.c_double
 
