@@ -222,12 +222,7 @@ struct Pipe {
         // divergent path stalls the whole warp, and the single-thread MMA issue took ~570 cycles instead of ~50 per stage
         // (tools/dbg_timeline_bwd.py).  Reconverge first.
         __syncwarp();
-#ifdef NGP_POLL_LANE0
-        if ((threadIdx.x & 31) == 0) { if (!mbar_wait(bar, phase)) { if (err) atomicExch(err, 1); } }
-        __syncwarp();
-#else
         if (!mbar_wait(bar, phase)) { if (err) atomicExch(err, 1); }
-#endif
         phase ^= 1;
         tc_fence_after();
     }

@@ -51,9 +51,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
 // ---- fences ---------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() {
     // make generic-proxy st.shared visible to the async proxy (UMMA operand reads)
-#ifndef NGP_EXP_NOFENCE   // timing experiments only (results are undefined without the fence)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#endif
 }
 __device__ __forceinline__ void tc_fence_before() {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
