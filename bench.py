@@ -163,6 +163,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; this arm is the CPU implementation with all the host threads it can
+    # use, and libgomp reads the variable when the oracle library is loaded (inside cpu_train_iteration)
+    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
     n_rays = max(64, min(256, 16384 // max(args.steps, 1)))    # bounded sample: the whole run stays within minutes
     for _ in range(max(args.warmup, 1)):
         cpu_train_iteration(64)
