@@ -73,7 +73,15 @@ int ngp_mlp_fwd(void* stream, const void* weights, const void* input, void* inte
  * dW: fp32, same flat layout as weights, OVERWRITTEN; rows >= n_out_valid of the last layer are zero (:136). */
 int ngp_mlp_bwd(void* stream, const void* weights, const void* input, const void* inter, const void* dY,
                 void* dX, void* temps, float* dW, uint32_t n_hidden_matmuls, uint32_t n_out_valid, uint32_t n);
+/* Data-gradient chain only -- what the reference's link-level mlp_fused_backward_func returns (fully_fused_mlp_header.h:29-43;
+ * call site OPS/fully_fused_mlp.py:101-115): dY_feature_major is (16,n) (the reference passes grads.transpose(), :117), temps
+ * as above, dX (n,32) optional; no weight gradients (the reference leaves those to five cuBLAS GEMMs, :123-143). */
+int ngp_mlp_bwd_dgrad(void* stream, const void* weights, const void* inter, const void* dY_feature_major, void* dX, void* temps,
+                      uint32_t n_hidden_matmuls, uint32_t n);
 int ngp_mlp_param_count(uint32_t n_hidden_matmuls);
+/* The two C++ symbols of the reference's prebuilt fully_fused_mlp_function.o (mlp_fused_forward_func / mlp_fused_backward_func,
+ * OPS/op_header/fully_fused_mlp_header.h:26-60) are exported too, with their original mangled names, by csrc/compat_tcnn.cu:
+ * OPS/fully_fused_mlp.py links against libngp_b200.so unchanged. */
 
 /* ---- R7+R2+R4 fused: NGPNetworks.execute (models/networks/ngp_network.py:77-84) -----------------------
  * coords (n_max,7) f32 = NerfCoordinate {pos[3], dt, dir[3]} (DGS/op_header/ray_sampler_header.h:548-574).

@@ -19,6 +19,7 @@ SOURCES = {
     "sampler.cu": ["-fmad=false"],
     "grid_update.cu": ["-fmad=false"],
     "optimizer.cu": [],
+    "compat_tcnn.cu": [],
 }
 
 

@@ -135,8 +135,10 @@ struct BwdLayout {
 
 __global__ void __launch_bounds__(128)
 mlp_bwd_kernel(const __half* __restrict__ W, const __half* __restrict__ X, const __half* __restrict__ inter,
-               const __half* __restrict__ dY, __half* __restrict__ dX, __half* __restrict__ temps, float* __restrict__ dW,
-               uint32_t nhm, uint32_t n_out_valid, uint32_t n, int* __restrict__ err) {
+               const __half* __restrict__ dY, int dy_feature_major, __half* __restrict__ dX, __half* __restrict__ temps,
+               float* __restrict__ dW, uint32_t nhm, uint32_t n_out_valid, uint32_t n, int* __restrict__ err) {
+    // dW == nullptr: dgrad chain only (the link-level mlp_fused_backward_func contract, compat_tcnn.cu); X may then be nullptr.
+    // dy_feature_major: dY is (16, n) -- the transposed gradient the reference hands to its backward (fully_fused_mlp.py:117).
     extern __shared__ __align__(1024) uint8_t smem[];
     const BwdLayout L{nhm};
     const uint32_t t = threadIdx.x, warp = t >> 5;
@@ -171,14 +173,24 @@ mlp_bwd_kernel(const __half* __restrict__ W, const __half* __restrict__ X, const
         {
             const uint4* src = reinterpret_cast<const uint4*>(X + (size_t)row * IN);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(act + g * GB + t * 16) = valid ? __ldg(src + g) : z;
+            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(act + g * GB + t * 16) = (valid && X) ? __ldg(src + g) : z;
             for (uint32_t k = 0; k < nh; ++k) {
                 const uint4* hs = reinterpret_cast<const uint4*>(inter + ((size_t)k * n + row) * WIDTH);
 #pragma unroll
                 for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(act + (4 + 8 * k + g) * GB + t * 16) = valid ? __ldg(hs + g) : z;
             }
-            const uint4* ds = reinterpret_cast<const uint4*>(dY + (size_t)row * OUTP);
-            uint4 d0 = valid ? __ldg(ds) : z, d1 = valid ? __ldg(ds + 1) : z;
+            uint4 d0 = z, d1 = z;
+            if (valid && !dy_feature_major) {
+                const uint4* ds = reinterpret_cast<const uint4*>(dY + (size_t)row * OUTP);
+                d0 = __ldg(ds);
+                d1 = __ldg(ds + 1);
+            } else if (valid) {                       // column c of this row sits at dY[c * n + row]: coalesced across the tile
+                __align__(16) __half col[OUTP];
+#pragma unroll
+                for (int c = 0; c < OUTP; ++c) col[c] = __ldg(dY + (size_t)c * n + row);
+                d0 = *reinterpret_cast<const uint4*>(col);
+                d1 = *reinterpret_cast<const uint4*>(col + 8);
+            }
             *reinterpret_cast<uint4*>(grd + 0 * GB + t * 16) = d0;
             *reinterpret_cast<uint4*>(grd + 1 * GB + t * 16) = d1;
         }
@@ -186,7 +198,7 @@ mlp_bwd_kernel(const __half* __restrict__ W, const __half* __restrict__ X, const
         // gradient at the last hidden layer, and the output layer's wgrad
         if (t == 0) {
             issue_dgrad(tbase + D_G, grd_s, 0, OUTP, smem_s + L.wout(), WIDTH);
-            issue_wgrad(tbase + D_WOUT, act_s, 4 + 8 * (nh - 1), grd_s, 0, OUTP, acc);
+            if (dW) issue_wgrad(tbase + D_WOUT, act_s, 4 + 8 * (nh - 1), grd_s, 0, OUTP, acc);
             pipe.commit();
         }
         pipe.wait();
@@ -197,7 +209,7 @@ mlp_bwd_kernel(const __half* __restrict__ W, const __half* __restrict__ X, const
             const uint32_t j = nh - 1 - k;            // gradient block holding g_k
             if (t == 0) {
                 issue_dgrad(tbase + D_G, grd_s, 2 + 8 * j, WIDTH, smem_s + L.wh() + (k - 1) * WIDTH * WIDTH * 2, WIDTH);
-                issue_wgrad(tbase + D_W + 64 * k, act_s, 4 + 8 * (k - 1), grd_s, 2 + 8 * j, WIDTH, acc);
+                if (dW) issue_wgrad(tbase + D_W + 64 * k, act_s, 4 + 8 * (k - 1), grd_s, 2 + 8 * j, WIDTH, acc);
                 pipe.commit();
             }
             pipe.wait();
@@ -206,9 +218,10 @@ mlp_bwd_kernel(const __half* __restrict__ W, const __half* __restrict__ X, const
             sync_before_issue();
         }
         // first layer: dX = g_0 * W0, wgrad W0 = g_0^T X
+        if (!dX && !dW) continue;     // dgrad-only call without dL/dinput: nothing left for this tile (uniform over the CTA)
         if (t == 0) {
             if (dX) issue_dgrad(tbase + D_X, grd_s, 2 + 8 * nhm, WIDTH, smem_s + L.w0(), IN);
-            issue_wgrad(tbase + D_W, act_s, 0, grd_s, 2 + 8 * nhm, WIDTH, acc);
+            if (dW) issue_wgrad(tbase + D_W, act_s, 0, grd_s, 2 + 8 * nhm, WIDTH, acc);
             pipe.commit();
         }
         pipe.wait();
@@ -225,7 +238,7 @@ mlp_bwd_kernel(const __half* __restrict__ W, const __half* __restrict__ X, const
         }
     }
     // flush the weight gradients: lane t = input feature, column = output feature
-    if (acc) {
+    if (acc && dW) {
         float* dW0 = dW;
         float* dWh = dW + WIDTH * IN;
         float* dWo = dWh + nhm * WIDTH * WIDTH;
@@ -299,12 +312,10 @@ int ngp_mlp_fwd(void* stream, const void* weights, const void* input, void* inte
     return 0;
 }
 
-int ngp_mlp_bwd(void* stream, const void* weights, const void* input, const void* inter, const void* dY, void* dX, void* temps,
-                float* dW, uint32_t nhm, uint32_t n_out_valid, uint32_t n) {
-    NGP_REQUIRE(nhm <= MAX_HM, "ngp_mlp_bwd: at most 3 hidden matmuls");
-    NGP_REQUIRE(dW != nullptr && inter != nullptr, "ngp_mlp_bwd: dW and inter are required");
+static int mlp_bwd_launch(void* stream, const void* weights, const void* input, const void* inter, const void* dY, int dy_feature_major,
+                          void* dX, void* temps, float* dW, uint32_t nhm, uint32_t n_out_valid, uint32_t n) {
     cudaStream_t s = (cudaStream_t)stream;
-    NGP_CHECK_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * ngp_mlp_param_count(nhm), s));
+    if (dW) NGP_CHECK_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * ngp_mlp_param_count(nhm), s));
     if (n == 0) return 0;
     const BwdLayout L{nhm};
     NGP_CHECK_CUDA(cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total()));
@@ -312,9 +323,23 @@ int ngp_mlp_bwd(void* stream, const void* weights, const void* input, const void
     const uint32_t per_sm = L.tmem_cols() <= 256 && L.total() <= 110 * 1024 ? 2u : 1u;
     const uint32_t grid = min(ntiles, (uint32_t)ngp_num_sms() * per_sm);
     mlp_bwd_kernel<<<grid, 128, L.total(), s>>>((const __half*)weights, (const __half*)input, (const __half*)inter, (const __half*)dY,
-                                                (__half*)dX, (__half*)temps, dW, nhm, n_out_valid, n, err_flag());
+                                                dy_feature_major, (__half*)dX, (__half*)temps, dW, nhm, n_out_valid, n, err_flag());
     NGP_LAUNCH_CHECK();
     return 0;
+}
+
+int ngp_mlp_bwd(void* stream, const void* weights, const void* input, const void* inter, const void* dY, void* dX, void* temps,
+                float* dW, uint32_t nhm, uint32_t n_out_valid, uint32_t n) {
+    NGP_REQUIRE(nhm <= MAX_HM, "ngp_mlp_bwd: at most 3 hidden matmuls");
+    NGP_REQUIRE(dW != nullptr && inter != nullptr && input != nullptr, "ngp_mlp_bwd: input, inter and dW are required");
+    return mlp_bwd_launch(stream, weights, input, inter, dY, 0, dX, temps, dW, nhm, n_out_valid, n);
+}
+
+int ngp_mlp_bwd_dgrad(void* stream, const void* weights, const void* inter, const void* dY_feature_major, void* dX, void* temps,
+                      uint32_t nhm, uint32_t n) {
+    NGP_REQUIRE(nhm <= MAX_HM, "ngp_mlp_bwd_dgrad: at most 3 hidden matmuls");
+    NGP_REQUIRE(inter != nullptr && (temps != nullptr || dX != nullptr), "ngp_mlp_bwd_dgrad: inter and one of temps / dX are required");
+    return mlp_bwd_launch(stream, weights, nullptr, inter, dY_feature_major, 1, dX, temps, nullptr, nhm, 16, n);
 }
 
 }  // extern "C"

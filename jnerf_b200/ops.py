@@ -80,6 +80,15 @@ def mlp_bwd(W, X, inter, dY, n_hidden_matmuls, n_out_valid, need_dx=True, need_t
     return dX, temps, dW
 
 
+def mlp_bwd_dgrad(W, inter, dY_feature_major, n_hidden_matmuls, need_dx=False):
+    """Data-gradient chain only (the contract of the reference's link-level mlp_fused_backward_func): dY is (16, n)."""
+    n = dY_feature_major.shape[1]
+    dX = torch.empty((n, 32), dtype=torch.float16, device=W.device) if need_dx else None
+    temps = torch.empty(((n_hidden_matmuls + 1) * n, 64), dtype=torch.float16, device=W.device)
+    lib.call("ngp_mlp_bwd_dgrad", _stream(), _p(W), _p(inter), _p(dY_feature_major), _p(dX), _p(temps), n_hidden_matmuls, n)
+    return dX, temps
+
+
 def network_fwd(coords, grid, levels, wd, wr, n_dev=None, save_enc=True, out=None, enc=None):
     n = coords.shape[0]
     if out is None:

@@ -37,6 +37,32 @@ def test_every_declared_symbol_is_exported(lib):
     assert set(SIGNATURES) == set(syms)
 
 
+def test_tiny_cuda_nn_link_symbols_are_exported(lib):
+    """the two C++ functions of the reference's prebuilt fully_fused_mlp_function.o, with the exact mangled names
+    OPS/fully_fused_mlp.py links against (declared in OPS/op_header/fully_fused_mlp_header.h:26-60)."""
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(ROOT, "jnerf_b200", "libngp_b200.so")], capture_output=True, text=True).stdout
+    syms = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    fwd = "_Z22mlp_fused_forward_funci10ActivationbP11CUstream_stS_P6__halfS3_S3_S3_jiiiiii"
+    bwd = "_Z23mlp_fused_backward_funci10ActivationP11CUstream_stP6__halfS3_S3_S3_S3_S3_jiii"
+    assert fwd in syms and bwd in syms
+    hdr = "/root/reference/python/jnerf/ops/code_ops/op_header/fully_fused_mlp_header.h"
+    if os.path.exists(hdr):
+        # a caller compiled against the reference's OWN header must resolve against our library (no GPU needed to link)
+        import tempfile
+        with tempfile.TemporaryDirectory() as d:
+            src = os.path.join(d, "caller.cu")
+            open(src, "w").write('#include <cuda_fp16.h>\n#include "fully_fused_mlp_header.h"\n'
+                                 "int main(int argc, char**) { if (argc > 100) { mlp_fused_forward_func(64, Activation::ReLU, false, 0, Activation::None,"
+                                 " nullptr, nullptr, nullptr, nullptr, 0, 0, 32, 32, 64, 0, 16);"
+                                 " mlp_fused_backward_func(64, Activation::ReLU, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 16, 0); } return 0; }\n")
+            exe = os.path.join(d, "caller")
+            r = subprocess.run(["nvcc", "-I", os.path.dirname(hdr), src, "-o", exe, "-Xlinker", os.path.join(ROOT, "jnerf_b200", "libngp_b200.so"),
+                                "-Xlinker", "-rpath=" + os.path.join(ROOT, "jnerf_b200")], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+            assert subprocess.run([exe]).returncode == 0
+
+
 def test_product_does_not_link_the_oracle(lib):
     import subprocess
     out = subprocess.run(["nm", "-D", os.path.join(ROOT, "jnerf_b200", "libngp_b200.so")], capture_output=True, text=True).stdout

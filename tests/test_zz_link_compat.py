@@ -1,0 +1,91 @@
+"""The two link-level C++ symbols of the reference's prebuilt tiny-cuda-nn object (mlp_fused_forward_func /
+mlp_fused_backward_func, OPS/op_header/fully_fused_mlp_header.h:26-60), exported by libngp_b200.so under their original
+mangled names (csrc/compat_tcnn.cu), called exactly as the jt.code bodies of OPS/fully_fused_mlp.py:58-75,101-115 call them
+and checked against the oracle and against the C-ABI entry points they share kernels with.
+
+(File name sorts last on purpose: these entry points were added after the round's last GPU session.)"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+FWD = "_Z22mlp_fused_forward_funci10ActivationbP11CUstream_stS_P6__halfS3_S3_S3_jiiiiii"
+BWD = "_Z23mlp_fused_backward_funci10ActivationP11CUstream_stP6__halfS3_S3_S3_S3_S3_jiii"
+RELU, NONE = 0, 6                     # enum Activation, fully_fused_mlp_header.h:19-27
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def _weights(nhm, seed):
+    rng = np.random.default_rng(seed)
+    shapes = [(64, 32)] + [(64, 64)] * nhm + [(16, 64)]
+    lim = lambda s: np.sqrt(6.0 / (s[0] + s[1]))                                  # noqa: E731
+    return np.concatenate([rng.uniform(-lim(s), lim(s), s).astype(np.float16).ravel() for s in shapes])
+
+
+@pytest.fixture(scope="module")
+def syms():
+    from jnerf_b200 import lib as L
+    lib = L.load()
+    fwd, bwd = getattr(lib, FWD), getattr(lib, BWD)
+    vp, i = C.c_void_p, C.c_int
+    fwd.restype, bwd.restype = None, None
+    fwd.argtypes = [i, i, C.c_bool, vp, i, vp, vp, vp, vp, C.c_uint32, i, i, i, i, i, i]
+    bwd.argtypes = [i, i, vp, vp, vp, vp, vp, vp, vp, C.c_uint32, i, i, i]
+    return lib, fwd, bwd
+
+
+@pytest.mark.parametrize("n_hidden_layers,B", [(0, 256), (1, 128 * 37)])     # density net / colour net (ngp_network.py:52-53)
+def test_link_symbols_match_oracle_and_c_abi(syms, n_hidden_layers, B):
+    from jnerf_b200 import ops
+    lib, fwd, bwd = syms
+    nhm = n_hidden_layers
+    rng = np.random.default_rng(5 + nhm)
+    W = _weights(nhm, 3)
+    X = np.clip(rng.standard_normal((B, 32)), -4, 4).astype(np.float16)
+    Wd, Xd = cu(W), cu(X)
+    inter = torch.zeros(((nhm + 1) * B, 64), dtype=torch.float16, device="cuda")
+    Y = torch.zeros((B, 16), dtype=torch.float16, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    # fully_fused_mlp.py:58-75
+    fwd(64, RELU, False, s, NONE, Wd.data_ptr(), Xd.data_ptr(), inter.data_ptr(), Y.data_ptr(), nhm, B, 32, 32, 64, B, 16)
+    torch.cuda.synchronize()
+    assert lib.ngp_debug_timeout_flag() == 0
+    Yr, interr = ol.mlp_fwd(W, X, nhm)
+    assert np.abs(npy(inter).astype(np.float32) - interr.astype(np.float32)).max() <= 4e-3     # same bounds as test_mlp_fwd_bwd
+    assert np.abs(npy(Y).astype(np.float32) - Yr.astype(np.float32)).max() <= 6e-3
+    Y2, inter2 = ops.mlp_fwd(Wd, Xd, nhm)
+    assert torch.equal(Y, Y2) and torch.equal(inter, inter2)                                   # one kernel behind both doors
+
+    # backward: dL_doutput arrives TRANSPOSED (16, B), fully_fused_mlp.py:117; temps in reverse layer order (:127-142)
+    n_valid = 16 if nhm == 0 else 3
+    dY = (rng.standard_normal((B, 16)) * 0.1).astype(np.float16)
+    dY[:, n_valid:] = 0
+    dYt = cu(np.ascontiguousarray(dY.T))
+    temps = torch.zeros(((nhm + 1) * B, 64), dtype=torch.float16, device="cuda")
+    dX_unused = torch.zeros((B, 32), dtype=torch.float16, device="cuda")
+    inter_ref = cu(interr)
+    bwd(64, RELU, s, Wd.data_ptr(), Wd.data_ptr() + 64 * 32 * 2, dYt.data_ptr(), temps.data_ptr(), inter_ref.data_ptr(), dX_unused.data_ptr(),
+        nhm, B, 16, 0)
+    torch.cuda.synchronize()
+    assert lib.ngp_debug_timeout_flag() == 0
+    _, tempsr, _ = ol.mlp_bwd(W, X, interr, dY, nhm, n_valid)
+    assert np.abs(npy(temps).astype(np.float32) - tempsr.astype(np.float32)).max() <= 3e-3
+    assert not dX_unused.any()                                                                 # need_last = 0: dL_dinput untouched
+    _, temps2, _ = ops.mlp_bwd(Wd, Xd, inter_ref, cu(dY), nhm, n_valid, need_dx=False, need_temps=True)
+    assert torch.equal(temps, temps2)                                                          # row-major and feature-major dY agree bit for bit
+    # the C-ABI twin of the symbol, with dL/dinput
+    dX3, temps3 = ops.mlp_bwd_dgrad(Wd, inter_ref, dYt, nhm, need_dx=True)
+    dX4, _, _ = ops.mlp_bwd(Wd, Xd, inter_ref, cu(dY), nhm, n_valid, need_dx=True)
+    assert torch.equal(temps3, temps) and torch.equal(dX3, dX4)
