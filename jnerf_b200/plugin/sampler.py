@@ -186,5 +186,9 @@ class DensityGridSampler(Module):
     def load_state_dict(self, sd, *args, **kwargs):
         for k in ("density_grid", "density_grid_bitfield", "density_grid_mean", "density_grid_ema_step"):
             getattr(self, k).copy_(sd[k])
-        self.n_rays_per_batch = int(sd["n_rays_per_batch"])
-        self.rng = sd["rng"].cpu().numpy().astype(np.uint64)
+        # the two entries below are not jt.Vars in the reference and hence absent from its params.pkl (utils/ckpt_compat.py)
+        if "n_rays_per_batch" in sd:
+            self.n_rays_per_batch = int(sd["n_rays_per_batch"])
+            self.dataset.batch_size = self.n_rays_per_batch
+        if "rng" in sd:
+            self.rng = sd["rng"].cpu().numpy().astype(np.uint64)

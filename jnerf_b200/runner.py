@@ -321,12 +321,28 @@ class Runner:
                 nested[key][k] = t
             if self.rank != 0:
                 return
-        torch.save({"global_step": self.cfg.m_training_step, "model": self.model.state_dict(), "sampler": self.sampler.state_dict(),
-                    "optimizer": self.optimizer.state_dict(), "nested_optimizer": nested,
-                    "ema_optimizer": self.ema_optimizer.state_dict()}, path)
+        ck = {"global_step": self.cfg.m_training_step, "model": self.model.state_dict(), "sampler": self.sampler.state_dict(),
+              "optimizer": self.optimizer.state_dict(), "nested_optimizer": nested, "ema_optimizer": self.ema_optimizer.state_dict()}
+        if str(path).endswith(".pkl"):
+            # the reference's params.pkl wire format (runner/runner.py:123-131), readable by its load_ckpt (:133-151)
+            from .utils import ckpt_compat as cc
+            dec = self.optimizer
+            ref = cc.native_to_reference(
+                ck, adam_hyper=dict(lr=adam.lr, eps=adam.eps, betas=tuple(adam.betas)),
+                expdecay_hyper=dict(base_lr=dec.base_lr, decay_start=dec.decay_start, decay_interval=dec.decay_interval, decay_base=dec.decay_base,
+                                    decay_end=dec.decay_end),
+                param_dtype=np.float16 if self.model.pos_encoder.m_grid.dtype == torch.float16 else np.float32)
+            cc.write_reference_ckpt(ref, path)
+            return
+        torch.save(ck, path)
 
     def load_ckpt(self, path):
-        ck = torch.load(path, map_location="cuda", weights_only=False)
+        if str(path).endswith(".pkl"):
+            from .utils import ckpt_compat as cc
+            ck = cc.load_native_from_reference_file(path, self.model.pos_encoder.m_grid.numel(), "cuda",
+                                                    {k: v.dtype for k, v in self.model.state_dict().items()})
+        else:
+            ck = torch.load(path, map_location="cuda", weights_only=False)
         self.cfg.m_training_step = self.start = ck["global_step"]
         self.model.load_state_dict(ck["model"])
         self.sampler.load_state_dict(ck["sampler"])

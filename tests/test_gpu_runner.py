@@ -83,7 +83,7 @@ def test_checkpoint_roundtrip(tmp_path):
     r = make_runner(seed=7)
     for _ in range(20):
         r.train_step()
-    p = str(tmp_path / "params.pkl")
+    p = str(tmp_path / "ckpt.pt")
     r.save_ckpt(p)
     g0 = r.model.pos_encoder.m_grid.detach().clone()
     r2 = make_runner(seed=9)

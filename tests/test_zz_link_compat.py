@@ -89,3 +89,36 @@ def test_link_symbols_match_oracle_and_c_abi(syms, n_hidden_layers, B):
     dX3, temps3 = ops.mlp_bwd_dgrad(Wd, inter_ref, dYt, nhm, need_dx=True)
     dX4, _, _ = ops.mlp_bwd(Wd, Xd, inter_ref, cu(dY), nhm, n_valid, need_dx=True)
     assert torch.equal(temps3, temps) and torch.equal(dX3, dX4)
+
+
+def test_runner_checkpoint_in_the_reference_wire_format(tmp_path):
+    """Runner.save_ckpt / load_ckpt with a `.pkl` path use the reference's params.pkl structure (runner/runner.py:123-151,
+    jnerf_b200/utils/ckpt_compat.py): a file written here has every field the reference's load_ckpt indexes, and reads back."""
+    from test_gpu_runner import make_runner
+    from jnerf_b200.utils import ckpt_compat as cc
+    r = make_runner(seed=9)
+    for _ in range(20):
+        r.train_step()
+    p = str(tmp_path / "params.pkl")
+    r.save_ckpt(p)
+    ref = cc.read_reference_ckpt(p)
+    assert ref["global_step"] == 20
+    pg = ref["nested_optimizer"]["defaults"]["param_groups"][0]                     # indexed like runner.py:141-145
+    assert [np.asarray(v).size for v in pg["values"]] == [12196240, 3072, 7168] and len(pg["m"]) == 3
+    ema = ref["ema_optimizer"]["defaults"]                                          # runner.py:146-150
+    assert ema["steps"] == 20 and len(ema["param_groups"][0]["values"]) == 3
+    assert ref["model"]["pos_encoder.m_grid"].dtype == np.float16
+    g0 = r.model.pos_encoder.m_grid.detach().clone()
+    r2 = make_runner(seed=10)
+    r2.load_ckpt(p)
+    assert torch.equal(r2.model.pos_encoder.m_grid.detach(), g0)
+    assert torch.equal(r2.model.rgb_mlp.con_weights.detach(), r.model.rgb_mlp.con_weights.detach())
+    assert torch.equal(r2.sampler.density_grid_bitfield, r.sampler.density_grid_bitfield)
+    assert torch.equal(r2.sampler.density_grid, r.sampler.density_grid)
+    assert r2.cfg.m_training_step == 20 and r2.optimizer._nested_optimizer.n_step == 20 and r2.ema_optimizer.steps == 20
+    assert r2.sampler.n_rays_per_batch == r.sampler.n_rays_per_batch and np.array_equal(r2.sampler.rng, r.sampler.rng)
+    # fp32 master weights are the fp16-rounded EMA values after a reference-format round trip (the reference keeps them in fp16)
+    st, st2 = r.optimizer._nested_optimizer.state[1], r2.optimizer._nested_optimizer.state[1]
+    assert torch.equal(st2.master, st.master.half().float())
+    loss = r2.train_step()                                                           # and training continues
+    assert torch.isfinite(loss).all()
