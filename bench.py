@@ -190,7 +190,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from jnerf_b200 import lib, ops, plugin  # noqa: F401
-    from jnerf_b200.runner import Runner, lego_cfg
+    from jnerf_b200.runner import Runner, fox_cfg, lego_cfg
     from jnerf_b200.utils.config import get_cfg, update_cfg
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -203,14 +203,22 @@ def run_ours(args):
         pg = dist.group.WORLD
     lib.load()
     get_cfg().clear()
-    update_cfg(**lego_cfg(fp16=True, synthetic=True, seed=1))
-    n_img = args.images
+    fox = args.workload == "fox"
+    update_cfg(**(fox_cfg if fox else lego_cfg)(fp16=True, synthetic=True, seed=1, target_batch_size=args.target_batch))
     cfg = get_cfg()
-    cfg.dataset.train.n_images = n_img
-    cfg.dataset.train.H = cfg.dataset.train.W = args.res
+    if fox:                                # BASELINE config #3: the capture's own frame count / resolution unless overridden
+        if args.images != 100:
+            cfg.dataset.train.n_images = args.images
+        if args.res != 800:
+            cfg.dataset.train.W, cfg.dataset.train.H = args.res, args.res * 16 // 9
+    else:
+        cfg.dataset.train.n_images = args.images
+        cfg.dataset.train.H = cfg.dataset.train.W = args.res
     cfg.dataset.val = None
     cfg.dataset.train.pop("root_dir", None)
     runner = Runner(rank=rank, world_size=world, process_group=pg)
+    ds0 = runner.dataset["train"]
+    n_img, res_txt = ds0.n_images, f"{ds0.W}x{ds0.H}"
 
     def sync():
         torch.cuda.synchronize()
@@ -306,13 +314,16 @@ def run_ours(args):
                            "frac": n_samples * algo["flops"] / t_dom / 1e12 / tfl},
                 "stage_ms": stage}
     out = {
-        "metric": "ngp_lego_train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": f"ngp_{args.workload}_train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "iters_per_s": args.steps / (ms * 1e-3), "published_iters_per_s_rtx3090": 133.0, "samples_per_s": None,
-        "config": {"workload": "Instant-NGP lego: projects/ngp/configs/ngp_base.py + fp16 fully-fused MLP (BASELINE config #2), "
-                               f"{n_img} synthetic {args.res}x{args.res} views, target_batch_size 2^18 samples/iter/GPU, adaptive ray batch "
+        "config": {"workload": ("Instant-NGP fox: projects/ngp/configs/ngp_fox.py (BASELINE config #3: aabb_scale 4, cone stepping, fp16 fully-fused MLP), "
+                                if fox else "Instant-NGP lego: projects/ngp/configs/ngp_base.py + fp16 fully-fused MLP (BASELINE config #2), ") +
+                               f"{n_img} synthetic {res_txt} views, target_batch_size {args.target_batch} samples/iter/GPU"
+                               f"{' (2^18)' if args.target_batch == 1 << 18 else ''}, adaptive ray batch "
                                f"({runner.sampler.n_rays_per_batch} rays/iter/GPU at measurement), pretrain {args.pretrain} steps",
-                   "parallelism": f"dp{world}", "l2": "per-step working set (24 MB table + 171 MB optimizer state + 7 MB samples) exceeds the 126 MB L2; no explicit flush"},
+                   "parallelism": f"dp{world}", "target_batch_size": args.target_batch,
+                   "l2": "per-step working set (24 MB table + 171 MB optimizer state + 7 MB samples) exceeds the 126 MB L2; no explicit flush"},
         "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline,
     }
     if rank == 0:
@@ -380,6 +391,10 @@ def main():
     ap.add_argument("--images", type=int, default=100)
     ap.add_argument("--res", type=int, default=800)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="lego", choices=["lego", "fox"],
+                    help="lego = BASELINE config #2 (the headline line); fox = config #3 (aabb_scale 4, cone stepping) on its synthetic stand-in")
+    ap.add_argument("--target-batch", type=int, default=1 << 18,
+                    help="target_batch_size, samples per iteration per GPU (ngp_base.py:75); BASELINE config #5 sweeps 2^16 .. 2^22 (tools/sweep.py)")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 32 if args.impl == "reference" else 1000

@@ -379,7 +379,7 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             DBGB(3);
             // B1: g_h2 = (dYr Woutr) . relu'(h2) ; wgrad Woutr
             if (t == 0) { run_ops(ops, OP_B1, 1, acc); DBGB(4); pipe.commit(); }
-            if (t == 32) { run_ops(ops, OP_B1 + 1, 8, acc); mma_commit(bar_w); }   // weight gradient: issued by a second thread, off the critical path
+            if (t == 32) { if (!(dbg & 4)) run_ops(ops, OP_B1 + 1, 8, acc); mma_commit(bar_w); }   // weight gradient: issued by a second thread, off the critical path
             pipe.wait();
             DBGB(5);
             epi_dgrad_mask(tbase, D_H, warp, act, G_H2B, grd, Q_GH2, t, nullptr);
@@ -388,7 +388,7 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             DBGB(7);
             // B2: g_h1 = (g_h2 W1r) . relu'(h1) ; wgrad W1r
             if (t == 0) { run_ops(ops, OP_B2, 4, acc); DBGB(8); pipe.commit(); }
-            if (t == 32) { run_ops(ops, OP_B2 + 4, 8, acc); mma_commit(bar_w); }   // weight gradient: issued by a second thread, off the critical path
+            if (t == 32) { if (!(dbg & 4)) run_ops(ops, OP_B2 + 4, 8, acc); mma_commit(bar_w); }   // weight gradient: issued by a second thread, off the critical path
             pipe.wait();
             DBGB(9);
             epi_dgrad_mask(tbase, D_H, warp, act, G_H1, grd, Q_GH1, t, nullptr);
@@ -396,7 +396,7 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             DBGB(10);
             // B3: d_rin = g_h1 W0r (32 cols; the last 16 are dL/dSH, unused) ; wgrad W0r
             if (t == 0) { run_ops(ops, OP_B3, 4, acc); pipe.commit(); }
-            if (t == 32) { run_ops(ops, OP_B3 + 4, 8, acc); mma_commit(bar_w); }   // weight gradient: issued by a second thread, off the critical path
+            if (t == 32) { if (!(dbg & 4)) run_ops(ops, OP_B3 + 4, 8, acc); mma_commit(bar_w); }   // weight gradient: issued by a second thread, off the critical path
             pipe.wait();
             {
                 float v[16];
@@ -409,13 +409,13 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             sync_before_issue<true>();
             // B4: g_hd = (dYd Woutd) . relu'(hd) ; wgrad Woutd
             if (t == 0) { run_ops(ops, OP_B4, 1, acc); pipe.commit(); }
-            if (t == 32) { run_ops(ops, OP_B4 + 1, 8, acc); mma_commit(bar_w); }   // weight gradient: issued by a second thread, off the critical path
+            if (t == 32) { if (!(dbg & 4)) run_ops(ops, OP_B4 + 1, 8, acc); mma_commit(bar_w); }   // weight gradient: issued by a second thread, off the critical path
             pipe.wait();
             epi_dgrad_mask(tbase, D_H, warp, act, G_HD, grd, Q_GHD, t, nullptr);
             sync_before_issue<true>();
             // B5: d_enc = g_hd W0d ; wgrad W0d
             if (t == 0) { run_ops(ops, OP_B5, 4, acc); pipe.commit(); }
-            if (t == 32) { run_ops(ops, OP_B5 + 4, 8, acc); mma_commit(bar_w); }   // weight gradient: issued by a second thread, off the critical path
+            if (t == 32) { if (!(dbg & 4)) run_ops(ops, OP_B5 + 4, 8, acc); mma_commit(bar_w); }   // weight gradient: issued by a second thread, off the critical path
             pipe.wait();
             {
                 float v[16];
@@ -863,7 +863,8 @@ int ngp_network_bwd(void* stream, uint32_t n_max, const uint32_t* n_dev, const f
     if (n_max == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t ntiles = (n_max + ROWS - 1) / ROWS;
-    static const uint32_t dbg = getenv("NGP_BWD_DEBUG") ? (uint32_t)atoi(getenv("NGP_BWD_DEBUG")) : 0u;   // timing experiments only: 1 = no atomics, 2 = no scatter
+    // timing experiments only (results are wrong with any bit set): 1 = no atomics, 2 = no scatter, 4 = no weight-gradient MMAs (v1 kernel)
+    static const uint32_t dbg = getenv("NGP_BWD_DEBUG") ? (uint32_t)atoi(getenv("NGP_BWD_DEBUG")) : 0u;
     static const bool use_v2 = getenv("NGP_BWD_V2") != nullptr;          // two chains per CTA with in-place gradient slabs: correct, not faster
     if (!use_v2) {
         NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd::total));

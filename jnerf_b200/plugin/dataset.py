@@ -133,14 +133,15 @@ class NerfDataset(_RayBatcher):
         self._finish_init()
 
 
-def synthetic_cameras(n_images, radius=4.0, seed=0):
+def synthetic_cameras(n_images, radius=4.0, seed=0, azimuth=(0.0, 360.0), elevation=(5.0, 85.0)):
     """Camera-to-world matrices (NeRF/blender convention, looking at the origin) on a sphere of `radius`,
-    upper hemisphere like NeRF-synthetic (cf. dataset/camera_path.py:27-28 which also uses radius 4)."""
+    upper hemisphere like NeRF-synthetic (cf. dataset/camera_path.py:27-28 which also uses radius 4); `azimuth` / `elevation`
+    (degrees) restrict the cap, e.g. to the frontal arc of a hand-held capture like data/fox."""
     rng = np.random.default_rng(seed)
     mats = []
     for _ in range(n_images):
-        theta = rng.uniform(0, 2 * math.pi)
-        phi = rng.uniform(math.radians(5), math.radians(85))
+        theta = rng.uniform(math.radians(azimuth[0]), math.radians(azimuth[1]))
+        phi = rng.uniform(math.radians(elevation[0]), math.radians(elevation[1]))
         pos = radius * np.array([math.cos(theta) * math.cos(phi), math.sin(theta) * math.cos(phi), math.sin(phi)])
         fwd = -pos / np.linalg.norm(pos)                 # camera looks along -z
         right = np.cross(fwd, np.array([0, 0, 1.0]))
@@ -165,18 +166,41 @@ class SyntheticNerfDataset(_RayBatcher):
         ((0.35, -0.55, 0.45), 0.2, (0.8, 0.4, 0.85)),
     ]
     SLAB_Z, SLAB_HALF, SLAB_THICK = -0.5, 1.0, 0.08
+    # style "fox": stand-in for the reference's data/fox (BASELINE config #3) with that capture's numbers
+    # (data/fox/transforms_train.json: 1080x1920 portrait frames, fl 1375.52 / 1374.49, principal point (554.558, 965.268),
+    # aabb_scale 4, 50 frames on disk, cameras ~5.15 NeRF units from the subject in a frontal arc, opaque RGB images):
+    # the same analytic objects enlarged so that they leave the unit cube (cascades 1 and 2 of the occupancy grid fill up),
+    # seen from inside an opaque textured backdrop sphere -- every pixel has alpha 1, as in a JPEG capture.
+    FOX = dict(H=1920, W=1080, fl=(1375.52, 1374.49), c=(554.558, 965.268), aabb_scale=4, n_images=50, radius=5.15, azimuth=(-55.0, 55.0),
+               elevation=(-8.0, 30.0), obj_scale=2.2, backdrop_radius=1.9)
 
     def __init__(self, batch_size=4096, mode="train", n_images=100, H=800, W=800, camera_angle_x=0.6911112070083618, aabb_scale=1, seed=0,
-                 root_dir=None, preload_shuffle=True):
-        self.batch_size, self.mode, self.seed = batch_size, mode, seed
-        self.H, self.W, self.aabb_scale = H, W, aabb_scale
+                 root_dir=None, preload_shuffle=True, style="lego"):
+        assert style in ("lego", "fox")
+        self.batch_size, self.mode, self.seed, self.style = batch_size, mode, seed, style
         self.scale, self.offset = NERF_SCALE, [0.5, 0.5, 0.5]
-        n = n_images if mode == "train" else max(1, n_images // 10)
-        mats = synthetic_cameras(n, seed=seed + (0 if mode == "train" else 1000))
+        self.obj_scale, self.backdrop_radius = 1.0, None
+        if style == "fox":
+            F = self.FOX
+            # explicit H / W (e.g. a reduced test size) keep the capture's aspect, field of view and principal-point offsets
+            full = (H, W) in ((800, 800), (0, 0), (F["H"], F["W"]))
+            self.H, self.W = (F["H"], F["W"]) if full else (H, W)
+            k = self.W / F["W"]
+            self._focal = (F["fl"][0] * k, F["fl"][1] * self.H / F["H"])
+            self._cx, self._cy = F["c"][0] * k, F["c"][1] * self.H / F["H"]
+            self.aabb_scale = F["aabb_scale"]
+            self.obj_scale, self.backdrop_radius = F["obj_scale"], F["backdrop_radius"]
+            n_images = F["n_images"] if n_images == 100 else n_images
+            n = n_images if mode == "train" else max(1, n_images // 10)
+            mats = synthetic_cameras(n, radius=F["radius"], seed=seed + (0 if mode == "train" else 1000), azimuth=F["azimuth"], elevation=F["elevation"])
+        else:
+            self.H, self.W, self.aabb_scale = H, W, aabb_scale
+            n = n_images if mode == "train" else max(1, n_images // 10)
+            mats = synthetic_cameras(n, seed=seed + (0 if mode == "train" else 1000))
+            fx = fov_to_focal_length(W, camera_angle_x * 180 / math.pi)
+            self._focal = (fx, fx)
+            self._cx, self._cy = W / 2, H / 2
         self._xforms = [matrix_nerf2ngp(m, self.scale, self.offset) for m in mats]
-        fx = fov_to_focal_length(W, camera_angle_x * 180 / math.pi)
-        self._focal = (fx, fx)
-        self._cx, self._cy = W / 2, H / 2
         self.have_img = True
         self._finish_init()
         self.image_data = self._render_all()
@@ -201,9 +225,10 @@ class SyntheticNerfDataset(_RayBatcher):
         nrm = torch.zeros((n, 3), device=o.device)
         light = torch.tensor(self._to_ngp((0.4, -0.3, 1.0)) - 0.5, device=o.device)
         light = light / light.norm()
+        k = float(getattr(self, "obj_scale", 1.0))
         for c, r, base in self.SPHERES:
-            c_n = torch.tensor(self._to_ngp(c), device=o.device)
-            r_n = r * self.scale
+            c_n = torch.tensor(self._to_ngp(tuple(k * x for x in c)), device=o.device)
+            r_n = r * self.scale * k
             oc = o - c_n
             b = (oc * d).sum(-1)
             disc = b * b - ((oc * oc).sum(-1) - r_n * r_n)
@@ -217,8 +242,8 @@ class SyntheticNerfDataset(_RayBatcher):
             col = torch.where(hit[:, None], cc, col)
             nrm = torch.where(hit[:, None], nn_, nrm)
         # slab: axis-aligned box in NeRF world coordinates -> box in NGP coordinates
-        lo = torch.tensor(self._to_ngp((-self.SLAB_HALF, -self.SLAB_HALF, self.SLAB_Z - self.SLAB_THICK)), device=o.device)
-        hi = torch.tensor(self._to_ngp((self.SLAB_HALF, self.SLAB_HALF, self.SLAB_Z)), device=o.device)
+        lo = torch.tensor(self._to_ngp((-k * self.SLAB_HALF, -k * self.SLAB_HALF, k * (self.SLAB_Z - self.SLAB_THICK))), device=o.device)
+        hi = torch.tensor(self._to_ngp((k * self.SLAB_HALF, k * self.SLAB_HALF, k * self.SLAB_Z)), device=o.device)
         lo, hi = torch.minimum(lo, hi), torch.maximum(lo, hi)
         inv = 1.0 / d
         t0, t1 = (lo - o) * inv, (hi - o) * inv
@@ -234,6 +259,22 @@ class SyntheticNerfDataset(_RayBatcher):
         t_best = torch.where(hit, tnear, t_best)
         col = torch.where(hit[:, None], cc, col)
         nrm = torch.where(hit[:, None], bn, nrm)
+        rb = getattr(self, "backdrop_radius", None)
+        if rb is not None:
+            # opaque backdrop: the inside of a sphere of radius rb (NGP units) around the scene centre, latitude / longitude pattern
+            ctr = torch.full((3,), 0.5, device=o.device)
+            oc = o - ctr
+            b = (oc * d).sum(-1)
+            t = -b + torch.sqrt((b * b - ((oc * oc).sum(-1) - rb * rb)).clamp_min(0))
+            hit = ~torch.isfinite(t_best) & (t > 0)
+            p = o + t[:, None] * d
+            q = (p - ctr) / rb
+            lon, lat = torch.atan2(q[:, 1], q[:, 0]), torch.asin(q[:, 2].clamp(-1, 1))
+            chk = (torch.floor(lon * (12 / math.pi)) + torch.floor(lat * (12 / math.pi))) % 2
+            cc = torch.stack([0.35 + 0.25 * chk, 0.45 + 0.2 * torch.sin(3 * lat), 0.6 - 0.2 * chk], -1)
+            t_best = torch.where(hit, t, t_best)
+            col = torch.where(hit[:, None], cc, col)
+            nrm = torch.where(hit[:, None], -q, nrm)
         alpha = torch.isfinite(t_best).float()
         lam = 0.35 + 0.65 * (nrm * light).sum(-1).clamp_min(0)
         rgb = (col * lam[:, None]).clamp(0, 1) * alpha[:, None]

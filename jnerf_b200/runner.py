@@ -379,3 +379,17 @@ def lego_cfg(fp16=True, synthetic=True, **over):
     )
     c.update(over)
     return c
+
+
+def fox_cfg(fp16=True, synthetic=True, **over):
+    """projects/ngp/configs/ngp_fox.py key for key (BASELINE config #3: aabb_scale 4 from the capture's transforms, cone stepping
+    `const_dt=False`, fp16, no validation split); `synthetic` swaps data/fox for the procedural stand-in with the capture's
+    resolution, intrinsics, camera arc and aabb_scale (plugin/dataset.py: SyntheticNerfDataset(style="fox"))."""
+    c = lego_cfg(fp16=fp16, synthetic=synthetic)
+    ds_type = "SyntheticNerfDataset" if synthetic else "NerfDataset"
+    extra = dict(style="fox") if synthetic else {}
+    c.update(dataset=dict(train=dict(type=ds_type, root_dir="data/fox", batch_size=4096, mode="train", **extra),
+                          test=dict(type=ds_type, root_dir="data/fox", batch_size=4096, mode="test", preload_shuffle=False, **extra)),
+             exp_name="fox", const_dt=False)
+    c.update(over)
+    return c

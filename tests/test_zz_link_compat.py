@@ -122,3 +122,34 @@ def test_runner_checkpoint_in_the_reference_wire_format(tmp_path):
     assert torch.equal(st2.master, st.master.half().float())
     loss = r2.train_step()                                                           # and training continues
     assert torch.isfinite(loss).all()
+
+
+def test_fox_like_training_cone_stepping_and_cascades():
+    """BASELINE config #3 end to end on its synthetic stand-in (runner.fox_cfg: ngp_fox.py key for key -- aabb_scale 4, cone
+    stepping, 3-cascade grid updates, opaque frames): the fused fast path trains, outer cascades of the occupancy grid fill, and a
+    training view renders."""
+    from jnerf_b200 import ops, plugin  # noqa: F401
+    from jnerf_b200.runner import Runner, fox_cfg
+    from jnerf_b200.utils.config import get_cfg, update_cfg
+    get_cfg().clear()
+    update_cfg(**fox_cfg(fp16=True, synthetic=True, seed=4))
+    cfg = get_cfg()
+    cfg.dataset.train.n_images = 8
+    cfg.dataset.train.W, cfg.dataset.train.H = 90, 160
+    r = Runner()
+    s = r.sampler
+    assert s.const_dt is False and r.dataset["train"].aabb_scale == 4 and s.max_cascade == 2 and s.NERF_CASCADES == 5
+    assert r.model.pos_encoder.m_grid.numel() == 2 * 6537456                                  # SURVEY appendix: fox table
+    first = float(r.train_step().mean())
+    for _ in range(299):
+        loss = r.train_step()
+    last = float(loss.mean())
+    assert np.isfinite(last) and last < 0.7 * first, (first, last)
+    G3 = 128 ** 3 // 8
+    bits = s.density_grid_bitfield
+    assert int(bits[:G3].count_nonzero()) > 0 and int(bits[G3:3 * G3].count_nonzero()) > 0    # cascade 0 and cascades 1-2
+    assert ops.lib.load().ngp_debug_timeout_flag() == 0
+    img, tar = r.render_img("train", 0)
+    assert img.shape == (160, 90, 3) and torch.isfinite(img).all()
+    mse = float(((img - tar) ** 2).mean())
+    assert mse < 0.05, mse                                                                     # 300 steps on 8 tiny views: roughly right, not sharp
