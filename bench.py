@@ -216,6 +216,8 @@ def run_ours(args):
         cfg.dataset.train.H = cfg.dataset.train.W = args.res
     cfg.dataset.val = None
     cfg.dataset.train.pop("root_dir", None)
+    if args.data_dir:                      # a real capture in the reference's layout (transforms*.json + images), e.g. data/lego or data/fox
+        cfg.dataset.train = dict(type="NerfDataset", root_dir=args.data_dir, batch_size=4096, mode="train")
     runner = Runner(rank=rank, world_size=world, process_group=pg)
     ds0 = runner.dataset["train"]
     n_img, res_txt = ds0.n_images, f"{ds0.W}x{ds0.H}"
@@ -315,11 +317,12 @@ def run_ours(args):
                 "stage_ms": stage}
     out = {
         "metric": f"ngp_{args.workload}_train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+        "data": f"real: {args.data_dir}" if args.data_dir else "synthetic",
         "iters_per_s": args.steps / (ms * 1e-3), "published_iters_per_s_rtx3090": 133.0, "samples_per_s": None,
         "config": {"workload": ("Instant-NGP fox: projects/ngp/configs/ngp_fox.py (BASELINE config #3: aabb_scale 4, cone stepping, fp16 fully-fused MLP), "
                                 if fox else "Instant-NGP lego: projects/ngp/configs/ngp_base.py + fp16 fully-fused MLP (BASELINE config #2), ") +
-                               f"{n_img} synthetic {res_txt} views, target_batch_size {args.target_batch} samples/iter/GPU"
+                               f"{n_img} {'real' if args.data_dir else 'synthetic'} {res_txt} views, target_batch_size {args.target_batch} samples/iter/GPU"
                                f"{' (2^18)' if args.target_batch == 1 << 18 else ''}, adaptive ray batch "
                                f"({runner.sampler.n_rays_per_batch} rays/iter/GPU at measurement), pretrain {args.pretrain} steps",
                    "parallelism": f"dp{world}", "target_batch_size": args.target_batch,
@@ -393,6 +396,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="lego", choices=["lego", "fox"],
                     help="lego = BASELINE config #2 (the headline line); fox = config #3 (aabb_scale 4, cone stepping) on its synthetic stand-in")
+    ap.add_argument("--data-dir", default=None, help="train on a real capture in the reference's dataset layout instead of the synthetic stand-in")
     ap.add_argument("--target-batch", type=int, default=1 << 18,
                     help="target_batch_size, samples per iteration per GPU (ngp_base.py:75); BASELINE config #5 sweeps 2^16 .. 2^22 (tools/sweep.py)")
     args = ap.parse_args()

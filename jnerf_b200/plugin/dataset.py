@@ -15,6 +15,7 @@ from .. import ops
 from ..utils.registry import DATASETS
 
 NERF_SCALE = 0.33
+DEVICE = "cuda"          # where the image / pose tensors live; tests of the file parsing set this to "cpu"
 
 
 def fov_to_focal_length(resolution, degrees):
@@ -35,7 +36,7 @@ class _RayBatcher:
     """Pixel shuffling + device ray generation shared by both datasets (dataset.py:57-66,172-188)."""
 
     def _finish_init(self):
-        dev = "cuda"
+        dev = DEVICE
         self.resolution = [self.W, self.H]
         self.n_images = len(self._xforms)
         xf = np.stack(self._xforms).astype(np.float32)                       # (n,3,4)
@@ -54,7 +55,7 @@ class _RayBatcher:
     def next_pixels(self, n=None):
         n = self.batch_size if n is None else n
         if self.idx_now + n >= self.shuffle_index.shape[0]:
-            self.shuffle_index = torch.randperm(self.n_images * self.H * self.W, device="cuda", generator=self._gen).int()
+            self.shuffle_index = torch.randperm(self.n_images * self.H * self.W, device=DEVICE, generator=self._gen).int()
             self.idx_now = 0
         pix = self.shuffle_index[self.idx_now:self.idx_now + n]
         self.idx_now += n
@@ -74,7 +75,7 @@ class _RayBatcher:
 
     def generate_rays_total_test(self, img_id):
         """All rays of one image in row-major pixel order (dataset.py:214-238)."""
-        pix = torch.arange(self.H * self.W, device="cuda", dtype=torch.int32) + int(img_id) * self.H * self.W
+        pix = torch.arange(self.H * self.W, device=DEVICE, dtype=torch.int32) + int(img_id) * self.H * self.W
         _, o, d = self.rays_for(pix)
         return o, d
 
@@ -118,15 +119,20 @@ class NerfDataset(_RayBatcher):
                 self.H, self.W = im.shape[0], im.shape[1]
             imgs.append(im)
             self._xforms.append(matrix_nerf2ngp(fr["transform_matrix"], self.scale, self.offset, correct_pose))
-        self.image_data = torch.from_numpy(np.stack(imgs)).cuda().reshape(len(imgs), -1, 4)
-        if "fl_x" in json_data:
-            fx = json_data["fl_x"]
-        elif "camera_angle_x" in json_data:
-            fx = fov_to_focal_length(self.W, json_data["camera_angle_x"] * 180 / math.pi)
+        self.image_data = torch.from_numpy(np.stack(imgs)).to(DEVICE).reshape(len(imgs), -1, 4)
+        def read_focal_length(resolution, axis):                                                   # dataset.py:125-131
+            if "fl_" + axis in json_data:
+                return float(json_data["fl_" + axis])
+            if "camera_angle_" + axis in json_data:
+                return fov_to_focal_length(resolution, json_data["camera_angle_" + axis] * 180 / math.pi)
+            return 0.0
+        x_fl, y_fl = read_focal_length(self.W, "x"), read_focal_length(self.H, "y")
+        if x_fl != 0:                                                                               # :134-142
+            self._focal = (x_fl, y_fl if y_fl != 0 else x_fl)
+        elif y_fl != 0:
+            self._focal = (y_fl, y_fl)
         else:
             raise RuntimeError("Couldn't read fov.")
-        fy = json_data.get("fl_y", fx)
-        self._focal = (float(fx), float(fy))
         self._cx, self._cy = json_data.get("cx", self.W / 2), json_data.get("cy", self.H / 2)
         self.aabb_scale = json_data.get("aabb_scale", 1) if aabb_scale is None else aabb_scale
         self.have_img = have_img
@@ -211,7 +217,7 @@ class SyntheticNerfDataset(_RayBatcher):
         return p[[1, 2, 0]]
 
     def _render_all(self):
-        out = torch.empty((self.n_images, self.H * self.W, 4), dtype=torch.uint8, device="cuda")
+        out = torch.empty((self.n_images, self.H * self.W, 4), dtype=torch.uint8, device=DEVICE)
         for i in range(self.n_images):
             o, d = self.generate_rays_total_test(i)
             out[i] = (self.shade(o, d) * 255.0 + 0.5).clamp(0, 255).to(torch.uint8)
