@@ -304,7 +304,11 @@ def run_ours(args):
     n_samples = stage.pop("_samples")
     hbm, tfl, src = peaks()
     dom = max(("network_fwd", "network_bwd"), key=lambda k: stage[k])
-    algo = ALGO[dom]
+    algo = dict(ALGO[dom])
+    if runner.save_act:                   # NGP_SAVE_ACT=1: + 416 B/sample of saved activations each way; the backward no longer recomputes the forward
+        algo["bytes"] += 416
+        if dom == "network_bwd":
+            algo["flops"] -= 20480
     t_dom = stage[dom] * 1e-3
     gbs = n_samples * algo["bytes"] / t_dom / 1e9
     roofline = {"kernel": dom, "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": measured_traffic(dom),
@@ -325,7 +329,7 @@ def run_ours(args):
                                f"{n_img} {'real' if args.data_dir else 'synthetic'} {res_txt} views, target_batch_size {args.target_batch} samples/iter/GPU"
                                f"{' (2^18)' if args.target_batch == 1 << 18 else ''}, adaptive ray batch "
                                f"({runner.sampler.n_rays_per_batch} rays/iter/GPU at measurement), pretrain {args.pretrain} steps",
-                   "parallelism": f"dp{world}", "target_batch_size": args.target_batch,
+                   "parallelism": f"dp{world}", "target_batch_size": args.target_batch, "save_act": bool(runner.save_act),
                    "l2": "per-step working set (24 MB table + 171 MB optimizer state + 7 MB samples) exceeds the 126 MB L2; no explicit flush"},
         "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline,
     }
@@ -361,14 +365,12 @@ def stage_times(runner, iters):
         s.sample(img_ids, rays_o, rays_d, is_training=True)
         ev[2].record()
         coords, n_dev = s.coords_compacted, s.n_samples_dev
-        ops.network_fwd(coords, m.pos_encoder.m_grid, m.pos_encoder.levels, m.density_mlp.con_weights, m.rgb_mlp.con_weights, n_dev=n_dev,
-                        out=runner.net_out, enc=runner.enc)
+        runner.net_forward(coords, n_dev)
         ev[3].record()
         ops.composite_loss_bwd(runner.net_out, coords, s._rays_numsteps, s._rays_numsteps_compacted, bg, target, s.density_grid_mean,
                                delta=0.1, cascades=s.NERF_CASCADES, dnet=runner.dnet)
         ev[4].record()
-        ops.network_bwd(coords, runner.enc, m.pos_encoder.levels, m.density_mlp.con_weights, m.rgb_mlp.con_weights, runner.dnet, runner.grid_grad,
-                        runner.dwd, runner.dwr, n_dev=n_dev)
+        runner.net_backward(coords, n_dev)
         ev[5].record()
         adam = runner.optimizer._nested_optimizer
         runner._optimizer_step(0.0, max(adam.n_step, 1))     # lr 0: timing only, parameters barely move; N>1: + reduce-scatter / all-gather

@@ -68,6 +68,18 @@ struct SmemBwd {
 constexpr uint32_t OP_L0D = 0, OP_L1D = 2, OP_L0R = 6, OP_L1R = 8, OP_L2R = 12, OP_FWD_END = 16;
 constexpr uint32_t OP_L0D_B1 = 16;   // forward kernel only: density layer 0 reading the second enc buffer
 
+// ---- saved-activation image (optional: ngp_network_fwd_saved / ngp_network_bwd_saved) -------------------------------------
+// The backward kernel recomputes the five forward stages of every tile because storing 416 B of hidden activations per sample
+// used to look more expensive than ~10 MMAs.  Measured, the chain is bound by its per-stage latency (MMA -> commit -> TMEM load ->
+// convert -> shared store -> barrier, ~2 k cycles a stage), not by tensor or memory throughput -- so the forward kernel can
+// instead write the post-ReLU activations as a per-tile SLAB IMAGE (the byte layout of the shared-memory operand slabs, 26 groups
+// of 8 features x 128 rows) and the backward kernel copies them straight back into its slabs with 16-byte cp.async transfers that
+// are contiguous across a warp.  Values are the same fp16 numbers the recomputation would produce: results are unchanged.
+//   image groups: hd [0,8) | h = density output, the first 16 colour-net inputs [8,10) | h1 [10,18) | h2 [18,26)
+// (the 16 SH inputs are recomputed from the direction: 3 loads and ~50 flops instead of 32 B).
+constexpr uint32_t IMG_HD = 0, IMG_H = 8, IMG_H1 = 10, IMG_H2 = 18, IMG_GROUPS = 26;
+constexpr uint32_t IMG_TILE_BYTES = IMG_GROUPS * GB;          // 53 248 B per 128-sample tile = 416 B per sample
+
 template <class S>
 __device__ __forceinline__ void stage_all_weights(uint8_t* smem, const __half* wd, const __half* wr, uint32_t t) {
     stage_weights(smem + S::w0d, wd + WD_W0, 64, 32, t, 128);
@@ -133,16 +145,17 @@ __device__ __forceinline__ void build_forward_program(uint8_t* smem, uint32_t tb
 
 // Forward chain up to (and including) the colour net's last hidden layer.  Expects enc in ACT[G_ENC..+4).
 // Returns the fp16 density output h[0] of row t (sigma_raw) and leaves hd / rin / h1 / h2 in the slab.
-template <uint32_t G_H2, bool CHAIN128 = false>
+template <uint32_t G_H2, bool CHAIN128 = false, bool SAVE = false>
 __device__ __forceinline__ uint32_t forward_chain(uint8_t* smem, uint32_t act_off, const MmaOp* ops, uint32_t op_l0d,
                                                   const float* s_coords, uint32_t tbase, Pipe& pipe, uint32_t t, uint32_t warp,
-                                                  bool density_only, uint32_t chain_bar = 1) {
+                                                  bool density_only, uint32_t chain_bar = 1, uint8_t* __restrict__ img = nullptr) {
     uint8_t* act = smem + act_off;
     const uint32_t D_H = 0, D_S = 64;
     // density L0: enc(32) -> hd(64)
     if (t == 0) { run_ops(ops, op_l0d, 2, 0); pipe.commit(); }
     pipe.wait();
-    epi_hidden_relu(tbase, D_H, warp, act, G_HD, t, nullptr);
+    if constexpr (SAVE) epi_hidden_relu_img(tbase, D_H, warp, act, G_HD, t, img, IMG_HD);
+    else epi_hidden_relu(tbase, D_H, warp, act, G_HD, t, nullptr);
     if constexpr (CHAIN128) sync_chain(chain_bar); else sync_before_issue<false>();
     // density L1: hd(64) -> h(16)
     if (t == 0) { run_ops(ops, OP_L1D, 4, 0); pipe.commit(); }
@@ -156,6 +169,10 @@ __device__ __forceinline__ uint32_t forward_chain(uint8_t* smem, uint32_t act_of
         sigma_half = lo.x & 0xFFFFu;
         if (density_only) return sigma_half;
         slab_store16(act, G_RIN, t, lo, hi);
+        if constexpr (SAVE) {
+            *reinterpret_cast<uint4*>(img + (size_t)IMG_H * GB + t * 16) = lo;
+            *reinterpret_cast<uint4*>(img + (size_t)(IMG_H + 1) * GB + t * 16) = hi;
+        }
         float sh[16];
         sh4(s_coords[t * 7 + 4], s_coords[t * 7 + 5], s_coords[t * 7 + 6], sh);
         pack16(sh, lo, hi);
@@ -165,12 +182,14 @@ __device__ __forceinline__ uint32_t forward_chain(uint8_t* smem, uint32_t act_of
     // colour L0: [h | sh](32) -> h1(64)
     if (t == 0) { run_ops(ops, OP_L0R, 2, 0); pipe.commit(); }
     pipe.wait();
-    epi_hidden_relu(tbase, D_H, warp, act, G_H1, t, nullptr);
+    if constexpr (SAVE) epi_hidden_relu_img(tbase, D_H, warp, act, G_H1, t, img, IMG_H1);
+    else epi_hidden_relu(tbase, D_H, warp, act, G_H1, t, nullptr);
     if constexpr (CHAIN128) sync_chain(chain_bar); else sync_before_issue<false>();
     // colour L1: h1(64) -> h2(64)
     if (t == 0) { run_ops(ops, OP_L1R, 4, 0); pipe.commit(); }
     pipe.wait();
-    epi_hidden_relu(tbase, D_H, warp, act, G_H2, t, nullptr);
+    if constexpr (SAVE) epi_hidden_relu_img(tbase, D_H, warp, act, G_H2, t, img, IMG_H2);
+    else epi_hidden_relu(tbase, D_H, warp, act, G_H2, t, nullptr);
     if constexpr (CHAIN128) sync_chain(chain_bar); else sync_before_issue<false>();
     return sigma_half;
 }
@@ -184,11 +203,11 @@ __device__ __forceinline__ uint32_t forward_chain(uint8_t* smem, uint32_t act_of
 constexpr int FWD_GW = 8;
 constexpr int FWD_THREADS = 128 + 32 * FWD_GW;
 
-template <bool DENSITY_ONLY>
+template <bool DENSITY_ONLY, bool SAVE_ACT = false>
 __global__ void __launch_bounds__(FWD_THREADS)
 network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const float* __restrict__ coords, const __half* __restrict__ grid,
                    const NgpLevel* __restrict__ levels, const __half* __restrict__ wd, const __half* __restrict__ wr,
-                   __half* __restrict__ out, __half* __restrict__ enc_save, int* __restrict__ err) {
+                   __half* __restrict__ out, __half* __restrict__ enc_save, int* __restrict__ err, uint8_t* __restrict__ act_img = nullptr) {
     extern __shared__ __align__(1024) uint8_t smem[];
     using S = SmemFwd;
     constexpr int CS = DENSITY_ONLY ? 3 : 7;
@@ -229,7 +248,8 @@ network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             tc_fence_after();
             // forward_chain releases nothing itself: the enc slab is dead after layer 0, the coordinates after the SH epilogue;
             // both are handed back together right after the chain (the gather runs a full tile ahead, so this is not on its path)
-            const uint32_t sig = forward_chain<G_H2F, true>(smem, S::act, ops, buf ? OP_L0D_B1 : OP_L0D, s_coords, tbase, pipe, t, warp, DENSITY_ONLY);
+            const uint32_t sig = forward_chain<G_H2F, true, SAVE_ACT>(smem, S::act, ops, buf ? OP_L0D_B1 : OP_L0D, s_coords, tbase, pipe, t, warp, DENSITY_ONLY,
+                                                                      1, SAVE_ACT ? act_img + (size_t)tile * IMG_TILE_BYTES : nullptr);
             if (tile + 2 * gridDim.x < ntiles) named_bar_arrive(4 + buf, FWD_THREADS);   // EMPTY[buf]
             if constexpr (DENSITY_ONLY) {
                 if (row < n_live) reinterpret_cast<uint16_t*>(out)[row] = (uint16_t)sig;
@@ -277,11 +297,21 @@ network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
 // Scatter warps: 4 (16-sample runs).  Measured on the lego stand-in, us per backward: 2 warps x 32-sample runs 294, 4 x 16 177,
 // 8 x 8 209, 8 warps x 16-sample runs with the cell's corners split over two threads 250 -- longer runs save atomics, but more
 // scatter warps starve the MLP chain, which is the critical path of this kernel.
+//
+// SAVED = true (ngp_network_bwd_saved): the five forward stages are not recomputed; the post-ReLU activations come back from the
+// slab image the forward kernel wrote (see IMG_* above) through 26 coalesced 16-byte cp.async copies per thread, the SH inputs
+// are recomputed from the direction.  Everything from stage B1 on is the same code.
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src_global) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(__cvta_generic_to_global(src_global)) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <bool SAVED>
 __global__ void __launch_bounds__(256)
 network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const float* __restrict__ coords, const __half* __restrict__ enc_save,
                    const NgpLevel* __restrict__ levels, const __half* __restrict__ wd, const __half* __restrict__ wr,
                    const __half* __restrict__ dout, __half* __restrict__ grid_grad, float* __restrict__ dwd, float* __restrict__ dwr,
-                   int* __restrict__ err, uint32_t dbg) {
+                   int* __restrict__ err, uint32_t dbg, const uint8_t* __restrict__ act_img) {
     extern __shared__ __align__(1024) uint8_t smem[];
     using S = SmemBwd;
     const uint32_t t = threadIdx.x, warp = t >> 5;
@@ -344,6 +374,7 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
         float pf_c[7];
         uint4 pf_e[4];
         uint2 pf_d;
+        float pf_dir[3] = {0.f, 0.f, 0.f};                   // SAVED only: this row's direction (SH inputs are recomputed)
         auto prefetch = [&](uint32_t tile_) {
             const uint32_t r0 = tile_ * ROWS, r = r0 + t;
             const bool ok = r < n_live;
@@ -356,6 +387,10 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
 #pragma unroll
             for (int g = 0; g < 4; ++g) pf_e[g] = ok ? __ldg(es + g) : make_uint4(0, 0, 0, 0);
             pf_d = ok ? __ldg(reinterpret_cast<const uint2*>(dout) + r) : make_uint2(0, 0);
+            if constexpr (SAVED) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) pf_dir[k] = ok ? __ldg(coords + (size_t)r * 7 + 4 + k) : 0.f;
+            }
         };
         if (blockIdx.x < ntiles) prefetch(blockIdx.x);
         uint32_t it = 0;
@@ -371,11 +406,27 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(act + (G_ENC + g) * GB + t * 16) = pf_e[g];
             const uint32_t dsig = pf_d.y >> 16;
             *reinterpret_cast<uint4*>(grd + Q_DYR * GB + t * 16) = make_uint4(pf_d.x, pf_d.y & 0xFFFFu, 0, 0);
+            if constexpr (SAVED) {
+                // saved activations: image groups -> the slab groups the recomputation would have filled (hd | h | h1 | h2)
+                const uint8_t* src = act_img + (size_t)tile * IMG_TILE_BYTES + t * 16;
+                const uint32_t dst = smem_u32(act) + t * 16;
+#pragma unroll
+                for (uint32_t g = 0; g < IMG_GROUPS; ++g) {
+                    const uint32_t sg = g < IMG_H ? G_HD + g : g < IMG_H1 ? G_RIN + (g - IMG_H) : g < IMG_H2 ? G_H1 + (g - IMG_H1) : G_H2B + (g - IMG_H2);
+                    cp_async16(dst + sg * GB, src + (size_t)g * GB);
+                }
+                float sh[16];                                            // colour-net inputs 16..31 (ngp_network.py:79,82)
+                sh4(pf_dir[0], pf_dir[1], pf_dir[2], sh);
+                uint4 lo, hi;
+                pack16(sh, lo, hi);
+                slab_store16(act, G_RIN + 2, t, lo, hi);
+            }
             if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x);   // in flight during the whole chain
             DBGB(1);
+            if constexpr (SAVED) cp_async_wait_all();
             sync_before_issue<true>();
             DBGB(2);
-            forward_chain<G_H2B, true>(smem, S::act, ops, OP_L0D, s_coords, tbase, pipe, t, warp, false);
+            if constexpr (!SAVED) forward_chain<G_H2B, true>(smem, S::act, ops, OP_L0D, s_coords, tbase, pipe, t, warp, false);
             DBGB(3);
             // B1: g_h2 = (dYr Woutr) . relu'(h2) ; wgrad Woutr
             if (t == 0) { run_ops(ops, OP_B1, 1, acc); DBGB(4); pipe.commit(); }
@@ -846,6 +897,43 @@ int ngp_network_fwd(void* stream, uint32_t n_max, const uint32_t* n_dev, const f
     return 0;
 }
 
+// Saved-activation pair (see IMG_* above): the forward also writes the per-tile activation image, the backward reads it instead of
+// recomputing the forward chain.  act_save: ngp_network_act_bytes(n_max) bytes, 16-byte aligned, written for every tile that holds
+// a live row.  Results equal ngp_network_fwd / ngp_network_bwd (the image holds the same fp16 values the recomputation produces).
+uint64_t ngp_network_act_bytes(uint32_t n_max) { return (uint64_t)((n_max + ROWS - 1) / ROWS) * IMG_TILE_BYTES; }
+
+int ngp_network_fwd_saved(void* stream, uint32_t n_max, const uint32_t* n_dev, const float* coords, const void* grid, const void* levels_dev,
+                          const void* w_density, const void* w_rgb, void* out, void* enc_save, void* act_save) {
+    NGP_REQUIRE(act_save != nullptr && enc_save != nullptr, "ngp_network_fwd_saved: enc_save and act_save are required");
+    if (n_max == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    NGP_CHECK_CUDA(cudaFuncSetAttribute(network_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemFwd::total));
+    const uint32_t ntiles = (n_max + ROWS - 1) / ROWS;
+    const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms() * 2u);
+    network_fwd_kernel<false, true><<<grid_dim, FWD_THREADS, SmemFwd::total, s>>>(n_max, n_dev, coords, (const __half*)grid, (const NgpLevel*)levels_dev,
+                                                                                 (const __half*)w_density, (const __half*)w_rgb, (__half*)out,
+                                                                                 (__half*)enc_save, ngp_err_flag(), (uint8_t*)act_save);
+    NGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int ngp_network_bwd_saved(void* stream, uint32_t n_max, const uint32_t* n_dev, const float* coords, const void* enc_save, const void* act_save,
+                          const void* levels_dev, const void* w_density, const void* w_rgb, const void* dout, void* grid_grad,
+                          float* dw_density, float* dw_rgb) {
+    NGP_REQUIRE(act_save != nullptr, "ngp_network_bwd_saved: act_save is required");
+    if (n_max == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t ntiles = (n_max + ROWS - 1) / ROWS;
+    static const uint32_t dbg = getenv("NGP_BWD_DEBUG") ? (uint32_t)atoi(getenv("NGP_BWD_DEBUG")) : 0u;
+    NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd::total));
+    const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms());
+    network_bwd_kernel<true><<<grid_dim, 256, SmemBwd::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
+                                                                  (const __half*)w_density, (const __half*)w_rgb, (const __half*)dout,
+                                                                  (__half*)grid_grad, dw_density, dw_rgb, ngp_err_flag(), dbg, (const uint8_t*)act_save);
+    NGP_LAUNCH_CHECK();
+    return 0;
+}
+
 int ngp_density_fwd(void* stream, uint32_t n, const float* pos, const void* grid, const void* levels_dev, const void* w_density, void* sigma_out) {
     if (n == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
@@ -867,11 +955,11 @@ int ngp_network_bwd(void* stream, uint32_t n_max, const uint32_t* n_dev, const f
     static const uint32_t dbg = getenv("NGP_BWD_DEBUG") ? (uint32_t)atoi(getenv("NGP_BWD_DEBUG")) : 0u;
     static const bool use_v2 = getenv("NGP_BWD_V2") != nullptr;          // two chains per CTA with in-place gradient slabs: correct, not faster
     if (!use_v2) {
-        NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd::total));
+        NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd::total));
         const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms());
-        network_bwd_kernel<<<grid_dim, 256, SmemBwd::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
-                                                                (const __half*)w_density, (const __half*)w_rgb, (const __half*)dout,
-                                                                (__half*)grid_grad, dw_density, dw_rgb, ngp_err_flag(), dbg);
+        network_bwd_kernel<false><<<grid_dim, 256, SmemBwd::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
+                                                                       (const __half*)w_density, (const __half*)w_rgb, (const __half*)dout,
+                                                                       (__half*)grid_grad, dw_density, dw_rgb, ngp_err_flag(), dbg, nullptr);
     } else {
         NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd2::total));
         const uint32_t grid_dim = min((ntiles + BW2_GROUPS - 1) / BW2_GROUPS, (uint32_t)ngp_num_sms());

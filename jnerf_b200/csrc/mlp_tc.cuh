@@ -130,6 +130,27 @@ static __device__ __noinline__ void epi_hidden_relu(uint32_t tbase, uint32_t dco
         }
     }
 }
+// Same, and the 8 groups are also written to global memory as a SLAB IMAGE: img + (g_img + k) * GB + t * 16 for k = 0..7 -- the
+// byte layout of the shared-memory slab itself, so that a later kernel can copy whole groups back with 16-byte transfers that are
+// contiguous across the threads of a warp (the saved-activation backward, fused_net.cu).
+static __device__ __noinline__ void epi_hidden_relu_img(uint32_t tbase, uint32_t dcol, uint32_t warp, uint8_t* slab, uint32_t g0, uint32_t t,
+                                                    uint8_t* __restrict__ img, uint32_t g_img) {
+    uint32_t r[4][16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tmem_ld16_nowait(tmem_addr(tbase, warp & 3, dcol + 16 * c), r[c]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(__uint_as_float(r[c][i]), 0.f);
+        uint4 lo, hi;
+        pack16(v, lo, hi);
+        slab_store16(slab, g0 + 2 * c, t, lo, hi);
+        *reinterpret_cast<uint4*>(img + (size_t)(g_img + 2 * c) * GB + t * 16) = lo;
+        *reinterpret_cast<uint4*>(img + (size_t)(g_img + 2 * c + 1) * GB + t * 16) = hi;
+    }
+}
 // dgrad epilogue: D[:, 0..64) -> fp16 -> masked by ReLU'(act) -> grad slab groups [g0,g0+8); optional global copy.
 static __device__ __noinline__ void epi_dgrad_mask(uint32_t tbase, uint32_t dcol, uint32_t warp, const uint8_t* act_slab, uint32_t ga,
                                                uint8_t* grd_slab, uint32_t g0, uint32_t t, __half* gdst) {

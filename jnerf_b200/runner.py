@@ -70,6 +70,10 @@ class Runner:
         self.last_loss = None
         self.last_rgb = None
         self._table_work = None
+        # NGP_SAVE_ACT=1: the forward kernel also writes the MLP activations (416 B/sample) and the backward kernel reads them back
+        # instead of recomputing the five forward stages (ngp_network_fwd_saved / ngp_network_bwd_saved; same results)
+        self.save_act = os.environ.get("NGP_SAVE_ACT", "0") == "1"
+        self.act = ops.network_act_buffer(cap) if self.save_act else None
         if self.world_size > 1:
             self._init_sharded_table()
 
@@ -192,12 +196,10 @@ class Runner:
         s.sample(img_ids, rays_o, rays_d, is_training=True, ray_index_offset=dp.shard_range(R, self.rank)[0])  # grid update /16, march, bookkeeping
         self._table_ready()
         coords, n_dev = s.coords_compacted, s.n_samples_dev
-        ops.network_fwd(coords, m.pos_encoder.m_grid, m.pos_encoder.levels, m.density_mlp.con_weights, m.rgb_mlp.con_weights,
-                        n_dev=n_dev, out=self.net_out, enc=self.enc)
+        self.net_forward(coords, n_dev)
         rgb, loss, _ = ops.composite_loss_bwd(self.net_out, coords, s._rays_numsteps, s._rays_numsteps_compacted, bg, target.contiguous(),
                                               s.density_grid_mean, delta=self.loss_func.delta, cascades=s.NERF_CASCADES, dnet=self.dnet)
-        ops.network_bwd(coords, self.enc, m.pos_encoder.levels, m.density_mlp.con_weights, m.rgb_mlp.con_weights, self.dnet,
-                        self.grid_grad, self.dwd, self.dwr, n_dev=n_dev)
+        self.net_backward(coords, n_dev)
         # local loss_scale is 128/R_local (calc_rgb.h:100-101): the all-reduced sum is W x the global-batch gradient
         lr = self.optimizer.advance_lr()
         adam = self.optimizer._nested_optimizer
@@ -207,6 +209,26 @@ class Runner:
         self.last_loss, self.last_rgb = loss, rgb
         cfg.m_training_step = i + 1
         return loss
+
+    def net_forward(self, coords, n_dev):
+        """Fused hash encode + SH + both MLPs on the sampler's coordinate rows -> self.net_out (+ self.enc, + self.act when saving)."""
+        m = self.model
+        if self.save_act:
+            ops.network_fwd_saved(coords, m.pos_encoder.m_grid, m.pos_encoder.levels, m.density_mlp.con_weights, m.rgb_mlp.con_weights, self.act,
+                                  n_dev=n_dev, out=self.net_out, enc=self.enc)
+        else:
+            ops.network_fwd(coords, m.pos_encoder.m_grid, m.pos_encoder.levels, m.density_mlp.con_weights, m.rgb_mlp.con_weights,
+                            n_dev=n_dev, out=self.net_out, enc=self.enc)
+
+    def net_backward(self, coords, n_dev):
+        """self.dnet -> gradients of the hash table (self.grid_grad) and of both weight vectors (self.dwd, self.dwr)."""
+        m = self.model
+        if self.save_act:
+            ops.network_bwd_saved(coords, self.enc, self.act, m.pos_encoder.levels, m.density_mlp.con_weights, m.rgb_mlp.con_weights, self.dnet,
+                                  self.grid_grad, self.dwd, self.dwr, n_dev=n_dev)
+        else:
+            ops.network_bwd(coords, self.enc, m.pos_encoder.levels, m.density_mlp.con_weights, m.rgb_mlp.con_weights, self.dnet,
+                            self.grid_grad, self.dwd, self.dwr, n_dev=n_dev)
 
     def _optimizer_step(self, lr, n_step):
         """Gradient exchange + fused Adam/EMA sweep(s) (optims/adam.py + ema.py; runner.py:75-76)."""
