@@ -438,12 +438,41 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             sync_before_issue<true>();
             DBGB(7);
             // B2: g_h1 = (g_h2 W1r) . relu'(h1) ; wgrad W1r
-            if (t == 0) { run_ops(ops, OP_B2, 4, acc); DBGB(8); pipe.commit(); }
+            if (t == 0) { run_ops(ops, OP_B2, 4, acc); DBGB(8); pipe.commit(); DBGB(21); }
             if (t == 32) { if (!(dbg & 4)) run_ops(ops, OP_B2 + 4, 8, acc); mma_commit(bar_w); }   // weight gradient: issued by a second thread, off the critical path
             pipe.wait();
             DBGB(9);
+#ifdef NGP_TIMELINE
+            {   // timeline builds only: epi_dgrad_mask + sync_before_issue of this stage spelled out, one stamp per step (16..20)
+                uint32_t r[4][16];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) tmem_ld16_nowait(tmem_addr(tbase, warp & 3, D_H + 16 * c), r[c]);
+                DBGB(16);
+                tmem_ld_wait();
+                DBGB(17);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[c][i]);
+                    uint4 lo, hi;
+                    pack16(v, lo, hi);
+                    lo = relu_mask8(lo, slab_load8(act, G_H1 + 2 * c, t));
+                    hi = relu_mask8(hi, slab_load8(act, G_H1 + 2 * c + 1, t));
+                    slab_store16(grd, Q_GH1 + 2 * c, t, lo, hi);
+                }
+                DBGB(18);
+                tc_fence_before();
+                fence_proxy_async_smem();
+                DBGB(19);
+                named_bar_sync(1, 128);
+                DBGB(20);
+                tc_fence_after();
+            }
+#else
             epi_dgrad_mask(tbase, D_H, warp, act, G_H1, grd, Q_GH1, t, nullptr);
             sync_before_issue<true>();
+#endif
             DBGB(10);
             // B3: d_rin = g_h1 W0r (32 cols; the last 16 are dL/dSH, unused) ; wgrad W0r
             if (t == 0) { run_ops(ops, OP_B3, 4, acc); pipe.commit(); }

@@ -16,3 +16,8 @@ torch.cuda.synchronize()
 h = np.zeros(64, np.int64); l = lib.load(); l.ngp_debug_read_timeline_bwd.argtypes = [C.c_void_p]; l.ngp_debug_read_timeline_bwd(h.ctypes.data)
 names = ['start', 'loads issued', 'sync', 'fwd chain (4 stages)', 'B1 issued', 'B1 waited', 'B1 epi', 'B1 sync', 'B2 issued', 'B2 waited', 'B2 epi+sync', 'B3..B5', 'scatter']
 for i in range(1, 13): print(f'  {names[i]:22s} +{h[i]-h[i-1]:7d}   (t={h[i]-h[0]})')
+print('B2 stage in detail (thread 0 of CTA 0; commit -> flip includes the MMA execution):')
+fine = [('B1 sync done -> 4 dgrad MMAs issued', 7, 8), ('tcgen05.commit issued', 8, 21), ('commit -> mbarrier flip observed (pipe.wait)', 21, 9),
+        ('4 x tcgen05.ld issued', 9, 16), ('tcgen05.wait::ld', 16, 17), ('convert + ReLU mask (8 LDS) + 8 STS', 17, 18),
+        ('tcgen05.fence + fence.proxy.async', 18, 19), ('named barrier (128 threads)', 19, 20)]
+for name, a, b in fine: print(f'  {name:48s} {h[b]-h[a]:7d}')
