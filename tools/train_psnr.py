@@ -23,6 +23,10 @@ def main():
     ap.add_argument("--evals", default="250,500,1000,2000,3500,5000")
     ap.add_argument("--val-images", type=int, default=4)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--budget-seconds", type=float, default=0.0,
+                    help="BASELINE metric 'PSNR@5min': keep training after --steps until this much device time has been spent on training "
+                         "steps or the configuration's tot_train_steps (40 000, ngp_base.py) is reached, then evaluate once more")
+    ap.add_argument("--data-dir", default=None, help="a real capture in the reference's dataset layout (train/val splits) instead of the stand-in")
     args = ap.parse_args()
 
     import torch
@@ -40,6 +44,9 @@ def main():
         d.H = d.W = args.res
         d.pop("root_dir", None)
     cfg.dataset.test = None
+    if args.data_dir:
+        for split in ("train", "val"):
+            cfg.dataset[split] = dict(type="NerfDataset", root_dir=args.data_dir, batch_size=4096, mode=split, preload_shuffle=split == "train")
     runner = Runner()
     evals = sorted({int(x) for x in args.evals.split(",") if int(x) <= args.steps} | {args.steps})
     rows, train_ms, done = [], 0.0, 0
@@ -61,6 +68,24 @@ def main():
         rows.append(row)
         print(json.dumps(row), flush=True)
     res = {"config": f"ngp_base + fp16, {args.images} synthetic {args.res}x{args.res} views, {args.val_images} held-out views", "curve": rows}
+    if args.data_dir:
+        res["config"] = f"ngp_base + fp16 on {args.data_dir}, {args.val_images} validation views"
+    if args.budget_seconds > 0:
+        tot = int(cfg.tot_train_steps or 40000)
+        while train_ms * 1e-3 < args.budget_seconds and done < tot:
+            n = min(1000, tot - done)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(n):
+                runner.train_step()
+            e1.record()
+            torch.cuda.synchronize()
+            train_ms += e0.elapsed_time(e1)
+            done += n
+        psnr = runner.psnr("val", max_images=args.val_images)
+        res["psnr_at_budget"] = {"budget_seconds": args.budget_seconds, "steps": done, "train_seconds": round(train_ms * 1e-3, 3),
+                                 "val_psnr_db": round(psnr, 3), "stopped_by": "tot_train_steps" if done >= tot else "budget"}
+        print(json.dumps(res["psnr_at_budget"]), flush=True)
     if args.out:
         os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
         json.dump(res, open(args.out, "w"), indent=1)
