@@ -306,14 +306,15 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src_gl
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <bool SAVED>
-__global__ void __launch_bounds__(256)
+template <bool SAVED, int SW = 4>                 // SW = scatter warps (4: 16-sample runs per thread; 8: 8-sample runs)
+__global__ void __launch_bounds__(128 + 32 * SW)
 network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const float* __restrict__ coords, const __half* __restrict__ enc_save,
                    const NgpLevel* __restrict__ levels, const __half* __restrict__ wd, const __half* __restrict__ wr,
                    const __half* __restrict__ dout, __half* __restrict__ grid_grad, float* __restrict__ dwd, float* __restrict__ dwr,
                    int* __restrict__ err, uint32_t dbg, const uint8_t* __restrict__ act_img) {
     extern __shared__ __align__(1024) uint8_t smem[];
     using S = SmemBwd;
+    constexpr uint32_t NT = 128 + 32 * SW;                 // threads per CTA
     const uint32_t t = threadIdx.x, warp = t >> 5;
     const bool is_chain = warp < 4;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::bar);
@@ -322,14 +323,14 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
     uint8_t* act = smem + S::act;
     uint8_t* grd = smem + S::grd;
 
-    stage_weights(smem + S::w0d, wd + WD_W0, 64, 32, t, 256);
-    stage_weights(smem + S::woutd, wd + WD_WOUT, 16, 64, t, 256);
-    stage_weights(smem + S::w0r, wr + WR_W0, 64, 32, t, 256);
-    stage_weights(smem + S::w1r, wr + WR_W1, 64, 64, t, 256);
-    stage_weights(smem + S::woutr, wr + WR_WOUT, 16, 64, t, 256);
+    stage_weights(smem + S::w0d, wd + WD_W0, 64, 32, t, NT);
+    stage_weights(smem + S::woutd, wd + WD_WOUT, 16, 64, t, NT);
+    stage_weights(smem + S::w0r, wr + WR_W0, 64, 32, t, NT);
+    stage_weights(smem + S::w1r, wr + WR_W1, 64, 64, t, NT);
+    stage_weights(smem + S::woutr, wr + WR_WOUT, 16, 64, t, NT);
     if (t < N_LEVELS) s_lv[t] = levels[t];
     // dYr columns 4..15, the dYd pad groups: zero once (never rewritten)
-    for (uint32_t i = t; i < Q_TOTAL * GB / 16; i += 256) *reinterpret_cast<uint4*>(grd + i * 16) = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = t; i < Q_TOTAL * GB / 16; i += NT) *reinterpret_cast<uint4*>(grd + i * 16) = make_uint4(0, 0, 0, 0);
     uint64_t* bar_w = bar + 2;                                   // completes when the 5 wgrad batches of a tile are done
     if (t == 0) { mbar_init(bar, 1); mbar_init(bar_w, 5); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(tmem_ptr, 512);
@@ -397,7 +398,7 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
         for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, acc = 1, ++it) {
             const uint32_t buf = it & 1;
             float* s_coords = reinterpret_cast<float*>(smem + S::coords + buf * 3584);
-            if (it >= 2) named_bar_sync(4 + buf, 256);          // the scatter of tile it-2 has released coords[buf] / d_enc[buf]
+            if (it >= 2) named_bar_sync(4 + buf, NT);          // the scatter of tile it-2 has released coords[buf] / d_enc[buf]
             if (it >= 1) { if (!mbar_wait(bar_w, (it - 1) & 1)) atomicExch(err, 2); }   // the previous tile's wgrad MMAs have read their slabs
             DBGB(0);
 #pragma unroll
@@ -508,7 +509,7 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
                 slab_store16(grd, Q_DENC + 4 * buf + 2, t, lo, hi);
             }
             tc_fence_before();
-            named_bar_arrive(2 + buf, 256);                      // FULL[buf]: dL/d(enc) and coords of this tile are ready
+            named_bar_arrive(2 + buf, NT);                      // FULL[buf]: dL/d(enc) and coords of this tile are ready
             DBGB(11);
         }
         // flush weight gradients (lane = input feature, column = output feature)
@@ -544,13 +545,14 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
         for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const uint32_t buf = it & 1, row0 = tile * ROWS;
             const float* s_coords = reinterpret_cast<const float*>(smem + S::coords + buf * 3584);
-            named_bar_sync(2 + buf, 256);                        // FULL[buf]
+            named_bar_sync(2 + buf, NT);                        // FULL[buf]
             uint32_t cgx = 0xffffffffu, cgy = 0, cgz = 0, idx[8];
             float2 accv[8];
             bool dirty = false;
 #pragma unroll 1
-            for (int k = 0; k < 16; ++k) {
-                const uint32_t p = 16 * sub + k;
+            constexpr int PTS = 64 / SW;                         // consecutive samples per scatter thread
+            for (int k = 0; k < PTS; ++k) {
+                const uint32_t p = PTS * sub + k;
                 if (row0 + p >= n_live || (dbg & 2)) break;
                 const __half2 d = *reinterpret_cast<const __half2*>(grd + (size_t)(Q_DENC + 4 * buf + (level >> 2)) * GB + p * 16 + (level & 3) * 4);
                 const float2 df = __half22float2(d);
@@ -576,7 +578,7 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
 #pragma unroll
                 for (int c = 0; c < 8; ++c) atomicAdd(gg + idx[c], __floats2half2_rn(accv[c].x, accv[c].y));
             }
-            if (tile + 2 * gridDim.x < ntiles) named_bar_arrive(4 + buf, 256);   // EMPTY[buf] for the chain's tile it+2
+            if (tile + 2 * gridDim.x < ntiles) named_bar_arrive(4 + buf, NT);   // EMPTY[buf] for the chain's tile it+2
         }
     }
     tc_fence_before();
@@ -954,11 +956,20 @@ int ngp_network_bwd_saved(void* stream, uint32_t n_max, const uint32_t* n_dev, c
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t ntiles = (n_max + ROWS - 1) / ROWS;
     static const uint32_t dbg = getenv("NGP_BWD_DEBUG") ? (uint32_t)atoi(getenv("NGP_BWD_DEBUG")) : 0u;
-    NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd::total));
+    // experiment knob: with half as many chain stages per tile the scatter side may want 8 warps (it lost with the recomputing chain)
+    static const bool sw8 = getenv("NGP_BWD_SCATTER_WARPS") && atoi(getenv("NGP_BWD_SCATTER_WARPS")) == 8;
     const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms());
-    network_bwd_kernel<true><<<grid_dim, 256, SmemBwd::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
-                                                                  (const __half*)w_density, (const __half*)w_rgb, (const __half*)dout,
-                                                                  (__half*)grid_grad, dw_density, dw_rgb, ngp_err_flag(), dbg, (const uint8_t*)act_save);
+    if (!sw8) {
+        NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd::total));
+        network_bwd_kernel<true, 4><<<grid_dim, 256, SmemBwd::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
+                                                                         (const __half*)w_density, (const __half*)w_rgb, (const __half*)dout,
+                                                                         (__half*)grid_grad, dw_density, dw_rgb, ngp_err_flag(), dbg, (const uint8_t*)act_save);
+    } else {
+        NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd::total));
+        network_bwd_kernel<true, 8><<<grid_dim, 384, SmemBwd::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
+                                                                         (const __half*)w_density, (const __half*)w_rgb, (const __half*)dout,
+                                                                         (__half*)grid_grad, dw_density, dw_rgb, ngp_err_flag(), dbg, (const uint8_t*)act_save);
+    }
     NGP_LAUNCH_CHECK();
     return 0;
 }
@@ -984,9 +995,9 @@ int ngp_network_bwd(void* stream, uint32_t n_max, const uint32_t* n_dev, const f
     static const uint32_t dbg = getenv("NGP_BWD_DEBUG") ? (uint32_t)atoi(getenv("NGP_BWD_DEBUG")) : 0u;
     static const bool use_v2 = getenv("NGP_BWD_V2") != nullptr;          // two chains per CTA with in-place gradient slabs: correct, not faster
     if (!use_v2) {
-        NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd::total));
+        NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd::total));
         const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms());
-        network_bwd_kernel<false><<<grid_dim, 256, SmemBwd::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
+        network_bwd_kernel<false, 4><<<grid_dim, 256, SmemBwd::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
                                                                        (const __half*)w_density, (const __half*)w_rgb, (const __half*)dout,
                                                                        (__half*)grid_grad, dw_density, dw_rgb, ngp_err_flag(), dbg, nullptr);
     } else {
