@@ -8,6 +8,7 @@
 // NerfCoordinate rows.  No 117 MB memset (DGS/ray_sampler.py:50), no host sync (:65,70).
 #include "ngp_common.cuh"
 #include <cfloat>
+#include <cstdlib>
 
 namespace {
 
@@ -118,7 +119,10 @@ __device__ __forceinline__ RayState ray_setup(uint32_t i, const float* __restric
 constexpr uint32_t MARCH_MAXC = 80;      // chunks (of 32 steps) recorded per ray by the count pass: 2560 steps >= sqrt(3)/min_dt
 struct ChunkRec { float t0; uint32_t mask; };
 
-template <bool EMIT>
+// PIPE (count pass, opt-in through NGP_MARCH_PIPE=1, not yet measured): the 31 dependent additions that produce the NEXT chunk's
+// t values do not depend on this chunk's occupancy bits, so they are issued between the bitfield load and its first use -- same
+// additions in the same order per lane, only scheduled under the L2 latency of the lookup.
+template <bool EMIT, bool PIPE = false>
 __device__ __forceinline__ uint32_t march_ray_warp(const RayState& r, float lo, float hi, float cone, const MarchCfg& c,
                                                    const uint8_t* __restrict__ bits, uint32_t limit, float* __restrict__ out,
                                                    ChunkRec* __restrict__ rec = nullptr, uint32_t* __restrict__ n_chunks = nullptr) {
@@ -131,9 +135,16 @@ __device__ __forceinline__ uint32_t march_ray_warp(const RayState& r, float lo, 
     float wd[3], diag = hi - lo;
     if (EMIT) { wd[0] = (r.d[0] + 1.0f) * 0.5f; wd[1] = (r.d[1] + 1.0f) * 0.5f; wd[2] = (r.d[2] + 1.0f) * 0.5f; }
     uint32_t chunk = 0;
+    float t_pipe = 0.f;           // PIPE: this lane's t of the current chunk, produced during the previous iteration
+    if (PIPE) {
+        t_pipe = t0;
+        for (uint32_t i = 0; i < lane; ++i) t_pipe += calc_dt(c, t_pipe, cone);
+    }
     for (uint32_t guard = 0; guard < (1u << 20); ++guard) {   // a degenerate ray (d == 0) would spin forever in the reference
         float t = t0;
-        for (uint32_t i = 0; i < lane; ++i) t += calc_dt(c, t, cone);          // t_k .. t_{k+31}, sequential float adds
+        if (PIPE) t = t_pipe;
+        else
+            for (uint32_t i = 0; i < lane; ++i) t += calc_dt(c, t, cone);      // t_k .. t_{k+31}, sequential float adds
         const float dt = calc_dt(c, t, cone);
         const float t_next_chunk = __shfl_sync(FULL, t + dt, 31);
         int cur = 0;
@@ -143,6 +154,10 @@ __device__ __forceinline__ uint32_t march_ray_warp(const RayState& r, float lo, 
                 if (!EMIT && rec && chunk < MARCH_MAXC && lane == 0) rec[chunk] = ChunkRec{t0, 0u};
                 ++chunk;
                 t0 = t_next_chunk;
+                if (PIPE) {
+                    t_pipe = t0;
+                    for (uint32_t i = 0; i < lane; ++i) t_pipe += calc_dt(c, t_pipe, cone);
+                }
                 continue;
             }
             cur = __ffs(ge) - 1;
@@ -153,9 +168,23 @@ __device__ __forceinline__ uint32_t march_ray_warp(const RayState& r, float lo, 
         uint32_t mip = 0;
         bool occ = false;
         float t_target = 0.f;
+        uint32_t occ_byte = 0, occ_bit = 0;
+        if (PIPE) {
+            if (inside) {                                                        // occupied_at(), split into load and test
+                mip = (uint32_t)mip_from_dt(c, dt, p[0], p[1], p[2]);
+                const uint32_t idx = grid_idx_at(p[0], p[1], p[2], mip);
+                occ_byte = __ldg(bits + idx / 8 + (NERF_GRID_N / 8) * mip);
+                occ_bit = 1u << (idx % 8);
+            }
+            t_pipe = t_next_chunk;                                               // next chunk's t values, under the load's latency
+            for (uint32_t i = 0; i < lane; ++i) t_pipe += calc_dt(c, t_pipe, cone);
+        }
         if (inside) {
-            mip = (uint32_t)mip_from_dt(c, dt, p[0], p[1], p[2]);
-            occ = occupied_at(p[0], p[1], p[2], bits, mip);
+            if (PIPE) occ = (occ_byte & occ_bit) != 0;
+            else {
+                mip = (uint32_t)mip_from_dt(c, dt, p[0], p[1], p[2]);
+                occ = occupied_at(p[0], p[1], p[2], bits, mip);
+            }
             if (!occ) {                                                          // distance_to_next_voxel, ray_sampler_header.h:728-739
                 const float rs = (float)(NERF_GRIDSIZE >> mip);
                 const float q[3] = {rs * p[0], rs * p[1], rs * p[2]};
@@ -201,6 +230,7 @@ __device__ __forceinline__ uint32_t march_ray_warp(const RayState& r, float lo, 
     return j;
 }
 
+template <bool PIPE>
 __global__ void __launch_bounds__(128) march_count_kernel(uint32_t n_rays, float lo, float hi, const float* __restrict__ rays_o,
                                                           const float* __restrict__ rays_d, const uint8_t* __restrict__ bits, float cone,
                                                           float near_distance, MarchCfg c, uint64_t rng_state, uint64_t rng_inc,
@@ -209,7 +239,7 @@ __global__ void __launch_bounds__(128) march_count_kernel(uint32_t n_rays, float
     const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per ray
     if (i >= n_rays) return;
     const RayState r = ray_setup(i, rays_o, rays_d, lo, hi, near_distance, cone, c, rng_state, rng_inc);
-    const uint32_t n = march_ray_warp<false>(r, lo, hi, cone, c, bits, NERF_STEPS, nullptr, recs + (size_t)i * MARCH_MAXC, n_chunks + i);
+    const uint32_t n = march_ray_warp<false, PIPE>(r, lo, hi, cone, c, bits, NERF_STEPS, nullptr, recs + (size_t)i * MARCH_MAXC, n_chunks + i);
     if ((threadIdx.x & 31) == 0) counts[i] = n;
 }
 
@@ -562,8 +592,13 @@ int ngp_march(void* stream, uint32_t n_rays, float aabb_lo, float aabb_hi, uint3
     uint32_t* n_chunks = counts + n_rays;
     ChunkRec* recs = reinterpret_cast<ChunkRec*>((reinterpret_cast<uintptr_t>(n_chunks + n_rays) + 15) & ~(uintptr_t)15);
     const uint32_t blocks = (n_rays + 3) / 4;             // one warp per ray, 4 rays per CTA
-    march_count_kernel<<<blocks, 128, 0, s>>>(n_rays, aabb_lo, aabb_hi, rays_o, rays_d, bitfield, cone_angle, near_distance, c, rng_state,
-                                              rng_inc, counts, recs, n_chunks);
+    static const bool pipe = getenv("NGP_MARCH_PIPE") && atoi(getenv("NGP_MARCH_PIPE")) == 1;   // opt-in scheduling variant of the count pass
+    if (pipe)
+        march_count_kernel<true><<<blocks, 128, 0, s>>>(n_rays, aabb_lo, aabb_hi, rays_o, rays_d, bitfield, cone_angle, near_distance, c, rng_state,
+                                                        rng_inc, counts, recs, n_chunks);
+    else
+        march_count_kernel<false><<<blocks, 128, 0, s>>>(n_rays, aabb_lo, aabb_hi, rays_o, rays_d, bitfield, cone_angle, near_distance, c, rng_state,
+                                                         rng_inc, counts, recs, n_chunks);
     NGP_LAUNCH_CHECK();
     march_scan_kernel<<<1, 1024, 0, s>>>(n_rays, max_samples, counts, numsteps, ray_indices, counters);
     NGP_LAUNCH_CHECK();

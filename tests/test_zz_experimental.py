@@ -54,3 +54,17 @@ def test_training_with_saved_activations_matches_default(monkeypatch):
     lb = [float(rb.train_step().mean()) for _ in range(20)]
     assert abs(la[0] - lb[0]) <= 1e-6 * max(1.0, abs(la[0]))                    # identical forward
     assert abs(la[-1] - lb[-1]) <= 5e-2 * max(abs(la[-1]), 1e-3)                # same trajectory up to atomic-order noise
+
+
+def test_pipelined_march_count_is_still_bit_exact():
+    """NGP_MARCH_PIPE=1 (count pass computes the next chunk's t values under the latency of the occupancy lookup): the same bit-exact
+    march comparisons as the default kernel.  The switch is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, NGP_MARCH_PIPE="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_ops.py"), "-q", "-x", "-m", "gpu", "-k", "march", "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-2000:]
