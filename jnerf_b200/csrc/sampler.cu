@@ -441,15 +441,45 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// forward over one ray: returns (all lanes) the composited colour WITHOUT background and the final transmittance
+// PIPE variants (opt-in through NGP_COMPOSITE_PIPE=1, not yet measured): a ray with many samples is one warp's serial loop over
+// 32-sample chunks, and the kernel lasts as long as its longest ray (6 % warps active in the ncu capture).  With PIPE the loads of
+// chunk j+1 are issued before chunk j is evaluated, so every iteration but the first finds its operands in registers; the arithmetic
+// and its order are unchanged.
 template <typename T>
+__device__ __forceinline__ void load_sample_raw(const T* __restrict__ net, const float* __restrict__ coords, size_t k, float4* raw, float* dt_warped) {
+    *raw = load_net<T>(net, k);
+    *dt_warped = __ldg(coords + k * 7 + 3);
+}
+__device__ __forceinline__ Sample make_sample(const float4& o, float dt_warped, uint32_t cascades) {   // eval_sample() after its loads
+    Sample s;
+    s.rgb[0] = logistic_f(o.x); s.rgb[1] = logistic_f(o.y); s.rgb[2] = logistic_f(o.z);
+    s.dt = nerf_unwarp_dt(dt_warped, cascades);
+    const float density = __expf(o.w);
+    s.alpha = 1.f - __expf(-density * s.dt);
+    s.sigma_raw = o.w;
+    return s;
+}
+
+// forward over one ray: returns (all lanes) the composited colour WITHOUT background and the final transmittance
+template <typename T, bool PIPE = false>
 __device__ __forceinline__ void composite_ray_fwd(uint32_t n, uint32_t base, const T* __restrict__ net, const float* __restrict__ coords,
                                                   uint32_t cascades, uint32_t lane, float rgb[3], float* T_final) {
     float carry = 1.f, acc[3] = {0.f, 0.f, 0.f};
+    float4 nraw = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ndt = 0.f;
+    if (PIPE && lane < n) load_sample_raw<T>(net, coords, (size_t)base + lane, &nraw, &ndt);
     for (uint32_t j0 = 0; j0 < n; j0 += 32) {
         const uint32_t j = j0 + lane;
         float a = 0.f, c[3] = {0.f, 0.f, 0.f};
-        if (j < n) {
+        if (PIPE) {
+            const float4 raw = nraw;
+            const float dtw = ndt;
+            if (j + 32 < n) load_sample_raw<T>(net, coords, (size_t)base + j + 32, &nraw, &ndt);
+            if (j < n) {
+                const Sample s = make_sample(raw, dtw, cascades);
+                a = s.alpha; c[0] = s.rgb[0]; c[1] = s.rgb[1]; c[2] = s.rgb[2];
+            }
+        } else if (j < n) {
             float4 raw;
             const Sample s = eval_sample<T>(net, coords, (size_t)base + j, cascades, &raw);
             a = s.alpha; c[0] = s.rgb[0]; c[1] = s.rgb[1]; c[2] = s.rgb[2];
@@ -465,16 +495,27 @@ __device__ __forceinline__ void composite_ray_fwd(uint32_t n, uint32_t base, con
     *T_final = carry;
 }
 
-template <typename T>
+template <typename T, bool PIPE = false>
 __device__ __forceinline__ void composite_ray_bwd(uint32_t n, uint32_t base, const T* __restrict__ net, const float* __restrict__ coords,
                                                   const float lg[3], const float rr[3], float loss_scale, float l1, uint32_t cascades,
                                                   uint32_t lane, T* __restrict__ dnet) {
     float carry_T = 1.f, carry_S[3] = {0.f, 0.f, 0.f};
+    float4 nraw = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ndt = 0.f;
+    if (PIPE && lane < n) load_sample_raw<T>(net, coords, (size_t)base + lane, &nraw, &ndt);
     for (uint32_t j0 = 0; j0 < n; j0 += 32) {
         const uint32_t j = j0 + lane;
         float a = 0.f, c[3] = {0.f, 0.f, 0.f}, dt = 0.f;
         float4 raw = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < n) {
+        if (PIPE) {
+            const float dtw = ndt;
+            if (j < n) raw = nraw;
+            if (j + 32 < n) load_sample_raw<T>(net, coords, (size_t)base + j + 32, &nraw, &ndt);
+            if (j < n) {
+                const Sample s = make_sample(raw, dtw, cascades);
+                a = s.alpha; c[0] = s.rgb[0]; c[1] = s.rgb[1]; c[2] = s.rgb[2]; dt = s.dt;
+            }
+        } else if (j < n) {
             const Sample s = eval_sample<T>(net, coords, (size_t)base + j, cascades, &raw);
             a = s.alpha; c[0] = s.rgb[0]; c[1] = s.rgb[1]; c[2] = s.rgb[2]; dt = s.dt;
         }
@@ -540,6 +581,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(uint32_t n_rays, con
 }
 
 // Fused training tail: composite forward, Huber gradient, composite backward -- one warp per ray.
+template <bool PIPE>
 __global__ void __launch_bounds__(256) composite_loss_bwd_kernel(uint32_t n_rays, const __half* __restrict__ net, const float* __restrict__ coords,
                                                                  const uint32_t* __restrict__ numsteps_in, const uint32_t* __restrict__ numsteps_c,
                                                                  const float* __restrict__ bg, const float* __restrict__ target, float delta,
@@ -551,7 +593,7 @@ __global__ void __launch_bounds__(256) composite_loss_bwd_kernel(uint32_t n_rays
     float T_ = 1.f, r[3] = {0.f, 0.f, 0.f};
     if (n == 0) { r[0] = bg[3 * i]; r[1] = bg[3 * i + 1]; r[2] = bg[3 * i + 2]; }
     else {
-        composite_ray_fwd<__half>(n, base, net, coords, cascades, lane, r, &T_);
+        composite_ray_fwd<__half, PIPE>(n, base, net, coords, cascades, lane, r, &T_);
         if (n == numsteps_in[2 * i]) {
             r[0] = __fmaf_rn(T_, bg[3 * i], r[0]); r[1] = __fmaf_rn(T_, bg[3 * i + 1], r[1]); r[2] = __fmaf_rn(T_, bg[3 * i + 2], r[2]);
         }
@@ -568,7 +610,7 @@ __global__ void __launch_bounds__(256) composite_loss_bwd_kernel(uint32_t n_rays
     float loss_scale = 128;
     loss_scale /= n_rays;
     const float l1 = *mean < 0.01f ? 1e-4f : 0.0f;
-    composite_ray_bwd<__half>(n, base, net, coords, lg, r, loss_scale, l1, cascades, lane, dnet);
+    composite_ray_bwd<__half, PIPE>(n, base, net, coords, lg, r, loss_scale, l1, cascades, lane, dnet);
 }
 
 }  // namespace
@@ -670,9 +712,15 @@ int ngp_composite_loss_bwd(void* stream, uint32_t n_rays, uint32_t n_elements, c
     (void)n_elements;   // rows not covered by a ray are never read downstream (the network backward is count-limited)
     if (n_rays == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    composite_loss_bwd_kernel<<<(n_rays + 7) / 8, 256, 0, s>>>(n_rays, (const __half*)net_out, coords, numsteps_in, numsteps_compacted, bg,
-                                                                  target, huber_delta, density_grid_mean, cascades, rgb_out, loss_out,
-                                                                  (__half*)dnet_out);
+    static const bool pipe = getenv("NGP_COMPOSITE_PIPE") && atoi(getenv("NGP_COMPOSITE_PIPE")) == 1;   // opt-in: next chunk's loads in flight
+    if (pipe)
+        composite_loss_bwd_kernel<true><<<(n_rays + 7) / 8, 256, 0, s>>>(n_rays, (const __half*)net_out, coords, numsteps_in, numsteps_compacted, bg,
+                                                                            target, huber_delta, density_grid_mean, cascades, rgb_out, loss_out,
+                                                                            (__half*)dnet_out);
+    else
+        composite_loss_bwd_kernel<false><<<(n_rays + 7) / 8, 256, 0, s>>>(n_rays, (const __half*)net_out, coords, numsteps_in, numsteps_compacted, bg,
+                                                                             target, huber_delta, density_grid_mean, cascades, rgb_out, loss_out,
+                                                                             (__half*)dnet_out);
     NGP_LAUNCH_CHECK();
     return 0;
 }

@@ -68,3 +68,17 @@ def test_pipelined_march_count_is_still_bit_exact():
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-2000:]
+
+
+def test_pipelined_composite_matches_oracle():
+    """NGP_COMPOSITE_PIPE=1 (fused composite + Huber + backward with the next chunk's loads in flight): the same oracle comparisons
+    as the default kernel (test_composite's fp16 branch covers ngp_composite_loss_bwd) plus the fused-step-vs-autograd check."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, NGP_COMPOSITE_PIPE="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_ops.py"), os.path.join(here, "test_gpu_runner.py"), "-q", "-x", "-m", "gpu",
+                        "-k", "test_composite or fused_step", "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "3 passed" in r.stdout, r.stdout[-2000:]
