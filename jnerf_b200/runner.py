@@ -319,6 +319,43 @@ class Runner:
         return img.reshape(H, W, 3), tar.reshape(H, W, 3)
 
     @torch.no_grad()
+    def render_img_nosync(self, dataset_mode="train", img_id=0):
+        """N3: the image of render_img without the reference tiler's host round trips (runner.py:206-228 reads the
+        sample count back with .item() and copies every tile to the host; 157 tiles per 800x800 image).  The march's device-side
+        counter bounds the fused network kernel (n_dev), ngp_composite_infer writes into the image buffer, nothing is read back
+        before the caller uses the result.  Same kernels, same RNG consumption, same pixels as render_img."""
+        assert self.fast, "render_img_nosync drives the fused network kernel"
+        self._table_ready()
+        ds = self.dataset[dataset_mode]
+        W, H = ds.resolution
+        rays_o, rays_d = ds.generate_rays_total_test(img_id)
+        tile = self.cfg.n_rays_per_batch
+        n_pix = H * W
+        n_pad = (n_pix + tile - 1) // tile * tile
+        if n_pad > n_pix:                                              # the reference pads the last tile with ones (runner.py:213-217)
+            fill = torch.ones((n_pad - n_pix, 3), device="cuda")
+            rays_o, rays_d = torch.cat([rays_o, fill]), torch.cat([rays_d, fill])
+        img = torch.empty((n_pad, 3), device="cuda")
+        alpha = torch.empty((n_pad, 1), device="cuda")
+        s, m = self.sampler, self.model
+        if getattr(self, "_infer_net_out", None) is None:
+            self._infer_net_out = torch.empty((s.max_samples, 4), dtype=torch.float16, device="cuda")
+        for p in range(0, n_pad, tile):
+            coords, _, numsteps, counters = ops.march(
+                rays_o[p:p + tile].contiguous(), rays_d[p:p + tile].contiguous(), s.density_grid_bitfield, s.aabb_range, s.max_samples,
+                s.cone_angle_constant, s.near_distance, s.NERF_CASCADES, s.const_dt, s.rng, coords=s._coords_raw, workspace=s._march_ws)
+            ops.pcg32_advance(s.rng)                                   # rng.advance(), ray_sampler.py:61
+            ops.network_fwd(coords, m.pos_encoder.m_grid, m.pos_encoder.levels, m.density_mlp.con_weights, m.rgb_mlp.con_weights,
+                            n_dev=counters[1:2], save_enc=False, out=self._infer_net_out)
+            rgb, a = ops.composite_infer(self._infer_net_out, coords, numsteps, s.NERF_CASCADES)
+            img[p:p + tile], alpha[p:p + tile] = rgb, a
+        bgc = torch.tensor(self.background_color, dtype=torch.float32, device="cuda")
+        img = img[:n_pix] + bgc * (1 - alpha[:n_pix])
+        tar = ds.rgba_for(torch.arange(n_pix, device="cuda", dtype=torch.int32) + int(img_id) * n_pix)
+        tar = tar[:, :3] * tar[:, 3:] + bgc * (1 - tar[:, 3:])
+        return img.reshape(H, W, 3), tar.reshape(H, W, 3)
+
+    @torch.no_grad()
     def psnr(self, dataset_mode="val", max_images=None):
         """mean over images of -10 log10(mse) (runner.py:86-99, mse_loss.py:6-7)."""
         ds = self.dataset[dataset_mode]

@@ -153,3 +153,21 @@ def test_fox_like_training_cone_stepping_and_cascades():
     assert img.shape == (160, 90, 3) and torch.isfinite(img).all()
     mse = float(((img - tar) ** 2).mean())
     assert mse < 0.05, mse                                                                     # 300 steps on 8 tiny views: roughly right, not sharp
+
+
+def test_render_without_host_round_trips_equals_the_tiled_render():
+    """N3: Runner.render_img_nosync (device-side sample count bounds the fused network kernel, no per-tile .item()) produces the
+    pixels of Runner.render_img (the reference's tiler, runner/runner.py:197-236) exactly."""
+    from test_gpu_runner import make_runner
+    r = make_runner(seed=6)
+    for _ in range(64):
+        r.train_step()
+    rng0 = r.sampler.rng.copy()
+    img_a, tar_a = r.render_img("train", 1)
+    rng1 = r.sampler.rng.copy()
+    r.sampler.rng = rng0.copy()
+    img_b, tar_b = r.render_img_nosync("train", 1)
+    assert np.array_equal(r.sampler.rng, rng1)                       # same RNG consumption
+    assert torch.equal(tar_a, tar_b)
+    assert torch.equal(img_a, img_b)
+    assert float(img_a.std()) > 0.01                                 # not a blank image
