@@ -26,6 +26,9 @@ Two reference behaviours that are NOT reproduced (documented deviations):
     resume; here n_step is restored from the EMA step counter (the two advance together, runner.py:75-76);
   * `n_rays_per_batch` and the pcg32 state are not Vars and are therefore not in the reference file; they are carried under
     extra keys ('sampler' -> 'n_rays_per_batch', 'rng') which the reference's load_state_dict ignores.
+  * Adam moments and EMA values are written in the PARAMETER dtype (fp16 for the NGP configs with fp16=True), as jt.nn.Adam / EMA
+    allocate them (`jt.zeros(p.shape, p.dtype)`, `p.copy()`): a .pkl round trip rounds this repo's fp32 optimizer state to fp16.
+    Use the native `.pt` format for a lossless resume; `.pkl` is the interchange format with the reference.
 All functions work on numpy arrays / python scalars; nothing here touches the GPU."""
 import hashlib
 import io
