@@ -130,3 +130,43 @@ def test_fox_stand_in_shading_is_opaque_and_textured():
     ds.obj_scale, ds.backdrop_radius = 1.0, None                                                        # lego style: transparent background
     rgba = ds.shade(torch.from_numpy(o.astype(np.float32)), torch.from_numpy(d.astype(np.float32)))
     assert 0.0 < float(rgba[:, 3].mean()) < 1.0
+
+
+def _cpu_rays_for(self, pix):
+    """dataset.py:172-188 restated with torch on the CPU (the product path is the CUDA kernel ngp_raygen)."""
+    pix = pix.long()
+    img_id = pix // (self.H * self.W)
+    off = pix % (self.H * self.W)
+    x = ((off % self.W).float() + 0.5) / self.W
+    y = ((off // self.W).float() + 0.5) / self.H
+    xy = torch.stack([x, y], -1)
+    res = torch.tensor([self.W, self.H], dtype=torch.float32)
+    d = torch.cat([(xy - self.principal[img_id]) * res / self.focal_lengths[img_id], torch.ones(len(pix), 1)], -1)
+    xf = self.transforms_gpu[img_id].reshape(-1, 4, 3).transpose(1, 2)              # back to (3,4)
+    d = torch.nn.functional.normalize((xf[:, :, :3] @ d[:, :, None])[:, :, 0], dim=-1)
+    return img_id.int(), xf[:, :, 3].contiguous(), d.contiguous()
+
+
+@pytest.mark.parametrize("style", ["lego", "fox"])
+def test_synthetic_datasets_construct_and_render(cpu_device, monkeypatch, style):
+    """Both stand-ins build end to end (camera poses, intrinsics, analytic renderer) with the ray generator swapped for its CPU
+    restatement: the lego style has a transparent background, the fox style is opaque, and every camera sees the objects."""
+    monkeypatch.setattr(D._RayBatcher, "rays_for", _cpu_rays_for)
+    kw = dict(n_images=3, H=48, W=27) if style == "fox" else dict(n_images=3, H=32, W=32)
+    ds = D.SyntheticNerfDataset(batch_size=64, mode="train", style=style, seed=1, **kw)
+    assert ds.n_images == 3 and ds.resolution == [kw["W"], kw["H"]]
+    assert ds.image_data.shape == (3, kw["H"] * kw["W"], 4) and ds.image_data.dtype == torch.uint8
+    a = ds.image_data[:, :, 3].float() / 255
+    if style == "fox":
+        assert ds.aabb_scale == 4 and ds.aabb_range == (-1.5, 2.5) and bool((a == 1).all())
+        F = D.SyntheticNerfDataset.FOX
+        assert abs(ds._focal[0] - F["fl"][0] * 27 / F["W"]) < 1e-6 and abs(ds._cy - F["c"][1] * 48 / F["H"]) < 1e-6
+    else:
+        assert ds.aabb_scale == 1 and ds.aabb_range == (0.0, 1.0) and 0.05 < float(a.mean()) < 0.95
+    for k in range(3):
+        assert float(ds.image_data[k, :, :3].float().std()) > 5.0                    # every view shows structure
+    img_ids, o, d, rgba = next(ds)
+    assert o.shape == (64, 3) and d.shape == (64, 3) and rgba.shape == (64, 4) and float(rgba.max()) <= 1.0
+    assert torch.allclose(d.norm(dim=-1), torch.ones(64), atol=1e-5)
+    val = D.SyntheticNerfDataset(batch_size=64, mode="val", style=style, seed=1, **dict(kw, n_images=20))
+    assert val.n_images == 2                                                        # a tenth of the views, other cameras than training
