@@ -1,0 +1,213 @@
+"""Host logic of the plugin classes and the Runner, exercised without a GPU: the operator layer is swapped for the oracle and
+torch's "cuda" for "cpu" (tests/cpu_backend.py).  What is under test is everything AROUND the kernels -- the order of the C-ABI
+calls in a training step (runner/runner.py:62-84 of the reference), buffer aliasing, gradient zeroing, the adaptive ray batch
+(density_grid_sampler.py:266-271), optimizer / EMA step order, both checkpoint formats, the two tiled renderers, the fox
+configuration -- not the kernels, which `-m gpu` checks against the same oracle."""
+import numpy as np
+import pytest
+import torch
+
+import cpu_backend
+import oracle_lib as ol
+
+
+def make_runner(monkeypatch, cfg_fn="lego_cfg", images=4, H=24, W=24, rays=64, target=32768, seed=1, start_step=1, **over):
+    fake = cpu_backend.install(monkeypatch)
+    from jnerf_b200 import plugin  # noqa: F401
+    from jnerf_b200 import runner as R
+    from jnerf_b200.utils.config import get_cfg, update_cfg
+    get_cfg().clear()
+    update_cfg(**getattr(R, cfg_fn)(fp16=True, synthetic=True, seed=seed, n_rays_per_batch=rays, target_batch_size=target, **over))
+    cfg = get_cfg()
+    cfg.dataset.train.n_images = images
+    cfg.dataset.train.H, cfg.dataset.train.W = H, W
+    cfg.dataset.val = None
+    r = R.Runner()
+    # skip the first occupancy-grid update (2 M density evaluations at step 0: minutes with the scalar oracle); it has its own test
+    bits, _ = ol.sphere_bitfield(0.35, cascades=r.sampler.NERF_CASCADES)
+    r.sampler.density_grid_bitfield.copy_(torch.from_numpy(bits[:r.sampler.density_grid_bitfield.numel()]))
+    cfg.m_training_step = start_step
+    return r, fake
+
+
+STEP_OPS = ["prepare_batch", "march", "compact", "network_fwd", "composite_loss_bwd", "network_bwd", "adam_ema", "adam_ema", "adam_ema"]
+
+
+def test_fast_path_step_sequence_and_bookkeeping(monkeypatch):
+    r, fake = make_runner(monkeypatch)
+    m, s = r.model, r.sampler
+    assert r.fast and m.pos_encoder.m_grid.numel() == 12196240 and s.max_samples == 64 * 1024
+    g0 = m.pos_encoder.m_grid.detach().clone()
+    w0 = m.rgb_mlp.con_weights.detach().clone()
+    rng0 = s.rng.copy()
+    fake.calls.clear()
+    loss = r.train_step()
+    assert fake.calls == STEP_OPS                                   # one C-ABI call per stage, in the reference's order
+    assert torch.isfinite(loss).all() and loss.shape == (64,)
+    assert r.cfg.m_training_step == 2 and r.optimizer._nested_optimizer.n_step == 1 and r.ema_optimizer.steps == 1 and r.optimizer.steps == 1
+    assert not torch.equal(m.pos_encoder.m_grid.detach(), g0) and not torch.equal(m.rgb_mlp.con_weights.detach(), w0)
+    assert not r.grid_grad.any() and not r.dwd.any() and not r.dwr.any()          # the optimizer sweep zeroes the gradients
+    assert np.array_equal(s.rng, ol.pcg32_advance(rng0.copy()))                   # one rng.advance() per march (ray_sampler.py:61)
+    n_samples = int(s.n_samples_dev.item())
+    assert 0 < n_samples <= s.target_batch_size and int(s.measured_batch_size.item()) == n_samples   # 64 rays fit the sample budget
+    # Adam's first moment after one step is (1 - beta1) * gradient: non-zero exactly where the table was touched
+    st = r.optimizer._nested_optimizer.state[0]
+    assert 0 < int((st.m != 0).sum()) < st.m.numel()
+    # steps 2..15: the 16th iteration of the window adapts the ray batch to the measured sample count (density_grid_sampler.py:266-271)
+    first = float(loss.mean())
+    for _ in range(13):
+        loss = r.train_step()
+    assert r.cfg.m_training_step == 15 and s.n_rays_per_batch == 64
+    measured = int(s.measured_batch_size.item())
+    loss = r.train_step()                                                          # i = 15
+    expect = int(64 * s.target_batch_size / max((measured + int(s.n_samples_dev.item())) / 16, 1))
+    expect = min((expect + 127) // 128 * 128, s.target_batch_size)
+    assert s.n_rays_per_batch == expect and r.dataset["train"].batch_size == expect and int(s.measured_batch_size.item()) == 0
+    assert np.isfinite(float(loss.mean())) and np.isfinite(first)
+
+
+def test_fused_step_equals_per_operator_autograd_step(monkeypatch):
+    """Runner.train_step (fused C-ABI calls) and Runner.train_step_autograd (the per-operator plugin classes under autograd, the way
+    JNeRF's Runner wires them) produce the same gradients: Adam's first moment after one step is (1 - beta1) * gradient."""
+    ra, _ = make_runner(monkeypatch, seed=3)
+    la = ra.train_step()
+    ma = [st.m.clone() for st in ra.optimizer._nested_optimizer.state]
+    rb, _ = make_runner(monkeypatch, seed=3)
+    lb = rb.train_step_autograd()
+    mb = [st.m for st in rb.optimizer._nested_optimizer.state]
+    assert abs(float(la.mean()) - float(lb.detach().mean())) < 2e-3 * max(1.0, float(lb.detach().mean()))
+    for a, b, tol in zip(ma, mb, (3e-2, 2e-2, 2e-2)):
+        scale = float(b.abs().max())
+        assert scale > 0 and float((a - b).abs().max()) <= tol * scale, (float((a - b).abs().max()), scale)
+
+
+def test_checkpoints_native_and_reference_format(monkeypatch, tmp_path):
+    r, _ = make_runner(monkeypatch, seed=5)
+    for _ in range(4):
+        r.train_step()
+    for name in ("ckpt.pt", "params.pkl"):
+        p = str(tmp_path / name)
+        r.cfg.m_training_step = 5                                 # cfg is a process-wide singleton (as in the reference): r2 below shares it
+        r.save_ckpt(p)
+        r2, _ = make_runner(monkeypatch, seed=6)
+        r2.load_ckpt(p)
+        assert torch.equal(r2.model.pos_encoder.m_grid.detach(), r.model.pos_encoder.m_grid.detach())
+        assert torch.equal(r2.model.density_mlp.con_weights.detach(), r.model.density_mlp.con_weights.detach())
+        assert torch.equal(r2.sampler.density_grid_bitfield, r.sampler.density_grid_bitfield)
+        assert r2.cfg.m_training_step == 5 and r2.start == 5 and r2.optimizer._nested_optimizer.n_step == 4 and r2.ema_optimizer.steps == 4
+        assert r2.optimizer.steps == 4 and np.array_equal(r2.sampler.rng, r.sampler.rng)
+        a, b = r.optimizer._nested_optimizer.state[2], r2.optimizer._nested_optimizer.state[2]
+        if name.endswith(".pt"):
+            assert torch.equal(a.m, b.m) and torch.equal(a.v, b.v) and torch.equal(a.master, b.master)
+        else:                                                     # the interchange format keeps optimizer state in the parameter dtype
+            assert torch.equal(b.m, a.m.half().float()) and torch.equal(b.master, a.master.half().float())
+            from jnerf_b200.utils import ckpt_compat as cc
+            ref = cc.read_reference_ckpt(p)                       # and has the fields the reference's load_ckpt indexes (runner.py:133-151)
+            assert ref["global_step"] == 5 and len(ref["nested_optimizer"]["defaults"]["param_groups"][0]["values"]) == 3
+            assert ref["ema_optimizer"]["defaults"]["steps"] == 4
+        assert torch.isfinite(r2.train_step()).all()
+
+
+def test_both_tiled_renderers_agree(monkeypatch):
+    r, fake = make_runner(monkeypatch, seed=7)
+    for _ in range(3):
+        r.train_step()
+    rng0 = r.sampler.rng.copy()
+    fake.calls.clear()
+    img_a, tar_a = r.render_img("train", 1)
+    n_tiles = (24 * 24 + 63) // 64
+    assert fake.calls.count("march") == n_tiles and fake.calls.count("composite_infer") == n_tiles
+    rng1 = r.sampler.rng.copy()
+    r.sampler.rng = rng0.copy()
+    img_b, tar_b = r.render_img_nosync("train", 1)
+    assert np.array_equal(r.sampler.rng, rng1)
+    assert torch.equal(tar_a, tar_b) and torch.equal(img_a, img_b)
+    assert img_a.shape == (24, 24, 3) and float(img_a.std()) > 0
+    assert np.isfinite(r.psnr("train", max_images=1))
+
+
+def test_fox_configuration_runs(monkeypatch):
+    r, fake = make_runner(monkeypatch, cfg_fn="fox_cfg", images=3, H=32, W=18, seed=2)
+    s = r.sampler
+    assert r.dataset["train"].aabb_scale == 4 and s.aabb_range == (-1.5, 2.5) and s.max_cascade == 2 and s.const_dt is False
+    assert r.model.pos_encoder.m_grid.numel() == 2 * 6537456
+    l0 = float(r.train_step().mean())
+    for _ in range(5):
+        loss = r.train_step()
+    assert np.isfinite(float(loss.mean())) and float(loss.mean()) < l0
+    assert fake.calls.count("march") == 6
+
+
+def test_occupancy_grid_update_glue(monkeypatch):
+    """update_density_grid_nerf (density_grid_sampler.py:204-250) at step 0 with a reduced sample count: mark_untrained, sample
+    generation with the shared RNG stream, density evaluation, splat, EMA, bitfield -- in that order, RNG advanced once per
+    non-empty generate call."""
+    r, fake = make_runner(monkeypatch, start_step=0)
+    s = r.sampler
+    rng0 = s.rng.copy()
+    fake.calls.clear()
+    s.update_density_grid_nerf(0.95, 20000, 0)
+    assert fake.calls == ["grid_mark_untrained", "grid_generate_samples", "density_fwd", "grid_splat", "grid_ema", "grid_update_bitfield"]
+    assert np.array_equal(s.rng, ol.pcg32_advance(rng0.copy())) and int(s.density_grid_ema_step.item()) == 1
+    assert int(s.density_grid_bitfield.count_nonzero()) > 0 and float(s.density_grid_mean.item()) > 0
+    r.cfg.m_training_step = 300
+    fake.calls.clear()
+    s.update_density_grid_nerf(0.95, 5000, 5000)
+    assert fake.calls == ["grid_generate_samples", "grid_generate_samples", "density_fwd", "grid_splat", "grid_ema", "grid_update_bitfield"]
+    assert np.array_equal(s.rng, ol.pcg32_advance(ol.pcg32_advance(ol.pcg32_advance(rng0.copy()))))
+
+
+# ------------------------------------------------------------------------------------------------ data parallel (gloo, 2 ranks)
+def _dp_worker(rank, world, port, tmp, ret):
+    import os
+    import sys
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), NGP_DP_EXCHANGE="nccl")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    torch.set_num_threads(1)
+    mp_ = pytest.MonkeyPatch()
+    try:
+        fake = cpu_backend.install(mp_)
+        from jnerf_b200 import plugin  # noqa: F401
+        from jnerf_b200 import runner as R
+        from jnerf_b200.utils.config import get_cfg, update_cfg
+        get_cfg().clear()
+        update_cfg(**R.lego_cfg(fp16=True, synthetic=True, seed=1, n_rays_per_batch=32, target_batch_size=16384))
+        cfg = get_cfg()
+        cfg.dataset.train.n_images, cfg.dataset.train.H, cfg.dataset.train.W = 4, 24, 24
+        cfg.dataset.val = None
+        r = R.Runner(rank=rank, world_size=world, process_group=dist.group.WORLD)
+        bits, _ = ol.sphere_bitfield(0.35)
+        r.sampler.density_grid_bitfield.copy_(torch.from_numpy(bits))
+        cfg.m_training_step = 1
+        assert r.dp_mode == "nccl" and r._hi - r._lo == r._table.numel() // world
+        losses = [float(r.train_step().mean()) for _ in range(3)]
+        r._table_ready()
+        g = r.model.pos_encoder.m_grid.detach().float()
+        st = r.optimizer._nested_optimizer.state[0]
+        r.save_ckpt(os.path.join(tmp, "dp.pt"))                                  # every rank calls; rank 0 writes the gathered state
+        ret[rank] = dict(losses=losses, table_sum=float(g.double().sum()), table_head=g[:4096].clone().numpy(), w=r.model.rgb_mlp.con_weights.detach().float().numpy(),
+                         slice_len=int(st.m.numel()), calls=list(fake.calls[-9:]), n_samples=int(r.sampler.n_samples_dev.item()))
+    finally:
+        mp_.undo()
+        dist.destroy_process_group()
+
+
+def test_two_rank_runner_sharded_optimizer_keeps_replicas_identical(tmp_path):
+    """Runner with world_size 2 over gloo (NCCL code path of runner._optimizer_step: reduce-scatter, Adam+EMA on this rank's slice of
+    the padded table, all-gather awaited after the next march): both ranks hold the same table and MLP weights after every step although
+    each optimises only half of the table; each rank marches its own shard of the global ray batch; the checkpoint gathers the slices."""
+    import os
+    import torch.multiprocessing as mp
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_dp_worker, args=(world, 29711 + os.getpid() % 1000, str(tmp_path), ret), nprocs=world, join=True)
+    a, b = ret[0], ret[1]
+    assert a["table_sum"] == b["table_sum"] and np.array_equal(a["table_head"], b["table_head"]) and np.array_equal(a["w"], b["w"])
+    assert a["slice_len"] == b["slice_len"] == (12196240 + 511) // 512 * 512 // 2
+    assert a["n_samples"] != b["n_samples"] or a["losses"] != b["losses"]        # different shards of the batch
+    assert all(np.isfinite(a["losses"])) and all(np.isfinite(b["losses"]))
+    assert a["calls"] == ["prepare_batch", "march", "compact", "network_fwd", "composite_loss_bwd", "network_bwd", "adam_ema", "adam_ema", "adam_ema"]
+    ck = torch.load(str(tmp_path / "dp.pt"), map_location="cpu", weights_only=False)
+    assert ck["nested_optimizer"]["m"][0].numel() == 12196240 and ck["global_step"] == 4
