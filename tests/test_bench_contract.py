@@ -44,3 +44,63 @@ def test_clock_sampler_selects_the_timed_window():
     cs.lines = [row(-1.0, 1900, "Active"), row(5.0, 1910)]
     out = cs.stop(t0, t0 + 0.1)                                  # too few samples inside: falls back to everything under load
     assert out["window"] != "timed region" and out["samples"] == 2 and out["reasons"] == ["sw_power_cap"]
+
+
+class _FakeEvent:
+    def __init__(self, enable_timing=True):
+        pass
+
+    def record(self):
+        pass
+
+    def elapsed_time(self, other):
+        return 1.0
+
+
+def _run_ours_on_cpu(monkeypatch, capsys, argv):
+    """bench.run_ours end to end with the operator layer swapped for the oracle (tests/cpu_backend.py): the control flow, the
+    argument handling and every key of the JSON line -- numbers are meaningless (fake CUDA events)."""
+    import argparse
+    import torch
+    import cpu_backend
+    import bench
+    cpu_backend.install(monkeypatch)
+    from jnerf_b200 import runner as R
+    from jnerf_b200.plugin.sampler import DensityGridSampler
+    for name in ("lego_cfg", "fox_cfg"):                                  # 32 rays per batch: the scalar oracle marches them in milliseconds
+        orig = getattr(R, name)
+        monkeypatch.setattr(R, name, lambda _o=orig, **k: _o(**dict(k, n_rays_per_batch=32)))
+    monkeypatch.setattr(DensityGridSampler, "update_density_grid", lambda self: self.update_density_grid_nerf(0.95, 20000, 0))
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "Event", _FakeEvent)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    st = bench.stage_times
+    monkeypatch.setattr(bench, "stage_times", lambda r, n: st(r, 2))
+    monkeypatch.setattr(sys, "argv", ["bench.py"] + argv)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    monkeypatch.delenv("RANK", raising=False)
+    bench.main()
+    return json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+
+
+def test_our_arm_control_flow_and_json_keys(monkeypatch, capsys):
+    line = _run_ours_on_cpu(monkeypatch, capsys, ["--steps", "2", "--warmup", "1", "--pretrain", "1", "--images", "3", "--res", "24", "--target-batch", "16384",
+                                                  "--no-cpu-baseline"])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+              "e2e", "gpu_launches", "clocks", "roofline", "iters_per_s", "samples_per_s"):
+        assert k in line, k
+    assert line["metric"] == "ngp_lego_train_rays_per_s" and line["unit"] == "rays/s" and line["n_gpus"] == 1 and line["steps"] == 2
+    assert line["scaling"] == "weak" and line["dtype"] == "f16" and line["data"] == "synthetic" and line["vs_baseline"] is None
+    assert line["config"]["target_batch_size"] == 16384 and "lego" in line["config"]["workload"] and "3 synthetic 24x24 views" in line["config"]["workload"]
+    assert line["config"]["save_act"] is False and line["config"]["parallelism"] == "dp1"
+    assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and line["e2e"]["h2d_bytes_per_step"] > 0
+    roof = line["roofline"]
+    assert roof["bound"] == "hbm" and roof["unit"] == "GB/s" and roof["kernel"] in ("network_fwd", "network_bwd") and roof["peak"] > 0
+    assert set(roof["stage_ms"]) == {"prepare_batch", "march", "network_fwd", "composite_loss_bwd", "network_bwd", "adam_ema"}
+    assert roof["algorithmic_bytes_per_sample"] in (624, 1124) and "tensor" in roof
+
+
+def test_our_arm_fox_workload(monkeypatch, capsys):
+    line = _run_ours_on_cpu(monkeypatch, capsys, ["--steps", "1", "--warmup", "1", "--pretrain", "1", "--images", "3", "--res", "18", "--workload", "fox",
+                                                  "--target-batch", "16384", "--no-cpu-baseline"])
+    assert line["metric"] == "ngp_fox_train_rays_per_s" and "ngp_fox.py" in line["config"]["workload"] and "18x32 views" in line["config"]["workload"]
