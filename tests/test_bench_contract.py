@@ -104,3 +104,15 @@ def test_our_arm_fox_workload(monkeypatch, capsys):
     line = _run_ours_on_cpu(monkeypatch, capsys, ["--steps", "1", "--warmup", "1", "--pretrain", "1", "--images", "3", "--res", "18", "--workload", "fox",
                                                   "--target-batch", "16384", "--no-cpu-baseline"])
     assert line["metric"] == "ngp_fox_train_rays_per_s" and "ngp_fox.py" in line["config"]["workload"] and "18x32 views" in line["config"]["workload"]
+
+
+def test_sweep_summary_from_a_committed_bench_line():
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sweep
+    line = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_full.json")))
+    row = sweep.summarise(18, 1, line)
+    assert row["log2_target"] == 18 and row["gpus"] == 1 and abs(row["iters_per_s"] - line["iters_per_s"]) < 1e-9
+    n = line["roofline"]["samples_per_launch"]
+    assert abs(row["bwd_gbs"] - n * 1124 / (line["roofline"]["stage_ms"]["network_bwd"] * 1e-3) / 1e9) < 1e-6
+    assert abs(row["bwd_gbs"] - line["roofline"]["achieved"]) < 1e-3 * line["roofline"]["achieved"]      # the same number bench.py reports
+    assert sweep.summarise(16, 2, {"error": "x" * 1000, "returncode": 1})["error"] == "x" * 300
