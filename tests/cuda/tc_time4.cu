@@ -16,6 +16,13 @@ __device__ __forceinline__ bool test_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 
+// bounded spin: a wrong descriptor must not hang the box (returns false after ~2^24 polls)
+__device__ __forceinline__ bool spin(uint64_t* bar, uint32_t parity) {
+    for (uint32_t i = 0; i < (1u << 24); ++i)
+        if (test_wait(bar, parity)) return true;
+    return false;
+}
+
 constexpr uint32_t GBY = 128 * 16;        // bytes of one slab feature group (8 features x 128 rows), as in mlp_tc.cuh
 struct Shape { const char* name; uint32_t a_mn, b_mn, N, n_per_batch; };
 
@@ -40,6 +47,58 @@ __device__ __forceinline__ void issue(uint32_t kind, uint32_t d, uint32_t s, uin
     }
 }
 
+// the measurements, by one thread; false = an mbarrier wait timed out
+__device__ __noinline__ bool measure(long long* out, uint64_t* bar, uint32_t tbase, uint32_t s) {
+    uint32_t ph = 0;
+    for (int w = 0; w < 100; ++w) {            // warm the tensor pipe / clocks
+        for (int r = 0; r < 8; ++r) issue(0, tbase, s, r & 1, 1);
+        mma_commit(bar);
+        if (!spin(bar, ph)) return false;
+        ph ^= 1;
+    }
+    int idx = 0;
+    const int counts[4] = {1, 4, 8, 32};
+    for (uint32_t kind = 0; kind < 7; ++kind) {
+        for (int c = 0; c < 4; ++c) {
+            const long long c0 = clock64();
+            for (int r = 0; r < counts[c]; ++r) issue(kind, tbase + 64 * (kind & 3), s, (uint32_t)r & (kind >= 4 ? 7u : 1u), r > 0);
+            const long long c1 = clock64();
+            mma_commit(bar);
+            if (!spin(bar, ph)) return false;
+            ph ^= 1;
+            const long long c2 = clock64();
+            out[idx++] = c1 - c0;
+            out[idx++] = c2 - c0;
+        }
+    }
+    // the B2 stage of the backward tile as issued today: 4 dgrad (N=64) on one commit, 8 wgrad (N=64) behind them on a second
+    uint64_t* bar2 = bar + 1;
+    mbar_init(bar2, 1);
+    fence_mbar_init();
+    uint32_t ph2 = 0;
+    for (int rep = 0; rep < 2; ++rep) {
+        const long long c0 = clock64();
+        for (int r = 0; r < 4; ++r) issue(2, tbase, s, r & 1, r > 0);
+        mma_commit(bar);
+        for (int r = 0; r < 8; ++r) issue(4, tbase + 128, s, r, 1);
+        mma_commit(bar2);
+        if (!spin(bar, ph)) return false;
+        ph ^= 1;
+        const long long c1 = clock64();
+        if (!spin(bar2, ph2)) return false;
+        ph2 ^= 1;
+        const long long c2 = clock64();
+        // and a dependent "next stage" dgrad queued right behind the wgrad batch: how long until IT completes?
+        for (int r = 0; r < 4; ++r) issue(2, tbase, s, r & 1, r > 0);
+        mma_commit(bar);
+        if (!spin(bar, ph)) return false;
+        ph ^= 1;
+        const long long c3 = clock64();
+        out[idx++] = c1 - c0; out[idx++] = c2 - c0; out[idx++] = c3 - c2;
+    }
+    return true;
+}
+
 __global__ void __launch_bounds__(128, 1) k(long long* out) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr uint32_t DATA = 96 * GBY;
@@ -51,61 +110,14 @@ __global__ void __launch_bounds__(128, 1) k(long long* out) {
     if (warp == 0) tmem_alloc(tmem_ptr, 512);
     fence_proxy_async_smem(); tc_fence_before(); __syncthreads(); tc_fence_after();
     const uint32_t tbase = *tmem_ptr, s = smem_u32(smem);
-    if (t == 0) {
-        uint32_t ph = 0;
-        for (int w = 0; w < 100; ++w) {            // warm the tensor pipe / clocks
-            for (int r = 0; r < 8; ++r) issue(0, tbase, s, r & 1, 1);
-            mma_commit(bar);
-            while (!test_wait(bar, ph)) {}
-            ph ^= 1;
-        }
-        int idx = 0;
-        const int counts[4] = {1, 4, 8, 32};
-        for (uint32_t kind = 0; kind < 7; ++kind) {
-            for (int c = 0; c < 4; ++c) {
-                const long long c0 = clock64();
-                for (int r = 0; r < counts[c]; ++r) issue(kind, tbase + 64 * (kind & 3), s, (uint32_t)r & (kind >= 4 ? 7u : 1u), r > 0);
-                const long long c1 = clock64();
-                mma_commit(bar);
-                while (!test_wait(bar, ph)) {}
-                ph ^= 1;
-                const long long c2 = clock64();
-                out[idx++] = c1 - c0;
-                out[idx++] = c2 - c0;
-            }
-        }
-        // the B2 stage of the backward tile as issued today: 4 dgrad (N=64) on one commit, 8 wgrad (N=64) behind them on a second
-        uint64_t* bar2 = bar + 1;
-        mbar_init(bar2, 1);
-        fence_mbar_init();
-        uint32_t ph2 = 0;
-        for (int rep = 0; rep < 2; ++rep) {
-            const long long c0 = clock64();
-            for (int r = 0; r < 4; ++r) issue(2, tbase, s, r & 1, r > 0);
-            mma_commit(bar);
-            for (int r = 0; r < 8; ++r) issue(4, tbase + 128, s, r, 1);
-            mma_commit(bar2);
-            while (!test_wait(bar, ph)) {}
-            ph ^= 1;
-            const long long c1 = clock64();
-            while (!test_wait(bar2, ph2)) {}
-            ph2 ^= 1;
-            const long long c2 = clock64();
-            // and a dependent "next stage" dgrad queued right behind the wgrad batch: how long until IT completes?
-            for (int r = 0; r < 4; ++r) issue(2, tbase, s, r & 1, r > 0);
-            mma_commit(bar);
-            while (!test_wait(bar, ph)) {}
-            ph ^= 1;
-            const long long c3 = clock64();
-            out[idx++] = c1 - c0; out[idx++] = c2 - c0; out[idx++] = c3 - c2;
-        }
-    }
+    if (t == 0 && !measure(out, bar, tbase, s)) out[127] = 1;
     tc_fence_before(); __syncthreads();
     if (warp == 0) tmem_free(tbase, 512);
 }
 
 int main() {
     long long* d; CK(cudaMalloc(&d, 128 * 8));
+    CK(cudaMemset(d, 0, 128 * 8));
     const int smem = 96 * GBY + 128;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const char* names[7] = {"fwd   A=K  B=K  N=64", "fwd   A=K  B=K  N=16", "dgrad A=K  B=MN N=64", "dgrad A=K  B=MN N=32",
@@ -121,6 +133,7 @@ int main() {
             for (int c = 0; c < 4; ++c, idx += 2) printf("  n=%2d issue %4lld done %5lld", counts[c], h[idx], h[idx + 1]);
             printf("   -> %.1f cyc/MMA marginal\n", (double)(h[idx - 1] - h[idx - 2 * 3 - 1]) / (32 - 1));
         }
+        if (h[127]) printf("!! an mbarrier wait timed out: the numbers below are incomplete\n");
         for (int r = 0; r < 2; ++r, idx += 3)
             printf("B2 stage: 4 dgrad done after %lld cyc, 8 wgrad behind them after %lld cyc; a following 4-dgrad batch takes %lld cyc\n", h[idx], h[idx + 1], h[idx + 2]);
     }
