@@ -10,6 +10,7 @@
 // Algorithmic bytes: fwd 588 B/point fp16 (512 gather + 12 pos + 64 out), bwd 1100 B/point.
 #include "ngp_common.cuh"
 #include <cmath>
+#include <cstdlib>
 
 namespace {
 
@@ -114,6 +115,98 @@ hash_bwd_kernel(uint32_t n, const float* __restrict__ x, const T* __restrict__ d
     }
 }
 
+// ---- run-length variants (opt-in through NGP_HASH_RUNLEN=1, not yet measured) ------------------------------------------------
+// The fused network kernels keep the 8 corner values (forward) / 8 fp32 corner accumulators (backward) of a grid cell while
+// CONSECUTIVE samples stay inside it -- samples arrive ray-ordered, so at the coarse levels dozens do -- which cut their L2
+// requests / f16x2 reductions by the mean run length ("Run-length reuse").  These are the same loops for the standalone
+// HashEncoder boundary: thread (level, sub) walks RUN consecutive points.  Uniformly random points (BASELINE config #1) have no runs
+// and gain nothing; the backward rounds each run's fp32 sum once instead of once per sample.
+constexpr int RUN = 16;
+constexpr int RUN_PTS_PER_BLOCK = (HASH_THREADS / N_LEVELS) * RUN;   // 256
+
+template <typename T>
+__global__ void __launch_bounds__(HASH_THREADS)
+hash_fwd_runlen_kernel(uint32_t n, const float* __restrict__ x, const T* __restrict__ grid, const NgpLevel* __restrict__ levels,
+                       T* __restrict__ out) {
+    using V = typename Vec2<T>::type;
+    __shared__ NgpLevel s_lv[N_LEVELS];
+    if (threadIdx.x < N_LEVELS) s_lv[threadIdx.x] = levels[threadIdx.x];
+    __syncthreads();
+    const uint32_t level = threadIdx.x & (N_LEVELS - 1), sub = threadIdx.x / N_LEVELS;
+    const NgpLevel lv = s_lv[level];
+    const V* __restrict__ g = reinterpret_cast<const V*>(grid) + lv.offset;
+    const uint32_t base = blockIdx.x * RUN_PTS_PER_BLOCK + sub * RUN;
+    uint32_t cgx = 0xffffffffu, cgy = 0, cgz = 0;
+    float2 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int k = 0; k < RUN; ++k) {
+        const uint32_t i = base + k;
+        if (i >= n) break;
+        const HashCell hc = hash_cell(lv, __ldg(x + 3 * (size_t)i), __ldg(x + 3 * (size_t)i + 1), __ldg(x + 3 * (size_t)i + 2));
+        if (hc.gx != cgx || hc.gy != cgy || hc.gz != cgz) {
+            cgx = hc.gx; cgy = hc.gy; cgz = hc.gz;
+            uint32_t idx[8];
+            hash_cell_indices(lv, cgx, cgy, cgz, idx);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[c] = to_f2(__ldg(g + idx[c]));
+        }
+        float w[8];
+        hash_cell_weights(hc, w);
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { a0 = fmaf(w[c], v[c].x, a0); a1 = fmaf(w[c], v[c].y, a1); }
+        V r;
+        if constexpr (sizeof(T) == 2) r = __floats2half2_rn(a0, a1); else r = make_float2(a0, a1);
+        reinterpret_cast<V*>(out)[(size_t)i * N_LEVELS + level] = r;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(HASH_THREADS)
+hash_bwd_runlen_kernel(uint32_t n, const float* __restrict__ x, const T* __restrict__ dy, const NgpLevel* __restrict__ levels,
+                       T* __restrict__ grid_grad) {
+    using V = typename Vec2<T>::type;
+    __shared__ NgpLevel s_lv[N_LEVELS];
+    if (threadIdx.x < N_LEVELS) s_lv[threadIdx.x] = levels[threadIdx.x];
+    __syncthreads();
+    const uint32_t level = threadIdx.x & (N_LEVELS - 1), sub = threadIdx.x / N_LEVELS;
+    const NgpLevel lv = s_lv[level];
+    V* __restrict__ g = reinterpret_cast<V*>(grid_grad) + lv.offset;
+    const uint32_t base = blockIdx.x * RUN_PTS_PER_BLOCK + sub * RUN;
+    uint32_t cgx = 0xffffffffu, cgy = 0, cgz = 0, idx[8];
+    float2 acc[8];
+    bool dirty = false;
+#pragma unroll 1
+    for (int k = 0; k < RUN; ++k) {
+        const uint32_t i = base + k;
+        if (i >= n) break;
+        const float2 d = to_f2(reinterpret_cast<const V*>(dy)[(size_t)i * N_LEVELS + level]);
+        if (d.x == 0.f && d.y == 0.f) continue;
+        const HashCell hc = hash_cell(lv, __ldg(x + 3 * (size_t)i), __ldg(x + 3 * (size_t)i + 1), __ldg(x + 3 * (size_t)i + 2));
+        if (hc.gx != cgx || hc.gy != cgy || hc.gz != cgz) {
+            if (dirty) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) red_add(g + idx[c], acc[c].x, acc[c].y);
+            }
+            cgx = hc.gx; cgy = hc.gy; cgz = hc.gz;
+            hash_cell_indices(lv, cgx, cgy, cgz, idx);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] = make_float2(0.f, 0.f);
+            dirty = true;
+        }
+        float w[8];
+        hash_cell_weights(hc, w);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { acc[c].x = fmaf(d.x, w[c], acc[c].x); acc[c].y = fmaf(d.y, w[c], acc[c].y); }
+    }
+    if (dirty) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) red_add(g + idx[c], acc[c].x, acc[c].y);
+    }
+}
+
 template <typename T>
 __global__ void sh_kernel(uint32_t n, const float* __restrict__ dirs, T* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -179,6 +272,14 @@ int ngp_hash_fwd(void* stream, uint32_t n, const float* x, const void* grid, int
     if (n == 0) return 0;                                                  // HE/grid_encode.py:78-80
     const uint32_t blocks = (n + PTS_PER_BLOCK - 1) / PTS_PER_BLOCK;
     cudaStream_t s = (cudaStream_t)stream;
+    static const bool runlen = getenv("NGP_HASH_RUNLEN") && atoi(getenv("NGP_HASH_RUNLEN")) == 1;   // opt-in run-length variants
+    if (runlen && (dtype == 0 || dtype == 1)) {
+        const uint32_t rb = (n + RUN_PTS_PER_BLOCK - 1) / RUN_PTS_PER_BLOCK;
+        if (dtype == 1) hash_fwd_runlen_kernel<__half><<<rb, HASH_THREADS, 0, s>>>(n, x, (const __half*)grid, (const NgpLevel*)levels_dev, (__half*)out);
+        else hash_fwd_runlen_kernel<float><<<rb, HASH_THREADS, 0, s>>>(n, x, (const float*)grid, (const NgpLevel*)levels_dev, (float*)out);
+        NGP_LAUNCH_CHECK();
+        return 0;
+    }
     if (dtype == 1) hash_fwd_kernel<__half><<<blocks, HASH_THREADS, 0, s>>>(n, x, (const __half*)grid, (const NgpLevel*)levels_dev, (__half*)out);
     else if (dtype == 0) hash_fwd_kernel<float><<<blocks, HASH_THREADS, 0, s>>>(n, x, (const float*)grid, (const NgpLevel*)levels_dev, (float*)out);
     else NGP_REQUIRE(false, "ngp_hash_fwd: dtype must be 0 (f32) or 1 (f16)");
@@ -192,6 +293,14 @@ int ngp_hash_bwd(void* stream, uint32_t n, const float* x, const void* dy, int d
     cudaStream_t s = (cudaStream_t)stream;
     if (n == 0) return 0;                                                  // HE/grid_encode.py:142-144 (returns before the memset)
     NGP_CHECK_CUDA(cudaMemsetAsync(grid_grad, 0, n_params * (dtype == 1 ? 2 : 4), s));   // :153
+    static const bool runlen = getenv("NGP_HASH_RUNLEN") && atoi(getenv("NGP_HASH_RUNLEN")) == 1;
+    if (runlen) {
+        const uint32_t rb = (n + RUN_PTS_PER_BLOCK - 1) / RUN_PTS_PER_BLOCK;
+        if (dtype == 1) hash_bwd_runlen_kernel<__half><<<rb, HASH_THREADS, 0, s>>>(n, x, (const __half*)dy, (const NgpLevel*)levels_dev, (__half*)grid_grad);
+        else hash_bwd_runlen_kernel<float><<<rb, HASH_THREADS, 0, s>>>(n, x, (const float*)dy, (const NgpLevel*)levels_dev, (float*)grid_grad);
+        NGP_LAUNCH_CHECK();
+        return 0;
+    }
     const uint32_t blocks = (n + PTS_PER_BLOCK - 1) / PTS_PER_BLOCK;
     if (dtype == 1) hash_bwd_kernel<__half><<<blocks, HASH_THREADS, 0, s>>>(n, x, (const __half*)dy, (const NgpLevel*)levels_dev, (__half*)grid_grad);
     else hash_bwd_kernel<float><<<blocks, HASH_THREADS, 0, s>>>(n, x, (const float*)dy, (const NgpLevel*)levels_dev, (float*)grid_grad);

@@ -82,3 +82,18 @@ def test_pipelined_composite_matches_oracle():
                         "-k", "test_composite or fused_step", "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "3 passed" in r.stdout, r.stdout[-2000:]
+
+
+def test_run_length_standalone_hash_kernels_match_oracle():
+    """NGP_HASH_RUNLEN=1 (standalone ngp_hash_fwd / ngp_hash_bwd walking 16 consecutive points per thread with the corner values /
+    fp32 corner accumulators kept while the grid cell does not change): the oracle comparisons of the default kernels, plus the
+    per-operator autograd step, which drives them on ray-ordered samples."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, NGP_HASH_RUNLEN="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_ops.py"), os.path.join(here, "test_gpu_runner.py"), "-q", "-x", "-m", "gpu",
+                        "-k", "test_hash or fused_step or api_surface", "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-2000:]

@@ -42,6 +42,11 @@ nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-const
 run probe_tc_time4 60 /tmp/tc_time4
 run probe_tc_stage 120 /tmp/tc_stage
 
+# 3b. standalone hash kernels on ray-ordered samples of a real training state, default vs run-length variants (and the reference's own kernels)
+run ref_gpu_compare_default 400 python tools/ref_gpu_compare.py
+run ref_gpu_compare_hash_runlen 400 env NGP_HASH_RUNLEN=1 python tools/ref_gpu_compare.py
+run microbench 300 python tools/microbench.py
+
 # 4. A/B of the opt-in variants on the headline workload (roofline.stage_ms shows the stage each one touches)
 bench default --
 bench save_act NGP_SAVE_ACT=1 --
