@@ -343,16 +343,18 @@ def run_ours(args):
 
 
 def stage_times(runner, iters):
-    """Average per-stage device time (ms) of the training step, CUDA events on the current stream."""
+    """Average per-stage device time (ms) of the training step, CUDA events on the current stream.  All `iters` iterations are
+    enqueued before the one synchronisation: the GPU then always has a backlog, so an interval between two events is the device
+    time of that stage and not the host's launch latency (a per-iteration sync inflated the stages made of many small launches)."""
     import torch
     from jnerf_b200 import ops
-    s, m = runner.sampler, runner.model
+    s = runner.sampler
     names = ["prepare_batch", "march", "network_fwd", "composite_loss_bwd", "network_bwd", "adam_ema"]
-    acc = {k: 0.0 for k in names}
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
-    nsamp = 0
-    for it in range(iters):
-        runner.cfg.m_training_step += 1 if runner.cfg.m_training_step % 16 == 0 else 0      # keep grid updates out of the per-stage split
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)] for _ in range(iters)]
+    n_dev = None
+    for ev in evs:
+        while runner.cfg.m_training_step % 16 in (0, 15):    # keep grid updates and the ray-batch adaptation (.item() sync) out of the split
+            runner.cfg.m_training_step += 1
         ev[0].record()
         ds = runner.dataset["train"]
         R = s.n_rays_per_batch
@@ -376,13 +378,10 @@ def stage_times(runner, iters):
         runner._optimizer_step(0.0, max(adam.n_step, 1))     # lr 0: timing only, parameters barely move; N>1: + reduce-scatter / all-gather
         runner._table_ready()
         ev[6].record()
-        torch.cuda.synchronize()
-        for k, name in enumerate(names):
-            acc[name] += ev[k].elapsed_time(ev[k + 1])
-        nsamp = min(int(n_dev.item()), s.target_batch_size)
         runner.cfg.m_training_step += 1
-    out = {k: v / iters for k, v in acc.items()}
-    out["_samples"] = nsamp
+    torch.cuda.synchronize()
+    out = {name: sum(ev[k].elapsed_time(ev[k + 1]) for ev in evs) / iters for k, name in enumerate(names)}
+    out["_samples"] = min(int(n_dev.item()), s.target_batch_size)
     return out
 
 
