@@ -170,3 +170,27 @@ def test_synthetic_datasets_construct_and_render(cpu_device, monkeypatch, style)
     assert torch.allclose(d.norm(dim=-1), torch.ones(64), atol=1e-5)
     val = D.SyntheticNerfDataset(batch_size=64, mode="val", style=style, seed=1, **dict(kw, n_images=20))
     assert val.n_images == 2                                                        # a tenth of the views, other cameras than training
+
+
+def test_reduced_fox_capture_fixture(tmp_path, cpu_device):
+    """tests/golden/fox_small: the reference's data/fox reduced 6x (make_fox_small.py), materialised in the reference's dataset layout
+    and read by NerfDataset -- the real-capture input of the GPU end-to-end test, which has no /root/reference to read."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_fox_small import materialise
+    root = materialise(str(tmp_path / "fox"))
+    jd = json.load(open(os.path.join(root, "transforms_train.json")))
+    assert len(jd["frames"]) == 67                                   # 17 of them have no image: skipped by the loader
+    ds = D.NerfDataset(root, 4096, mode="train")
+    check_against_json(ds, jd, root, 50)
+    assert ds.resolution == [180, 320] and ds.aabb_scale == 4 and bool((ds.image_data[:, :, 3] == 255).all())
+    assert D.NerfDataset(root, 4096, mode="test", preload_shuffle=False).n_images == 2
+    ref = "/root/reference/data/fox/transforms_train.json"
+    if os.path.exists(ref):                                          # same poses as the capture, intrinsics scaled by the reduction
+        rj = json.load(open(ref))
+        assert [f["file_path"] for f in rj["frames"]] == [f["file_path"] for f in jd["frames"]]
+        assert np.array_equal(np.array([f["transform_matrix"] for f in rj["frames"]]), np.array([f["transform_matrix"] for f in jd["frames"]]))
+        for k in ("fl_x", "fl_y", "cx", "cy"):
+            assert abs(jd[k] * 6 - rj[k]) < 1e-9
+        assert jd["aabb_scale"] == rj["aabb_scale"] and (jd["w"], jd["h"]) == (rj["w"] // 6, rj["h"] // 6)
+    assert float(ds.image_data[:, :, :3].float().std()) > 20         # photographs, not blanks

@@ -211,3 +211,31 @@ def test_two_rank_runner_sharded_optimizer_keeps_replicas_identical(tmp_path):
     assert a["calls"] == ["prepare_batch", "march", "compact", "network_fwd", "composite_loss_bwd", "network_bwd", "adam_ema", "adam_ema", "adam_ema"]
     ck = torch.load(str(tmp_path / "dp.pt"), map_location="cpu", weights_only=False)
     assert ck["nested_optimizer"]["m"][0].numel() == 12196240 and ck["global_step"] == 4
+
+
+def test_real_capture_through_the_runner(monkeypatch, tmp_path):
+    """ngp_fox.py on the reduced real capture (tests/golden/fox_small, NerfDataset): a few training steps and a rendered tile."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_fox_small import materialise
+    root = materialise(str(tmp_path / "fox"))
+    fake = cpu_backend.install(monkeypatch)
+    from jnerf_b200 import plugin  # noqa: F401
+    from jnerf_b200 import runner as R
+    from jnerf_b200.utils.config import get_cfg, update_cfg
+    get_cfg().clear()
+    update_cfg(**R.fox_cfg(fp16=True, synthetic=False, seed=1, n_rays_per_batch=48, target_batch_size=32768))
+    cfg = get_cfg()
+    cfg.dataset.train.root_dir = root
+    cfg.dataset.test.root_dir = root
+    r = R.Runner()
+    ds = r.dataset["train"]
+    assert type(ds).__name__ == "NerfDataset" and ds.n_images == 50 and ds.aabb_scale == 4 and r.sampler.aabb_range == (-1.5, 2.5)
+    bits, _ = ol.sphere_bitfield(0.35)
+    r.sampler.density_grid_bitfield.copy_(torch.from_numpy(bits))
+    cfg.m_training_step = 1
+    losses = [float(r.train_step().mean()) for _ in range(4)]
+    assert all(np.isfinite(losses)) and fake.calls.count("prepare_batch") == 4
+    img_ids, o, d, rgba = next(ds)
+    assert bool((rgba[:, 3] == 1).all()) and int(img_ids.max()) < 50          # opaque JPEG frames

@@ -171,3 +171,32 @@ def test_render_without_host_round_trips_equals_the_tiled_render():
     assert torch.equal(tar_a, tar_b)
     assert torch.equal(img_a, img_b)
     assert float(img_a.std()) > 0.01                                 # not a blank image
+
+
+def test_real_capture_trains_end_to_end(tmp_path):
+    """BASELINE config #3 on REAL data: the reference's own capture data/fox, reduced 6x to a fixture (tests/golden/fox_small +
+    make_fox_small.py), through NerfDataset and the unchanged ngp_fox.py settings (aabb_scale 4 from the capture, cone stepping)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_fox_small import materialise
+    from jnerf_b200 import ops, plugin  # noqa: F401
+    from jnerf_b200.runner import Runner, fox_cfg
+    from jnerf_b200.utils.config import get_cfg, update_cfg
+    root = materialise(str(tmp_path / "fox"))
+    get_cfg().clear()
+    update_cfg(**fox_cfg(fp16=True, synthetic=False, seed=2))
+    cfg = get_cfg()
+    cfg.dataset.train.root_dir = root
+    cfg.dataset.test.root_dir = root
+    r = Runner()
+    ds = r.dataset["train"]
+    assert ds.n_images == 50 and ds.resolution == [180, 320] and ds.aabb_scale == 4
+    first = float(r.train_step().mean())
+    for _ in range(499):
+        loss = r.train_step()
+    last = float(loss.mean())
+    assert np.isfinite(last) and last < 0.6 * first, (first, last)
+    assert ops.lib.load().ngp_debug_timeout_flag() == 0
+    psnr = r.psnr("train", max_images=2)
+    assert psnr > 16.0, psnr                                         # 500 steps (about 0.3 s of training) on a real hand-held capture

@@ -60,6 +60,8 @@ bench default_again --
 
 # 5. BASELINE config #3 (fox stand-in) and config #5 (batch-size sweep, one GPU)
 bench fox -- --workload fox
+python -c "import sys; sys.path.insert(0, 'tests/golden'); from make_fox_small import materialise; materialise('/tmp/fox_small')" > "$OUT/fox_small.log" 2>&1
+bench fox_real_capture_180x320 -- --workload fox --data-dir /tmp/fox_small
 run sweep_1gpu 900 python tools/sweep.py --gpus 1 --tag r02 --steps 100
 cp profiles/r02_sweep_lego.json "$OUT/" 2>/dev/null
 
