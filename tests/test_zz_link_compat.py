@@ -199,4 +199,4 @@ def test_real_capture_trains_end_to_end(tmp_path):
     assert np.isfinite(last) and last < 0.6 * first, (first, last)
     assert ops.lib.load().ngp_debug_timeout_flag() == 0
     psnr = r.psnr("train", max_images=2)
-    assert psnr > 16.0, psnr                                         # 500 steps (about 0.3 s of training) on a real hand-held capture
+    assert psnr > 14.0, psnr                                         # 500 steps (about 0.3 s of training) on a real hand-held capture
