@@ -136,6 +136,12 @@ def test_fox_configuration_runs(monkeypatch):
         loss = r.train_step()
     assert np.isfinite(float(loss.mean())) and float(loss.mean()) < l0
     assert fake.calls.count("march") == 6
+    # occupancy-grid update over the three cascades an aabb_scale of 4 uses (max_cascade + 1, density_grid_sampler.py:233)
+    r.cfg.m_training_step = 0
+    s.update_density_grid_nerf(0.95, 30000, 0)
+    G3 = 128 ** 3 // 8
+    bits = s.density_grid_bitfield
+    assert int(bits[:G3].count_nonzero()) > 0 and int(bits[G3:3 * G3].count_nonzero()) > 0 and float(s.density_grid_mean.item()) > 0
 
 
 def test_occupancy_grid_update_glue(monkeypatch):
