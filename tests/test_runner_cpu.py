@@ -245,3 +245,19 @@ def test_real_capture_through_the_runner(monkeypatch, tmp_path):
     assert all(np.isfinite(losses)) and fake.calls.count("prepare_batch") == 4
     img_ids, o, d, rgba = next(ds)
     assert bool((rgba[:, 3] == 1).all()) and int(img_ids.max()) < 50          # opaque JPEG frames
+
+
+def test_saved_activation_mode_glue(monkeypatch):
+    """NGP_SAVE_ACT=1: the Runner allocates the activation image once (ngp_network_act_bytes of the sample capacity), hands the same
+    buffer to the forward and the backward of every step, and the bench's per-stage path goes through the same two methods."""
+    monkeypatch.setenv("NGP_SAVE_ACT", "1")
+    r, fake = make_runner(monkeypatch, seed=4)
+    assert r.save_act and r.act.numel() == (r.sampler.target_batch_size + 127) // 128 * 26 * 2048 and r.act.dtype == torch.uint8
+    fake.calls.clear()
+    loss = r.train_step()
+    assert fake.calls == [c if not c.startswith("network_") else c + "_saved" for c in STEP_OPS] and torch.isfinite(loss).all()
+    monkeypatch.delenv("NGP_SAVE_ACT")
+    r2, _ = make_runner(monkeypatch, seed=4)
+    assert not r2.save_act and r2.act is None
+    l2 = r2.train_step()
+    assert torch.equal(loss, l2)                                   # same results either way
