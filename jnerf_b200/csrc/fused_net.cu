@@ -529,7 +529,7 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
                     if (t < f_in[m]) {
 #pragma unroll
                         for (int o = 0; o < 16; ++o)
-                            if (16 * c + o < f_valid[m]) atomicAdd(f_dst[m] + (size_t)(16 * c + o) * f_in[m] + t, v[o]);
+                            if (16 * c + o < f_valid[m]) red_add_f32(f_dst[m] + (size_t)(16 * c + o) * f_in[m] + t, v[o]);
                     }
                 }
             }
@@ -561,7 +561,7 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
                 if (hc.gx != cgx || hc.gy != cgy || hc.gz != cgz) {
                     if (dirty && !(dbg & 1)) {
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) atomicAdd(gg + idx[c], __floats2half2_rn(accv[c].x, accv[c].y));
+                        for (int c = 0; c < 8; ++c) red_add_h2(gg + idx[c], accv[c].x, accv[c].y);
                     }
                     cgx = hc.gx; cgy = hc.gy; cgz = hc.gz;
                     hash_cell_indices(lv, cgx, cgy, cgz, idx);
@@ -576,7 +576,7 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             }
             if (dirty && !(dbg & 1)) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) atomicAdd(gg + idx[c], __floats2half2_rn(accv[c].x, accv[c].y));
+                for (int c = 0; c < 8; ++c) red_add_h2(gg + idx[c], accv[c].x, accv[c].y);
             }
             if (tile + 2 * gridDim.x < ntiles) named_bar_arrive(4 + buf, NT);   // EMPTY[buf] for the chain's tile it+2
         }
@@ -850,7 +850,7 @@ network_bwd2_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const fl
 #pragma unroll
                         for (int o = 0; o < 16; ++o) {
                             const uint32_t out_f = f_tr[m] ? t : 16 * c + o, in_f = f_tr[m] ? 16 * c + o : t;
-                            if (out_f < f_valid[m]) atomicAdd(f_dst[m] + (size_t)out_f * f_in[m] + in_f, v[o]);
+                            if (out_f < f_valid[m]) red_add_f32(f_dst[m] + (size_t)out_f * f_in[m] + in_f, v[o]);
                         }
                     }
                 }
@@ -881,7 +881,7 @@ network_bwd2_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const fl
                 if (hc.gx != cgx || hc.gy != cgy || hc.gz != cgz) {
                     if (dirty && !(dbg & 1)) {
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) atomicAdd(gg + idx[c], __floats2half2_rn(accv[c].x, accv[c].y));
+                        for (int c = 0; c < 8; ++c) red_add_h2(gg + idx[c], accv[c].x, accv[c].y);
                     }
                     cgx = hc.gx; cgy = hc.gy; cgz = hc.gz;
                     hash_cell_indices(lv, cgx, cgy, cgz, idx);
@@ -896,7 +896,7 @@ network_bwd2_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const fl
             }
             if (dirty && !(dbg & 1)) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) atomicAdd(gg + idx[c], __floats2half2_rn(accv[c].x, accv[c].y));
+                for (int c = 0; c < 8; ++c) red_add_h2(gg + idx[c], accv[c].x, accv[c].y);
             }
             if (tile + 2 * tile_step < ntiles) named_bar_arrive(B_EMPTY + buf, 256);   // EMPTY[buf] for the chain's tile it+2
         }

@@ -86,8 +86,8 @@ hash_fwd_kernel(uint32_t n, const float* __restrict__ x, const T* __restrict__ g
     }
 }
 
-__device__ __forceinline__ void red_add(__half2* addr, float a, float b) { atomicAdd(addr, __floats2half2_rn(a, b)); }
-__device__ __forceinline__ void red_add(float2* addr, float a, float b) { atomicAdd(addr, make_float2(a, b)); }
+__device__ __forceinline__ void red_add(__half2* addr, float a, float b) { red_add_h2(addr, a, b); }
+__device__ __forceinline__ void red_add(float2* addr, float a, float b) { red_add_f2(addr, a, b); }
 
 template <typename T>
 __global__ void __launch_bounds__(HASH_THREADS)

@@ -247,7 +247,7 @@ mlp_bwd_kernel(const __half* __restrict__ W, const __half* __restrict__ X, const
             tmem_ld16(tmem_addr(tbase, warp, D_WOUT), v);
 #pragma unroll
             for (int o = 0; o < 16; ++o)
-                if ((uint32_t)o < n_out_valid) atomicAdd(dWo + o * WIDTH + t, v[o]);
+                if ((uint32_t)o < n_out_valid) red_add_f32(dWo + o * WIDTH + t, v[o]);
         } else {
             tmem_ld16(tmem_addr(tbase, warp, D_WOUT), v);   // keep the warp-collective tcgen05.ld uniform
         }
@@ -258,7 +258,7 @@ mlp_bwd_kernel(const __half* __restrict__ W, const __half* __restrict__ X, const
                 tmem_ld16(tmem_addr(tbase, warp, D_W + 64 * k + 16 * c), v);
                 if (t < in_dim) {
 #pragma unroll
-                    for (int o = 0; o < 16; ++o) atomicAdd(dst + (size_t)(16 * c + o) * in_dim + t, v[o]);
+                    for (int o = 0; o < 16; ++o) red_add_f32(dst + (size_t)(16 * c + o) * in_dim + t, v[o]);
                 }
             }
         }

@@ -26,6 +26,21 @@ void ngp_set_error(const std::string& msg);
 
 int ngp_num_sms();
 
+// ---- fire-and-forget reductions --------------------------------------------------------------------
+// atomicAdd(__half2*) on a generic pointer compiles to QSPC + ATOM (returning a predicate) + a CAS spin fallback, i.e. every
+// reduction waits for its round trip.  With the address converted to the global window the same operation is a single
+// RED.E.ADD.F16x2 that retires at issue (HashEncode.h:339-347 only needs the sum, never the old value).
+__device__ __forceinline__ void red_add_h2(__half2* addr, float a, float b) {
+    const __half2 v = __floats2half2_rn(a, b);
+    asm volatile("red.global.add.noftz.f16x2 [%0], %1;" ::"l"(__cvta_generic_to_global(addr)), "r"(*reinterpret_cast<const uint32_t*>(&v)) : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(__cvta_generic_to_global(addr)), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_f2(float2* addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(__cvta_generic_to_global(addr)), "f"(a), "f"(b) : "memory");
+}
+
 // ---- hash-grid level record (R1) ------------------------------------------------------------------
 struct __align__(32) NgpLevel {
     float scale;          // exp2f(level*log2_pls)*base - 1        (HashEncode.h:149)
