@@ -52,7 +52,9 @@ def hash_fwd(x, grid, levels):
 
 def hash_bwd(x, dy, levels, grid_grad=None):
     if grid_grad is None:
-        grid_grad = torch.empty(levels.n_params, dtype=dy.dtype, device=x.device)
+        # the kernel's memset is skipped for an empty batch (as HE/grid_encode.py:142-144 does): hand out zeros in that case
+        alloc = torch.zeros if x.shape[0] == 0 else torch.empty
+        grid_grad = alloc(levels.n_params, dtype=dy.dtype, device=x.device)
     lib.call("ngp_hash_bwd", _stream(), x.shape[0], _p(x), _p(dy), _dt(dy), _p(levels.table), _p(grid_grad), levels.n_params)
     return grid_grad
 

@@ -47,6 +47,12 @@ class Runner:
         cfg.m_training_step = 0
         self.val_freq = 4096
         self.fast = bool(getattr(self.model, "fused", False))
+        # state the evaluation / checkpoint code reads on EVERY kind of model (fused or the nn.Linear fallback)
+        self._table_work, self._pending_epoch = None, None
+        self._st = {id(s.p): s for s in self.optimizer._nested_optimizer.state}
+        if world_size > 1 and not self.fast:
+            raise ValueError("data-parallel training needs the fused model (fp16=True, use_fully=True): the per-operator autograd step "
+                             "shards the ray batch but has no gradient exchange, the replicas would silently diverge")
         if self.fast:
             self._init_fast_path()
         self._bg_gen = torch.Generator(device="cuda").manual_seed(int(cfg.seed or 1) + 7)
@@ -65,11 +71,8 @@ class Runner:
         self.net_out = torch.zeros((cap, 4), dtype=torch.float16, device=dev)
         self.enc = torch.empty((cap, 32), dtype=torch.float16, device=dev)
         self.dnet = torch.zeros((cap, 4), dtype=torch.float16, device=dev)
-        adam = self.optimizer._nested_optimizer
-        self._st = {id(s.p): s for s in adam.state}
         self.last_loss = None
         self.last_rgb = None
-        self._table_work = None
         # NGP_SAVE_ACT=1: the forward kernel also writes the MLP activations (416 B/sample) and the backward kernel reads them back
         # instead of recomputing the five forward stages (ngp_network_fwd_saved / ngp_network_bwd_saved; same results)
         self.save_act = os.environ.get("NGP_SAVE_ACT", "0") == "1"
@@ -382,6 +385,9 @@ class Runner:
                 return
         ck = {"global_step": self.cfg.m_training_step, "model": self.model.state_dict(), "sampler": self.sampler.state_dict(),
               "optimizer": self.optimizer.state_dict(), "nested_optimizer": nested, "ema_optimizer": self.ema_optimizer.state_dict()}
+        if str(path).endswith(".pkl") and not hasattr(self.model.density_mlp, "con_weights"):
+            raise NotImplementedError("the .pkl interchange format is written for the fused-MLP parameter layout (con_weights); "
+                                      "save the nn.Linear fallback model to a .pt path")
         if str(path).endswith(".pkl"):
             # the reference's params.pkl wire format (runner/runner.py:123-131), readable by its load_ckpt (:133-151)
             from .utils import ckpt_compat as cc
@@ -396,12 +402,18 @@ class Runner:
         torch.save(ck, path)
 
     def load_ckpt(self, path):
+        self._table_ready()                                          # an exchange of the previous step may still be writing the table
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.pg)                              # no peer may still push into this rank's table while it is overwritten
+        if str(path).endswith(".pkl") and not hasattr(self.model.density_mlp, "con_weights"):
+            raise NotImplementedError("the .pkl interchange format carries the fused-MLP parameter layout; load a .pt checkpoint instead")
         if str(path).endswith(".pkl"):
             from .utils import ckpt_compat as cc
             ck = cc.load_native_from_reference_file(path, self.model.pos_encoder.m_grid.numel(), "cuda",
                                                     {k: v.dtype for k, v in self.model.state_dict().items()})
         else:
-            ck = torch.load(path, map_location="cuda", weights_only=False)
+            ck = torch.load(path, map_location="cuda", weights_only=True)      # tensors, numbers, lists and dicts only
         self.cfg.m_training_step = self.start = ck["global_step"]
         self.model.load_state_dict(ck["model"])
         self.sampler.load_state_dict(ck["sampler"])

@@ -148,9 +148,29 @@ def reference_to_native(ref, n_table):
     pg = nested["param_groups"][0]
     ema_d = ref["ema_optimizer"]["defaults"]
     try:
-        v = _by_size(pg["values"], sizes)
-        m = _by_size(pg["m"], sizes)
-        ema_vals = _by_size(ema_d["param_groups"][0]["values"], sizes)
+        if "values_f32" in pg:
+            # written by native_to_reference: the fp32 optimizer state next to the parameter-dtype copies the reference reads
+            v = _by_size(pg["values_f32"], sizes)
+            m = _by_size(pg["m_f32"], sizes)
+            ema_vals = _by_size(ema_d["param_groups"][0].get("values_f32", ema_d["param_groups"][0]["values"]), sizes)
+        else:
+            v = _by_size(pg["values"], sizes)
+            m = _by_size(pg["m"], sizes)
+            ema_vals = _by_size(ema_d["param_groups"][0]["values"], sizes)
+            # a reference-written file holds fp16 moments: second moments below fp16's smallest subnormal (6e-8) are stored as 0
+            # while the first moment survives, and lr * m / (sqrt(0) + 1e-15) would throw the entry to inf on the next step.
+            # Floor v at m^2 (|update| <= lr, Adam's own bound) for exactly those entries.
+            fixed = []
+            for mm, vv in zip(m, v):
+                mm32, vv32 = np.asarray(mm, np.float32), np.asarray(vv, np.float32).copy()
+                bad = (vv32 == 0) & (mm32 != 0)
+                vv32[bad] = mm32[bad] * mm32[bad]
+                still = bad & (vv32 == 0)                            # m^2 underflows fp32 as well: drop the momentum
+                if still.any():
+                    mm32 = mm32.copy()
+                    mm32[still] = 0
+                fixed.append((mm32, vv32))
+            m, v = [f[0] for f in fixed], [f[1] for f in fixed]
     except KeyError:
         # nn.Linear checkpoints keep one moment tensor per matrix; the flat fused layout restarts the moments and takes the
         # parameters themselves as EMA values (after every ema_step the two are equal, ema.py:33-36)
@@ -187,6 +207,7 @@ def native_to_reference(nat, adam_hyper=None, expdecay_hyper=None, param_dtype=n
     order = ["pos_encoder.m_grid", "density_mlp.con_weights", "rgb_mlp.con_weights"]
     nested, ema = nat["nested_optimizer"], nat["ema_optimizer"]
     cast = lambda a: np.asarray(a).astype(param_dtype)                                   # noqa: E731  Jittor keeps m / values in the parameter dtype
+    f32 = lambda a: np.asarray(a, np.float32)                                            # noqa: E731
     hyper = dict(lr=float(nested["lr"]), eps=1e-15, betas=(0.9, 0.99), weight_decay=0)
     hyper.update(adam_hyper or {})
     dec = dict(base_lr=hyper["lr"], decay_start=20000, decay_interval=10000, decay_base=0.33, decay_end=10000000)
@@ -204,9 +225,13 @@ def native_to_reference(nat, adam_hyper=None, expdecay_hyper=None, param_dtype=n
         "model": {k: model[k] for k in order},
         "sampler": sampler,
         "optimizer": {"defaults": dict(dec, steps=int(nat["optimizer"]["steps"]), m_learning_rate_factor=nat["optimizer"]["m_learning_rate_factor"])},
-        "nested_optimizer": {"defaults": dict(hyper, param_groups=[{"values": [cast(x) for x in nested["v"]], "m": [cast(x) for x in nested["m"]]}])},
+        # "values"/"m" in the parameter dtype are what the reference's load_ckpt reads (runner.py:133-151); the *_f32 keys are ignored
+        # by it and preferred by reference_to_native, so a save -> load in this repo is lossless (fp16 flushes most second moments to 0)
+        "nested_optimizer": {"defaults": dict(hyper, param_groups=[{"values": [cast(x) for x in nested["v"]], "m": [cast(x) for x in nested["m"]],
+                                                                    "values_f32": [f32(x) for x in nested["v"]], "m_f32": [f32(x) for x in nested["m"]]}])},
         "ema_optimizer": {"defaults": {"lr": 0, "decay": float(ema["decay"]), "steps": int(ema["steps"]),
-                                       "param_groups": [{"values": [cast(x) for x in nested["master"]]}]}},
+                                       "param_groups": [{"values": [cast(x) for x in nested["master"]],
+                                                         "values_f32": [f32(x) for x in nested["master"]]}]}},
     }
 
 

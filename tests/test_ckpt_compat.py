@@ -81,8 +81,10 @@ def test_reference_to_native_and_back():
     pg = ref["nested_optimizer"]["defaults"]["param_groups"][0]
     for k in range(3):
         assert nat["nested_optimizer"]["v"][k].dtype == np.float32
-        assert np.array_equal(nat["nested_optimizer"]["v"][k], pg["values"][k].astype(np.float32))       # jt.nn.Adam: values = 2nd moment
-        assert np.array_equal(nat["nested_optimizer"]["m"][k], pg["m"][k].astype(np.float32))
+        v16, m16 = pg["values"][k].astype(np.float32), pg["m"][k].astype(np.float32)
+        flushed = (v16 == 0) & (m16 != 0)                          # fp16 second moment flushed to 0 under a live first moment: floored at m^2
+        assert np.array_equal(nat["nested_optimizer"]["v"][k], np.where(flushed, m16 * m16, v16))         # jt.nn.Adam: values = 2nd moment
+        assert np.array_equal(nat["nested_optimizer"]["m"][k], m16)
     assert np.array_equal(nat["nested_optimizer"]["master"][0], ref["model"]["pos_encoder.m_grid"].astype(np.float32))
     assert nat["nested_optimizer"]["n_step"] == nat["ema_optimizer"]["steps"] == 1234
     assert nat["sampler"]["density_grid_mean"].shape == (1,) and abs(nat["sampler"]["density_grid_mean"][0] - 0.0123) < 1e-7
@@ -97,7 +99,9 @@ def test_reference_to_native_and_back():
     nested = ref2["nested_optimizer"]["defaults"]["param_groups"][0]
     ema = ref2["ema_optimizer"]["defaults"]
     for i in range(3):
-        assert np.array_equal(nested["values"][i], pg["values"][i]) and np.array_equal(nested["m"][i], pg["m"][i])
+        assert np.array_equal(nested["m"][i], pg["m"][i])
+        keep = ~((pg["values"][i] == 0) & (pg["m"][i] != 0))
+        assert np.array_equal(nested["values"][i][keep], pg["values"][i][keep])
         assert np.array_equal(ema["param_groups"][0]["values"][i], ref["ema_optimizer"]["defaults"]["param_groups"][0]["values"][i])
     assert ema["steps"] == 1234 and ref2["optimizer"]["defaults"]["steps"] == 1234
     assert ref2["sampler"]["density_grid_mean"].shape == (16384,) and np.array_equal(ref2["sampler"]["density_grid"], ref["sampler"]["density_grid"])

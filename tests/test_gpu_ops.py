@@ -153,8 +153,8 @@ def test_mlp_fwd_bwd(ops, nhm, n):
 
 
 # ------------------------------------------------------------------------------------------------ fused network
-def _net_inputs(n, seed=21, log2T=19):
-    cfg = ol.HashCfg(1, log2_hashmap_size=log2T)
+def _net_inputs(n, seed=21, log2T=19, aabb=1):
+    cfg = ol.HashCfg(aabb, log2_hashmap_size=log2T)
     rng = np.random.default_rng(seed)
     coords = np.zeros((n, 7), np.float32)
     coords[:, :3] = rng.random((n, 3), dtype=np.float32)
@@ -189,10 +189,12 @@ def test_network_fwd_live_count(ops):
     assert torch.equal(out[:300], full[:300]) and (out[384:] == 7.0).all()
 
 
-def test_network_bwd(ops):
+@pytest.mark.parametrize("aabb,log2T", [(1, 14), (1, 19), (4, 19)])
+def test_network_bwd(ops, aabb, log2T):
+    """(1,14): BASELINE config #1's table; (1,19): the production lego table; (4,19): the fox table (ngp_fox.py, aabb_scale 4)."""
     n = 3000
-    cfg, coords, grid, Wd, Wr = _net_inputs(n, log2T=14)
-    lv = ops.HashLevels(1, log2_hashmap_size=14)
+    cfg, coords, grid, Wd, Wr = _net_inputs(n, log2T=log2T, aabb=aabb)
+    lv = ops.HashLevels(aabb, log2_hashmap_size=log2T)
     rng = np.random.default_rng(5)
     dout = (rng.standard_normal((n, 4)) * 0.05).astype(np.float16)
     out, enc = ops.network_fwd(cu(coords), cu(grid), lv, cu(Wd), cu(Wr))
@@ -456,7 +458,7 @@ def test_network_bwd_two_chain_variant():
     here = os.path.dirname(os.path.abspath(__file__))
     env = dict(os.environ, NGP_BWD_V2="1")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_ops.py"), os.path.join(here, "test_gpu_runner.py"), "-q", "-x",
-                        "-m", "gpu", "-k", "(test_network_bwd and not two_chain) or fused_step", "-p", "no:cacheprovider"],
+                        "-m", "gpu", "-k", "(test_network_bwd and 1-14 and not two_chain) or fused_step", "-p", "no:cacheprovider"],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "2 passed" in r.stdout, r.stdout[-2000:]

@@ -99,11 +99,13 @@ def test_checkpoints_native_and_reference_format(monkeypatch, tmp_path):
         a, b = r.optimizer._nested_optimizer.state[2], r2.optimizer._nested_optimizer.state[2]
         if name.endswith(".pt"):
             assert torch.equal(a.m, b.m) and torch.equal(a.v, b.v) and torch.equal(a.master, b.master)
-        else:                                                     # the interchange format keeps optimizer state in the parameter dtype
-            assert torch.equal(b.m, a.m.half().float()) and torch.equal(b.master, a.master.half().float())
+        else:
+            # a .pkl written here round-trips losslessly (fp32 state under extra keys the reference ignores) ...
+            assert torch.equal(a.m, b.m) and torch.equal(a.v, b.v) and torch.equal(a.master, b.master)
             from jnerf_b200.utils import ckpt_compat as cc
-            ref = cc.read_reference_ckpt(p)                       # and has the fields the reference's load_ckpt indexes (runner.py:133-151)
-            assert ref["global_step"] == 5 and len(ref["nested_optimizer"]["defaults"]["param_groups"][0]["values"]) == 3
+            ref = cc.read_reference_ckpt(p)                       # ... and has the fields the reference's load_ckpt indexes (runner.py:133-151),
+            pg = ref["nested_optimizer"]["defaults"]["param_groups"][0]      # in the parameter dtype, as Jittor keeps them
+            assert ref["global_step"] == 5 and len(pg["values"]) == 3 and pg["values"][0].dtype == np.float16 and pg["m"][0].dtype == np.float16
             assert ref["ema_optimizer"]["defaults"]["steps"] == 4
         assert torch.isfinite(r2.train_step()).all()
 
@@ -261,3 +263,71 @@ def test_saved_activation_mode_glue(monkeypatch):
     assert not r2.save_act and r2.act is None
     l2 = r2.train_step()
     assert torch.equal(loss, l2)                                   # same results either way
+
+
+def test_reference_written_pkl_with_flushed_second_moments_keeps_training_finite(monkeypatch, tmp_path):
+    """A params.pkl written by the REFERENCE holds fp16 Adam moments: second moments of the hash table (g^2 ~ 1e-10) flush to 0 while the
+    first moment survives.  Loading such a file and training on must not blow entries up (lr * m / (sqrt(0) + 1e-15))."""
+    from jnerf_b200.utils import ckpt_compat as cc
+    r, _ = make_runner(monkeypatch, seed=5)
+    for _ in range(4):
+        r.train_step()
+    p = str(tmp_path / "params.pkl")
+    r.cfg.m_training_step = 5
+    r.save_ckpt(p)
+    ref = cc.read_reference_ckpt(p)
+    pg = ref["nested_optimizer"]["defaults"]["param_groups"][0]
+    for k in ("values_f32", "m_f32"):                              # what a reference-written file lacks
+        del pg[k]
+    del ref["ema_optimizer"]["defaults"]["param_groups"][0]["values_f32"]
+    v16, m16 = np.asarray(pg["values"][0]), np.asarray(pg["m"][0])
+    assert ((v16 == 0) & (m16 != 0)).any()                         # the hazard is really present in the fp16 copies
+    cc.write_reference_ckpt(ref, p)
+    r2, _ = make_runner(monkeypatch, seed=6)
+    r2.load_ckpt(p)
+    st = r2.optimizer._nested_optimizer.state[0]
+    assert not ((st.v == 0) & (st.m != 0)).any()
+    g_before = r2.model.pos_encoder.m_grid.detach().float().clone()
+    for _ in range(3):
+        assert torch.isfinite(r2.train_step()).all()
+    g = r2.model.pos_encoder.m_grid.detach().float()
+    assert torch.isfinite(g).all() and float((g - g_before).abs().max()) <= 3 * 0.1 + 1e-3      # |Adam update| <= lr per step
+
+
+def test_runner_on_the_linear_fallback_model_renders_and_saves(monkeypatch, tmp_path):
+    """The reference's own fallback (ngp_network.py:54-67: nn.Linear chains when the fused MLP is off): the Runner must still train
+    through the per-operator path, render, compute PSNR and write / read a native checkpoint; the .pkl interchange format (fused
+    parameter layout) and data-parallel training are refused with a clear error."""
+    cpu_backend.install(monkeypatch)
+    from jnerf_b200 import plugin  # noqa: F401
+    from jnerf_b200 import runner as R
+    from jnerf_b200.utils.config import get_cfg, update_cfg
+    get_cfg().clear()
+    update_cfg(**R.lego_cfg(fp16=True, synthetic=True, seed=2, n_rays_per_batch=64, target_batch_size=32768))
+    cfg = get_cfg()
+    cfg.model.fused = False
+    cfg.model.use_fully = False
+    cfg.dataset.train.n_images, cfg.dataset.train.H, cfg.dataset.train.W = 3, 16, 16
+    cfg.dataset.val = None
+    r = R.Runner()
+    assert not r.fast and not hasattr(r.model.density_mlp, "con_weights")
+    bits, _ = ol.sphere_bitfield(0.35, cascades=r.sampler.NERF_CASCADES)
+    r.sampler.density_grid_bitfield.copy_(torch.from_numpy(bits[:r.sampler.density_grid_bitfield.numel()]))
+    cfg.m_training_step = 1
+    r.train(steps=2)
+    img, tar = r.render_img("train", 0)
+    assert img.shape == (16, 16, 3) and torch.isfinite(img).all() and np.isfinite(r.psnr("train", max_images=1))
+    p = str(tmp_path / "ckpt.pt")
+    r.save_ckpt(p)
+    r.load_ckpt(p)
+    with pytest.raises(NotImplementedError):
+        r.save_ckpt(str(tmp_path / "params.pkl"))
+    get_cfg().clear()
+    update_cfg(**R.lego_cfg(fp16=True, synthetic=True, seed=2, n_rays_per_batch=64, target_batch_size=32768))
+    cfg = get_cfg()
+    cfg.model.fused = False
+    cfg.model.use_fully = False
+    cfg.dataset.train.n_images, cfg.dataset.train.H, cfg.dataset.train.W = 3, 16, 16
+    cfg.dataset.val = None
+    with pytest.raises(ValueError, match="data-parallel"):
+        R.Runner(rank=0, world_size=2, process_group=None)
