@@ -305,10 +305,6 @@ def run_ours(args):
     hbm, tfl, src = peaks()
     dom = max(("network_fwd", "network_bwd"), key=lambda k: stage[k])
     algo = dict(ALGO[dom])
-    if runner.save_act:                   # NGP_SAVE_ACT=1: + 416 B/sample of saved activations each way; the backward no longer recomputes the forward
-        algo["bytes"] += 416
-        if dom == "network_bwd":
-            algo["flops"] -= 20480
     t_dom = stage[dom] * 1e-3
     gbs = n_samples * algo["bytes"] / t_dom / 1e9
     roofline = {"kernel": dom, "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": measured_traffic(dom),
@@ -329,7 +325,7 @@ def run_ours(args):
                                f"{n_img} {'real' if args.data_dir else 'synthetic'} {res_txt} views, target_batch_size {args.target_batch} samples/iter/GPU"
                                f"{' (2^18)' if args.target_batch == 1 << 18 else ''}, adaptive ray batch "
                                f"({runner.sampler.n_rays_per_batch} rays/iter/GPU at measurement), pretrain {args.pretrain} steps",
-                   "parallelism": f"dp{world}", "target_batch_size": args.target_batch, "save_act": bool(runner.save_act),
+                   "parallelism": f"dp{world}", "target_batch_size": args.target_batch,
                    "l2": "per-step working set (24 MB table + 171 MB optimizer state + 7 MB samples) exceeds the 126 MB L2; no explicit flush"},
         "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline,
     }

@@ -94,17 +94,6 @@ int ngp_network_fwd(void* stream, uint32_t n_max, const uint32_t* n_dev, const f
 int ngp_network_bwd(void* stream, uint32_t n_max, const uint32_t* n_dev, const float* coords, const void* enc_save,
                     const void* levels_dev, const void* w_density, const void* w_rgb, const void* dout,
                     void* grid_grad, float* dw_density, float* dw_rgb);
-/* Saved-activation variant of the pair above (same results): the forward additionally writes the post-ReLU activations of both
- * MLPs (416 B per sample, a per-tile image of the kernels' shared-memory operand layout) and the backward reads them back instead
- * of recomputing the five forward stages -- what the reference does with `output_intermediate` (OPS/fully_fused_mlp.py:83,103),
- * here as an option because it trades 2 x 109 MB of HBM traffic per 2^18-sample iteration for half of the backward chain's stages.
- * act_save: ngp_network_act_bytes(n_max) bytes owned by the caller; only meaningful between a fwd_saved / bwd_saved pair. */
-uint64_t ngp_network_act_bytes(uint32_t n_max);
-int ngp_network_fwd_saved(void* stream, uint32_t n_max, const uint32_t* n_dev, const float* coords, const void* grid,
-                          const void* levels_dev, const void* w_density, const void* w_rgb, void* out, void* enc_save, void* act_save);
-int ngp_network_bwd_saved(void* stream, uint32_t n_max, const uint32_t* n_dev, const float* coords, const void* enc_save,
-                          const void* act_save, const void* levels_dev, const void* w_density, const void* w_rgb, const void* dout,
-                          void* grid_grad, float* dw_density, float* dw_rgb);
 /* NGPNetworks.density (ngp_network.py:86-89): pos (n,3) f32 -> sigma_raw (n) fp16 */
 int ngp_density_fwd(void* stream, uint32_t n, const float* pos, const void* grid, const void* levels_dev,
                     const void* w_density, void* sigma_out);

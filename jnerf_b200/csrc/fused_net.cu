@@ -68,18 +68,6 @@ struct SmemBwd {
 constexpr uint32_t OP_L0D = 0, OP_L1D = 2, OP_L0R = 6, OP_L1R = 8, OP_L2R = 12, OP_FWD_END = 16;
 constexpr uint32_t OP_L0D_B1 = 16;   // forward kernel only: density layer 0 reading the second enc buffer
 
-// ---- saved-activation image (optional: ngp_network_fwd_saved / ngp_network_bwd_saved) -------------------------------------
-// The backward kernel recomputes the five forward stages of every tile because storing 416 B of hidden activations per sample
-// used to look more expensive than ~10 MMAs.  Measured, the chain is bound by its per-stage latency (MMA -> commit -> TMEM load ->
-// convert -> shared store -> barrier, ~2 k cycles a stage), not by tensor or memory throughput -- so the forward kernel can
-// instead write the post-ReLU activations as a per-tile SLAB IMAGE (the byte layout of the shared-memory operand slabs, 26 groups
-// of 8 features x 128 rows) and the backward kernel copies them straight back into its slabs with 16-byte cp.async transfers that
-// are contiguous across a warp.  Values are the same fp16 numbers the recomputation would produce: results are unchanged.
-//   image groups: hd [0,8) | h = density output, the first 16 colour-net inputs [8,10) | h1 [10,18) | h2 [18,26)
-// (the 16 SH inputs are recomputed from the direction: 3 loads and ~50 flops instead of 32 B).
-constexpr uint32_t IMG_HD = 0, IMG_H = 8, IMG_H1 = 10, IMG_H2 = 18, IMG_GROUPS = 26;
-constexpr uint32_t IMG_TILE_BYTES = IMG_GROUPS * GB;          // 53 248 B per 128-sample tile = 416 B per sample
-
 template <class S>
 __device__ __forceinline__ void stage_all_weights(uint8_t* smem, const __half* wd, const __half* wr, uint32_t t) {
     stage_weights(smem + S::w0d, wd + WD_W0, 64, 32, t, 128);
@@ -145,20 +133,19 @@ __device__ __forceinline__ void build_forward_program(uint8_t* smem, uint32_t tb
 
 // Forward chain up to (and including) the colour net's last hidden layer.  Expects enc in ACT[G_ENC..+4).
 // Returns the fp16 density output h[0] of row t (sigma_raw) and leaves hd / rin / h1 / h2 in the slab.
-template <uint32_t G_H2, bool CHAIN128 = false, bool SAVE = false>
+template <uint32_t G_H2, bool CHAIN128 = false>
 __device__ __forceinline__ uint32_t forward_chain(uint8_t* smem, uint32_t act_off, const MmaOp* ops, uint32_t op_l0d,
                                                   const float* s_coords, uint32_t tbase, Pipe& pipe, uint32_t t, uint32_t warp,
-                                                  bool density_only, uint32_t chain_bar = 1, uint8_t* __restrict__ img = nullptr) {
+                                                  bool density_only, uint32_t chain_bar = 1) {
     uint8_t* act = smem + act_off;
     const uint32_t D_H = 0, D_S = 64;
     // density L0: enc(32) -> hd(64)
-    if (t == 0) { run_ops(ops, op_l0d, 2, 0); pipe.commit(); }
+    if (warp == 0) { if (elect_one()) { run_ops(ops, op_l0d, 2, 0); pipe.commit(); } __syncwarp(); }
     pipe.wait();
-    if constexpr (SAVE) epi_hidden_relu_img(tbase, D_H, warp, act, G_HD, t, img, IMG_HD);
-    else epi_hidden_relu(tbase, D_H, warp, act, G_HD, t, nullptr);
+    epi_hidden_relu(tbase, D_H, warp, act, G_HD, t, nullptr);
     if constexpr (CHAIN128) sync_chain(chain_bar); else sync_before_issue<false>();
     // density L1: hd(64) -> h(16)
-    if (t == 0) { run_ops(ops, OP_L1D, 4, 0); pipe.commit(); }
+    if (warp == 0) { if (elect_one()) { run_ops(ops, OP_L1D, 4, 0); pipe.commit(); } __syncwarp(); }
     pipe.wait();
     uint32_t sigma_half;
     {
@@ -169,10 +156,6 @@ __device__ __forceinline__ uint32_t forward_chain(uint8_t* smem, uint32_t act_of
         sigma_half = lo.x & 0xFFFFu;
         if (density_only) return sigma_half;
         slab_store16(act, G_RIN, t, lo, hi);
-        if constexpr (SAVE) {
-            *reinterpret_cast<uint4*>(img + (size_t)IMG_H * GB + t * 16) = lo;
-            *reinterpret_cast<uint4*>(img + (size_t)(IMG_H + 1) * GB + t * 16) = hi;
-        }
         float sh[16];
         sh4(s_coords[t * 7 + 4], s_coords[t * 7 + 5], s_coords[t * 7 + 6], sh);
         pack16(sh, lo, hi);
@@ -180,16 +163,14 @@ __device__ __forceinline__ uint32_t forward_chain(uint8_t* smem, uint32_t act_of
     }
     if constexpr (CHAIN128) sync_chain(chain_bar); else sync_before_issue<false>();
     // colour L0: [h | sh](32) -> h1(64)
-    if (t == 0) { run_ops(ops, OP_L0R, 2, 0); pipe.commit(); }
+    if (warp == 0) { if (elect_one()) { run_ops(ops, OP_L0R, 2, 0); pipe.commit(); } __syncwarp(); }
     pipe.wait();
-    if constexpr (SAVE) epi_hidden_relu_img(tbase, D_H, warp, act, G_H1, t, img, IMG_H1);
-    else epi_hidden_relu(tbase, D_H, warp, act, G_H1, t, nullptr);
+    epi_hidden_relu(tbase, D_H, warp, act, G_H1, t, nullptr);
     if constexpr (CHAIN128) sync_chain(chain_bar); else sync_before_issue<false>();
     // colour L1: h1(64) -> h2(64)
-    if (t == 0) { run_ops(ops, OP_L1R, 4, 0); pipe.commit(); }
+    if (warp == 0) { if (elect_one()) { run_ops(ops, OP_L1R, 4, 0); pipe.commit(); } __syncwarp(); }
     pipe.wait();
-    if constexpr (SAVE) epi_hidden_relu_img(tbase, D_H, warp, act, G_H2, t, img, IMG_H2);
-    else epi_hidden_relu(tbase, D_H, warp, act, G_H2, t, nullptr);
+    epi_hidden_relu(tbase, D_H, warp, act, G_H2, t, nullptr);
     if constexpr (CHAIN128) sync_chain(chain_bar); else sync_before_issue<false>();
     return sigma_half;
 }
@@ -203,11 +184,11 @@ __device__ __forceinline__ uint32_t forward_chain(uint8_t* smem, uint32_t act_of
 constexpr int FWD_GW = 8;
 constexpr int FWD_THREADS = 128 + 32 * FWD_GW;
 
-template <bool DENSITY_ONLY, bool SAVE_ACT = false>
+template <bool DENSITY_ONLY>
 __global__ void __launch_bounds__(FWD_THREADS)
 network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const float* __restrict__ coords, const __half* __restrict__ grid,
                    const NgpLevel* __restrict__ levels, const __half* __restrict__ wd, const __half* __restrict__ wr,
-                   __half* __restrict__ out, __half* __restrict__ enc_save, int* __restrict__ err, uint8_t* __restrict__ act_img = nullptr) {
+                   __half* __restrict__ out, __half* __restrict__ enc_save, int* __restrict__ err) {
     extern __shared__ __align__(1024) uint8_t smem[];
     using S = SmemFwd;
     constexpr int CS = DENSITY_ONLY ? 3 : 7;
@@ -248,14 +229,13 @@ network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             tc_fence_after();
             // forward_chain releases nothing itself: the enc slab is dead after layer 0, the coordinates after the SH epilogue;
             // both are handed back together right after the chain (the gather runs a full tile ahead, so this is not on its path)
-            const uint32_t sig = forward_chain<G_H2F, true, SAVE_ACT>(smem, S::act, ops, buf ? OP_L0D_B1 : OP_L0D, s_coords, tbase, pipe, t, warp, DENSITY_ONLY,
-                                                                      1, SAVE_ACT ? act_img + (size_t)tile * IMG_TILE_BYTES : nullptr);
+            const uint32_t sig = forward_chain<G_H2F, true>(smem, S::act, ops, buf ? OP_L0D_B1 : OP_L0D, s_coords, tbase, pipe, t, warp, DENSITY_ONLY);
             if (tile + 2 * gridDim.x < ntiles) named_bar_arrive(4 + buf, FWD_THREADS);   // EMPTY[buf]
             if constexpr (DENSITY_ONLY) {
                 if (row < n_live) reinterpret_cast<uint16_t*>(out)[row] = (uint16_t)sig;
                 sync_before_issue<true>();                      // TMEM reads of this tile precede the next tile's MMAs
             } else {
-                if (t == 0) { run_ops(ops, OP_L2R, 4, 0); pipe.commit(); }
+                if (warp == 0) { if (elect_one()) { run_ops(ops, OP_L2R, 4, 0); pipe.commit(); } __syncwarp(); }
                 pipe.wait();
                 float v[16];
                 tmem_ld16(tmem_addr(tbase, warp, 64), v);
@@ -297,21 +277,12 @@ network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
 // Scatter warps: 4 (16-sample runs).  Measured on the lego stand-in, us per backward: 2 warps x 32-sample runs 294, 4 x 16 177,
 // 8 x 8 209, 8 warps x 16-sample runs with the cell's corners split over two threads 250 -- longer runs save atomics, but more
 // scatter warps starve the MLP chain, which is the critical path of this kernel.
-//
-// SAVED = true (ngp_network_bwd_saved): the five forward stages are not recomputed; the post-ReLU activations come back from the
-// slab image the forward kernel wrote (see IMG_* above) through 26 coalesced 16-byte cp.async copies per thread, the SH inputs
-// are recomputed from the direction.  Everything from stage B1 on is the same code.
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src_global) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(__cvta_generic_to_global(src_global)) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-template <bool SAVED, int SW = 4>                 // SW = scatter warps (4: 16-sample runs per thread; 8: 8-sample runs)
+constexpr int SW = 4;                             // scatter warps (16-sample runs per thread)
 __global__ void __launch_bounds__(128 + 32 * SW)
 network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const float* __restrict__ coords, const __half* __restrict__ enc_save,
                    const NgpLevel* __restrict__ levels, const __half* __restrict__ wd, const __half* __restrict__ wr,
                    const __half* __restrict__ dout, __half* __restrict__ grid_grad, float* __restrict__ dwd, float* __restrict__ dwr,
-                   int* __restrict__ err, uint32_t dbg, const uint8_t* __restrict__ act_img) {
+                   int* __restrict__ err, uint32_t dbg) {
     extern __shared__ __align__(1024) uint8_t smem[];
     using S = SmemBwd;
     constexpr uint32_t NT = 128 + 32 * SW;                 // threads per CTA
@@ -375,7 +346,6 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
         float pf_c[7];
         uint4 pf_e[4];
         uint2 pf_d;
-        float pf_dir[3] = {0.f, 0.f, 0.f};                   // SAVED only: this row's direction (SH inputs are recomputed)
         auto prefetch = [&](uint32_t tile_) {
             const uint32_t r0 = tile_ * ROWS, r = r0 + t;
             const bool ok = r < n_live;
@@ -388,10 +358,6 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
 #pragma unroll
             for (int g = 0; g < 4; ++g) pf_e[g] = ok ? __ldg(es + g) : make_uint4(0, 0, 0, 0);
             pf_d = ok ? __ldg(reinterpret_cast<const uint2*>(dout) + r) : make_uint2(0, 0);
-            if constexpr (SAVED) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) pf_dir[k] = ok ? __ldg(coords + (size_t)r * 7 + 4 + k) : 0.f;
-            }
         };
         if (blockIdx.x < ntiles) prefetch(blockIdx.x);
         uint32_t it = 0;
@@ -407,31 +373,15 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(act + (G_ENC + g) * GB + t * 16) = pf_e[g];
             const uint32_t dsig = pf_d.y >> 16;
             *reinterpret_cast<uint4*>(grd + Q_DYR * GB + t * 16) = make_uint4(pf_d.x, pf_d.y & 0xFFFFu, 0, 0);
-            if constexpr (SAVED) {
-                // saved activations: image groups -> the slab groups the recomputation would have filled (hd | h | h1 | h2)
-                const uint8_t* src = act_img + (size_t)tile * IMG_TILE_BYTES + t * 16;
-                const uint32_t dst = smem_u32(act) + t * 16;
-#pragma unroll
-                for (uint32_t g = 0; g < IMG_GROUPS; ++g) {
-                    const uint32_t sg = g < IMG_H ? G_HD + g : g < IMG_H1 ? G_RIN + (g - IMG_H) : g < IMG_H2 ? G_H1 + (g - IMG_H1) : G_H2B + (g - IMG_H2);
-                    cp_async16(dst + sg * GB, src + (size_t)g * GB);
-                }
-                float sh[16];                                            // colour-net inputs 16..31 (ngp_network.py:79,82)
-                sh4(pf_dir[0], pf_dir[1], pf_dir[2], sh);
-                uint4 lo, hi;
-                pack16(sh, lo, hi);
-                slab_store16(act, G_RIN + 2, t, lo, hi);
-            }
             if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x);   // in flight during the whole chain
             DBGB(1);
-            if constexpr (SAVED) cp_async_wait_all();
             sync_before_issue<true>();
             DBGB(2);
-            if constexpr (!SAVED) forward_chain<G_H2B, true>(smem, S::act, ops, OP_L0D, s_coords, tbase, pipe, t, warp, false);
+            forward_chain<G_H2B, true>(smem, S::act, ops, OP_L0D, s_coords, tbase, pipe, t, warp, false);
             DBGB(3);
             // B1: g_h2 = (dYr Woutr) . relu'(h2) ; wgrad Woutr
-            if (t == 0) { run_ops(ops, OP_B1, 1, acc); DBGB(4); pipe.commit(); }
-            if (t == 32) { if (!(dbg & 4)) run_ops(ops, OP_B1 + 1, 8, acc); mma_commit(bar_w); }   // weight gradient: issued by a second thread, off the critical path
+            if (warp == 0) { if (elect_one()) { run_ops(ops, OP_B1, 1, acc); DBGB(4); pipe.commit(); } __syncwarp(); }
+            if (warp == 1) { if (elect_one()) { if (!(dbg & 4)) run_ops(ops, OP_B1 + 1, 8, acc); mma_commit(bar_w); } __syncwarp(); }   // weight gradient: issued by a second thread, off the critical path
             pipe.wait();
             DBGB(5);
             epi_dgrad_mask(tbase, D_H, warp, act, G_H2B, grd, Q_GH2, t, nullptr);
@@ -439,8 +389,8 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             sync_before_issue<true>();
             DBGB(7);
             // B2: g_h1 = (g_h2 W1r) . relu'(h1) ; wgrad W1r
-            if (t == 0) { run_ops(ops, OP_B2, 4, acc); DBGB(8); pipe.commit(); DBGB(21); }
-            if (t == 32) { if (!(dbg & 4)) run_ops(ops, OP_B2 + 4, 8, acc); mma_commit(bar_w); }   // weight gradient: issued by a second thread, off the critical path
+            if (warp == 0) { if (elect_one()) { run_ops(ops, OP_B2, 4, acc); DBGB(8); pipe.commit(); DBGB(21); } __syncwarp(); }
+            if (warp == 1) { if (elect_one()) { if (!(dbg & 4)) run_ops(ops, OP_B2 + 4, 8, acc); mma_commit(bar_w); } __syncwarp(); }   // weight gradient: issued by a second thread, off the critical path
             pipe.wait();
             DBGB(9);
 #ifdef NGP_TIMELINE
@@ -476,8 +426,8 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
 #endif
             DBGB(10);
             // B3: d_rin = g_h1 W0r (32 cols; the last 16 are dL/dSH, unused) ; wgrad W0r
-            if (t == 0) { run_ops(ops, OP_B3, 4, acc); pipe.commit(); }
-            if (t == 32) { if (!(dbg & 4)) run_ops(ops, OP_B3 + 4, 8, acc); mma_commit(bar_w); }   // weight gradient: issued by a second thread, off the critical path
+            if (warp == 0) { if (elect_one()) { run_ops(ops, OP_B3, 4, acc); pipe.commit(); } __syncwarp(); }
+            if (warp == 1) { if (elect_one()) { if (!(dbg & 4)) run_ops(ops, OP_B3 + 4, 8, acc); mma_commit(bar_w); } __syncwarp(); }   // weight gradient: issued by a second thread, off the critical path
             pipe.wait();
             {
                 float v[16];
@@ -489,14 +439,14 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             }
             sync_before_issue<true>();
             // B4: g_hd = (dYd Woutd) . relu'(hd) ; wgrad Woutd
-            if (t == 0) { run_ops(ops, OP_B4, 1, acc); pipe.commit(); }
-            if (t == 32) { if (!(dbg & 4)) run_ops(ops, OP_B4 + 1, 8, acc); mma_commit(bar_w); }   // weight gradient: issued by a second thread, off the critical path
+            if (warp == 0) { if (elect_one()) { run_ops(ops, OP_B4, 1, acc); pipe.commit(); } __syncwarp(); }
+            if (warp == 1) { if (elect_one()) { if (!(dbg & 4)) run_ops(ops, OP_B4 + 1, 8, acc); mma_commit(bar_w); } __syncwarp(); }   // weight gradient: issued by a second thread, off the critical path
             pipe.wait();
             epi_dgrad_mask(tbase, D_H, warp, act, G_HD, grd, Q_GHD, t, nullptr);
             sync_before_issue<true>();
             // B5: d_enc = g_hd W0d ; wgrad W0d
-            if (t == 0) { run_ops(ops, OP_B5, 4, acc); pipe.commit(); }
-            if (t == 32) { if (!(dbg & 4)) run_ops(ops, OP_B5 + 4, 8, acc); mma_commit(bar_w); }   // weight gradient: issued by a second thread, off the critical path
+            if (warp == 0) { if (elect_one()) { run_ops(ops, OP_B5, 4, acc); pipe.commit(); } __syncwarp(); }
+            if (warp == 1) { if (elect_one()) { if (!(dbg & 4)) run_ops(ops, OP_B5 + 4, 8, acc); mma_commit(bar_w); } __syncwarp(); }   // weight gradient: issued by a second thread, off the critical path
             pipe.wait();
             {
                 float v[16];
@@ -549,8 +499,8 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             uint32_t cgx = 0xffffffffu, cgy = 0, cgz = 0, idx[8];
             float2 accv[8];
             bool dirty = false;
-#pragma unroll 1
             constexpr int PTS = 64 / SW;                         // consecutive samples per scatter thread
+#pragma unroll 1
             for (int k = 0; k < PTS; ++k) {
                 const uint32_t p = PTS * sub + k;
                 if (row0 + p >= n_live || (dbg & 2)) break;
@@ -587,325 +537,6 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
 }
 
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Backward, version 2: TWO MLP chains per CTA.
-//
-// The v1 kernel above runs one serial chain of ~9 MMA-commit-epilogue-barrier stages per SM (tools/dbg_timeline_bwd.py: ~20 k
-// cycles per 128-sample tile even with the scatter switched off), during most of which the tensor pipe, the LSU and three
-// quarters of the issue slots idle.  A second CTA per SM is not available: kernels that allocate tensor memory are limited to one
-// resident CTA per SM on this stack (cudaOccupancyMaxActiveBlocksPerMultiprocessor returns 1 whatever the shared-memory /
-// register footprint, measured).  So the second chain lives in the SAME CTA: 16 warps =
-//     chain group 0 (warps 0-3) | chain group 1 (warps 4-7) | scatter group 0 (warps 8-11) | scatter group 1 (warps 12-15),
-// each chain group with its own tile stream, activation slabs, MMA program, TMEM columns, mbarriers and named barriers.
-// That fits because the per-chain footprint is halved:
-//   * every gradient slab is written IN PLACE over the activation it is derived from: g_h2 over h2, g_h1 over h1,
-//     dYd over the colour net's input, g_hd over hd.  Safe because the only other reader of that activation is the
-//     weight-gradient MMA of the SAME stage (issued together with the dgrad MMA, tracked by its own mbarrier), and each
-//     thread reads and writes only its own row;
-//   * dYr (the 4-wide output gradient padded to K = 16) borrows the first two groups of the dL/d(enc) buffer of the tile,
-//     which is written only at the very end of the chain;
-//   * the W0 weight gradients (32 inputs x 64 outputs) are accumulated transposed (lane = output feature, 32 columns):
-//     160 accumulator + 96 working columns = 256 TMEM columns per chain, 512 per CTA.
-// Shared memory per chain: 7 KB coords + 64 KB activations + 16 KB dL/d(enc) (2 buffers); shared: 20 KB weights, MMA programs.
-constexpr uint32_t BW2_GROUPS = 2;
-struct SmemBwd2 {
-    static constexpr uint32_t coords = 0;                         // per chain group: two buffers of 128 x 7 f32 (3584 B each)
-    static constexpr uint32_t act = coords + BW2_GROUPS * 2 * 3584;   // per chain group: 32 activation groups + 8 dL/d(enc) groups (must follow: M=128 wgrad reads run into them)
-    static constexpr uint32_t act_stride = 40 * GB;
-    static constexpr uint32_t w0d = act + BW2_GROUPS * act_stride;
-    static constexpr uint32_t woutd = w0d + 64 * 32 * 2;
-    static constexpr uint32_t w0r = woutd + 16 * 64 * 2;
-    static constexpr uint32_t w1r = w0r + 64 * 32 * 2;
-    static constexpr uint32_t woutr = w1r + 64 * 64 * 2;
-    static constexpr uint32_t levels = woutr + 16 * 64 * 2;
-    static constexpr uint32_t ops = levels + N_LEVELS * 32;      // per chain group: 80 ops
-    static constexpr uint32_t bar = ops + BW2_GROUPS * 80 * 32;   // per chain group: 2 mbarriers; then the TMEM base word
-    static constexpr uint32_t total = bar + 64;
-};
-static_assert(SmemBwd2::total <= 227 * 1024, "backward CTA does not fit");
-
-// dgrad epilogue, in place: D[:, 0..64) -> fp16 -> masked by ReLU'(h) -> written over h (groups [g, g+8)).  The stores wait for
-// `bar_w`: the weight-gradient MMAs of this stage, which read h through the async proxy.
-static __device__ __noinline__ bool epi_dgrad_mask_inplace(uint32_t tbase, uint32_t dcol, uint32_t warp, uint8_t* slab, uint32_t g, uint32_t t,
-                                                           uint64_t* bar_w, uint32_t phase_w) {
-    uint32_t r[4][16];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) tmem_ld16_nowait(tmem_addr(tbase, warp & 3, dcol + 16 * c), r[c]);
-    tmem_ld_wait();
-    uint4 o[8];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[c][i]);
-        uint4 lo, hi;
-        pack16(v, lo, hi);
-        o[2 * c] = relu_mask8(lo, slab_load8(slab, g + 2 * c, t));
-        o[2 * c + 1] = relu_mask8(hi, slab_load8(slab, g + 2 * c + 1, t));
-    }
-    const bool ok = mbar_wait(bar_w, phase_w);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(slab + (size_t)(g + c) * GB + t * 16) = o[c];
-    return ok;
-}
-
-__global__ void __launch_bounds__(512, 1)
-network_bwd2_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const float* __restrict__ coords, const __half* __restrict__ enc_save,
-                    const NgpLevel* __restrict__ levels, const __half* __restrict__ wd, const __half* __restrict__ wr,
-                    const __half* __restrict__ dout, __half* __restrict__ grid_grad, float* __restrict__ dwd, float* __restrict__ dwr,
-                    int* __restrict__ err, uint32_t dbg) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    using S = SmemBwd2;
-    const uint32_t tid = threadIdx.x, warp = tid >> 5;
-    const bool is_chain = warp < 8;
-    const uint32_t cg = (warp >> 2) & 1;                        // chain / scatter group of this warp
-    const uint32_t t = tid & 127, tq = warp & 3;               // row inside the tile, TMEM lane quarter
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::bar);
-    uint64_t* bar = bars + 2 * cg;                               // dgrad / forward MMAs of this chain group are done
-    uint64_t* bar_w = bar + 1;                                   // the weight-gradient MMAs of the current stage are done
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
-    NgpLevel* s_lv = reinterpret_cast<NgpLevel*>(smem + S::levels);
-    uint8_t* act = smem + S::act + cg * S::act_stride;
-    uint8_t* denc = act + 32 * GB;
-    const uint32_t coords_off = S::coords + cg * 2 * 3584;
-    // named barriers of this group: chain 1|7, FULL[b] 2+b|8+b, EMPTY[b] 4+b|10+b
-    const uint32_t B_CHAIN = 1 + 6 * cg, B_FULL = 2 + 6 * cg, B_EMPTY = 4 + 6 * cg;
-
-    stage_weights(smem + S::w0d, wd + WD_W0, 64, 32, tid, 512);
-    stage_weights(smem + S::woutd, wd + WD_WOUT, 16, 64, tid, 512);
-    stage_weights(smem + S::w0r, wr + WR_W0, 64, 32, tid, 512);
-    stage_weights(smem + S::w1r, wr + WR_W1, 64, 64, tid, 512);
-    stage_weights(smem + S::woutr, wr + WR_WOUT, 16, 64, tid, 512);
-    if (tid < N_LEVELS) s_lv[tid] = levels[tid];
-    // M = 128 weight-gradient operands run past their 8-group slab into whatever follows: keep it finite
-    for (uint32_t i = tid; i < BW2_GROUPS * S::act_stride / 16; i += 512) *reinterpret_cast<uint4*>(smem + S::act + i * 16) = make_uint4(0, 0, 0, 0);
-    if (tid == 0) {
-        for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);
-        fence_mbar_init();
-    }
-    if (warp == 0) tmem_alloc(tmem_ptr, 512);
-    sync_before_issue();
-    const uint32_t tbase = *tmem_ptr + cg * 256;                 // this chain group's 256 columns
-    const uint32_t smem_s = smem_u32(smem), act_s = smem_s + S::act + cg * S::act_stride, denc_s = act_s + 32 * GB;
-    // TMEM columns (relative to the group's base): working tiles, then the five weight-gradient accumulators
-    // (W0d / W0r transposed: lane = output feature)
-    const uint32_t D_H = 0, D_S = 64, A_W0D = 96, A_WOUTD = 128, A_W0R = 144, A_W1R = 176, A_WOUTR = 240;
-    // backward MMA program: per stage the dgrad ops, then the wgrad ops that read the same operands.  Stage 1 exists twice
-    // (dYr lives in the dL/d(enc) buffer of the tile, which alternates).
-    constexpr uint32_t OP_B1 = 16, OP_B1_ALT = OP_B1 + 9, OP_B2 = OP_B1_ALT + 9, OP_B3 = OP_B2 + 12, OP_B4 = OP_B3 + 12, OP_B5 = OP_B4 + 9,
-                       OP_END = OP_B5 + 12;
-    static_assert(OP_END <= 80, "MMA program does not fit");
-    MmaOp* const prog = reinterpret_cast<MmaOp*>(smem + S::ops) + cg * 80;
-    if (is_chain) {
-        const uint32_t l = tid & 31;
-        if (tq == 0) {
-            build_fwd(prog + OP_L0D, l, tbase + D_H, act_s, G_ENC, 32, smem_s + S::w0d, 64);
-            build_fwd(prog + OP_L1D, l, tbase + D_S, act_s, G_HD, 64, smem_s + S::woutd, 16);
-            build_fwd(prog + OP_L0R, l, tbase + D_H, act_s, G_RIN, 32, smem_s + S::w0r, 64);
-            build_fwd(prog + OP_L1R, l, tbase + D_H, act_s, G_H1, 64, smem_s + S::w1r, 64);
-            build_fwd(prog + OP_L2R, l, tbase + D_S, act_s, G_H2B, 64, smem_s + S::woutr, 16);
-        }
-        if (tq == 1) {
-            for (uint32_t b = 0; b < 2; ++b) {
-                MmaOp* q = prog + (b ? OP_B1_ALT : OP_B1);
-                build_dgrad(q, l, tbase + D_H, denc_s + b * 4 * GB, 0, 16, smem_s + S::woutr, 64);
-                build_wgrad(q + 1, l, tbase + A_WOUTR, act_s, G_H2B, denc_s + b * 4 * GB, 0, 16);
-            }
-            build_dgrad(prog + OP_B2, l, tbase + D_H, act_s, G_H2B, 64, smem_s + S::w1r, 64);
-            build_wgrad(prog + OP_B2 + 4, l, tbase + A_W1R, act_s, G_H1, act_s, G_H2B, 64);
-        }
-        if (tq == 2) {
-            build_dgrad(prog + OP_B3, l, tbase + D_S, act_s, G_H1, 64, smem_s + S::w0r, 32);
-            build_wgrad(prog + OP_B3 + 4, l, tbase + A_W0R, act_s, G_H1, act_s, G_RIN, 32);          // transposed: A = g_h1, B = colour input
-            build_dgrad(prog + OP_B4, l, tbase + D_H, act_s, G_RIN, 16, smem_s + S::woutd, 64);
-            build_wgrad(prog + OP_B4 + 1, l, tbase + A_WOUTD, act_s, G_HD, act_s, G_RIN, 16);
-        }
-        if (tq == 3) {
-            build_dgrad(prog + OP_B5, l, tbase + D_S, act_s, G_HD, 64, smem_s + S::w0d, 32);
-            build_wgrad(prog + OP_B5 + 4, l, tbase + A_W0D, act_s, G_HD, act_s, G_ENC, 32);          // transposed: A = g_hd, B = enc
-        }
-    }
-    __syncthreads();
-    const MmaOp* ops = prog;
-    const uint32_t n_live = n_dev ? min(*n_dev, n_max) : n_max;
-    const uint32_t ntiles = (n_live + ROWS - 1) / ROWS;
-    const uint32_t tile0 = blockIdx.x * BW2_GROUPS + cg, tile_step = gridDim.x * BW2_GROUPS;   // tile stream of this group
-    uint32_t acc = 0;
-
-    if (is_chain) {
-        // ------------------------------------------------------------------ MLP chain (128 threads per group, thread t = row t)
-        Pipe pipe{bar, 0, err};
-        uint32_t phase_w = 0;
-        // software prefetch of the next tile's inputs (7 coordinate words, the 64 B encoded row, the 8 B output gradient)
-        float pf_c[7];
-        uint4 pf_e[4];
-        uint2 pf_d;
-        auto prefetch = [&](uint32_t tile_) {
-            const uint32_t r0 = tile_ * ROWS, r = r0 + t;
-            const bool ok = r < n_live;
-#pragma unroll
-            for (int j = 0; j < 7; ++j) {
-                const uint32_t i = t + 128 * j;
-                pf_c[j] = (r0 + i / 7 < n_live) ? __ldg(coords + (size_t)r0 * 7 + i) : 0.f;
-            }
-            const uint4* es = reinterpret_cast<const uint4*>(enc_save + (size_t)r * 32);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) pf_e[g] = ok ? __ldg(es + g) : make_uint4(0, 0, 0, 0);
-            pf_d = ok ? __ldg(reinterpret_cast<const uint2*>(dout) + r) : make_uint2(0, 0);
-        };
-        // one stage: thread 0 of the group issues `nd` dgrad ops (-> bar) and the 8 wgrad ops behind them (-> bar_w)
-        auto issue = [&](uint32_t first, uint32_t nd) {
-            if (t == 0) {
-                run_ops(ops, first, nd, acc);
-                pipe.commit();
-                run_ops(ops, first + nd, 8, acc);
-                mma_commit(bar_w);
-            }
-        };
-        auto wait_w = [&]() {
-            if (!mbar_wait(bar_w, phase_w)) atomicExch(err, 2);
-            phase_w ^= 1;
-        };
-        if (tile0 < ntiles) prefetch(tile0);
-        uint32_t it = 0;
-        for (uint32_t tile = tile0; tile < ntiles; tile += tile_step, acc = 1, ++it) {
-            const uint32_t buf = it & 1;
-            float* s_coords = reinterpret_cast<float*>(smem + coords_off + buf * 3584);
-            uint8_t* denc_b = denc + buf * 4 * GB;
-            if (it >= 2) named_bar_sync(B_EMPTY + buf, 256);    // the scatter of tile it-2 has released coords[buf] / d_enc[buf]
-#pragma unroll
-            for (int j = 0; j < 7; ++j) s_coords[t + 128 * j] = pf_c[j];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(act + (G_ENC + g) * GB + t * 16) = pf_e[g];
-            const uint32_t dsig = pf_d.y >> 16;
-            *reinterpret_cast<uint4*>(denc_b + t * 16) = make_uint4(pf_d.x, pf_d.y & 0xFFFFu, 0, 0);     // dYr: 3 colour gradients, K padded to 16
-            *reinterpret_cast<uint4*>(denc_b + GB + t * 16) = make_uint4(0, 0, 0, 0);
-            if (tile + tile_step < ntiles) prefetch(tile + tile_step);   // in flight during the whole chain
-            sync_chain(B_CHAIN);
-            forward_chain<G_H2B, true>(smem, S::act + cg * S::act_stride, ops, OP_L0D, s_coords, tbase, pipe, t, tq, false, B_CHAIN);
-            // B1: g_h2 = (dYr Woutr) . relu'(h2) over h2 ; wgrad Woutr (h2^T dYr)
-            issue(buf ? OP_B1_ALT : OP_B1, 1);
-            pipe.wait();
-            if (!epi_dgrad_mask_inplace(tbase, D_H, tq, act, G_H2B, t, bar_w, phase_w)) atomicExch(err, 2);
-            phase_w ^= 1;
-            sync_chain(B_CHAIN);
-            // B2: g_h1 = (g_h2 W1r) . relu'(h1) over h1 ; wgrad W1r (h1^T g_h2)
-            issue(OP_B2, 4);
-            pipe.wait();
-            if (!epi_dgrad_mask_inplace(tbase, D_H, tq, act, G_H1, t, bar_w, phase_w)) atomicExch(err, 2);
-            phase_w ^= 1;
-            sync_chain(B_CHAIN);
-            // B3: d_rin = g_h1 W0r (32 cols; the last 16 are dL/dSH, unused) -> dYd over the colour input ; wgrad W0r (g_h1^T rin)
-            issue(OP_B3, 4);
-            pipe.wait();
-            {
-                float v[16];
-                tmem_ld16(tmem_addr(tbase, tq, D_S), v);
-                v[0] += __half2float(__ushort_as_half((unsigned short)dsig));   // + dL/dsigma (ngp_network.py:83)
-                uint4 lo, hi;
-                pack16(v, lo, hi);
-                wait_w();
-                slab_store16(act, G_RIN, t, lo, hi);
-            }
-            sync_chain(B_CHAIN);
-            // B4: g_hd = (dYd Woutd) . relu'(hd) over hd ; wgrad Woutd (hd^T dYd)
-            issue(OP_B4, 1);
-            pipe.wait();
-            if (!epi_dgrad_mask_inplace(tbase, D_H, tq, act, G_HD, t, bar_w, phase_w)) atomicExch(err, 2);
-            phase_w ^= 1;
-            sync_chain(B_CHAIN);
-            // B5: d_enc = g_hd W0d -> dL/d(enc) buffer ; wgrad W0d (g_hd^T enc)
-            issue(OP_B5, 4);
-            pipe.wait();
-            {
-                float v[16];
-                uint4 lo, hi;
-                tmem_ld16(tmem_addr(tbase, tq, D_S), v);
-                pack16(v, lo, hi);
-                slab_store16(denc_b, 0, t, lo, hi);
-                tmem_ld16(tmem_addr(tbase, tq, D_S + 16), v);
-                pack16(v, lo, hi);
-                slab_store16(denc_b, 2, t, lo, hi);
-            }
-            wait_w();                                            // enc / g_hd may be overwritten by the next tile from here on
-            tc_fence_before();
-            named_bar_arrive(B_FULL + buf, 256);                 // FULL[buf]: dL/d(enc) and coords of this tile are ready
-        }
-        // flush this group's weight gradients
-        if (acc) {
-            tc_fence_after();
-            float v[16];
-            const uint32_t f_col[5] = {A_W0D, A_WOUTD, A_W0R, A_W1R, A_WOUTR};
-            const uint32_t f_out[5] = {64, 16, 64, 64, 16}, f_valid[5] = {64, 16, 64, 64, 3};   // colour Wout rows >= 3 stay zero (fully_fused_mlp.py:136)
-            const uint32_t f_in[5] = {32, 64, 32, 64, 64};
-            const bool f_tr[5] = {true, false, true, false, false};                          // transposed: lane = output feature, column = input
-            float* const f_dst[5] = {dwd + WD_W0, dwd + WD_WOUT, dwr + WR_W0, dwr + WR_W1, dwr + WR_WOUT};
-#pragma unroll 1
-            for (int m = 0; m < 5; ++m) {
-                const uint32_t ncols = f_tr[m] ? f_in[m] : f_out[m], nlanes = f_tr[m] ? f_out[m] : f_in[m];
-#pragma unroll 1
-                for (uint32_t c = 0; c < ncols / 16; ++c) {
-                    tmem_ld16(tmem_addr(tbase, tq, f_col[m] + 16 * c), v);
-                    if (t < nlanes) {
-#pragma unroll
-                        for (int o = 0; o < 16; ++o) {
-                            const uint32_t out_f = f_tr[m] ? t : 16 * c + o, in_f = f_tr[m] ? 16 * c + o : t;
-                            if (out_f < f_valid[m]) red_add_f32(f_dst[m] + (size_t)out_f * f_in[m] + in_f, v[o]);
-                        }
-                    }
-                }
-            }
-        }
-    } else {
-        // ------------------------------------------------------------------ scatter (128 threads per group), as in v1
-        const uint32_t level = t & 15, sub = t >> 4;
-        const NgpLevel lv = s_lv[level];
-        __half2* gg = reinterpret_cast<__half2*>(grid_grad) + lv.offset;
-        uint32_t it = 0;
-        for (uint32_t tile = tile0; tile < ntiles; tile += tile_step, ++it) {
-            const uint32_t buf = it & 1, row0 = tile * ROWS;
-            const float* s_coords = reinterpret_cast<const float*>(smem + coords_off + buf * 3584);
-            const uint8_t* denc_b = denc + buf * 4 * GB;
-            named_bar_sync(B_FULL + buf, 256);                   // FULL[buf]
-            uint32_t cgx = 0xffffffffu, cgy = 0, cgz = 0, idx[8];
-            float2 accv[8];
-            bool dirty = false;
-#pragma unroll 1
-            for (int k = 0; k < 16; ++k) {
-                const uint32_t p = 16 * sub + k;
-                if (row0 + p >= n_live || (dbg & 2)) break;
-                const __half2 d = *reinterpret_cast<const __half2*>(denc_b + (size_t)(level >> 2) * GB + p * 16 + (level & 3) * 4);
-                const float2 df = __half22float2(d);
-                if (df.x == 0.f && df.y == 0.f) continue;
-                const HashCell hc = hash_cell(lv, s_coords[p * 7], s_coords[p * 7 + 1], s_coords[p * 7 + 2]);
-                if (hc.gx != cgx || hc.gy != cgy || hc.gz != cgz) {
-                    if (dirty && !(dbg & 1)) {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) red_add_h2(gg + idx[c], accv[c].x, accv[c].y);
-                    }
-                    cgx = hc.gx; cgy = hc.gy; cgz = hc.gz;
-                    hash_cell_indices(lv, cgx, cgy, cgz, idx);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) accv[c] = make_float2(0.f, 0.f);
-                    dirty = true;
-                }
-                float w[8];
-                hash_cell_weights(hc, w);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) { accv[c].x = fmaf(df.x, w[c], accv[c].x); accv[c].y = fmaf(df.y, w[c], accv[c].y); }
-            }
-            if (dirty && !(dbg & 1)) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) red_add_h2(gg + idx[c], accv[c].x, accv[c].y);
-            }
-            if (tile + 2 * tile_step < ntiles) named_bar_arrive(B_EMPTY + buf, 256);   // EMPTY[buf] for the chain's tile it+2
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_free(*tmem_ptr, 512);
-}
-
 }  // namespace
 
 extern "C" {
@@ -928,52 +559,6 @@ int ngp_network_fwd(void* stream, uint32_t n_max, const uint32_t* n_dev, const f
     return 0;
 }
 
-// Saved-activation pair (see IMG_* above): the forward also writes the per-tile activation image, the backward reads it instead of
-// recomputing the forward chain.  act_save: ngp_network_act_bytes(n_max) bytes, 16-byte aligned, written for every tile that holds
-// a live row.  Results equal ngp_network_fwd / ngp_network_bwd (the image holds the same fp16 values the recomputation produces).
-uint64_t ngp_network_act_bytes(uint32_t n_max) { return (uint64_t)((n_max + ROWS - 1) / ROWS) * IMG_TILE_BYTES; }
-
-int ngp_network_fwd_saved(void* stream, uint32_t n_max, const uint32_t* n_dev, const float* coords, const void* grid, const void* levels_dev,
-                          const void* w_density, const void* w_rgb, void* out, void* enc_save, void* act_save) {
-    NGP_REQUIRE(act_save != nullptr && enc_save != nullptr, "ngp_network_fwd_saved: enc_save and act_save are required");
-    if (n_max == 0) return 0;
-    cudaStream_t s = (cudaStream_t)stream;
-    NGP_CHECK_CUDA(cudaFuncSetAttribute(network_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemFwd::total));
-    const uint32_t ntiles = (n_max + ROWS - 1) / ROWS;
-    const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms() * 2u);
-    network_fwd_kernel<false, true><<<grid_dim, FWD_THREADS, SmemFwd::total, s>>>(n_max, n_dev, coords, (const __half*)grid, (const NgpLevel*)levels_dev,
-                                                                                 (const __half*)w_density, (const __half*)w_rgb, (__half*)out,
-                                                                                 (__half*)enc_save, ngp_err_flag(), (uint8_t*)act_save);
-    NGP_LAUNCH_CHECK();
-    return 0;
-}
-
-int ngp_network_bwd_saved(void* stream, uint32_t n_max, const uint32_t* n_dev, const float* coords, const void* enc_save, const void* act_save,
-                          const void* levels_dev, const void* w_density, const void* w_rgb, const void* dout, void* grid_grad,
-                          float* dw_density, float* dw_rgb) {
-    NGP_REQUIRE(act_save != nullptr, "ngp_network_bwd_saved: act_save is required");
-    if (n_max == 0) return 0;
-    cudaStream_t s = (cudaStream_t)stream;
-    const uint32_t ntiles = (n_max + ROWS - 1) / ROWS;
-    static const uint32_t dbg = getenv("NGP_BWD_DEBUG") ? (uint32_t)atoi(getenv("NGP_BWD_DEBUG")) : 0u;
-    // experiment knob: with half as many chain stages per tile the scatter side may want 8 warps (it lost with the recomputing chain)
-    static const bool sw8 = getenv("NGP_BWD_SCATTER_WARPS") && atoi(getenv("NGP_BWD_SCATTER_WARPS")) == 8;
-    const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms());
-    if (!sw8) {
-        NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd::total));
-        network_bwd_kernel<true, 4><<<grid_dim, 256, SmemBwd::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
-                                                                         (const __half*)w_density, (const __half*)w_rgb, (const __half*)dout,
-                                                                         (__half*)grid_grad, dw_density, dw_rgb, ngp_err_flag(), dbg, (const uint8_t*)act_save);
-    } else {
-        NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd::total));
-        network_bwd_kernel<true, 8><<<grid_dim, 384, SmemBwd::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
-                                                                         (const __half*)w_density, (const __half*)w_rgb, (const __half*)dout,
-                                                                         (__half*)grid_grad, dw_density, dw_rgb, ngp_err_flag(), dbg, (const uint8_t*)act_save);
-    }
-    NGP_LAUNCH_CHECK();
-    return 0;
-}
-
 int ngp_density_fwd(void* stream, uint32_t n, const float* pos, const void* grid, const void* levels_dev, const void* w_density, void* sigma_out) {
     if (n == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
@@ -991,22 +576,13 @@ int ngp_network_bwd(void* stream, uint32_t n_max, const uint32_t* n_dev, const f
     if (n_max == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t ntiles = (n_max + ROWS - 1) / ROWS;
-    // timing experiments only (results are wrong with any bit set): 1 = no atomics, 2 = no scatter, 4 = no weight-gradient MMAs (v1 kernel)
+    // timing experiments only (results are wrong with any bit set): 1 = no atomics, 2 = no scatter, 4 = no weight-gradient MMAs
     static const uint32_t dbg = getenv("NGP_BWD_DEBUG") ? (uint32_t)atoi(getenv("NGP_BWD_DEBUG")) : 0u;
-    static const bool use_v2 = getenv("NGP_BWD_V2") != nullptr;          // two chains per CTA with in-place gradient slabs: correct, not faster
-    if (!use_v2) {
-        NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd::total));
-        const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms());
-        network_bwd_kernel<false, 4><<<grid_dim, 256, SmemBwd::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
-                                                                       (const __half*)w_density, (const __half*)w_rgb, (const __half*)dout,
-                                                                       (__half*)grid_grad, dw_density, dw_rgb, ngp_err_flag(), dbg, nullptr);
-    } else {
-        NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd2::total));
-        const uint32_t grid_dim = min((ntiles + BW2_GROUPS - 1) / BW2_GROUPS, (uint32_t)ngp_num_sms());
-        network_bwd2_kernel<<<grid_dim, 512, SmemBwd2::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
-                                                                  (const __half*)w_density, (const __half*)w_rgb, (const __half*)dout,
-                                                                  (__half*)grid_grad, dw_density, dw_rgb, ngp_err_flag(), dbg);
-    }
+    NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd::total));
+    const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms());
+    network_bwd_kernel<<<grid_dim, 128 + 32 * SW, SmemBwd::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
+                                                                     (const __half*)w_density, (const __half*)w_rgb, (const __half*)dout,
+                                                                     (__half*)grid_grad, dw_density, dw_rgb, ngp_err_flag(), dbg);
     NGP_LAUNCH_CHECK();
     return 0;
 }

@@ -75,7 +75,7 @@ mlp_fwd_kernel(const __half* __restrict__ W, const __half* __restrict__ X, __hal
         DBG(2);
         uint32_t cur = FwdSmem::slab0, nxt = FwdSmem::slab1;
         // layer 0
-        if (t == 0) { issue_fwd(tbase + D_H, smem_s + cur, 0, IN, smem_s + FwdSmem::w0, WIDTH); DBG(3); pipe.commit(); }
+        if (warp == 0) { if (elect_one()) { issue_fwd(tbase + D_H, smem_s + cur, 0, IN, smem_s + FwdSmem::w0, WIDTH); pipe.commit(); } __syncwarp(); }
         pipe.wait();
         DBG(4);
         epi_hidden_relu(tbase, D_H, warp, smem + nxt, 0, t, (inter && valid) ? inter + ((size_t)0 * n + row) * WIDTH : nullptr);
@@ -84,14 +84,14 @@ mlp_fwd_kernel(const __half* __restrict__ W, const __half* __restrict__ X, __hal
         DBG(6);
         { uint32_t s = cur; cur = nxt; nxt = s; }
         for (uint32_t j = 0; j < nhm; ++j) {
-            if (t == 0) { issue_fwd(tbase + D_H, smem_s + cur, 0, WIDTH, smem_s + FwdSmem::wh + j * WIDTH * WIDTH * 2, WIDTH); pipe.commit(); }
+            if (warp == 0) { if (elect_one()) { issue_fwd(tbase + D_H, smem_s + cur, 0, WIDTH, smem_s + FwdSmem::wh + j * WIDTH * WIDTH * 2, WIDTH); pipe.commit(); } __syncwarp(); }
             pipe.wait();
             epi_hidden_relu(tbase, D_H, warp, smem + nxt, 0, t, (inter && valid) ? inter + ((size_t)(j + 1) * n + row) * WIDTH : nullptr);
             sync_before_issue();
             { uint32_t s = cur; cur = nxt; nxt = s; }
         }
         DBG(7);
-        if (t == 0) { issue_fwd(tbase + D_O, smem_s + cur, 0, WIDTH, smem_s + FwdSmem::wout(nhm), OUTP); pipe.commit(); }
+        if (warp == 0) { if (elect_one()) { issue_fwd(tbase + D_O, smem_s + cur, 0, WIDTH, smem_s + FwdSmem::wout(nhm), OUTP); pipe.commit(); } __syncwarp(); }
         pipe.wait();
         DBG(8);
         {
@@ -196,10 +196,13 @@ mlp_bwd_kernel(const __half* __restrict__ W, const __half* __restrict__ X, const
         }
         sync_before_issue();
         // gradient at the last hidden layer, and the output layer's wgrad
-        if (t == 0) {
-            issue_dgrad(tbase + D_G, grd_s, 0, OUTP, smem_s + L.wout(), WIDTH);
-            if (dW) issue_wgrad(tbase + D_WOUT, act_s, 4 + 8 * (nh - 1), grd_s, 0, OUTP, acc);
-            pipe.commit();
+        if (warp == 0) {
+            if (elect_one()) {
+                issue_dgrad(tbase + D_G, grd_s, 0, OUTP, smem_s + L.wout(), WIDTH);
+                if (dW) issue_wgrad(tbase + D_WOUT, act_s, 4 + 8 * (nh - 1), grd_s, 0, OUTP, acc);
+                pipe.commit();
+            }
+            __syncwarp();
         }
         pipe.wait();
         epi_dgrad_mask(tbase, D_G, warp, act, 4 + 8 * (nh - 1), grd, 2, t, (temps && valid) ? temps + ((size_t)0 * n + row) * WIDTH : nullptr);
@@ -207,10 +210,13 @@ mlp_bwd_kernel(const __half* __restrict__ W, const __half* __restrict__ X, const
         // hidden matmuls, last to first: Wh_{k-1} maps hidden k-1 -> hidden k
         for (uint32_t k = nh - 1; k >= 1; --k) {
             const uint32_t j = nh - 1 - k;            // gradient block holding g_k
-            if (t == 0) {
-                issue_dgrad(tbase + D_G, grd_s, 2 + 8 * j, WIDTH, smem_s + L.wh() + (k - 1) * WIDTH * WIDTH * 2, WIDTH);
-                if (dW) issue_wgrad(tbase + D_W + 64 * k, act_s, 4 + 8 * (k - 1), grd_s, 2 + 8 * j, WIDTH, acc);
-                pipe.commit();
+            if (warp == 0) {
+                if (elect_one()) {
+                    issue_dgrad(tbase + D_G, grd_s, 2 + 8 * j, WIDTH, smem_s + L.wh() + (k - 1) * WIDTH * WIDTH * 2, WIDTH);
+                    if (dW) issue_wgrad(tbase + D_W + 64 * k, act_s, 4 + 8 * (k - 1), grd_s, 2 + 8 * j, WIDTH, acc);
+                    pipe.commit();
+                }
+                __syncwarp();
             }
             pipe.wait();
             epi_dgrad_mask(tbase, D_G, warp, act, 4 + 8 * (k - 1), grd, 2 + 8 * (j + 1), t,
@@ -219,10 +225,13 @@ mlp_bwd_kernel(const __half* __restrict__ W, const __half* __restrict__ X, const
         }
         // first layer: dX = g_0 * W0, wgrad W0 = g_0^T X
         if (!dX && !dW) continue;     // dgrad-only call without dL/dinput: nothing left for this tile (uniform over the CTA)
-        if (t == 0) {
-            if (dX) issue_dgrad(tbase + D_X, grd_s, 2 + 8 * nhm, WIDTH, smem_s + L.w0(), IN);
-            if (dW) issue_wgrad(tbase + D_W, act_s, 0, grd_s, 2 + 8 * nhm, WIDTH, acc);
-            pipe.commit();
+        if (warp == 0) {
+            if (elect_one()) {
+                if (dX) issue_dgrad(tbase + D_X, grd_s, 2 + 8 * nhm, WIDTH, smem_s + L.w0(), IN);
+                if (dW) issue_wgrad(tbase + D_W, act_s, 0, grd_s, 2 + 8 * nhm, WIDTH, acc);
+                pipe.commit();
+            }
+            __syncwarp();
         }
         pipe.wait();
         if (dX) {

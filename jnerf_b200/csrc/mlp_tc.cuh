@@ -21,17 +21,18 @@ static __device__ __noinline__ void stage_weights(uint8_t* dst, const __half* __
     }
 }
 
-// NOTE on code size: these helpers are deliberately __noinline__ with rolled loops.  With everything inlined and unrolled the
+// NOTE on code size: the epilogue helpers are deliberately __noinline__ and the issue loops are rolled (the issue helpers themselves must
+// be inlined into the elect.sync-guarded block of their caller, see tc05::elect_one).  With everything inlined and unrolled the
 // per-tile body of the fused backward kernel was 77 KB of SASS -- larger than the SM's 32 KB L1.5 instruction cache -- and the
 // 4 warps of a CTA spent most of their time waiting for instruction fetches from L2 (measured: ~44k cycles per tile).
 // D[128 x N] (+)= ACT[:, 8*g0 .. 8*g0+K) * W^T          (W staged with rows = N)
-static __device__ __noinline__ void issue_fwd(uint32_t d, uint32_t act_s, uint32_t g0, uint32_t K, uint32_t w_s, uint32_t N) {
+__device__ __forceinline__ void issue_fwd(uint32_t d, uint32_t act_s, uint32_t g0, uint32_t K, uint32_t w_s, uint32_t N) {
 #pragma unroll 1
     for (uint32_t kb = 0; kb < K / 16; ++kb)
         mma_f16_ss(d, slab_desc_kmajor(act_s, ROWS, g0, kb), slab_desc_kmajor(w_s, N, 0, kb), idesc_f16(128, N, 0, 0), kb > 0);
 }
 // D[128 x Nin] = GRD[:, 8*g0 .. 8*g0+Kout) * W          (W staged with rows = Kout, K = Nin; read MN-major)
-static __device__ __noinline__ void issue_dgrad(uint32_t d, uint32_t grd_s, uint32_t g0, uint32_t Kout, uint32_t w_s, uint32_t Nin,
+__device__ __forceinline__ void issue_dgrad(uint32_t d, uint32_t grd_s, uint32_t g0, uint32_t Kout, uint32_t w_s, uint32_t Nin,
                                             uint32_t accumulate_first = 0) {
 #pragma unroll 1
     for (uint32_t kb = 0; kb < Kout / 16; ++kb)
@@ -40,7 +41,7 @@ static __device__ __noinline__ void issue_dgrad(uint32_t d, uint32_t grd_s, uint
 }
 // D[128 x N] (+)= A^T B : lanes = features [8*ga, 8*ga+128) of slab a, columns = features [8*gb, 8*gb+N) of slab b,
 // contraction over the 128 rows of the tile.  `accumulate` = 0 only for the very first tile of the CTA.
-static __device__ __noinline__ void issue_wgrad(uint32_t d, uint32_t a_s, uint32_t ga, uint32_t b_s, uint32_t gb, uint32_t N, uint32_t accumulate) {
+__device__ __forceinline__ void issue_wgrad(uint32_t d, uint32_t a_s, uint32_t ga, uint32_t b_s, uint32_t gb, uint32_t N, uint32_t accumulate) {
 #pragma unroll 1
     for (uint32_t kb = 0; kb < ROWS / 16; ++kb)
         mma_f16_ss(d, slab_desc_mnmajor(a_s, ROWS, ga, kb), slab_desc_mnmajor(b_s, ROWS, gb, kb), idesc_f16(128, N, 1, 1),
@@ -74,8 +75,10 @@ __device__ __forceinline__ uint32_t build_wgrad(MmaOp* ops, uint32_t lane, uint3
     if (lane < n) ops[lane] = MmaOp{slab_desc_mnmajor(a_s, ROWS, ga, lane), slab_desc_mnmajor(b_s, ROWS, gb, lane), d, idesc_f16(128, N, 1, 1), lane > 0, 1};
     return n;
 }
-// issue ops[first, first+count) (one thread); tile_acc = 1 once the CTA's wgrad accumulators hold a previous tile
-static __device__ __noinline__ void run_ops(const MmaOp* ops, uint32_t first, uint32_t count, uint32_t tile_acc) {
+// issue ops[first, first+count) (one ELECTED thread, see tc05::elect_one); tile_acc = 1 once the CTA's wgrad accumulators hold a
+// previous tile.  Inlined on purpose: inside a non-inlined function ptxas cannot know that a single thread is active and wraps
+// every UTCHMMA in a waterfall loop again.
+__device__ __forceinline__ void run_ops(const MmaOp* ops, uint32_t first, uint32_t count, uint32_t tile_acc) {
 #pragma unroll 1
     for (uint32_t i = first; i < first + count; ++i) {
         const uint4 lo = *reinterpret_cast<const uint4*>(&ops[i]);
@@ -128,27 +131,6 @@ static __device__ __noinline__ void epi_hidden_relu(uint32_t tbase, uint32_t dco
             reinterpret_cast<uint4*>(gdst)[2 * c] = lo;
             reinterpret_cast<uint4*>(gdst)[2 * c + 1] = hi;
         }
-    }
-}
-// Same, and the 8 groups are also written to global memory as a SLAB IMAGE: img + (g_img + k) * GB + t * 16 for k = 0..7 -- the
-// byte layout of the shared-memory slab itself, so that a later kernel can copy whole groups back with 16-byte transfers that are
-// contiguous across the threads of a warp (the saved-activation backward, fused_net.cu).
-static __device__ __noinline__ void epi_hidden_relu_img(uint32_t tbase, uint32_t dcol, uint32_t warp, uint8_t* slab, uint32_t g0, uint32_t t,
-                                                    uint8_t* __restrict__ img, uint32_t g_img) {
-    uint32_t r[4][16];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) tmem_ld16_nowait(tmem_addr(tbase, warp & 3, dcol + 16 * c), r[c]);
-    tmem_ld_wait();
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(__uint_as_float(r[c][i]), 0.f);
-        uint4 lo, hi;
-        pack16(v, lo, hi);
-        slab_store16(slab, g0 + 2 * c, t, lo, hi);
-        *reinterpret_cast<uint4*>(img + (size_t)(g_img + 2 * c) * GB + t * 16) = lo;
-        *reinterpret_cast<uint4*>(img + (size_t)(g_img + 2 * c + 1) * GB + t * 16) = hi;
     }
 }
 // dgrad epilogue: D[:, 0..64) -> fp16 -> masked by ReLU'(act) -> grad slab groups [g0,g0+8); optional global copy.

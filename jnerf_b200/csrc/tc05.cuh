@@ -90,6 +90,18 @@ __host__ __device__ constexpr uint32_t idesc_f16(uint32_t M, uint32_t N, uint32_
            | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// ---- leader election -----------------------------------------------------------
+// tcgen05.mma / tcgen05.commit must be issued by ONE thread, and ptxas must be able to PROVE that: under a plain `if (tid == 0)` the
+// descriptor operands (uniform registers in SASS) are not provably warp-uniform, and every UTCHMMA gets wrapped in an
+// ELECT / BRA.U.ANY "waterfall" loop whose back-edge waits on the instruction's scoreboard -- measured 190 cycles per MMA issue
+// (tests/cuda/tc_time4.cu).  Under elect.sync in a converged warp the same loop compiles to LDS -> R2UR -> UTCHMMA.
+// All 32 lanes of the warp must execute this convergently.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- MMA issue (single thread) --------------------------------------------
 __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                            uint32_t accumulate) {

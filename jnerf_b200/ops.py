@@ -106,26 +106,6 @@ def network_bwd(coords, enc, levels, wd, wr, dout, grid_grad, dwd, dwr, n_dev=No
              _p(grid_grad), _p(dwd), _p(dwr))
 
 
-def network_act_buffer(n_max, device="cuda"):
-    """Caller-owned buffer for the saved-activation pair (ngp_network_fwd_saved / ngp_network_bwd_saved)."""
-    return torch.empty(int(lib.load().ngp_network_act_bytes(int(n_max))), dtype=torch.uint8, device=device)
-
-
-def network_fwd_saved(coords, grid, levels, wd, wr, act, n_dev=None, out=None, enc=None):
-    n = coords.shape[0]
-    if out is None:
-        out = torch.empty((n, 4), dtype=torch.float16, device=coords.device)
-    if enc is None:
-        enc = torch.empty((n, 32), dtype=torch.float16, device=coords.device)
-    lib.call("ngp_network_fwd_saved", _stream(), n, _p(n_dev), _p(coords), _p(grid), _p(levels.table), _p(wd), _p(wr), _p(out), _p(enc), _p(act))
-    return out, enc
-
-
-def network_bwd_saved(coords, enc, act, levels, wd, wr, dout, grid_grad, dwd, dwr, n_dev=None):
-    lib.call("ngp_network_bwd_saved", _stream(), coords.shape[0], _p(n_dev), _p(coords), _p(enc), _p(act), _p(levels.table), _p(wd), _p(wr),
-             _p(dout), _p(grid_grad), _p(dwd), _p(dwr))
-
-
 def density_fwd(pos, grid, levels, wd):
     out = torch.empty(pos.shape[0], dtype=torch.float16, device=pos.device)
     lib.call("ngp_density_fwd", _stream(), pos.shape[0], _p(pos), _p(grid), _p(levels.table), _p(wd), _p(out))

@@ -73,10 +73,6 @@ class Runner:
         self.dnet = torch.zeros((cap, 4), dtype=torch.float16, device=dev)
         self.last_loss = None
         self.last_rgb = None
-        # NGP_SAVE_ACT=1: the forward kernel also writes the MLP activations (416 B/sample) and the backward kernel reads them back
-        # instead of recomputing the five forward stages (ngp_network_fwd_saved / ngp_network_bwd_saved; same results)
-        self.save_act = os.environ.get("NGP_SAVE_ACT", "0") == "1"
-        self.act = ops.network_act_buffer(cap) if self.save_act else None
         if self.world_size > 1:
             self._init_sharded_table()
 
@@ -214,24 +210,16 @@ class Runner:
         return loss
 
     def net_forward(self, coords, n_dev):
-        """Fused hash encode + SH + both MLPs on the sampler's coordinate rows -> self.net_out (+ self.enc, + self.act when saving)."""
+        """Fused hash encode + SH + both MLPs on the sampler's coordinate rows -> self.net_out (+ self.enc)."""
         m = self.model
-        if self.save_act:
-            ops.network_fwd_saved(coords, m.pos_encoder.m_grid, m.pos_encoder.levels, m.density_mlp.con_weights, m.rgb_mlp.con_weights, self.act,
-                                  n_dev=n_dev, out=self.net_out, enc=self.enc)
-        else:
-            ops.network_fwd(coords, m.pos_encoder.m_grid, m.pos_encoder.levels, m.density_mlp.con_weights, m.rgb_mlp.con_weights,
-                            n_dev=n_dev, out=self.net_out, enc=self.enc)
+        ops.network_fwd(coords, m.pos_encoder.m_grid, m.pos_encoder.levels, m.density_mlp.con_weights, m.rgb_mlp.con_weights,
+                        n_dev=n_dev, out=self.net_out, enc=self.enc)
 
     def net_backward(self, coords, n_dev):
         """self.dnet -> gradients of the hash table (self.grid_grad) and of both weight vectors (self.dwd, self.dwr)."""
         m = self.model
-        if self.save_act:
-            ops.network_bwd_saved(coords, self.enc, self.act, m.pos_encoder.levels, m.density_mlp.con_weights, m.rgb_mlp.con_weights, self.dnet,
-                                  self.grid_grad, self.dwd, self.dwr, n_dev=n_dev)
-        else:
-            ops.network_bwd(coords, self.enc, m.pos_encoder.levels, m.density_mlp.con_weights, m.rgb_mlp.con_weights, self.dnet,
-                            self.grid_grad, self.dwd, self.dwr, n_dev=n_dev)
+        ops.network_bwd(coords, self.enc, m.pos_encoder.levels, m.density_mlp.con_weights, m.rgb_mlp.con_weights, self.dnet,
+                        self.grid_grad, self.dwd, self.dwr, n_dev=n_dev)
 
     def _optimizer_step(self, lr, n_step):
         """Gradient exchange + fused Adam/EMA sweep(s) (optims/adam.py + ema.py; runner.py:75-76)."""

@@ -142,22 +142,6 @@ class OracleOps:
         Y, _ = ol.mlp_fwd(_np(wd), e, 0)
         return torch.from_numpy(np.ascontiguousarray(Y[:, 0]))
 
-    def network_act_buffer(self, n_max, device="cpu"):
-        return torch.zeros(int(self.lib.load().ngp_network_act_bytes(int(n_max))), dtype=torch.uint8)
-
-    # saved-activation pair: same results as the recomputing pair by contract; the stand-in marks the image buffer so that a test
-    # can see that the backward was handed the buffer the forward of the same step wrote
-    def network_fwd_saved(self, coords, grid, levels, wd, wr, act, n_dev=None, out=None, enc=None):
-        out, enc = self.network_fwd(coords, grid, levels, wd, wr, n_dev=n_dev, save_enc=True, out=out, enc=enc)
-        self.calls[-1] = "network_fwd_saved"
-        act[:8] = torch.tensor(list(int(_live(n_dev, coords.shape[0])).to_bytes(8, "little")), dtype=torch.uint8)
-        return out, enc
-
-    def network_bwd_saved(self, coords, enc, act, levels, wd, wr, dout, grid_grad, dwd, dwr, n_dev=None):
-        assert int.from_bytes(bytes(act[:8].tolist()), "little") == _live(n_dev, coords.shape[0]), "activation image of another batch"
-        self.network_bwd(coords, enc, levels, wd, wr, dout, grid_grad, dwd, dwr, n_dev=n_dev)
-        self.calls[-1] = "network_bwd_saved"
-
     # ---- sampler -------------------------------------------------------------------------------------------
     def march(self, rays_o, rays_d, bitfield, aabb, max_samples, cone_angle, near, cascades, const_dt, rng, coords=None, workspace=None):
         self._log("march")
@@ -274,7 +258,7 @@ def install(monkeypatch):
         if name.startswith("_") or name in ("calls", "lib"):
             continue
         monkeypatch.setattr(real_ops, name, getattr(fake, name), raising=False)
-    # everything else in ops.py (dp exchange, saved-activation pair) needs the GPU: make an accidental call obvious
+    # everything else in ops.py (dp exchange) needs the GPU: make an accidental call obvious
     for name in ("dp_exchange_step", "dp_exchange_wait", "mlp_bwd_dgrad"):
         monkeypatch.setattr(real_ops, name, lambda *a, _n=name, **k: (_ for _ in ()).throw(RuntimeError(f"{_n} has no CPU stand-in")))
 

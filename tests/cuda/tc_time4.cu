@@ -48,7 +48,7 @@ __device__ __forceinline__ void issue(uint32_t kind, uint32_t d, uint32_t s, uin
 }
 
 // the measurements, by one thread; false = an mbarrier wait timed out
-__device__ __noinline__ bool measure(long long* out, uint64_t* bar, uint32_t tbase, uint32_t s) {
+__device__ __forceinline__ bool measure(long long* out, uint64_t* bar, uint32_t tbase, uint32_t s) {
     uint32_t ph = 0;
     for (int w = 0; w < 100; ++w) {            // warm the tensor pipe / clocks
         for (int r = 0; r < 8; ++r) issue(0, tbase, s, r & 1, 1);
@@ -110,7 +110,11 @@ __global__ void __launch_bounds__(128, 1) k(long long* out) {
     if (warp == 0) tmem_alloc(tmem_ptr, 512);
     fence_proxy_async_smem(); tc_fence_before(); __syncthreads(); tc_fence_after();
     const uint32_t tbase = *tmem_ptr, s = smem_u32(smem);
-    if (t == 0 && !measure(out, bar, tbase, s)) out[127] = 1;
+    // issue under elect.sync in a converged warp (tc05::elect_one): without it every UTCHMMA sits in an ELECT / BRA.U.ANY loop
+    if (warp == 0) {
+        if (elect_one()) { if (!measure(out, bar, tbase, s)) out[127] = 1; }
+        __syncwarp();
+    }
     tc_fence_before(); __syncthreads();
     if (warp == 0) tmem_free(tbase, 512);
 }

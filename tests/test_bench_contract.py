@@ -92,7 +92,7 @@ def test_our_arm_control_flow_and_json_keys(monkeypatch, capsys):
     assert line["metric"] == "ngp_lego_train_rays_per_s" and line["unit"] == "rays/s" and line["n_gpus"] == 1 and line["steps"] == 2
     assert line["scaling"] == "weak" and line["dtype"] == "f16" and line["data"] == "synthetic" and line["vs_baseline"] is None
     assert line["config"]["target_batch_size"] == 16384 and "lego" in line["config"]["workload"] and "3 synthetic 24x24 views" in line["config"]["workload"]
-    assert line["config"]["save_act"] is False and line["config"]["parallelism"] == "dp1"
+    assert line["config"]["parallelism"] == "dp1"
     assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and line["e2e"]["h2d_bytes_per_step"] > 0
     roof = line["roofline"]
     assert roof["bound"] == "hbm" and roof["unit"] == "GB/s" and roof["kernel"] in ("network_fwd", "network_bwd") and roof["peak"] > 0

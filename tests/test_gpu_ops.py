@@ -448,17 +448,3 @@ def test_dp_exchange_kernel_two_ranks_on_one_device(ops):
             assert torch.equal(state[r]["w"], ref["w"]), f"epoch {epoch}: MLP weights of rank {r} differ"
             assert torch.equal(state[r]["master"], ref["master"][r * sl:(r + 1) * sl])
             assert int(a.table_grad.abs().sum()) == 0 and int(a.flags[32]) == 0
-
-
-@pytest.mark.gpu
-def test_network_bwd_two_chain_variant():
-    """network_bwd2_kernel (two MLP chains per CTA, gradient slabs written in place over the activations; NGP_BWD_V2=1) against the
-    same oracle comparisons as the default kernel.  The switch is read once per process, hence the subprocess."""
-    import subprocess
-    here = os.path.dirname(os.path.abspath(__file__))
-    env = dict(os.environ, NGP_BWD_V2="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_ops.py"), os.path.join(here, "test_gpu_runner.py"), "-q", "-x",
-                        "-m", "gpu", "-k", "(test_network_bwd and 1-14 and not two_chain) or fused_step", "-p", "no:cacheprovider"],
-                       env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
-    assert "2 passed" in r.stdout, r.stdout[-2000:]

@@ -249,22 +249,6 @@ def test_real_capture_through_the_runner(monkeypatch, tmp_path):
     assert bool((rgba[:, 3] == 1).all()) and int(img_ids.max()) < 50          # opaque JPEG frames
 
 
-def test_saved_activation_mode_glue(monkeypatch):
-    """NGP_SAVE_ACT=1: the Runner allocates the activation image once (ngp_network_act_bytes of the sample capacity), hands the same
-    buffer to the forward and the backward of every step, and the bench's per-stage path goes through the same two methods."""
-    monkeypatch.setenv("NGP_SAVE_ACT", "1")
-    r, fake = make_runner(monkeypatch, seed=4)
-    assert r.save_act and r.act.numel() == (r.sampler.target_batch_size + 127) // 128 * 26 * 2048 and r.act.dtype == torch.uint8
-    fake.calls.clear()
-    loss = r.train_step()
-    assert fake.calls == [c if not c.startswith("network_") else c + "_saved" for c in STEP_OPS] and torch.isfinite(loss).all()
-    monkeypatch.delenv("NGP_SAVE_ACT")
-    r2, _ = make_runner(monkeypatch, seed=4)
-    assert not r2.save_act and r2.act is None
-    l2 = r2.train_step()
-    assert torch.equal(loss, l2)                                   # same results either way
-
-
 def test_reference_written_pkl_with_flushed_second_moments_keeps_training_finite(monkeypatch, tmp_path):
     """A params.pkl written by the REFERENCE holds fp16 Adam moments: second moments of the hash table (g^2 ~ 1e-10) flush to 0 while the
     first moment survives.  Loading such a file and training on must not blow entries up (lr * m / (sqrt(0) + 1e-15))."""
