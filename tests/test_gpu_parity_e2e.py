@@ -85,15 +85,19 @@ def test_identical_ray_batch_to_radiance(kind):
     # every layer; they agree bit for bit except where a sum lands on a rounding boundary
     d_out = np.abs(npy(out).astype(np.float32) - out_ref.astype(np.float32))
     ulp = np.spacing(np.abs(out_ref).astype(np.float16)).astype(np.float32)
-    frac_exact = float((d_out == 0).mean())
-    assert frac_exact > 0.80, frac_exact
-    assert float((d_out <= 2 * ulp).mean()) > 0.999 and float((d_out / np.maximum(ulp, 2.0 ** -14)).max()) <= 16
-    # radiance: north_star's bar
     err = np.abs(rgb - rgb_ref)
-    assert err.max() <= 1e-3, (err.max(), err.mean())
     bright = rgb_ref > 0.1
-    assert (err[bright] / rgb_ref[bright]).max() <= 1e-3 * 2                                # relative to the pixel (>= 0.1): 2e-3 worst case
-    assert np.abs(npy(rgb_i) - ri_ref).max() <= 1e-3 and np.abs(npy(alpha_i) - ai_ref).max() <= 1e-3
+    stats = dict(samples=S, frac_bit_identical=float((d_out == 0).mean()), frac_within_2ulp=float((d_out <= 2 * ulp).mean()),
+                 out_max_abs=float(d_out.max()), out_absmax_ref=float(np.abs(out_ref).max()), rgb_max_abs=float(err.max()), rgb_mean_abs=float(err.mean()),
+                 rgb_max_rel_bright=float((err[bright] / rgb_ref[bright]).max()) if bright.any() else 0.0,
+                 infer_rgb_max_abs=float(np.abs(npy(rgb_i) - ri_ref).max()), infer_alpha_max_abs=float(np.abs(npy(alpha_i) - ai_ref).max()))
+    print("parity", kind, stats)
+    # per sample: bit-identical for the bulk, within 2 fp16 ulp for 99.9 %; the tail is a hidden activation that rounded the other way
+    # (1 ulp of an O(1..8) activation times an O(0.3) weight), bounded absolutely
+    assert stats["frac_bit_identical"] > 0.80 and stats["frac_within_2ulp"] > 0.999 and stats["out_max_abs"] <= 1e-2, stats
+    # radiance: north_star's bar, 1e-3 (absolute on [0,1] radiance, and relative to the pixel for pixels brighter than 0.1)
+    assert stats["rgb_max_abs"] <= 1e-3 and stats["rgb_max_rel_bright"] <= 1e-3, stats
+    assert stats["infer_rgb_max_abs"] <= 1e-3 and stats["infer_alpha_max_abs"] <= 1e-3, stats
 
 
 # --------------------------------------------------------------------------------------------- MLP vs torch fp32 Linear/ReLU

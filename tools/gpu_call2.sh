@@ -12,7 +12,7 @@ bench() { local name=$1; shift; local envs=(); while [ "$1" != "--" ]; do envs+=
           run "bench_$name" 300 env "${envs[@]}" python bench.py --steps 300 --warmup 5 --no-cpu-baseline "$@"
           python tools/bench_line_summary.py "$OUT/bench_$name.log" "$name" >> "$SUM"; }
 python -c "import __graft_entry__ as g; g.build()" > "$OUT/build.log" 2>&1 || echo "build failed" >> "$SUM"
-run pytest_gpu 1200 python -m pytest tests -m gpu -q -p no:cacheprovider -x
+run pytest_gpu 1200 python -m pytest tests -m gpu -q -p no:cacheprovider -s
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o /tmp/tc_time4 tests/cuda/tc_time4.cu > "$OUT/nvcc_probes.log" 2>&1
 run probe_tc_time4_elect 60 /tmp/tc_time4
 bench default --
