@@ -43,8 +43,7 @@ struct SmemFwd {
     static constexpr uint32_t w1r = w0r + 64 * 32 * 2;
     static constexpr uint32_t woutr = w1r + 64 * 64 * 2;
     static constexpr uint32_t levels = woutr + 16 * 64 * 2;
-    static constexpr uint32_t ops = levels + N_LEVELS * 32;          // MMA program (<= 72 ops)
-    static constexpr uint32_t bar = ops + 72 * 32;
+    static constexpr uint32_t bar = levels + N_LEVELS * 32;
     static constexpr uint32_t total = bar + 64;
 };
 // gradient slab groups (backward)
@@ -59,14 +58,9 @@ struct SmemBwd {
     static constexpr uint32_t w1r = w0r + 64 * 32 * 2;
     static constexpr uint32_t woutr = w1r + 64 * 64 * 2;
     static constexpr uint32_t levels = woutr + 16 * 64 * 2;
-    static constexpr uint32_t ops = levels + N_LEVELS * 32;
-    static constexpr uint32_t bar = ops + 72 * 32;
+    static constexpr uint32_t bar = levels + N_LEVELS * 32;
     static constexpr uint32_t total = bar + 64;
 };
-
-// MMA program layout (op indices) shared by the forward chain of both kernels
-constexpr uint32_t OP_L0D = 0, OP_L1D = 2, OP_L0R = 6, OP_L1R = 8, OP_L2R = 12, OP_FWD_END = 16;
-constexpr uint32_t OP_L0D_B1 = 16;   // forward kernel only: density layer 0 reading the second enc buffer
 
 template <class S>
 __device__ __forceinline__ void stage_all_weights(uint8_t* smem, const __half* wd, const __half* wr, uint32_t t) {
@@ -118,34 +112,22 @@ __device__ __forceinline__ void gather_tile(const float* __restrict__ s_pos /* s
     }
 }
 
-// Forward MMA program (ops [0,16)): built once per kernel by warp 0's lanes.
-template <class S, uint32_t G_H2>
-__device__ __forceinline__ void build_forward_program(uint8_t* smem, uint32_t tbase, uint32_t lane) {
-    MmaOp* ops = reinterpret_cast<MmaOp*>(smem + S::ops);
-    const uint32_t smem_s = smem_u32(smem), act_s = smem_s + S::act;
-    const uint32_t D_H = 0, D_S = 64;
-    build_fwd(ops + OP_L0D, lane, tbase + D_H, act_s, G_ENC, 32, smem_s + S::w0d, 64);
-    build_fwd(ops + OP_L1D, lane, tbase + D_S, act_s, G_HD, 64, smem_s + S::woutd, 16);
-    build_fwd(ops + OP_L0R, lane, tbase + D_H, act_s, G_RIN, 32, smem_s + S::w0r, 64);
-    build_fwd(ops + OP_L1R, lane, tbase + D_H, act_s, G_H1, 64, smem_s + S::w1r, 64);
-    build_fwd(ops + OP_L2R, lane, tbase + D_S, act_s, G_H2, 64, smem_s + S::woutr, 16);
-}
-
 // Forward chain up to (and including) the colour net's last hidden layer.  Expects enc in ACT[G_ENC..+4).
 // Returns the fp16 density output h[0] of row t (sigma_raw) and leaves hd / rin / h1 / h2 in the slab.
-template <uint32_t G_H2, bool CHAIN128 = false>
-__device__ __forceinline__ uint32_t forward_chain(uint8_t* smem, uint32_t act_off, const MmaOp* ops, uint32_t op_l0d,
+template <class S, uint32_t G_H2, bool CHAIN128 = false>
+__device__ __forceinline__ uint32_t forward_chain(uint8_t* smem, uint32_t g_enc /* G_ENC or G_ENC1 */,
                                                   const float* s_coords, uint32_t tbase, Pipe& pipe, uint32_t t, uint32_t warp,
                                                   bool density_only, uint32_t chain_bar = 1) {
-    uint8_t* act = smem + act_off;
+    uint8_t* act = smem + S::act;
+    const uint32_t smem_s = smem_u32(smem), act_s = smem_s + S::act;
     const uint32_t D_H = 0, D_S = 64;
     // density L0: enc(32) -> hd(64)
-    if (warp == 0) { if (elect_one()) { run_ops(ops, op_l0d, 2, 0); pipe.commit(); } __syncwarp(); }
+    if (warp == 0) { if (elect_one()) { issue_fwd<32, 64>(tbase + D_H, act_s, g_enc, smem_s + S::w0d); pipe.commit(); } __syncwarp(); }
     pipe.wait();
     epi_hidden_relu(tbase, D_H, warp, act, G_HD, t, nullptr);
     if constexpr (CHAIN128) sync_chain(chain_bar); else sync_before_issue<false>();
     // density L1: hd(64) -> h(16)
-    if (warp == 0) { if (elect_one()) { run_ops(ops, OP_L1D, 4, 0); pipe.commit(); } __syncwarp(); }
+    if (warp == 0) { if (elect_one()) { issue_fwd<64, 16>(tbase + D_S, act_s, G_HD, smem_s + S::woutd); pipe.commit(); } __syncwarp(); }
     pipe.wait();
     uint32_t sigma_half;
     {
@@ -163,12 +145,12 @@ __device__ __forceinline__ uint32_t forward_chain(uint8_t* smem, uint32_t act_of
     }
     if constexpr (CHAIN128) sync_chain(chain_bar); else sync_before_issue<false>();
     // colour L0: [h | sh](32) -> h1(64)
-    if (warp == 0) { if (elect_one()) { run_ops(ops, OP_L0R, 2, 0); pipe.commit(); } __syncwarp(); }
+    if (warp == 0) { if (elect_one()) { issue_fwd<32, 64>(tbase + D_H, act_s, G_RIN, smem_s + S::w0r); pipe.commit(); } __syncwarp(); }
     pipe.wait();
     epi_hidden_relu(tbase, D_H, warp, act, G_H1, t, nullptr);
     if constexpr (CHAIN128) sync_chain(chain_bar); else sync_before_issue<false>();
     // colour L1: h1(64) -> h2(64)
-    if (warp == 0) { if (elect_one()) { run_ops(ops, OP_L1R, 4, 0); pipe.commit(); } __syncwarp(); }
+    if (warp == 0) { if (elect_one()) { issue_fwd<64, 64>(tbase + D_H, act_s, G_H1, smem_s + S::w1r); pipe.commit(); } __syncwarp(); }
     pipe.wait();
     epi_hidden_relu(tbase, D_H, warp, act, G_H2, t, nullptr);
     if constexpr (CHAIN128) sync_chain(chain_bar); else sync_before_issue<false>();
@@ -210,12 +192,6 @@ network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
     if (warp == 0) tmem_alloc(tmem_ptr, 128);
     sync_before_issue();
     const uint32_t tbase = *tmem_ptr;
-    if (warp == 0) {
-        build_forward_program<S, G_H2F>(smem, tbase, t);
-        build_fwd(reinterpret_cast<MmaOp*>(smem + S::ops) + OP_L0D_B1, t, tbase + 0, smem_u32(smem) + S::act, G_ENC1, 32, smem_u32(smem) + S::w0d, 64);
-    }
-    __syncthreads();
-    const MmaOp* ops = reinterpret_cast<const MmaOp*>(smem + S::ops);
     const uint32_t n_live = n_dev ? min(*n_dev, n_max) : n_max;
     const uint32_t ntiles = (n_live + ROWS - 1) / ROWS;
 
@@ -229,13 +205,13 @@ network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             tc_fence_after();
             // forward_chain releases nothing itself: the enc slab is dead after layer 0, the coordinates after the SH epilogue;
             // both are handed back together right after the chain (the gather runs a full tile ahead, so this is not on its path)
-            const uint32_t sig = forward_chain<G_H2F, true>(smem, S::act, ops, buf ? OP_L0D_B1 : OP_L0D, s_coords, tbase, pipe, t, warp, DENSITY_ONLY);
+            const uint32_t sig = forward_chain<S, G_H2F, true>(smem, buf ? G_ENC1 : G_ENC, s_coords, tbase, pipe, t, warp, DENSITY_ONLY);
             if (tile + 2 * gridDim.x < ntiles) named_bar_arrive(4 + buf, FWD_THREADS);   // EMPTY[buf]
             if constexpr (DENSITY_ONLY) {
                 if (row < n_live) reinterpret_cast<uint16_t*>(out)[row] = (uint16_t)sig;
                 sync_before_issue<true>();                      // TMEM reads of this tile precede the next tile's MMAs
             } else {
-                if (warp == 0) { if (elect_one()) { run_ops(ops, OP_L2R, 4, 0); pipe.commit(); } __syncwarp(); }
+                if (warp == 0) { if (elect_one()) { issue_fwd<64, 16>(tbase + 64, smem_u32(smem) + S::act, G_H2F, smem_u32(smem) + S::woutr); pipe.commit(); } __syncwarp(); }
                 pipe.wait();
                 float v[16];
                 tmem_ld16(tmem_addr(tbase, warp, 64), v);
@@ -310,31 +286,6 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
     const uint32_t smem_s = smem_u32(smem), act_s = smem_s + S::act, grd_s = smem_s + S::grd;
     // TMEM columns
     const uint32_t D_H = 0, D_S = 64, A_W0D = 96, A_WOUTD = 160, A_W0R = 176, A_W1R = 240, A_WOUTR = 304;
-    // backward MMA program: each stage = dgrad ops followed by the wgrad ops that become ready with it
-    constexpr uint32_t OP_B1 = 16, OP_B2 = OP_B1 + 1 + 8, OP_B3 = OP_B2 + 4 + 8, OP_B4 = OP_B3 + 4 + 8, OP_B5 = OP_B4 + 1 + 8, OP_END = OP_B5 + 4 + 8;
-    static_assert(OP_END <= 72, "MMA program does not fit");
-    {
-        MmaOp* w = reinterpret_cast<MmaOp*>(smem + S::ops);
-        if (warp == 0) build_forward_program<S, G_H2B>(smem, tbase, t);
-        if (warp == 1) {
-            const uint32_t l = t & 31;
-            build_dgrad(w + OP_B1, l, tbase + D_H, grd_s, Q_DYR, 16, smem_s + S::woutr, 64);
-            build_wgrad(w + OP_B1 + 1, l, tbase + A_WOUTR, act_s, G_H2B, grd_s, Q_DYR, 16);
-            build_dgrad(w + OP_B2, l, tbase + D_H, grd_s, Q_GH2, 64, smem_s + S::w1r, 64);
-            build_wgrad(w + OP_B2 + 4, l, tbase + A_W1R, act_s, G_H1, grd_s, Q_GH2, 64);
-            build_dgrad(w + OP_B3, l, tbase + D_S, grd_s, Q_GH1, 64, smem_s + S::w0r, 32);
-            build_wgrad(w + OP_B3 + 4, l, tbase + A_W0R, act_s, G_RIN, grd_s, Q_GH1, 64);
-        }
-        if (warp == 2) {
-            const uint32_t l = t & 31;
-            build_dgrad(w + OP_B4, l, tbase + D_H, grd_s, Q_DYD, 16, smem_s + S::woutd, 64);
-            build_wgrad(w + OP_B4 + 1, l, tbase + A_WOUTD, act_s, G_HD, grd_s, Q_DYD, 16);
-            build_dgrad(w + OP_B5, l, tbase + D_S, grd_s, Q_GHD, 64, smem_s + S::w0d, 32);
-            build_wgrad(w + OP_B5 + 4, l, tbase + A_W0D, act_s, G_ENC, grd_s, Q_GHD, 64);
-        }
-        __syncthreads();
-    }
-    const MmaOp* ops = reinterpret_cast<const MmaOp*>(smem + S::ops);
     const uint32_t n_live = n_dev ? min(*n_dev, n_max) : n_max;
     const uint32_t ntiles = (n_live + ROWS - 1) / ROWS;
     uint32_t acc = 0;
@@ -377,11 +328,11 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             DBGB(1);
             sync_before_issue<true>();
             DBGB(2);
-            forward_chain<G_H2B, true>(smem, S::act, ops, OP_L0D, s_coords, tbase, pipe, t, warp, false);
+            forward_chain<S, G_H2B, true>(smem, G_ENC, s_coords, tbase, pipe, t, warp, false);
             DBGB(3);
             // B1: g_h2 = (dYr Woutr) . relu'(h2) ; wgrad Woutr
-            if (warp == 0) { if (elect_one()) { run_ops(ops, OP_B1, 1, acc); DBGB(4); pipe.commit(); } __syncwarp(); }
-            if (warp == 1) { if (elect_one()) { if (!(dbg & 4)) run_ops(ops, OP_B1 + 1, 8, acc); mma_commit(bar_w); } __syncwarp(); }   // weight gradient: issued by a second thread, off the critical path
+            if (warp == 0) { if (elect_one()) { issue_dgrad<16, 64>(tbase + D_H, grd_s, Q_DYR, smem_s + S::woutr); DBGB(4); pipe.commit(); } __syncwarp(); }
+            if (warp == 1) { if (elect_one()) { if (!(dbg & 4)) issue_wgrad<16>(tbase + A_WOUTR, act_s, G_H2B, grd_s, Q_DYR, acc); mma_commit(bar_w); } __syncwarp(); }   // weight gradient: issued by a second thread, off the critical path
             pipe.wait();
             DBGB(5);
             epi_dgrad_mask(tbase, D_H, warp, act, G_H2B, grd, Q_GH2, t, nullptr);
@@ -389,8 +340,8 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             sync_before_issue<true>();
             DBGB(7);
             // B2: g_h1 = (g_h2 W1r) . relu'(h1) ; wgrad W1r
-            if (warp == 0) { if (elect_one()) { run_ops(ops, OP_B2, 4, acc); DBGB(8); pipe.commit(); DBGB(21); } __syncwarp(); }
-            if (warp == 1) { if (elect_one()) { if (!(dbg & 4)) run_ops(ops, OP_B2 + 4, 8, acc); mma_commit(bar_w); } __syncwarp(); }   // weight gradient: issued by a second thread, off the critical path
+            if (warp == 0) { if (elect_one()) { issue_dgrad<64, 64>(tbase + D_H, grd_s, Q_GH2, smem_s + S::w1r); DBGB(8); pipe.commit(); DBGB(21); } __syncwarp(); }
+            if (warp == 1) { if (elect_one()) { if (!(dbg & 4)) issue_wgrad<64>(tbase + A_W1R, act_s, G_H1, grd_s, Q_GH2, acc); mma_commit(bar_w); } __syncwarp(); }   // weight gradient: issued by a second thread, off the critical path
             pipe.wait();
             DBGB(9);
 #ifdef NGP_TIMELINE
@@ -426,8 +377,8 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
 #endif
             DBGB(10);
             // B3: d_rin = g_h1 W0r (32 cols; the last 16 are dL/dSH, unused) ; wgrad W0r
-            if (warp == 0) { if (elect_one()) { run_ops(ops, OP_B3, 4, acc); pipe.commit(); } __syncwarp(); }
-            if (warp == 1) { if (elect_one()) { if (!(dbg & 4)) run_ops(ops, OP_B3 + 4, 8, acc); mma_commit(bar_w); } __syncwarp(); }   // weight gradient: issued by a second thread, off the critical path
+            if (warp == 0) { if (elect_one()) { issue_dgrad<64, 32>(tbase + D_S, grd_s, Q_GH1, smem_s + S::w0r); pipe.commit(); } __syncwarp(); }
+            if (warp == 1) { if (elect_one()) { if (!(dbg & 4)) issue_wgrad<64>(tbase + A_W0R, act_s, G_RIN, grd_s, Q_GH1, acc); mma_commit(bar_w); } __syncwarp(); }   // weight gradient: issued by a second thread, off the critical path
             pipe.wait();
             {
                 float v[16];
@@ -439,14 +390,14 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             }
             sync_before_issue<true>();
             // B4: g_hd = (dYd Woutd) . relu'(hd) ; wgrad Woutd
-            if (warp == 0) { if (elect_one()) { run_ops(ops, OP_B4, 1, acc); pipe.commit(); } __syncwarp(); }
-            if (warp == 1) { if (elect_one()) { if (!(dbg & 4)) run_ops(ops, OP_B4 + 1, 8, acc); mma_commit(bar_w); } __syncwarp(); }   // weight gradient: issued by a second thread, off the critical path
+            if (warp == 0) { if (elect_one()) { issue_dgrad<16, 64>(tbase + D_H, grd_s, Q_DYD, smem_s + S::woutd); pipe.commit(); } __syncwarp(); }
+            if (warp == 1) { if (elect_one()) { if (!(dbg & 4)) issue_wgrad<16>(tbase + A_WOUTD, act_s, G_HD, grd_s, Q_DYD, acc); mma_commit(bar_w); } __syncwarp(); }   // weight gradient: issued by a second thread, off the critical path
             pipe.wait();
             epi_dgrad_mask(tbase, D_H, warp, act, G_HD, grd, Q_GHD, t, nullptr);
             sync_before_issue<true>();
             // B5: d_enc = g_hd W0d ; wgrad W0d
-            if (warp == 0) { if (elect_one()) { run_ops(ops, OP_B5, 4, acc); pipe.commit(); } __syncwarp(); }
-            if (warp == 1) { if (elect_one()) { if (!(dbg & 4)) run_ops(ops, OP_B5 + 4, 8, acc); mma_commit(bar_w); } __syncwarp(); }   // weight gradient: issued by a second thread, off the critical path
+            if (warp == 0) { if (elect_one()) { issue_dgrad<64, 32>(tbase + D_S, grd_s, Q_GHD, smem_s + S::w0d); pipe.commit(); } __syncwarp(); }
+            if (warp == 1) { if (elect_one()) { if (!(dbg & 4)) issue_wgrad<64>(tbase + A_W0D, act_s, G_ENC, grd_s, Q_GHD, acc); mma_commit(bar_w); } __syncwarp(); }   // weight gradient: issued by a second thread, off the critical path
             pipe.wait();
             {
                 float v[16];

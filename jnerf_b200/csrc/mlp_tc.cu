@@ -75,7 +75,7 @@ mlp_fwd_kernel(const __half* __restrict__ W, const __half* __restrict__ X, __hal
         DBG(2);
         uint32_t cur = FwdSmem::slab0, nxt = FwdSmem::slab1;
         // layer 0
-        if (warp == 0) { if (elect_one()) { issue_fwd(tbase + D_H, smem_s + cur, 0, IN, smem_s + FwdSmem::w0, WIDTH); pipe.commit(); } __syncwarp(); }
+        if (warp == 0) { if (elect_one()) { issue_fwd<IN, WIDTH>(tbase + D_H, smem_s + cur, 0, smem_s + FwdSmem::w0); pipe.commit(); } __syncwarp(); }
         pipe.wait();
         DBG(4);
         epi_hidden_relu(tbase, D_H, warp, smem + nxt, 0, t, (inter && valid) ? inter + ((size_t)0 * n + row) * WIDTH : nullptr);
@@ -84,14 +84,14 @@ mlp_fwd_kernel(const __half* __restrict__ W, const __half* __restrict__ X, __hal
         DBG(6);
         { uint32_t s = cur; cur = nxt; nxt = s; }
         for (uint32_t j = 0; j < nhm; ++j) {
-            if (warp == 0) { if (elect_one()) { issue_fwd(tbase + D_H, smem_s + cur, 0, WIDTH, smem_s + FwdSmem::wh + j * WIDTH * WIDTH * 2, WIDTH); pipe.commit(); } __syncwarp(); }
+            if (warp == 0) { if (elect_one()) { issue_fwd<WIDTH, WIDTH>(tbase + D_H, smem_s + cur, 0, smem_s + FwdSmem::wh + j * WIDTH * WIDTH * 2); pipe.commit(); } __syncwarp(); }
             pipe.wait();
             epi_hidden_relu(tbase, D_H, warp, smem + nxt, 0, t, (inter && valid) ? inter + ((size_t)(j + 1) * n + row) * WIDTH : nullptr);
             sync_before_issue();
             { uint32_t s = cur; cur = nxt; nxt = s; }
         }
         DBG(7);
-        if (warp == 0) { if (elect_one()) { issue_fwd(tbase + D_O, smem_s + cur, 0, WIDTH, smem_s + FwdSmem::wout(nhm), OUTP); pipe.commit(); } __syncwarp(); }
+        if (warp == 0) { if (elect_one()) { issue_fwd<WIDTH, OUTP>(tbase + D_O, smem_s + cur, 0, smem_s + FwdSmem::wout(nhm)); pipe.commit(); } __syncwarp(); }
         pipe.wait();
         DBG(8);
         {
@@ -198,8 +198,8 @@ mlp_bwd_kernel(const __half* __restrict__ W, const __half* __restrict__ X, const
         // gradient at the last hidden layer, and the output layer's wgrad
         if (warp == 0) {
             if (elect_one()) {
-                issue_dgrad(tbase + D_G, grd_s, 0, OUTP, smem_s + L.wout(), WIDTH);
-                if (dW) issue_wgrad(tbase + D_WOUT, act_s, 4 + 8 * (nh - 1), grd_s, 0, OUTP, acc);
+                issue_dgrad<OUTP, WIDTH>(tbase + D_G, grd_s, 0, smem_s + L.wout());
+                if (dW) issue_wgrad<OUTP>(tbase + D_WOUT, act_s, 4 + 8 * (nh - 1), grd_s, 0, acc);
                 pipe.commit();
             }
             __syncwarp();
@@ -212,8 +212,8 @@ mlp_bwd_kernel(const __half* __restrict__ W, const __half* __restrict__ X, const
             const uint32_t j = nh - 1 - k;            // gradient block holding g_k
             if (warp == 0) {
                 if (elect_one()) {
-                    issue_dgrad(tbase + D_G, grd_s, 2 + 8 * j, WIDTH, smem_s + L.wh() + (k - 1) * WIDTH * WIDTH * 2, WIDTH);
-                    if (dW) issue_wgrad(tbase + D_W + 64 * k, act_s, 4 + 8 * (k - 1), grd_s, 2 + 8 * j, WIDTH, acc);
+                    issue_dgrad<WIDTH, WIDTH>(tbase + D_G, grd_s, 2 + 8 * j, smem_s + L.wh() + (k - 1) * WIDTH * WIDTH * 2);
+                    if (dW) issue_wgrad<WIDTH>(tbase + D_W + 64 * k, act_s, 4 + 8 * (k - 1), grd_s, 2 + 8 * j, acc);
                     pipe.commit();
                 }
                 __syncwarp();
@@ -227,8 +227,8 @@ mlp_bwd_kernel(const __half* __restrict__ W, const __half* __restrict__ X, const
         if (!dX && !dW) continue;     // dgrad-only call without dL/dinput: nothing left for this tile (uniform over the CTA)
         if (warp == 0) {
             if (elect_one()) {
-                if (dX) issue_dgrad(tbase + D_X, grd_s, 2 + 8 * nhm, WIDTH, smem_s + L.w0(), IN);
-                if (dW) issue_wgrad(tbase + D_W, act_s, 0, grd_s, 2 + 8 * nhm, WIDTH, acc);
+                if (dX) issue_dgrad<WIDTH, IN>(tbase + D_X, grd_s, 2 + 8 * nhm, smem_s + L.w0());
+                if (dW) issue_wgrad<WIDTH>(tbase + D_W, act_s, 0, grd_s, 2 + 8 * nhm, acc);
                 pipe.commit();
             }
             __syncwarp();

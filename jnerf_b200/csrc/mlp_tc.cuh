@@ -21,71 +21,34 @@ static __device__ __noinline__ void stage_weights(uint8_t* dst, const __half* __
     }
 }
 
-// NOTE on code size: the epilogue helpers are deliberately __noinline__ and the issue loops are rolled (the issue helpers themselves must
-// be inlined into the elect.sync-guarded block of their caller, see tc05::elect_one).  With everything inlined and unrolled the
-// per-tile body of the fused backward kernel was 77 KB of SASS -- larger than the SM's 32 KB L1.5 instruction cache -- and the
-// 4 warps of a CTA spent most of their time waiting for instruction fetches from L2 (measured: ~44k cycles per tile).
+// ---- MMA issue -------------------------------------------------------------------------------------------
+// Issued by ONE elected thread (tc05::elect_one) with every shape a template parameter and every shared-memory offset a constant of
+// the kernel: fully unrolled, the descriptors fold into the uniform datapath (UIADD3 / UMOV) and the UTCHMMAs issue back to back.
+// History (tests/cuda/tc_time4.cu, tc_time5.cu): under `if (tid == 0)` every UTCHMMA sat in an ELECT / BRA.U.ANY waterfall loop
+// (190 cycles per MMA); with descriptor records streamed from shared memory (LDS -> R2UR x6 -> UTCHMMA) the issue loop still cost
+// 75-150 cycles per MMA -- more than the 32 cycles a 128 x 64 x 16 MMA executes in -- whatever the operand layout.
+//
 // D[128 x N] (+)= ACT[:, 8*g0 .. 8*g0+K) * W^T          (W staged with rows = N)
-__device__ __forceinline__ void issue_fwd(uint32_t d, uint32_t act_s, uint32_t g0, uint32_t K, uint32_t w_s, uint32_t N) {
-#pragma unroll 1
+template <uint32_t K, uint32_t N>
+__device__ __forceinline__ void issue_fwd(uint32_t d, uint32_t act_s, uint32_t g0, uint32_t w_s) {
+#pragma unroll
     for (uint32_t kb = 0; kb < K / 16; ++kb)
-        mma_f16_ss(d, slab_desc_kmajor(act_s, ROWS, g0, kb), slab_desc_kmajor(w_s, N, 0, kb), idesc_f16(128, N, 0, 0), kb > 0);
+        mma_f16_ss(d, slab_desc_kmajor(act_s, ROWS, g0, kb), slab_desc_kmajor(w_s, N, 0, kb), idesc_f16(128, N, 0, 0), kb > 0 ? 1u : 0u);
 }
-// D[128 x Nin] = GRD[:, 8*g0 .. 8*g0+Kout) * W          (W staged with rows = Kout, K = Nin; read MN-major)
-__device__ __forceinline__ void issue_dgrad(uint32_t d, uint32_t grd_s, uint32_t g0, uint32_t Kout, uint32_t w_s, uint32_t Nin,
-                                            uint32_t accumulate_first = 0) {
-#pragma unroll 1
-    for (uint32_t kb = 0; kb < Kout / 16; ++kb)
-        mma_f16_ss(d, slab_desc_kmajor(grd_s, ROWS, g0, kb), slab_desc_mnmajor(w_s, Kout, 0, kb), idesc_f16(128, Nin, 0, 1),
-                   (kb > 0) | accumulate_first);
+// D[128 x NIN] = GRD[:, 8*g0 .. 8*g0+KOUT) * W          (W staged with rows = KOUT, K = NIN; read MN-major)
+template <uint32_t KOUT, uint32_t NIN>
+__device__ __forceinline__ void issue_dgrad(uint32_t d, uint32_t grd_s, uint32_t g0, uint32_t w_s) {
+#pragma unroll
+    for (uint32_t kb = 0; kb < KOUT / 16; ++kb)
+        mma_f16_ss(d, slab_desc_kmajor(grd_s, ROWS, g0, kb), slab_desc_mnmajor(w_s, KOUT, 0, kb), idesc_f16(128, NIN, 0, 1), kb > 0 ? 1u : 0u);
 }
 // D[128 x N] (+)= A^T B : lanes = features [8*ga, 8*ga+128) of slab a, columns = features [8*gb, 8*gb+N) of slab b,
 // contraction over the 128 rows of the tile.  `accumulate` = 0 only for the very first tile of the CTA.
-__device__ __forceinline__ void issue_wgrad(uint32_t d, uint32_t a_s, uint32_t ga, uint32_t b_s, uint32_t gb, uint32_t N, uint32_t accumulate) {
-#pragma unroll 1
+template <uint32_t N>
+__device__ __forceinline__ void issue_wgrad(uint32_t d, uint32_t a_s, uint32_t ga, uint32_t b_s, uint32_t gb, uint32_t accumulate) {
+#pragma unroll
     for (uint32_t kb = 0; kb < ROWS / 16; ++kb)
-        mma_f16_ss(d, slab_desc_mnmajor(a_s, ROWS, ga, kb), slab_desc_mnmajor(b_s, ROWS, gb, kb), idesc_f16(128, N, 1, 1),
-                   (kb > 0) | accumulate);
-}
-
-// ---- precomputed MMA programs ---------------------------------------------------------------------------
-// All operand addresses are compile-time-constant offsets inside the CTA's shared memory, so every descriptor is built ONCE
-// per kernel (by as many threads as there are MMAs) and the issuing thread only streams 32-byte records.  Building the
-// two 64-bit descriptors inline cost ~200 cycles per MMA of single-thread latency (tools/dbg_timeline.py), which dominated
-// stages with 9-12 MMAs (dgrad + wgrad).
-struct __align__(16) MmaOp {
-    uint64_t a, b;
-    uint32_t d, idesc, acc, flags;      // flags bit0: wgrad op (accumulate across tiles: acc |= tile_acc)
-};
-static_assert(sizeof(MmaOp) == 32, "MmaOp must be 32 bytes");
-
-// op builders (any thread): write `n` ops starting at ops[0]; return n
-__device__ __forceinline__ uint32_t build_fwd(MmaOp* ops, uint32_t lane, uint32_t d, uint32_t act_s, uint32_t g0, uint32_t K, uint32_t w_s, uint32_t N) {
-    const uint32_t n = K / 16;
-    if (lane < n) ops[lane] = MmaOp{slab_desc_kmajor(act_s, ROWS, g0, lane), slab_desc_kmajor(w_s, N, 0, lane), d, idesc_f16(128, N, 0, 0), lane > 0, 0};
-    return n;
-}
-__device__ __forceinline__ uint32_t build_dgrad(MmaOp* ops, uint32_t lane, uint32_t d, uint32_t grd_s, uint32_t g0, uint32_t Kout, uint32_t w_s, uint32_t Nin) {
-    const uint32_t n = Kout / 16;
-    if (lane < n) ops[lane] = MmaOp{slab_desc_kmajor(grd_s, ROWS, g0, lane), slab_desc_mnmajor(w_s, Kout, 0, lane), d, idesc_f16(128, Nin, 0, 1), lane > 0, 0};
-    return n;
-}
-__device__ __forceinline__ uint32_t build_wgrad(MmaOp* ops, uint32_t lane, uint32_t d, uint32_t a_s, uint32_t ga, uint32_t b_s, uint32_t gb, uint32_t N) {
-    const uint32_t n = ROWS / 16;
-    if (lane < n) ops[lane] = MmaOp{slab_desc_mnmajor(a_s, ROWS, ga, lane), slab_desc_mnmajor(b_s, ROWS, gb, lane), d, idesc_f16(128, N, 1, 1), lane > 0, 1};
-    return n;
-}
-// issue ops[first, first+count) (one ELECTED thread, see tc05::elect_one); tile_acc = 1 once the CTA's wgrad accumulators hold a
-// previous tile.  Inlined on purpose: inside a non-inlined function ptxas cannot know that a single thread is active and wraps
-// every UTCHMMA in a waterfall loop again.
-__device__ __forceinline__ void run_ops(const MmaOp* ops, uint32_t first, uint32_t count, uint32_t tile_acc) {
-#pragma unroll 1
-    for (uint32_t i = first; i < first + count; ++i) {
-        const uint4 lo = *reinterpret_cast<const uint4*>(&ops[i]);
-        const uint4 hi = *(reinterpret_cast<const uint4*>(&ops[i]) + 1);
-        const uint64_t a = ((uint64_t)lo.y << 32) | lo.x, b = ((uint64_t)lo.w << 32) | lo.z;
-        mma_f16_ss(hi.x, a, b, hi.y, hi.z | (hi.w & tile_acc));
-    }
+        mma_f16_ss(d, slab_desc_mnmajor(a_s, ROWS, ga, kb), slab_desc_mnmajor(b_s, ROWS, gb, kb), idesc_f16(128, N, 1, 1), kb > 0 ? 1u : accumulate);
 }
 
 // ---- epilogue helpers (thread t = row t) ----------------------------------------------------------
