@@ -167,7 +167,7 @@ constexpr int FWD_GW = 8;
 constexpr int FWD_THREADS = 128 + 32 * FWD_GW;
 
 template <bool DENSITY_ONLY>
-__global__ void __launch_bounds__(FWD_THREADS)
+__global__ void __launch_bounds__(FWD_THREADS, 2)   // two CTAs per SM (128 TMEM columns each): <= 85 registers per thread
 network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const float* __restrict__ coords, const __half* __restrict__ grid,
                    const NgpLevel* __restrict__ levels, const __half* __restrict__ wd, const __half* __restrict__ wr,
                    __half* __restrict__ out, __half* __restrict__ enc_save, int* __restrict__ err) {

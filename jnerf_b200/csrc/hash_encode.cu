@@ -38,95 +38,24 @@ __device__ __forceinline__ float2 to_f2(float2 v) { return v; }
 __device__ __forceinline__ float2 to_f2(__half2 v) { return __half22float2(v); }
 
 constexpr int HASH_THREADS = 256;
-constexpr int PPT = 4;                                  // points per thread
-constexpr int PTS_PER_BLOCK = (HASH_THREADS / N_LEVELS) * PPT;  // 64
-
-template <typename T>
-__global__ void __launch_bounds__(HASH_THREADS)
-hash_fwd_kernel(uint32_t n, const float* __restrict__ x, const T* __restrict__ grid, const NgpLevel* __restrict__ levels,
-                T* __restrict__ out) {
-    using V = typename Vec2<T>::type;
-    __shared__ NgpLevel s_lv[N_LEVELS];
-    if (threadIdx.x < N_LEVELS) s_lv[threadIdx.x] = levels[threadIdx.x];
-    __syncthreads();
-    const uint32_t level = threadIdx.x & (N_LEVELS - 1), sub = threadIdx.x / N_LEVELS;
-    const NgpLevel lv = s_lv[level];
-    const V* __restrict__ g = reinterpret_cast<const V*>(grid) + lv.offset;
-    const uint32_t base = blockIdx.x * PTS_PER_BLOCK + sub;
-
-    uint32_t idx[PPT][8];
-    float w[PPT][8];
-#pragma unroll
-    for (int p = 0; p < PPT; ++p) {
-        const uint32_t i = base + p * (HASH_THREADS / N_LEVELS);
-        float px = 0.f, py = 0.f, pz = 0.f;
-        if (i < n) { px = __ldg(x + 3 * (size_t)i); py = __ldg(x + 3 * (size_t)i + 1); pz = __ldg(x + 3 * (size_t)i + 2); }
-        hash_corners(lv, px, py, pz, idx[p], w[p]);
-    }
-    V v[PPT][8];
-#pragma unroll
-    for (int p = 0; p < PPT; ++p)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) v[p][c] = __ldg(g + idx[p][c]);
-#pragma unroll
-    for (int p = 0; p < PPT; ++p) {
-        const uint32_t i = base + p * (HASH_THREADS / N_LEVELS);
-        float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {               // corner order and fma chain of HashEncode.h:171-201
-            const float2 f = to_f2(v[p][c]);
-            a0 = fmaf(w[p][c], f.x, a0);
-            a1 = fmaf(w[p][c], f.y, a1);
-        }
-        if (i < n) {
-            V r;
-            if constexpr (sizeof(T) == 2) r = __floats2half2_rn(a0, a1); else r = make_float2(a0, a1);
-            reinterpret_cast<V*>(out)[(size_t)i * N_LEVELS + level] = r;
-        }
-    }
-}
 
 __device__ __forceinline__ void red_add(__half2* addr, float a, float b) { red_add_h2(addr, a, b); }
 __device__ __forceinline__ void red_add(float2* addr, float a, float b) { red_add_f2(addr, a, b); }
 
-template <typename T>
-__global__ void __launch_bounds__(HASH_THREADS)
-hash_bwd_kernel(uint32_t n, const float* __restrict__ x, const T* __restrict__ dy, const NgpLevel* __restrict__ levels,
-                T* __restrict__ grid_grad) {
-    using V = typename Vec2<T>::type;
-    __shared__ NgpLevel s_lv[N_LEVELS];
-    if (threadIdx.x < N_LEVELS) s_lv[threadIdx.x] = levels[threadIdx.x];
-    __syncthreads();
-    const uint32_t level = threadIdx.x & (N_LEVELS - 1), sub = threadIdx.x / N_LEVELS;
-    const NgpLevel lv = s_lv[level];
-    V* __restrict__ g = reinterpret_cast<V*>(grid_grad) + lv.offset;
-    const uint32_t base = blockIdx.x * PTS_PER_BLOCK + sub;
-#pragma unroll
-    for (int p = 0; p < PPT; ++p) {
-        const uint32_t i = base + p * (HASH_THREADS / N_LEVELS);
-        if (i >= n) continue;
-        const float px = __ldg(x + 3 * (size_t)i), py = __ldg(x + 3 * (size_t)i + 1), pz = __ldg(x + 3 * (size_t)i + 2);
-        uint32_t idx[8];
-        float w[8];
-        hash_corners(lv, px, py, pz, idx, w);
-        const float2 d = to_f2(reinterpret_cast<const V*>(dy)[(size_t)i * N_LEVELS + level]);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) red_add(g + idx[c], d.x * w[c], d.y * w[c]);   // HashEncode.h:339-356
-    }
-}
-
-// ---- run-length variants (opt-in through NGP_HASH_RUNLEN=1, not yet measured) ------------------------------------------------
-// The fused network kernels keep the 8 corner values (forward) / 8 fp32 corner accumulators (backward) of a grid cell while
-// CONSECUTIVE samples stay inside it -- samples arrive ray-ordered, so at the coarse levels dozens do -- which cut their L2
-// requests / f16x2 reductions by the mean run length ("Run-length reuse").  These are the same loops for the standalone
-// HashEncoder boundary: thread (level, sub) walks RUN consecutive points.  Uniformly random points (BASELINE config #1) have no runs
-// and gain nothing; the backward rounds each run's fp32 sum once instead of once per sample.
+// ---- HashEncoder forward / backward (R2 / R3), run-length form -------------------------------------------------------------------
+// Thread (level, sub) walks RUN consecutive points and keeps the 8 corner values (forward) / 8 fp32 corner accumulators (backward) of
+// a grid cell while CONSECUTIVE points stay inside it -- the sampler hands points over ray-ordered, so at the coarse levels dozens
+// do -- which cuts the L2 requests / f16x2 reductions by the mean run length.  Measured on a B200 against the one-point-per-thread
+// kernels of round 1 (profiles/r02_first_call, r02_call2): ray-ordered samples of a training state, forward 61 -> 49 us, backward
+// 277 -> 99 us (the reference's own kernels recompiled for sm_100a: 97 / 417 us); uniformly random points (no runs), forward
+// 109 -> 95 us, backward 216 -> 224 us.  Per point the arithmetic is the reference's (corner order and fma chain of
+// HashEncode.h:171-201); the backward rounds each run's fp32 sum once instead of once per point.
 constexpr int RUN = 16;
 constexpr int RUN_PTS_PER_BLOCK = (HASH_THREADS / N_LEVELS) * RUN;   // 256
 
 template <typename T>
 __global__ void __launch_bounds__(HASH_THREADS)
-hash_fwd_runlen_kernel(uint32_t n, const float* __restrict__ x, const T* __restrict__ grid, const NgpLevel* __restrict__ levels,
+hash_fwd_kernel(uint32_t n, const float* __restrict__ x, const T* __restrict__ grid, const NgpLevel* __restrict__ levels,
                        T* __restrict__ out) {
     using V = typename Vec2<T>::type;
     __shared__ NgpLevel s_lv[N_LEVELS];
@@ -165,7 +94,7 @@ hash_fwd_runlen_kernel(uint32_t n, const float* __restrict__ x, const T* __restr
 
 template <typename T>
 __global__ void __launch_bounds__(HASH_THREADS)
-hash_bwd_runlen_kernel(uint32_t n, const float* __restrict__ x, const T* __restrict__ dy, const NgpLevel* __restrict__ levels,
+hash_bwd_kernel(uint32_t n, const float* __restrict__ x, const T* __restrict__ dy, const NgpLevel* __restrict__ levels,
                        T* __restrict__ grid_grad) {
     using V = typename Vec2<T>::type;
     __shared__ NgpLevel s_lv[N_LEVELS];
@@ -270,18 +199,10 @@ int ngp_hash_level_table(void* stream, const uint32_t* offsets_host, int n_level
 
 int ngp_hash_fwd(void* stream, uint32_t n, const float* x, const void* grid, int dtype, const void* levels_dev, void* out) {
     if (n == 0) return 0;                                                  // HE/grid_encode.py:78-80
-    const uint32_t blocks = (n + PTS_PER_BLOCK - 1) / PTS_PER_BLOCK;
     cudaStream_t s = (cudaStream_t)stream;
-    static const bool runlen = getenv("NGP_HASH_RUNLEN") && atoi(getenv("NGP_HASH_RUNLEN")) == 1;   // opt-in run-length variants
-    if (runlen && (dtype == 0 || dtype == 1)) {
-        const uint32_t rb = (n + RUN_PTS_PER_BLOCK - 1) / RUN_PTS_PER_BLOCK;
-        if (dtype == 1) hash_fwd_runlen_kernel<__half><<<rb, HASH_THREADS, 0, s>>>(n, x, (const __half*)grid, (const NgpLevel*)levels_dev, (__half*)out);
-        else hash_fwd_runlen_kernel<float><<<rb, HASH_THREADS, 0, s>>>(n, x, (const float*)grid, (const NgpLevel*)levels_dev, (float*)out);
-        NGP_LAUNCH_CHECK();
-        return 0;
-    }
-    if (dtype == 1) hash_fwd_kernel<__half><<<blocks, HASH_THREADS, 0, s>>>(n, x, (const __half*)grid, (const NgpLevel*)levels_dev, (__half*)out);
-    else if (dtype == 0) hash_fwd_kernel<float><<<blocks, HASH_THREADS, 0, s>>>(n, x, (const float*)grid, (const NgpLevel*)levels_dev, (float*)out);
+    const uint32_t rb = (n + RUN_PTS_PER_BLOCK - 1) / RUN_PTS_PER_BLOCK;
+    if (dtype == 1) hash_fwd_kernel<__half><<<rb, HASH_THREADS, 0, s>>>(n, x, (const __half*)grid, (const NgpLevel*)levels_dev, (__half*)out);
+    else if (dtype == 0) hash_fwd_kernel<float><<<rb, HASH_THREADS, 0, s>>>(n, x, (const float*)grid, (const NgpLevel*)levels_dev, (float*)out);
     else NGP_REQUIRE(false, "ngp_hash_fwd: dtype must be 0 (f32) or 1 (f16)");
     NGP_LAUNCH_CHECK();
     return 0;
@@ -293,17 +214,9 @@ int ngp_hash_bwd(void* stream, uint32_t n, const float* x, const void* dy, int d
     cudaStream_t s = (cudaStream_t)stream;
     if (n == 0) return 0;                                                  // HE/grid_encode.py:142-144 (returns before the memset)
     NGP_CHECK_CUDA(cudaMemsetAsync(grid_grad, 0, n_params * (dtype == 1 ? 2 : 4), s));   // :153
-    static const bool runlen = getenv("NGP_HASH_RUNLEN") && atoi(getenv("NGP_HASH_RUNLEN")) == 1;
-    if (runlen) {
-        const uint32_t rb = (n + RUN_PTS_PER_BLOCK - 1) / RUN_PTS_PER_BLOCK;
-        if (dtype == 1) hash_bwd_runlen_kernel<__half><<<rb, HASH_THREADS, 0, s>>>(n, x, (const __half*)dy, (const NgpLevel*)levels_dev, (__half*)grid_grad);
-        else hash_bwd_runlen_kernel<float><<<rb, HASH_THREADS, 0, s>>>(n, x, (const float*)dy, (const NgpLevel*)levels_dev, (float*)grid_grad);
-        NGP_LAUNCH_CHECK();
-        return 0;
-    }
-    const uint32_t blocks = (n + PTS_PER_BLOCK - 1) / PTS_PER_BLOCK;
-    if (dtype == 1) hash_bwd_kernel<__half><<<blocks, HASH_THREADS, 0, s>>>(n, x, (const __half*)dy, (const NgpLevel*)levels_dev, (__half*)grid_grad);
-    else hash_bwd_kernel<float><<<blocks, HASH_THREADS, 0, s>>>(n, x, (const float*)dy, (const NgpLevel*)levels_dev, (float*)grid_grad);
+    const uint32_t rb = (n + RUN_PTS_PER_BLOCK - 1) / RUN_PTS_PER_BLOCK;
+    if (dtype == 1) hash_bwd_kernel<__half><<<rb, HASH_THREADS, 0, s>>>(n, x, (const __half*)dy, (const NgpLevel*)levels_dev, (__half*)grid_grad);
+    else hash_bwd_kernel<float><<<rb, HASH_THREADS, 0, s>>>(n, x, (const float*)dy, (const NgpLevel*)levels_dev, (float*)grid_grad);
     NGP_LAUNCH_CHECK();
     return 0;
 }

@@ -116,16 +116,12 @@ __device__ __forceinline__ RayState ray_setup(uint32_t i, const float* __restric
 // therefore materialises 32 consecutive t_k (same float additions, same order), evaluates position, mip level, occupancy
 // bit and the distance to the next voxel of all 32 in parallel, and then replays the reference's sequential control flow
 // on two ballot masks -- identical arithmetic per visited step, 32 occupancy lookups in flight instead of one.
-constexpr uint32_t MARCH_MAXC = 80;      // chunks (of 32 steps) recorded per ray by the count pass: 2560 steps >= sqrt(3)/min_dt
-struct ChunkRec { float t0; uint32_t mask; };
-
-// PIPE (count pass, opt-in through NGP_MARCH_PIPE=1, not yet measured): the 31 dependent additions that produce the NEXT chunk's
-// t values do not depend on this chunk's occupancy bits, so they are issued between the bitfield load and its first use -- same
-// additions in the same order per lane, only scheduled under the L2 latency of the lookup.
-template <bool EMIT, bool PIPE = false>
+//
+// This monolithic form (everything of a ray in one warp's serial loop) is the FALLBACK for rays with more than MARCH_MAXC chunks;
+// the production path below splits the same computation into a chunk evaluation pass and a replay pass.
+template <bool EMIT>
 __device__ __forceinline__ uint32_t march_ray_warp(const RayState& r, float lo, float hi, float cone, const MarchCfg& c,
-                                                   const uint8_t* __restrict__ bits, uint32_t limit, float* __restrict__ out,
-                                                   ChunkRec* __restrict__ rec = nullptr, uint32_t* __restrict__ n_chunks = nullptr) {
+                                                   const uint8_t* __restrict__ bits, uint32_t limit, float* __restrict__ out) {
     const uint32_t lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     uint32_t j = 0;
@@ -135,29 +131,17 @@ __device__ __forceinline__ uint32_t march_ray_warp(const RayState& r, float lo, 
     float wd[3], diag = hi - lo;
     if (EMIT) { wd[0] = (r.d[0] + 1.0f) * 0.5f; wd[1] = (r.d[1] + 1.0f) * 0.5f; wd[2] = (r.d[2] + 1.0f) * 0.5f; }
     uint32_t chunk = 0;
-    float t_pipe = 0.f;           // PIPE: this lane's t of the current chunk, produced during the previous iteration
-    if (PIPE) {
-        t_pipe = t0;
-        for (uint32_t i = 0; i < lane; ++i) t_pipe += calc_dt(c, t_pipe, cone);
-    }
     for (uint32_t guard = 0; guard < (1u << 20); ++guard) {   // a degenerate ray (d == 0) would spin forever in the reference
         float t = t0;
-        if (PIPE) t = t_pipe;
-        else
-            for (uint32_t i = 0; i < lane; ++i) t += calc_dt(c, t, cone);      // t_k .. t_{k+31}, sequential float adds
+        for (uint32_t i = 0; i < lane; ++i) t += calc_dt(c, t, cone);          // t_k .. t_{k+31}, sequential float adds
         const float dt = calc_dt(c, t, cone);
         const float t_next_chunk = __shfl_sync(FULL, t + dt, 31);
         int cur = 0;
         if (pending) {
             const uint32_t ge = __ballot_sync(FULL, !(t < pending_tt));
             if (ge == 0) {                                                      // the whole chunk lies inside the skipped span
-                if (!EMIT && rec && chunk < MARCH_MAXC && lane == 0) rec[chunk] = ChunkRec{t0, 0u};
                 ++chunk;
                 t0 = t_next_chunk;
-                if (PIPE) {
-                    t_pipe = t0;
-                    for (uint32_t i = 0; i < lane; ++i) t_pipe += calc_dt(c, t_pipe, cone);
-                }
                 continue;
             }
             cur = __ffs(ge) - 1;
@@ -168,23 +152,9 @@ __device__ __forceinline__ uint32_t march_ray_warp(const RayState& r, float lo, 
         uint32_t mip = 0;
         bool occ = false;
         float t_target = 0.f;
-        uint32_t occ_byte = 0, occ_bit = 0;
-        if (PIPE) {
-            if (inside) {                                                        // occupied_at(), split into load and test
-                mip = (uint32_t)mip_from_dt(c, dt, p[0], p[1], p[2]);
-                const uint32_t idx = grid_idx_at(p[0], p[1], p[2], mip);
-                occ_byte = __ldg(bits + idx / 8 + (NERF_GRID_N / 8) * mip);
-                occ_bit = 1u << (idx % 8);
-            }
-            t_pipe = t_next_chunk;                                               // next chunk's t values, under the load's latency
-            for (uint32_t i = 0; i < lane; ++i) t_pipe += calc_dt(c, t_pipe, cone);
-        }
         if (inside) {
-            if (PIPE) occ = (occ_byte & occ_bit) != 0;
-            else {
-                mip = (uint32_t)mip_from_dt(c, dt, p[0], p[1], p[2]);
-                occ = occupied_at(p[0], p[1], p[2], bits, mip);
-            }
+            mip = (uint32_t)mip_from_dt(c, dt, p[0], p[1], p[2]);
+            occ = occupied_at(p[0], p[1], p[2], bits, mip);
             if (!occ) {                                                          // distance_to_next_voxel, ray_sampler_header.h:728-739
                 const float rs = (float)(NERF_GRIDSIZE >> mip);
                 const float q[3] = {rs * p[0], rs * p[1], rs * p[2]};
@@ -221,26 +191,195 @@ __device__ __forceinline__ uint32_t march_ray_warp(const RayState& r, float lo, 
                 else { pending = true; pending_tt = tt; cur = 32; }
             }
         }
-        if (!EMIT && rec && chunk < MARCH_MAXC && lane == 0) rec[chunk] = ChunkRec{t0, emit_m};
         ++chunk;
         if (done) break;
         t0 = t_next_chunk;
     }
-    if (!EMIT && n_chunks && lane == 0) *n_chunks = chunk;
     return j;
 }
 
-template <bool PIPE>
-__global__ void __launch_bounds__(128) march_count_kernel(uint32_t n_rays, float lo, float hi, const float* __restrict__ rays_o,
-                                                          const float* __restrict__ rays_d, const uint8_t* __restrict__ bits, float cone,
-                                                          float near_distance, MarchCfg c, uint64_t rng_state, uint64_t rng_inc,
-                                                          uint32_t* __restrict__ counts, ChunkRec* __restrict__ recs,
-                                                          uint32_t* __restrict__ n_chunks) {
-    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per ray
+// ---- chunk-parallel march -----------------------------------------------------------------------------------------------------
+// Round 1 ran the whole loop above per ray in one warp: ~1.2 k cycles per 32-step chunk, 40-64 chunks in sequence, and the kernel
+// lasted as long as its longest ray (80 us for ~2 200 rays at 16 % of the warp slots).  Everything in a chunk except the replay of the
+// control flow is independent of every other chunk -- the t sequence is fixed, and position / mip level / occupancy bit / distance to
+// the next voxel are functions of t alone.  So:
+//   pass 1 (march_eval_kernel, warp per ray): walk the t sequence (the same float additions in the same order; lane k keeps t_k of
+//           the current chunk), evaluate the 32 steps of every chunk, and record per chunk {inside mask, occupied mask}, per step t,
+//           the skip target t_target and the in-chunk skip destination.  No control flow depends on loaded data: the occupancy
+//           byte of chunk c is consumed one iteration later (software pipeline), so the lookups of consecutive chunks overlap;
+//   pass 2 (march_replay_kernel, warp per ray): the reference's sequential control flow on the recorded masks -- a few integer
+//           operations and one shuffle per visited run / skip, records prefetched one chunk ahead;
+//   scan, then pass 3 (march_emit_kernel, CTA per ray, warp per chunk): rows of the emitting chunks from the stored t values.
+// Same arithmetic per visited step as the reference, hence the same samples bit for bit (tests/test_gpu_ops.py::test_march_bit_exact).
+constexpr uint32_t MARCH_MAXC = 72;      // chunks (of 32 steps) recorded per ray: 2304 steps >= sqrt(3) / (min_cone / 2) + the terminal chunk
+struct __align__(16) ChunkHdr { float t0; uint32_t inside, occ, emit, j0, pad0, pad1, pad2; };
+static_assert(sizeof(ChunkHdr) == 32, "ChunkHdr must be 32 bytes");
+constexpr size_t MARCH_RAY_BYTES = (size_t)MARCH_MAXC * (sizeof(ChunkHdr) + 32 + 128 + 128);
+struct RayWs {
+    ChunkHdr* hdr;      // [MAXC]
+    uint8_t* dest;      // [MAXC][32]  first lane > l with !(t < t_target[l]) inside the chunk, 32 = beyond the chunk
+    float* t;           // [MAXC][32]
+    float* tt;          // [MAXC][32]  t_target of empty steps (distance_to_next_voxel)
+};
+__device__ __forceinline__ RayWs ray_ws(uint8_t* ws, uint32_t ray) {
+    uint8_t* b = ws + (size_t)ray * MARCH_RAY_BYTES;
+    RayWs w;
+    w.hdr = reinterpret_cast<ChunkHdr*>(b);
+    w.dest = b + MARCH_MAXC * sizeof(ChunkHdr);
+    w.t = reinterpret_cast<float*>(w.dest + MARCH_MAXC * 32);
+    w.tt = w.t + MARCH_MAXC * 32;
+    return w;
+}
+
+struct ChunkState {           // per lane: one step of a chunk between the two halves of the evaluation
+    float t0, t, dt, p[3];
+    uint32_t inside_m, mip, byte, bit;
+    bool inside;
+};
+
+__global__ void __launch_bounds__(128) march_eval_kernel(uint32_t n_rays, float lo, float hi, const float* __restrict__ rays_o,
+                                                         const float* __restrict__ rays_d, const uint8_t* __restrict__ bits, float cone,
+                                                         float near_distance, MarchCfg c, uint64_t rng_state, uint64_t rng_inc,
+                                                         uint8_t* __restrict__ ws, uint32_t* __restrict__ n_chunks) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= n_rays) return;
+    const unsigned FULL = 0xffffffffu;
     const RayState r = ray_setup(i, rays_o, rays_d, lo, hi, near_distance, cone, c, rng_state, rng_inc);
-    const uint32_t n = march_ray_warp<false, PIPE>(r, lo, hi, cone, c, bits, NERF_STEPS, nullptr, recs + (size_t)i * MARCH_MAXC, n_chunks + i);
-    if ((threadIdx.x & 31) == 0) counts[i] = n;
+    const RayWs w = ray_ws(ws, i);
+    float tc = r.startt;                 // running t of the sequence (identical in all lanes)
+    ChunkState cur, prev;
+    bool prev_valid = false, stopped = false;
+    uint32_t nch = 0;
+    for (;;) {
+        bool cur_valid = false;
+        if (!stopped && nch < MARCH_MAXC) {
+            // ---- first half: t values, positions, occupancy lookup issued
+            cur.t0 = tc;
+            float t = tc;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {                                        // t_k .. t_{k+31}: the reference's float additions, in order
+                if ((int)lane == k) t = tc;
+                tc += calc_dt(c, tc, cone);
+            }
+            cur.t = t;
+            cur.dt = calc_dt(c, t, cone);
+            cur.p[0] = __fmaf_rn(t, r.d[0], r.o[0]); cur.p[1] = __fmaf_rn(t, r.d[1], r.o[1]); cur.p[2] = __fmaf_rn(t, r.d[2], r.o[2]);
+            cur.inside = contains(lo, hi, cur.p);
+            cur.inside_m = __ballot_sync(FULL, cur.inside);
+            cur.mip = 0; cur.byte = 0; cur.bit = 0;
+            if (cur.inside) {                                                      // occupied_at(), load now, test in the second half
+                cur.mip = (uint32_t)mip_from_dt(c, cur.dt, cur.p[0], cur.p[1], cur.p[2]);
+                const uint32_t idx = grid_idx_at(cur.p[0], cur.p[1], cur.p[2], cur.mip);
+                cur.byte = __ldg(bits + idx / 8 + (NERF_GRID_N / 8) * cur.mip);
+                cur.bit = 1u << (idx % 8);
+            }
+            cur_valid = true;
+            if (cur.inside_m == 0) stopped = true;                                 // the ray has left the box: this is its terminal chunk
+        }
+        if (prev_valid) {
+            // ---- second half (of the previous chunk): occupancy test, skip target, in-chunk skip destination, records
+            const uint32_t ch = nch - 1;                                           // nch = chunks handed over so far; prev is the last of them
+            const bool occ = prev.inside && (prev.byte & prev.bit) != 0;
+            const uint32_t occ_m = __ballot_sync(FULL, occ);
+            float tt = 0.f;
+            if (prev.inside && !occ) {                                             // distance_to_next_voxel, ray_sampler_header.h:728-739
+                const float rs = (float)(NERF_GRIDSIZE >> prev.mip);
+                const float q[3] = {rs * prev.p[0], rs * prev.p[1], rs * prev.p[2]};
+                const float tx = (floorf(q[0] + 0.5f + 0.5f * sgn(r.d[0])) - q[0]) * r.id[0];
+                const float ty = (floorf(q[1] + 0.5f + 0.5f * sgn(r.d[1])) - q[1]) * r.id[1];
+                const float tz = (floorf(q[2] + 0.5f + 0.5f * sgn(r.d[2])) - q[2]) * r.id[2];
+                tt = prev.t + fmaxf(fminf(fminf(tx, ty), tz) / rs, 0.0f);
+            }
+            // advance_to_next_voxel: do { t += dt } while (t < t_target) = the first later step with !(t < t_target); t increases
+            // with the lane, so that step is found by bisection over the lanes (5 shuffles instead of a ballot per source lane)
+            uint32_t lo_l = lane + 1, hi_l = 32;
+#pragma unroll
+            for (int it = 0; it < 5; ++it) {
+                const uint32_t mid = (lo_l + hi_l) >> 1;
+                const float tm = __shfl_sync(FULL, prev.t, mid & 31);
+                const bool less = mid < 32 && tm < tt;
+                if (lo_l < hi_l) { if (less) lo_l = mid + 1; else hi_l = mid; }
+            }
+            if (lane == 0) w.hdr[ch] = ChunkHdr{prev.t0, prev.inside_m, occ_m, 0u, 0u, 0u, 0u, 0u};
+            w.dest[ch * 32 + lane] = (uint8_t)lo_l;
+            w.t[ch * 32 + lane] = prev.t;
+            w.tt[ch * 32 + lane] = tt;
+        }
+        if (!cur_valid) break;
+        prev = cur;
+        prev_valid = true;
+        ++nch;
+    }
+    // overflow: MARCH_MAXC chunks and the ray is still inside the box -> the replay / emit passes re-march it the slow way
+    if (lane == 0) n_chunks[i] = nch | (stopped ? 0u : 0x80000000u);
+}
+
+// Replay of ray_sampler.h:50-72 on the recorded masks.  counts[i] = samples of ray i (<= NERF_STEPS); hdr[].emit / hdr[].j0 = which
+// steps of the chunk emit and the ray-local index of the first of them; n_replayed[i] = chunks the replay visited.
+__global__ void __launch_bounds__(128) march_replay_kernel(uint32_t n_rays, float lo, float hi, const float* __restrict__ rays_o,
+                                                           const float* __restrict__ rays_d, const uint8_t* __restrict__ bits, float cone,
+                                                           float near_distance, MarchCfg c, uint64_t rng_state, uint64_t rng_inc,
+                                                           uint8_t* __restrict__ ws, const uint32_t* __restrict__ n_chunks,
+                                                           uint32_t* __restrict__ counts, uint32_t* __restrict__ n_replayed) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n_rays) return;
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t nraw = n_chunks[i], nch = nraw & 0x7fffffffu;
+    if (nraw >> 31) {                                                              // more chunks than the workspace records
+        const RayState r = ray_setup(i, rays_o, rays_d, lo, hi, near_distance, cone, c, rng_state, rng_inc);
+        const uint32_t n = march_ray_warp<false>(r, lo, hi, cone, c, bits, NERF_STEPS, nullptr);
+        if (lane == 0) { counts[i] = n; n_replayed[i] = 0; }
+        return;
+    }
+    const RayWs w = ray_ws(ws, i);
+    const uint32_t limit = NERF_STEPS;
+    uint32_t j = 0, ch = 0;
+    bool pending = false;
+    float pending_tt = 0.f;
+    // records of the chunk being replayed and of the next one (prefetched: the replay itself is a few dozen cycles per chunk)
+    ChunkHdr h = nch ? w.hdr[0] : ChunkHdr{0.f, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    uint32_t d = nch ? w.dest[lane] : 32u;
+    for (; ch < nch; ++ch) {
+        ChunkHdr hn = h;
+        uint32_t dn = 32u;
+        if (ch + 1 < nch) { hn = w.hdr[ch + 1]; dn = w.dest[(ch + 1) * 32 + lane]; }
+        int cur = 0;
+        uint32_t emit_m = 0;
+        const uint32_t j0 = j;
+        bool done = false, skip = false;
+        if (pending) {
+            if (ch + 1 < nch && !(pending_tt < hn.t0)) skip = true;                // every t of this chunk < t0 of the next <= target
+            else {
+                const float t = w.t[ch * 32 + lane];
+                const uint32_t ge = __ballot_sync(FULL, !(t < pending_tt));
+                if (ge == 0) skip = true;
+                else { cur = __ffs(ge) - 1; pending = false; }
+            }
+        }
+        if (!skip) {
+            const uint32_t inside_m = h.inside, occ_m = h.occ;
+            while (cur < 32) {
+                if (!((inside_m >> cur) & 1u) || j >= limit) { done = true; break; }   // while (aabb.contains(pos) && j < NERF_STEPS)
+                if ((occ_m >> cur) & 1u) {
+                    const uint32_t run_m = (occ_m & inside_m) >> cur;                 // consecutive occupied steps are taken one by one
+                    uint32_t n_run = (run_m == 0xffffffffu) ? 32u : (uint32_t)__ffs(~run_m) - 1u;
+                    n_run = min(n_run, limit - j);
+                    emit_m |= (n_run >= 32u ? 0xffffffffu : ((1u << n_run) - 1u)) << cur;
+                    j += n_run;
+                    cur += n_run;
+                } else {
+                    const uint32_t dc = __shfl_sync(FULL, d, cur);
+                    if (dc < 32) cur = (int)dc;
+                    else { pending = true; pending_tt = w.tt[ch * 32 + cur]; cur = 32; }
+                }
+            }
+        }
+        if (lane == 0) { w.hdr[ch].emit = emit_m; w.hdr[ch].j0 = j0; }
+        if (done) { ++ch; break; }
+        h = hn;
+        d = dn;
+    }
+    if (lane == 0) { counts[i] = j; n_replayed[i] = ch; }
 }
 
 // Single-CTA exclusive scan over ray counts (R <= a few 100k): numsteps[i] = {count or 0, base}, ray index of accepted rays.
@@ -290,51 +429,51 @@ __global__ void __launch_bounds__(1024) march_scan_kernel(uint32_t n_rays, uint3
     if (t == 1023) { counters[0] = s_acc[1023]; counters[1] = s_sum[1023]; }
 }
 
-// Emit pass.  The count pass left, per ray, the start t and the emit mask of each 32-step chunk; only chunks that emit samples
-// are revisited (typically 4-5 of ~36), each by re-deriving its 32 t values with the same sequential float additions.  Rays with
-// more than MARCH_MAXC chunks (long cone-stepped rays) fall back to a full re-march.
+// Emit pass: one CTA per ray, one warp per emitting chunk.  The rows of a chunk are contiguous in the output (ray-ordered, the
+// replay left the ray-local index of the chunk's first sample), so they are staged in shared memory and written as one coalesced
+// block of n x 7 floats instead of 7 strided 4-byte stores per lane.
 __global__ void __launch_bounds__(128) march_emit_kernel(uint32_t n_rays, float lo, float hi, const float* __restrict__ rays_o,
                                                          const float* __restrict__ rays_d, const uint8_t* __restrict__ bits, float cone,
                                                          float near_distance, MarchCfg c, uint64_t rng_state, uint64_t rng_inc,
                                                          const uint32_t* __restrict__ numsteps, float* __restrict__ coords,
-                                                         const ChunkRec* __restrict__ recs, const uint32_t* __restrict__ n_chunks) {
-    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (i >= n_rays) return;
+                                                         uint8_t* __restrict__ ws, const uint32_t* __restrict__ n_chunks,
+                                                         const uint32_t* __restrict__ n_replayed) {
+    __shared__ float s_rows[4][32 * 7];
+    const uint32_t i = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n = numsteps[2 * i], base = numsteps[2 * i + 1];
     if (n == 0) return;
-    const uint32_t nc = n_chunks[i];
     float* out = coords + (size_t)base * 7;
-    if (nc > MARCH_MAXC) {
-        const RayState r = ray_setup(i, rays_o, rays_d, lo, hi, near_distance, cone, c, rng_state, rng_inc);
-        march_ray_warp<true>(r, lo, hi, cone, c, bits, n, out);
+    if (n_chunks[i] >> 31) {
+        if (warp == 0) {
+            const RayState r = ray_setup(i, rays_o, rays_d, lo, hi, near_distance, cone, c, rng_state, rng_inc);
+            march_ray_warp<true>(r, lo, hi, cone, c, bits, n, out);
+        }
         return;
     }
+    const RayWs w = ray_ws(ws, i);
+    const uint32_t nrep = n_replayed[i];
     float o[3], d[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) { o[k] = rays_o[3 * (size_t)i + k]; d[k] = rays_d[3 * (size_t)i + k]; }
     const float wd[3] = {(d[0] + 1.0f) * 0.5f, (d[1] + 1.0f) * 0.5f, (d[2] + 1.0f) * 0.5f}, diag = hi - lo;
-    const ChunkRec* rec = recs + (size_t)i * MARCH_MAXC;
-    uint32_t j = 0;
-    for (uint32_t g0 = 0; g0 < nc; g0 += 32) {               // 32 chunk records per coalesced load, then visit the non-empty ones in order
-        ChunkRec mine = ChunkRec{0.f, 0u};
-        if (g0 + lane < nc) mine = rec[g0 + lane];
-        uint32_t nz = __ballot_sync(0xffffffffu, mine.mask != 0);
-        while (nz) {
-            const int ch = __ffs(nz) - 1;
-            nz &= nz - 1;
-            const uint32_t mask = __shfl_sync(0xffffffffu, mine.mask, ch);
-            float t = __shfl_sync(0xffffffffu, mine.t0, ch);
-            for (uint32_t k = 0; k < lane; ++k) t += calc_dt(c, t, cone);
-            if ((mask >> lane) & 1u) {
-                const float dt = calc_dt(c, t, cone);
-                const float p[3] = {__fmaf_rn(t, d[0], o[0]), __fmaf_rn(t, d[1], o[1]), __fmaf_rn(t, d[2], o[2])};
-                float* q = out + (size_t)(j + __popc(mask & ((1u << lane) - 1u))) * 7;
-                q[0] = (p[0] - lo) / diag; q[1] = (p[1] - lo) / diag; q[2] = (p[2] - lo) / diag;   // warp_position
-                q[3] = nerf_warp_dt(dt, c.cascades);
-                q[4] = wd[0]; q[5] = wd[1]; q[6] = wd[2];
-            }
-            j += __popc(mask);
+    float* rows = s_rows[warp];
+    for (uint32_t ch = warp; ch < nrep; ch += 4) {
+        const uint32_t mask = w.hdr[ch].emit;
+        if (mask == 0) continue;
+        const uint32_t j0 = w.hdr[ch].j0, cnt = __popc(mask);
+        if ((mask >> lane) & 1u) {
+            const float t = w.t[ch * 32 + lane];
+            const float dt = calc_dt(c, t, cone);
+            const float p[3] = {__fmaf_rn(t, d[0], o[0]), __fmaf_rn(t, d[1], o[1]), __fmaf_rn(t, d[2], o[2])};
+            float* q = rows + __popc(mask & ((1u << lane) - 1u)) * 7;
+            q[0] = (p[0] - lo) / diag; q[1] = (p[1] - lo) / diag; q[2] = (p[2] - lo) / diag;   // warp_position
+            q[3] = nerf_warp_dt(dt, c.cascades);
+            q[4] = wd[0]; q[5] = wd[1]; q[6] = wd[2];
         }
+        __syncwarp();
+        float* dst = out + (size_t)j0 * 7;
+        for (uint32_t k = lane; k < cnt * 7; k += 32) dst[k] = rows[k];
+        __syncwarp();
     }
 }
 
@@ -408,20 +547,6 @@ template <> __device__ __forceinline__ void store_net<__half>(__half* dst, size_
 struct Sample {
     float rgb[3], alpha, dt, sigma_raw;
 };
-template <typename T>
-__device__ __forceinline__ Sample eval_sample(const T* __restrict__ net, const float* __restrict__ coords, size_t k, uint32_t cascades,
-                                              float4* raw) {
-    const float4 o = load_net<T>(net, k);
-    *raw = o;
-    Sample s;
-    s.rgb[0] = logistic_f(o.x); s.rgb[1] = logistic_f(o.y); s.rgb[2] = logistic_f(o.z);   // network_to_rgb, Logistic
-    s.dt = nerf_unwarp_dt(__ldg(coords + k * 7 + 3), cascades);
-    const float density = __expf(o.w);                                                     // network_to_density, Exponential
-    s.alpha = 1.f - __expf(-density * s.dt);
-    s.sigma_raw = o.w;
-    return s;
-}
-
 // ---- warp-per-ray composite -----------------------------------------------------------------------------------
 // Lane l handles samples l, l+32, ... of its ray.  Transmittance T_j = prod_{k<j}(1-alpha_k) and the running colour are
 // warp scans (the reference accumulates them serially per thread, calc_rgb.h:45-65): same formulae, reassociated sums.
@@ -441,16 +566,15 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// PIPE variants (opt-in through NGP_COMPOSITE_PIPE=1, not yet measured): a ray with many samples is one warp's serial loop over
-// 32-sample chunks, and the kernel lasts as long as its longest ray (6 % warps active in the ncu capture).  With PIPE the loads of
-// chunk j+1 are issued before chunk j is evaluated, so every iteration but the first finds its operands in registers; the arithmetic
-// and its order are unchanged.
+// A ray with many samples is one warp's serial loop over 32-sample chunks, and the kernel lasts as long as its longest ray: the loads
+// of chunk j+1 are issued before chunk j is evaluated, so every iteration but the first finds its operands in registers (measured
+// 42 -> 36 us for the fused training tail, profiles/r02_first_call).
 template <typename T>
 __device__ __forceinline__ void load_sample_raw(const T* __restrict__ net, const float* __restrict__ coords, size_t k, float4* raw, float* dt_warped) {
     *raw = load_net<T>(net, k);
     *dt_warped = __ldg(coords + k * 7 + 3);
 }
-__device__ __forceinline__ Sample make_sample(const float4& o, float dt_warped, uint32_t cascades) {   // eval_sample() after its loads
+__device__ __forceinline__ Sample make_sample(const float4& o, float dt_warped, uint32_t cascades) {   // network_to_rgb (Logistic), network_to_density (Exponential)
     Sample s;
     s.rgb[0] = logistic_f(o.x); s.rgb[1] = logistic_f(o.y); s.rgb[2] = logistic_f(o.z);
     s.dt = nerf_unwarp_dt(dt_warped, cascades);
@@ -461,17 +585,17 @@ __device__ __forceinline__ Sample make_sample(const float4& o, float dt_warped, 
 }
 
 // forward over one ray: returns (all lanes) the composited colour WITHOUT background and the final transmittance
-template <typename T, bool PIPE = false>
+template <typename T>
 __device__ __forceinline__ void composite_ray_fwd(uint32_t n, uint32_t base, const T* __restrict__ net, const float* __restrict__ coords,
                                                   uint32_t cascades, uint32_t lane, float rgb[3], float* T_final) {
     float carry = 1.f, acc[3] = {0.f, 0.f, 0.f};
     float4 nraw = make_float4(0.f, 0.f, 0.f, 0.f);
     float ndt = 0.f;
-    if (PIPE && lane < n) load_sample_raw<T>(net, coords, (size_t)base + lane, &nraw, &ndt);
+    if (lane < n) load_sample_raw<T>(net, coords, (size_t)base + lane, &nraw, &ndt);
     for (uint32_t j0 = 0; j0 < n; j0 += 32) {
         const uint32_t j = j0 + lane;
         float a = 0.f, c[3] = {0.f, 0.f, 0.f};
-        if (PIPE) {
+        {
             const float4 raw = nraw;
             const float dtw = ndt;
             if (j + 32 < n) load_sample_raw<T>(net, coords, (size_t)base + j + 32, &nraw, &ndt);
@@ -479,10 +603,6 @@ __device__ __forceinline__ void composite_ray_fwd(uint32_t n, uint32_t base, con
                 const Sample s = make_sample(raw, dtw, cascades);
                 a = s.alpha; c[0] = s.rgb[0]; c[1] = s.rgb[1]; c[2] = s.rgb[2];
             }
-        } else if (j < n) {
-            float4 raw;
-            const Sample s = eval_sample<T>(net, coords, (size_t)base + j, cascades, &raw);
-            a = s.alpha; c[0] = s.rgb[0]; c[1] = s.rgb[1]; c[2] = s.rgb[2];
         }
         const float incl = warp_incl_prod(1.f - a, lane);
         float excl = __shfl_up_sync(0xffffffffu, incl, 1);
@@ -495,19 +615,19 @@ __device__ __forceinline__ void composite_ray_fwd(uint32_t n, uint32_t base, con
     *T_final = carry;
 }
 
-template <typename T, bool PIPE = false>
+template <typename T>
 __device__ __forceinline__ void composite_ray_bwd(uint32_t n, uint32_t base, const T* __restrict__ net, const float* __restrict__ coords,
                                                   const float lg[3], const float rr[3], float loss_scale, float l1, uint32_t cascades,
                                                   uint32_t lane, T* __restrict__ dnet) {
     float carry_T = 1.f, carry_S[3] = {0.f, 0.f, 0.f};
     float4 nraw = make_float4(0.f, 0.f, 0.f, 0.f);
     float ndt = 0.f;
-    if (PIPE && lane < n) load_sample_raw<T>(net, coords, (size_t)base + lane, &nraw, &ndt);
+    if (lane < n) load_sample_raw<T>(net, coords, (size_t)base + lane, &nraw, &ndt);
     for (uint32_t j0 = 0; j0 < n; j0 += 32) {
         const uint32_t j = j0 + lane;
         float a = 0.f, c[3] = {0.f, 0.f, 0.f}, dt = 0.f;
         float4 raw = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (PIPE) {
+        {
             const float dtw = ndt;
             if (j < n) raw = nraw;
             if (j + 32 < n) load_sample_raw<T>(net, coords, (size_t)base + j + 32, &nraw, &ndt);
@@ -515,9 +635,6 @@ __device__ __forceinline__ void composite_ray_bwd(uint32_t n, uint32_t base, con
                 const Sample s = make_sample(raw, dtw, cascades);
                 a = s.alpha; c[0] = s.rgb[0]; c[1] = s.rgb[1]; c[2] = s.rgb[2]; dt = s.dt;
             }
-        } else if (j < n) {
-            const Sample s = eval_sample<T>(net, coords, (size_t)base + j, cascades, &raw);
-            a = s.alpha; c[0] = s.rgb[0]; c[1] = s.rgb[1]; c[2] = s.rgb[2]; dt = s.dt;
         }
         const float incl = warp_incl_prod(1.f - a, lane);
         float excl = __shfl_up_sync(0xffffffffu, incl, 1);
@@ -581,7 +698,6 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(uint32_t n_rays, con
 }
 
 // Fused training tail: composite forward, Huber gradient, composite backward -- one warp per ray.
-template <bool PIPE>
 __global__ void __launch_bounds__(256) composite_loss_bwd_kernel(uint32_t n_rays, const __half* __restrict__ net, const float* __restrict__ coords,
                                                                  const uint32_t* __restrict__ numsteps_in, const uint32_t* __restrict__ numsteps_c,
                                                                  const float* __restrict__ bg, const float* __restrict__ target, float delta,
@@ -593,7 +709,7 @@ __global__ void __launch_bounds__(256) composite_loss_bwd_kernel(uint32_t n_rays
     float T_ = 1.f, r[3] = {0.f, 0.f, 0.f};
     if (n == 0) { r[0] = bg[3 * i]; r[1] = bg[3 * i + 1]; r[2] = bg[3 * i + 2]; }
     else {
-        composite_ray_fwd<__half, PIPE>(n, base, net, coords, cascades, lane, r, &T_);
+        composite_ray_fwd<__half>(n, base, net, coords, cascades, lane, r, &T_);
         if (n == numsteps_in[2 * i]) {
             r[0] = __fmaf_rn(T_, bg[3 * i], r[0]); r[1] = __fmaf_rn(T_, bg[3 * i + 1], r[1]); r[2] = __fmaf_rn(T_, bg[3 * i + 2], r[2]);
         }
@@ -610,7 +726,7 @@ __global__ void __launch_bounds__(256) composite_loss_bwd_kernel(uint32_t n_rays
     float loss_scale = 128;
     loss_scale /= n_rays;
     const float l1 = *mean < 0.01f ? 1e-4f : 0.0f;
-    composite_ray_bwd<__half, PIPE>(n, base, net, coords, lg, r, loss_scale, l1, cascades, lane, dnet);
+    composite_ray_bwd<__half>(n, base, net, coords, lg, r, loss_scale, l1, cascades, lane, dnet);
 }
 
 }  // namespace
@@ -618,8 +734,8 @@ __global__ void __launch_bounds__(256) composite_loss_bwd_kernel(uint32_t n_rays
 extern "C" {
 
 uint64_t ngp_march_workspace_bytes(uint32_t n_rays) {
-    // counts[n] | n_chunks[n] | ChunkRec[n][MARCH_MAXC]
-    return (uint64_t)n_rays * (4 + 4 + MARCH_MAXC * sizeof(ChunkRec)) + 512;
+    // counts[n] | n_chunks[n] | n_replayed[n] | per ray: ChunkHdr[MAXC], dest[MAXC][32], t[MAXC][32], t_target[MAXC][32]
+    return (uint64_t)n_rays * (12 + MARCH_RAY_BYTES) + 1024;
 }
 
 int ngp_march(void* stream, uint32_t n_rays, float aabb_lo, float aabb_hi, uint32_t max_samples, const float* rays_o, const float* rays_d,
@@ -632,20 +748,19 @@ int ngp_march(void* stream, uint32_t n_rays, float aabb_lo, float aabb_hi, uint3
     const MarchCfg c = make_cfg(cascades, const_dt);
     uint32_t* counts = (uint32_t*)workspace;
     uint32_t* n_chunks = counts + n_rays;
-    ChunkRec* recs = reinterpret_cast<ChunkRec*>((reinterpret_cast<uintptr_t>(n_chunks + n_rays) + 15) & ~(uintptr_t)15);
+    uint32_t* n_replayed = n_chunks + n_rays;
+    uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(n_replayed + n_rays) + 255) & ~(uintptr_t)255);
     const uint32_t blocks = (n_rays + 3) / 4;             // one warp per ray, 4 rays per CTA
-    static const bool pipe = getenv("NGP_MARCH_PIPE") && atoi(getenv("NGP_MARCH_PIPE")) == 1;   // opt-in scheduling variant of the count pass
-    if (pipe)
-        march_count_kernel<true><<<blocks, 128, 0, s>>>(n_rays, aabb_lo, aabb_hi, rays_o, rays_d, bitfield, cone_angle, near_distance, c, rng_state,
-                                                        rng_inc, counts, recs, n_chunks);
-    else
-        march_count_kernel<false><<<blocks, 128, 0, s>>>(n_rays, aabb_lo, aabb_hi, rays_o, rays_d, bitfield, cone_angle, near_distance, c, rng_state,
-                                                         rng_inc, counts, recs, n_chunks);
+    march_eval_kernel<<<blocks, 128, 0, s>>>(n_rays, aabb_lo, aabb_hi, rays_o, rays_d, bitfield, cone_angle, near_distance, c, rng_state, rng_inc,
+                                             ws, n_chunks);
+    NGP_LAUNCH_CHECK();
+    march_replay_kernel<<<blocks, 128, 0, s>>>(n_rays, aabb_lo, aabb_hi, rays_o, rays_d, bitfield, cone_angle, near_distance, c, rng_state,
+                                               rng_inc, ws, n_chunks, counts, n_replayed);
     NGP_LAUNCH_CHECK();
     march_scan_kernel<<<1, 1024, 0, s>>>(n_rays, max_samples, counts, numsteps, ray_indices, counters);
     NGP_LAUNCH_CHECK();
-    march_emit_kernel<<<blocks, 128, 0, s>>>(n_rays, aabb_lo, aabb_hi, rays_o, rays_d, bitfield, cone_angle, near_distance, c, rng_state,
-                                             rng_inc, numsteps, coords, recs, n_chunks);
+    march_emit_kernel<<<n_rays, 128, 0, s>>>(n_rays, aabb_lo, aabb_hi, rays_o, rays_d, bitfield, cone_angle, near_distance, c, rng_state,
+                                             rng_inc, numsteps, coords, ws, n_chunks, n_replayed);
     NGP_LAUNCH_CHECK();
     return 0;
 }
@@ -712,15 +827,8 @@ int ngp_composite_loss_bwd(void* stream, uint32_t n_rays, uint32_t n_elements, c
     (void)n_elements;   // rows not covered by a ray are never read downstream (the network backward is count-limited)
     if (n_rays == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    static const bool pipe = getenv("NGP_COMPOSITE_PIPE") && atoi(getenv("NGP_COMPOSITE_PIPE")) == 1;   // opt-in: next chunk's loads in flight
-    if (pipe)
-        composite_loss_bwd_kernel<true><<<(n_rays + 7) / 8, 256, 0, s>>>(n_rays, (const __half*)net_out, coords, numsteps_in, numsteps_compacted, bg,
-                                                                            target, huber_delta, density_grid_mean, cascades, rgb_out, loss_out,
-                                                                            (__half*)dnet_out);
-    else
-        composite_loss_bwd_kernel<false><<<(n_rays + 7) / 8, 256, 0, s>>>(n_rays, (const __half*)net_out, coords, numsteps_in, numsteps_compacted, bg,
-                                                                             target, huber_delta, density_grid_mean, cascades, rgb_out, loss_out,
-                                                                             (__half*)dnet_out);
+    composite_loss_bwd_kernel<<<(n_rays + 7) / 8, 256, 0, s>>>(n_rays, (const __half*)net_out, coords, numsteps_in, numsteps_compacted, bg, target,
+                                                               huber_delta, density_grid_mean, cascades, rgb_out, loss_out, (__half*)dnet_out);
     NGP_LAUNCH_CHECK();
     return 0;
 }

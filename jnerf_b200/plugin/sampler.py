@@ -79,12 +79,22 @@ class DensityGridSampler(Module):
         self.rng = ops.pcg32_seed(1337)                              # jittor::rng, global_vars.py:17
         self.max_samples = self.cfg.n_rays_per_batch * self.MAX_STEP  # raw sample capacity, ray_sampler.py:15,30
         self._coords_raw = torch.zeros((self.max_samples, 7), dtype=torch.float32, device=dev)
-        self._march_ws = torch.empty(int(ops.lib.load().ngp_march_workspace_bytes(self.target_batch_size)) + 16, dtype=torch.uint8, device=dev)
+        # march workspace (per-ray chunk records, ~23 KB a ray): sized for the current ray batch with head room and re-grown when the
+        # adaptive ray batch (density_grid_sampler.py:266-271) outgrows it -- that only happens at the 16-step host sync
+        self._march_ws_rays = 0
+        self._march_ws = None
+        self._ensure_march_ws(max(2 * self.n_rays_per_batch, 8192))
         self.dp_group = None                                         # (process_group, world_size) when data parallel
         self._coords = None
         self._rays_numsteps = None
         self._rays_numsteps_compacted = None
         self._counters_compacted = None
+
+    def _ensure_march_ws(self, n_rays):
+        if n_rays > self._march_ws_rays:
+            self._march_ws = None                                      # release before the larger allocation
+            self._march_ws_rays = int(n_rays)
+            self._march_ws = torch.empty(int(ops.lib.load().ngp_march_workspace_bytes(self._march_ws_rays)) + 16, dtype=torch.uint8, device="cuda")
 
     # ---- R6 + R5 -------------------------------------------------------------------------------------------
     def sample(self, img_ids, rays_o, rays_d, rgb_target=None, is_training=False, ray_index_offset=0):
@@ -92,6 +102,8 @@ class DensityGridSampler(Module):
         global ray id so that a data-parallel shard reproduces the single-GPU samples (ray_sampler.h:30)."""
         if is_training and self.cfg.m_training_step % self.update_den_freq == 0:
             self.update_density_grid()
+        if rays_o.shape[0] > self._march_ws_rays:
+            self._ensure_march_ws(2 * rays_o.shape[0])
         coords, rays_index, rays_numsteps, counters = ops.march(
             rays_o.contiguous(), rays_d.contiguous(), self.density_grid_bitfield, self.aabb_range, self.max_samples, self.cone_angle_constant,
             self.near_distance, self.NERF_CASCADES, self.const_dt,

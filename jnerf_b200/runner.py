@@ -331,6 +331,7 @@ class Runner:
         s, m = self.sampler, self.model
         if getattr(self, "_infer_net_out", None) is None:
             self._infer_net_out = torch.empty((s.max_samples, 4), dtype=torch.float16, device="cuda")
+        s._ensure_march_ws(tile)
         for p in range(0, n_pad, tile):
             coords, _, numsteps, counters = ops.march(
                 rays_o[p:p + tile].contiguous(), rays_d[p:p + tile].contiguous(), s.density_grid_bitfield, s.aabb_range, s.max_samples,

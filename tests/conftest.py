@@ -24,9 +24,3 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
-
-
-def experimental(reason):
-    """Marker for GPU tests of opt-in kernel variants that were written after the round's last GPU session: they run only with
-    NGP_EXPERIMENTAL=1 (first thing to do in the next GPU session), so an unmeasured variant can never break the default suite."""
-    return pytest.mark.skipif(os.environ.get("NGP_EXPERIMENTAL", "0") != "1", reason=f"experimental ({reason}): set NGP_EXPERIMENTAL=1")

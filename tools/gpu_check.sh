@@ -1,8 +1,8 @@
 #!/usr/bin/env bash
-# Fully unrolled MMA issue with compile-time descriptors (no MMA program in shared memory): tests, bench, timeline, layout probe
+# One GPU call: layout probe, the full GPU suite, bench (lego, fox, timing-only knobs), microbench, backward timeline.  usage: gpu_check.sh [tag]
 set -u
 cd "$(dirname "$0")/.."
-OUT=gpurun_out/${1:-call4}
+OUT=gpurun_out/${1:-check}
 mkdir -p "$OUT"
 SUM="$OUT/SUMMARY.txt"
 : > "$SUM"
@@ -20,6 +20,7 @@ bench bwd_no_wgrad_TIMING_ONLY NGP_BWD_DEBUG=4 --
 bench bwd_no_scatter_TIMING_ONLY NGP_BWD_DEBUG=2 --
 bench fox -- --workload fox
 run microbench 300 python tools/microbench.py
+run ref_gpu_compare 400 python tools/ref_gpu_compare.py
 if NGP_NVCC_FLAGS=-DNGP_TIMELINE python jnerf_b200/build.py --force > "$OUT/build_timeline.log" 2>&1; then
     run timeline_bwd 120 python tools/dbg_timeline_bwd.py
 fi
