@@ -10,6 +10,8 @@
 #include <cfloat>
 #include <cstdlib>
 
+int* ngp_err_flag();
+
 namespace {
 
 struct MarchCfg {
@@ -198,97 +200,120 @@ __device__ __forceinline__ uint32_t march_ray_warp(const RayState& r, float lo, 
     return j;
 }
 
-// ---- chunk-parallel march -----------------------------------------------------------------------------------------------------
+// ---- producer / consumer march --------------------------------------------------------------------------------------------------
 // Round 1 ran the whole loop above per ray in one warp: ~1.2 k cycles per 32-step chunk, 40-64 chunks in sequence, and the kernel
 // lasted as long as its longest ray (80 us for ~2 200 rays at 16 % of the warp slots).  Everything in a chunk except the replay of the
 // control flow is independent of every other chunk -- the t sequence is fixed, and position / mip level / occupancy bit / distance to
-// the next voxel are functions of t alone.  So:
-//   pass 1 (march_eval_kernel, warp per ray): walk the t sequence (the same float additions in the same order; lane k keeps t_k of
-//           the current chunk), evaluate the 32 steps of every chunk, and record per chunk {inside mask, occupied mask}, per step t,
-//           the skip target t_target and the in-chunk skip destination.  No control flow depends on loaded data: the occupancy
-//           byte of chunk c is consumed one iteration later (software pipeline), so the lookups of consecutive chunks overlap;
-//   pass 2 (march_replay_kernel, warp per ray): the reference's sequential control flow on the recorded masks -- a few integer
-//           operations and one shuffle per visited run / skip, records prefetched one chunk ahead;
-//   scan, then pass 3 (march_emit_kernel, CTA per ray, warp per chunk): rows of the emitting chunks from the stored t values.
-// Same arithmetic per visited step as the reference, hence the same samples bit for bit (tests/test_gpu_ops.py::test_march_bit_exact).
-constexpr uint32_t MARCH_MAXC = 72;      // chunks (of 32 steps) recorded per ray: 2304 steps >= sqrt(3) / (min_cone / 2) + the terminal chunk
-struct __align__(16) ChunkHdr { float t0; uint32_t inside, occ, emit, j0, pad0, pad1, pad2; };
-static_assert(sizeof(ChunkHdr) == 32, "ChunkHdr must be 32 bytes");
-constexpr size_t MARCH_RAY_BYTES = (size_t)MARCH_MAXC * (sizeof(ChunkHdr) + 32 + 128 + 128);
-struct RayWs {
-    ChunkHdr* hdr;      // [MAXC]
-    uint8_t* dest;      // [MAXC][32]  first lane > l with !(t < t_target[l]) inside the chunk, 32 = beyond the chunk
-    float* t;           // [MAXC][32]
-    float* tt;          // [MAXC][32]  t_target of empty steps (distance_to_next_voxel)
+// the next voxel are functions of t alone.  march_count_kernel therefore runs TWO warps per ray:
+//   producer: walks the t sequence (the same float additions in the same order; lane k keeps t_k of the current chunk), evaluates the
+//             32 steps of every chunk and pushes {inside mask, occupied mask, per step t, skip target t_target, in-chunk skip
+//             destination} into a 4-slot ring in shared memory.  No control flow depends on loaded data: the occupancy byte of a
+//             chunk is tested while the next chunk's lookup is in flight (two chunk states in ping-pong registers);
+//   consumer: the reference's sequential control flow (ray_sampler.h:50-72) replayed on the masks -- a few integer operations and one
+//             shuffle per visited run / skip -- and, for every chunk that emits samples, {t values, emit mask, first ray-local
+//             index} appended to the ray's emit list in global memory.
+// Hand-over through mbarriers (FULL / EMPTY per slot).  After the scan, march_emit_kernel (CTA per ray, warp per list entry) turns
+// the list into rows.  Same arithmetic per visited step as the reference, hence the same samples bit for bit
+// (tests/test_gpu_ops.py::test_march_bit_exact).
+constexpr uint32_t MARCH_SLOTS = 4;
+constexpr uint32_t MARCH_EMIT_CAP = 64;        // emitting chunks recorded per ray (a 1024-sample ray of solid runs needs 33); more -> re-march
+constexpr uint32_t MARCH_CHUNK_GUARD = 1u << 15;   // a degenerate ray (d == 0, NaN) would never leave the box: forced terminal chunk
+struct __align__(16) EmitRec { float t[32]; uint32_t mask, j0, pad0, pad1; };
+static_assert(sizeof(EmitRec) == 144, "EmitRec must be 144 bytes");
+constexpr size_t MARCH_RAY_BYTES = (size_t)MARCH_EMIT_CAP * sizeof(EmitRec);
+
+struct __align__(16) RingSlot {
+    uint32_t inside, occ, terminal;
+    float t0_next;                 // t of the first step of the NEXT chunk (every t of this chunk is smaller)
+    uint8_t dest[32];              // first lane > l with !(t < t_target[l]) inside the chunk, 32 = beyond the chunk
+    float t[32];
+    float tt[32];                  // t_target of empty steps (distance_to_next_voxel)
 };
-__device__ __forceinline__ RayWs ray_ws(uint8_t* ws, uint32_t ray) {
-    uint8_t* b = ws + (size_t)ray * MARCH_RAY_BYTES;
-    RayWs w;
-    w.hdr = reinterpret_cast<ChunkHdr*>(b);
-    w.dest = b + MARCH_MAXC * sizeof(ChunkHdr);
-    w.t = reinterpret_cast<float*>(w.dest + MARCH_MAXC * 32);
-    w.tt = w.t + MARCH_MAXC * 32;
-    return w;
+struct RayRing {
+    uint64_t full[MARCH_SLOTS], empty[MARCH_SLOTS];
+    RingSlot slot[MARCH_SLOTS];
+};
+
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr_u32(bar)) : "memory");
+}
+// bounded wait (a protocol mistake must not hang the GPU box): false on timeout
+__device__ __forceinline__ bool mb_wait(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_addr_u32(bar)), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    return false;
 }
 
 struct ChunkState {           // per lane: one step of a chunk between the two halves of the evaluation
-    float t0, t, dt, p[3];
+    float t0_next, t, dt, p[3];
     uint32_t inside_m, mip, byte, bit;
     bool inside;
 };
 
-__global__ void __launch_bounds__(128) march_eval_kernel(uint32_t n_rays, float lo, float hi, const float* __restrict__ rays_o,
-                                                         const float* __restrict__ rays_d, const uint8_t* __restrict__ bits, float cone,
-                                                         float near_distance, MarchCfg c, uint64_t rng_state, uint64_t rng_inc,
-                                                         uint8_t* __restrict__ ws, uint32_t* __restrict__ n_chunks) {
-    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+constexpr int MARCH_RAYS_PER_CTA = 4;
+__global__ void __launch_bounds__(64 * MARCH_RAYS_PER_CTA)
+march_count_kernel(uint32_t n_rays, float lo, float hi, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                   const uint8_t* __restrict__ bits, float cone, float near_distance, MarchCfg c, uint64_t rng_state, uint64_t rng_inc,
+                   uint8_t* __restrict__ ws, uint32_t* __restrict__ counts, uint32_t* __restrict__ n_emit, int* __restrict__ err) {
+    __shared__ RayRing s_ring[MARCH_RAYS_PER_CTA];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rl = warp % MARCH_RAYS_PER_CTA;                    // ray slot of this warp inside the CTA
+    const bool producer = warp < MARCH_RAYS_PER_CTA;
+    const uint32_t i = blockIdx.x * MARCH_RAYS_PER_CTA + rl;
+    RayRing& ring = s_ring[rl];
+    if (producer && lane == 0) {
+        for (uint32_t k = 0; k < MARCH_SLOTS; ++k) { mb_init(&ring.full[k], 1); mb_init(&ring.empty[k], 1); }
+    }
+    __syncthreads();
     if (i >= n_rays) return;
     const unsigned FULL = 0xffffffffu;
-    const RayState r = ray_setup(i, rays_o, rays_d, lo, hi, near_distance, cone, c, rng_state, rng_inc);
-    const RayWs w = ray_ws(ws, i);
-    float tc = r.startt;                 // running t of the sequence (identical in all lanes)
-    ChunkState cur, prev;
-    bool prev_valid = false, stopped = false;
-    uint32_t nch = 0;
-    for (;;) {
-        bool cur_valid = false;
-        if (!stopped && nch < MARCH_MAXC) {
-            // ---- first half: t values, positions, occupancy lookup issued
-            cur.t0 = tc;
+
+    if (producer) {
+        const RayState r = ray_setup(i, rays_o, rays_d, lo, hi, near_distance, cone, c, rng_state, rng_inc);
+        float tc = r.startt;                 // running t of the sequence (identical in all lanes)
+        // first half of a chunk: t values, positions, occupancy lookup issued (not consumed)
+        auto stage1 = [&](ChunkState& st) {
             float t = tc;
 #pragma unroll
             for (int k = 0; k < 32; ++k) {                                        // t_k .. t_{k+31}: the reference's float additions, in order
                 if ((int)lane == k) t = tc;
                 tc += calc_dt(c, tc, cone);
             }
-            cur.t = t;
-            cur.dt = calc_dt(c, t, cone);
-            cur.p[0] = __fmaf_rn(t, r.d[0], r.o[0]); cur.p[1] = __fmaf_rn(t, r.d[1], r.o[1]); cur.p[2] = __fmaf_rn(t, r.d[2], r.o[2]);
-            cur.inside = contains(lo, hi, cur.p);
-            cur.inside_m = __ballot_sync(FULL, cur.inside);
-            cur.mip = 0; cur.byte = 0; cur.bit = 0;
-            if (cur.inside) {                                                      // occupied_at(), load now, test in the second half
-                cur.mip = (uint32_t)mip_from_dt(c, cur.dt, cur.p[0], cur.p[1], cur.p[2]);
-                const uint32_t idx = grid_idx_at(cur.p[0], cur.p[1], cur.p[2], cur.mip);
-                cur.byte = __ldg(bits + idx / 8 + (NERF_GRID_N / 8) * cur.mip);
-                cur.bit = 1u << (idx % 8);
+            st.t0_next = tc;
+            st.t = t;
+            st.dt = calc_dt(c, t, cone);
+            st.p[0] = __fmaf_rn(t, r.d[0], r.o[0]); st.p[1] = __fmaf_rn(t, r.d[1], r.o[1]); st.p[2] = __fmaf_rn(t, r.d[2], r.o[2]);
+            st.inside = contains(lo, hi, st.p);
+            st.inside_m = __ballot_sync(FULL, st.inside);
+            st.mip = 0; st.byte = 0; st.bit = 0;
+            if (st.inside) {                                                       // occupied_at(): load now, test in the second half
+                st.mip = (uint32_t)mip_from_dt(c, st.dt, st.p[0], st.p[1], st.p[2]);
+                const uint32_t idx = grid_idx_at(st.p[0], st.p[1], st.p[2], st.mip);
+                st.byte = __ldg(bits + idx / 8 + (NERF_GRID_N / 8) * st.mip);
+                st.bit = 1u << (idx % 8);
             }
-            cur_valid = true;
-            if (cur.inside_m == 0) stopped = true;                                 // the ray has left the box: this is its terminal chunk
-        }
-        if (prev_valid) {
-            // ---- second half (of the previous chunk): occupancy test, skip target, in-chunk skip destination, records
-            const uint32_t ch = nch - 1;                                           // nch = chunks handed over so far; prev is the last of them
-            const bool occ = prev.inside && (prev.byte & prev.bit) != 0;
+        };
+        // second half: occupancy test, skip target, in-chunk skip destination; push into the ring.  false = hand-over timed out
+        auto stage2 = [&](const ChunkState& st, uint32_t ch, bool terminal) -> bool {
+            const bool occ = st.inside && (st.byte & st.bit) != 0;
             const uint32_t occ_m = __ballot_sync(FULL, occ);
             float tt = 0.f;
-            if (prev.inside && !occ) {                                             // distance_to_next_voxel, ray_sampler_header.h:728-739
-                const float rs = (float)(NERF_GRIDSIZE >> prev.mip);
-                const float q[3] = {rs * prev.p[0], rs * prev.p[1], rs * prev.p[2]};
+            if (st.inside && !occ) {                                               // distance_to_next_voxel, ray_sampler_header.h:728-739
+                const float rs = (float)(NERF_GRIDSIZE >> st.mip);
+                const float q[3] = {rs * st.p[0], rs * st.p[1], rs * st.p[2]};
                 const float tx = (floorf(q[0] + 0.5f + 0.5f * sgn(r.d[0])) - q[0]) * r.id[0];
                 const float ty = (floorf(q[1] + 0.5f + 0.5f * sgn(r.d[1])) - q[1]) * r.id[1];
                 const float tz = (floorf(q[2] + 0.5f + 0.5f * sgn(r.d[2])) - q[2]) * r.id[2];
-                tt = prev.t + fmaxf(fminf(fminf(tx, ty), tz) / rs, 0.0f);
+                tt = st.t + fmaxf(fminf(fminf(tx, ty), tz) / rs, 0.0f);
             }
             // advance_to_next_voxel: do { t += dt } while (t < t_target) = the first later step with !(t < t_target); t increases
             // with the lane, so that step is found by bisection over the lanes (5 shuffles instead of a ballot per source lane)
@@ -296,90 +321,96 @@ __global__ void __launch_bounds__(128) march_eval_kernel(uint32_t n_rays, float 
 #pragma unroll
             for (int it = 0; it < 5; ++it) {
                 const uint32_t mid = (lo_l + hi_l) >> 1;
-                const float tm = __shfl_sync(FULL, prev.t, mid & 31);
+                const float tm = __shfl_sync(FULL, st.t, mid & 31);
                 const bool less = mid < 32 && tm < tt;
                 if (lo_l < hi_l) { if (less) lo_l = mid + 1; else hi_l = mid; }
             }
-            if (lane == 0) w.hdr[ch] = ChunkHdr{prev.t0, prev.inside_m, occ_m, 0u, 0u, 0u, 0u, 0u};
-            w.dest[ch * 32 + lane] = (uint8_t)lo_l;
-            w.t[ch * 32 + lane] = prev.t;
-            w.tt[ch * 32 + lane] = tt;
+            const uint32_t k = ch % MARCH_SLOTS;
+            if (!mb_wait(&ring.empty[k], ((ch / MARCH_SLOTS) & 1u) ^ 1u)) return false;   // the consumer has released this slot
+            RingSlot& sl = ring.slot[k];
+            if (lane == 0) { sl.inside = st.inside_m; sl.occ = occ_m; sl.terminal = terminal ? 1u : 0u; sl.t0_next = st.t0_next; }
+            sl.dest[lane] = (uint8_t)lo_l;
+            sl.t[lane] = st.t;
+            sl.tt[lane] = tt;
+            __syncwarp();
+            if (lane == 0) mb_arrive(&ring.full[k]);
+            return true;
+        };
+        // two chunk states in ping-pong: no register copy ever waits for a lookup that is still in flight
+        ChunkState A, B;
+        uint32_t ch = 0;
+        bool ok = true;
+        stage1(A);
+        bool a_term = A.inside_m == 0, b_term = false;
+        for (;;) {
+            const bool b_valid = !a_term;
+            if (b_valid) { stage1(B); b_term = B.inside_m == 0 || ch + 2 >= MARCH_CHUNK_GUARD; }
+            ok = stage2(A, ch++, a_term);
+            if (!ok || !b_valid) break;
+            const bool a_valid = !b_term;
+            if (a_valid) { stage1(A); a_term = A.inside_m == 0 || ch + 2 >= MARCH_CHUNK_GUARD; }
+            ok = stage2(B, ch++, b_term);
+            if (!ok || !a_valid) break;
         }
-        if (!cur_valid) break;
-        prev = cur;
-        prev_valid = true;
-        ++nch;
-    }
-    // overflow: MARCH_MAXC chunks and the ray is still inside the box -> the replay / emit passes re-march it the slow way
-    if (lane == 0) n_chunks[i] = nch | (stopped ? 0u : 0x80000000u);
-}
-
-// Replay of ray_sampler.h:50-72 on the recorded masks.  counts[i] = samples of ray i (<= NERF_STEPS); hdr[].emit / hdr[].j0 = which
-// steps of the chunk emit and the ray-local index of the first of them; n_replayed[i] = chunks the replay visited.
-__global__ void __launch_bounds__(128) march_replay_kernel(uint32_t n_rays, float lo, float hi, const float* __restrict__ rays_o,
-                                                           const float* __restrict__ rays_d, const uint8_t* __restrict__ bits, float cone,
-                                                           float near_distance, MarchCfg c, uint64_t rng_state, uint64_t rng_inc,
-                                                           uint8_t* __restrict__ ws, const uint32_t* __restrict__ n_chunks,
-                                                           uint32_t* __restrict__ counts, uint32_t* __restrict__ n_replayed) {
-    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (i >= n_rays) return;
-    const unsigned FULL = 0xffffffffu;
-    const uint32_t nraw = n_chunks[i], nch = nraw & 0x7fffffffu;
-    if (nraw >> 31) {                                                              // more chunks than the workspace records
-        const RayState r = ray_setup(i, rays_o, rays_d, lo, hi, near_distance, cone, c, rng_state, rng_inc);
-        const uint32_t n = march_ray_warp<false>(r, lo, hi, cone, c, bits, NERF_STEPS, nullptr);
-        if (lane == 0) { counts[i] = n; n_replayed[i] = 0; }
-        return;
-    }
-    const RayWs w = ray_ws(ws, i);
-    const uint32_t limit = NERF_STEPS;
-    uint32_t j = 0, ch = 0;
-    bool pending = false;
-    float pending_tt = 0.f;
-    // records of the chunk being replayed and of the next one (prefetched: the replay itself is a few dozen cycles per chunk)
-    ChunkHdr h = nch ? w.hdr[0] : ChunkHdr{0.f, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-    uint32_t d = nch ? w.dest[lane] : 32u;
-    for (; ch < nch; ++ch) {
-        ChunkHdr hn = h;
-        uint32_t dn = 32u;
-        if (ch + 1 < nch) { hn = w.hdr[ch + 1]; dn = w.dest[(ch + 1) * 32 + lane]; }
-        int cur = 0;
-        uint32_t emit_m = 0;
-        const uint32_t j0 = j;
-        bool done = false, skip = false;
-        if (pending) {
-            if (ch + 1 < nch && !(pending_tt < hn.t0)) skip = true;                // every t of this chunk < t0 of the next <= target
-            else {
-                const float t = w.t[ch * 32 + lane];
-                const uint32_t ge = __ballot_sync(FULL, !(t < pending_tt));
-                if (ge == 0) skip = true;
-                else { cur = __ffs(ge) - 1; pending = false; }
-            }
-        }
-        if (!skip) {
-            const uint32_t inside_m = h.inside, occ_m = h.occ;
-            while (cur < 32) {
-                if (!((inside_m >> cur) & 1u) || j >= limit) { done = true; break; }   // while (aabb.contains(pos) && j < NERF_STEPS)
-                if ((occ_m >> cur) & 1u) {
-                    const uint32_t run_m = (occ_m & inside_m) >> cur;                 // consecutive occupied steps are taken one by one
-                    uint32_t n_run = (run_m == 0xffffffffu) ? 32u : (uint32_t)__ffs(~run_m) - 1u;
-                    n_run = min(n_run, limit - j);
-                    emit_m |= (n_run >= 32u ? 0xffffffffu : ((1u << n_run) - 1u)) << cur;
-                    j += n_run;
-                    cur += n_run;
-                } else {
-                    const uint32_t dc = __shfl_sync(FULL, d, cur);
-                    if (dc < 32) cur = (int)dc;
-                    else { pending = true; pending_tt = w.tt[ch * 32 + cur]; cur = 32; }
+        if (!ok && lane == 0) atomicExch(err, 3);
+    } else {
+        // ---- consumer: ray_sampler.h:50-72 on the masks
+        EmitRec* elist = reinterpret_cast<EmitRec*>(ws + (size_t)i * MARCH_RAY_BYTES);
+        const uint32_t limit = NERF_STEPS;
+        uint32_t j = 0, ne = 0;
+        bool pending = false, finished = false, ok = true;
+        float pending_tt = 0.f;
+        for (uint32_t ch = 0;; ++ch) {
+            const uint32_t k = ch % MARCH_SLOTS;
+            if (!mb_wait(&ring.full[k], (ch / MARCH_SLOTS) & 1u)) { ok = false; break; }
+            const RingSlot& sl = ring.slot[k];
+            const uint32_t inside_m = sl.inside, occ_m = sl.occ, terminal = sl.terminal;
+            if (!finished) {
+                int cur = 0;
+                uint32_t emit_m = 0;
+                const uint32_t j0 = j;
+                bool skip = false;
+                if (pending) {
+                    if (!(pending_tt < sl.t0_next) && !terminal) skip = true;       // every t of this chunk < t0 of the next <= target
+                    else {
+                        const uint32_t ge = __ballot_sync(FULL, !(sl.t[lane] < pending_tt));
+                        if (ge == 0) skip = true;
+                        else { cur = __ffs(ge) - 1; pending = false; }
+                    }
+                }
+                if (!skip) {
+                    const uint32_t d = sl.dest[lane];
+                    while (cur < 32) {
+                        if (!((inside_m >> cur) & 1u) || j >= limit) { finished = true; break; }   // while (aabb.contains(pos) && j < NERF_STEPS)
+                        if ((occ_m >> cur) & 1u) {
+                            const uint32_t run_m = (occ_m & inside_m) >> cur;             // consecutive occupied steps are taken one by one
+                            uint32_t n_run = (run_m == 0xffffffffu) ? 32u : (uint32_t)__ffs(~run_m) - 1u;
+                            n_run = min(n_run, limit - j);
+                            emit_m |= (n_run >= 32u ? 0xffffffffu : ((1u << n_run) - 1u)) << cur;
+                            j += n_run;
+                            cur += n_run;
+                        } else {
+                            const uint32_t dc = __shfl_sync(FULL, d, cur);
+                            if (dc < 32) cur = (int)dc;
+                            else { pending = true; pending_tt = sl.tt[cur]; cur = 32; }
+                        }
+                    }
+                }
+                if (emit_m) {                                                      // this chunk emits: append to the ray's emit list
+                    if (ne < MARCH_EMIT_CAP) {
+                        elist[ne].t[lane] = sl.t[lane];
+                        if (lane == 0) { elist[ne].mask = emit_m; elist[ne].j0 = j0; }
+                    }
+                    ++ne;
                 }
             }
+            __syncwarp();
+            if (lane == 0) mb_arrive(&ring.empty[k]);                              // (after `finished` the remaining chunks are only drained)
+            if (terminal) break;
         }
-        if (lane == 0) { w.hdr[ch].emit = emit_m; w.hdr[ch].j0 = j0; }
-        if (done) { ++ch; break; }
-        h = hn;
-        d = dn;
+        if (!ok && lane == 0) atomicExch(err, 3);
+        if (lane == 0) { counts[i] = j; n_emit[i] = ne; }
     }
-    if (lane == 0) { counts[i] = j; n_replayed[i] = ch; }
 }
 
 // Single-CTA exclusive scan over ray counts (R <= a few 100k): numsteps[i] = {count or 0, base}, ray index of accepted rays.
@@ -429,40 +460,37 @@ __global__ void __launch_bounds__(1024) march_scan_kernel(uint32_t n_rays, uint3
     if (t == 1023) { counters[0] = s_acc[1023]; counters[1] = s_sum[1023]; }
 }
 
-// Emit pass: one CTA per ray, one warp per emitting chunk.  The rows of a chunk are contiguous in the output (ray-ordered, the
-// replay left the ray-local index of the chunk's first sample), so they are staged in shared memory and written as one coalesced
-// block of n x 7 floats instead of 7 strided 4-byte stores per lane.
+// Emit pass: one CTA per ray, one warp per entry of the ray's emit list.  The rows of a chunk are contiguous in the output
+// (ray-ordered, the replay left the ray-local index of the chunk's first sample), so they are staged in shared memory and written as
+// one coalesced block of n x 7 floats instead of 7 strided 4-byte stores per lane.  A ray whose list overflowed is re-marched.
 __global__ void __launch_bounds__(128) march_emit_kernel(uint32_t n_rays, float lo, float hi, const float* __restrict__ rays_o,
                                                          const float* __restrict__ rays_d, const uint8_t* __restrict__ bits, float cone,
                                                          float near_distance, MarchCfg c, uint64_t rng_state, uint64_t rng_inc,
                                                          const uint32_t* __restrict__ numsteps, float* __restrict__ coords,
-                                                         uint8_t* __restrict__ ws, const uint32_t* __restrict__ n_chunks,
-                                                         const uint32_t* __restrict__ n_replayed) {
+                                                         const uint8_t* __restrict__ ws, const uint32_t* __restrict__ n_emit) {
     __shared__ float s_rows[4][32 * 7];
     const uint32_t i = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n = numsteps[2 * i], base = numsteps[2 * i + 1];
     if (n == 0) return;
     float* out = coords + (size_t)base * 7;
-    if (n_chunks[i] >> 31) {
+    const uint32_t ne = n_emit[i];
+    if (ne > MARCH_EMIT_CAP) {
         if (warp == 0) {
             const RayState r = ray_setup(i, rays_o, rays_d, lo, hi, near_distance, cone, c, rng_state, rng_inc);
             march_ray_warp<true>(r, lo, hi, cone, c, bits, n, out);
         }
         return;
     }
-    const RayWs w = ray_ws(ws, i);
-    const uint32_t nrep = n_replayed[i];
+    const EmitRec* elist = reinterpret_cast<const EmitRec*>(ws + (size_t)i * MARCH_RAY_BYTES);
     float o[3], d[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) { o[k] = rays_o[3 * (size_t)i + k]; d[k] = rays_d[3 * (size_t)i + k]; }
     const float wd[3] = {(d[0] + 1.0f) * 0.5f, (d[1] + 1.0f) * 0.5f, (d[2] + 1.0f) * 0.5f}, diag = hi - lo;
     float* rows = s_rows[warp];
-    for (uint32_t ch = warp; ch < nrep; ch += 4) {
-        const uint32_t mask = w.hdr[ch].emit;
-        if (mask == 0) continue;
-        const uint32_t j0 = w.hdr[ch].j0, cnt = __popc(mask);
+    for (uint32_t e = warp; e < ne; e += 4) {
+        const uint32_t mask = elist[e].mask, j0 = elist[e].j0, cnt = __popc(mask);
         if ((mask >> lane) & 1u) {
-            const float t = w.t[ch * 32 + lane];
+            const float t = elist[e].t[lane];
             const float dt = calc_dt(c, t, cone);
             const float p[3] = {__fmaf_rn(t, d[0], o[0]), __fmaf_rn(t, d[1], o[1]), __fmaf_rn(t, d[2], o[2])};
             float* q = rows + __popc(mask & ((1u << lane) - 1u)) * 7;
@@ -734,8 +762,8 @@ __global__ void __launch_bounds__(256) composite_loss_bwd_kernel(uint32_t n_rays
 extern "C" {
 
 uint64_t ngp_march_workspace_bytes(uint32_t n_rays) {
-    // counts[n] | n_chunks[n] | n_replayed[n] | per ray: ChunkHdr[MAXC], dest[MAXC][32], t[MAXC][32], t_target[MAXC][32]
-    return (uint64_t)n_rays * (12 + MARCH_RAY_BYTES) + 1024;
+    // counts[n] | n_emit[n] | per ray: EmitRec[MARCH_EMIT_CAP]
+    return (uint64_t)n_rays * (8 + MARCH_RAY_BYTES) + 1024;
 }
 
 int ngp_march(void* stream, uint32_t n_rays, float aabb_lo, float aabb_hi, uint32_t max_samples, const float* rays_o, const float* rays_d,
@@ -747,20 +775,16 @@ int ngp_march(void* stream, uint32_t n_rays, float aabb_lo, float aabb_hi, uint3
     if (n_rays == 0) return 0;
     const MarchCfg c = make_cfg(cascades, const_dt);
     uint32_t* counts = (uint32_t*)workspace;
-    uint32_t* n_chunks = counts + n_rays;
-    uint32_t* n_replayed = n_chunks + n_rays;
-    uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(n_replayed + n_rays) + 255) & ~(uintptr_t)255);
-    const uint32_t blocks = (n_rays + 3) / 4;             // one warp per ray, 4 rays per CTA
-    march_eval_kernel<<<blocks, 128, 0, s>>>(n_rays, aabb_lo, aabb_hi, rays_o, rays_d, bitfield, cone_angle, near_distance, c, rng_state, rng_inc,
-                                             ws, n_chunks);
-    NGP_LAUNCH_CHECK();
-    march_replay_kernel<<<blocks, 128, 0, s>>>(n_rays, aabb_lo, aabb_hi, rays_o, rays_d, bitfield, cone_angle, near_distance, c, rng_state,
-                                               rng_inc, ws, n_chunks, counts, n_replayed);
+    uint32_t* n_emit = counts + n_rays;
+    uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(n_emit + n_rays) + 255) & ~(uintptr_t)255);
+    const uint32_t blocks = (n_rays + MARCH_RAYS_PER_CTA - 1) / MARCH_RAYS_PER_CTA;   // two warps (producer, consumer) per ray
+    march_count_kernel<<<blocks, 64 * MARCH_RAYS_PER_CTA, 0, s>>>(n_rays, aabb_lo, aabb_hi, rays_o, rays_d, bitfield, cone_angle, near_distance, c,
+                                                                 rng_state, rng_inc, ws, counts, n_emit, ngp_err_flag());
     NGP_LAUNCH_CHECK();
     march_scan_kernel<<<1, 1024, 0, s>>>(n_rays, max_samples, counts, numsteps, ray_indices, counters);
     NGP_LAUNCH_CHECK();
     march_emit_kernel<<<n_rays, 128, 0, s>>>(n_rays, aabb_lo, aabb_hi, rays_o, rays_d, bitfield, cone_angle, near_distance, c, rng_state,
-                                             rng_inc, numsteps, coords, ws, n_chunks, n_replayed);
+                                             rng_inc, numsteps, coords, ws, n_emit);
     NGP_LAUNCH_CHECK();
     return 0;
 }
