@@ -488,6 +488,307 @@ network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
 }
 
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Backward with TWO MLP chains per CTA (network_bwd2_kernel).
+//
+// One chain is a strictly serial sequence of 10 MMA -> commit -> TMEM load -> convert -> shared store -> barrier stages per
+// 128-sample tile (tools/dbg_timeline_bwd.py: ~1.6 k cycles a stage once the MMAs issue at the hardware rate), during which the
+// tensor pipe, the LSU and three quarters of the issue slots idle.  So the CTA runs two of them on independent tile streams:
+//     chain group 0 (warps 0-3) | chain group 1 (warps 4-7) | scatter group 0 (warps 8-11) | scatter group 1 (warps 12-15),
+// each chain group with its own activation slabs, TMEM columns, mbarriers and named barriers.  That fits because the per-chain
+// footprint is halved:
+//   * every gradient slab is written IN PLACE over the activation it is derived from: g_h2 over h2, g_h1 over h1, dYd over the
+//     colour net's input, g_hd over hd.  Safe because the only other reader of that activation is the weight-gradient MMA of the
+//     SAME stage (issued together with the dgrad MMA, tracked by its own mbarrier), and each thread reads and writes only its own row;
+//   * dYr (the 4-wide output gradient padded to K = 16) borrows the first two groups of the dL/d(enc) buffer of the tile, which is
+//     written only at the very end of the chain;
+//   * the W0 weight gradients (32 inputs x 64 outputs) are accumulated transposed (lane = output feature, 32 columns):
+//     160 accumulator + 96 working columns = 256 TMEM columns per chain, 512 per CTA.
+// Shared memory per chain: 7 KB coords + 64 KB activations + 16 KB dL/d(enc) (2 buffers); shared by both: 20 KB weights.
+// The group index is a template parameter so that every MMA descriptor stays a compile-time offset (see issue_fwd).
+constexpr uint32_t BW2_GROUPS = 2;
+struct SmemBwd2 {
+    static constexpr uint32_t coords = 0;                         // per chain group: two buffers of 128 x 7 f32 (3584 B each)
+    static constexpr uint32_t act0 = coords + BW2_GROUPS * 2 * 3584;  // per chain group: 32 activation groups + 8 dL/d(enc) groups (must follow: M=128 wgrad reads run into them)
+    static constexpr uint32_t act_stride = 40 * GB;
+    static constexpr uint32_t w0d = act0 + BW2_GROUPS * act_stride;
+    static constexpr uint32_t woutd = w0d + 64 * 32 * 2;
+    static constexpr uint32_t w0r = woutd + 16 * 64 * 2;
+    static constexpr uint32_t w1r = w0r + 64 * 32 * 2;
+    static constexpr uint32_t woutr = w1r + 64 * 64 * 2;
+    static constexpr uint32_t levels = woutr + 16 * 64 * 2;
+    static constexpr uint32_t bar = levels + N_LEVELS * 32;       // per chain group: 2 mbarriers; then the TMEM base word
+    static constexpr uint32_t total = bar + 64;
+};
+static_assert(SmemBwd2::total <= 227 * 1024, "backward CTA does not fit");
+template <uint32_t CG>
+struct SmemBwd2G : SmemBwd2 {                                     // the view forward_chain needs: this group's activation slabs
+    static constexpr uint32_t act = SmemBwd2::act0 + CG * SmemBwd2::act_stride;
+};
+
+// dgrad epilogue, in place: D[:, 0..64) -> fp16 -> masked by ReLU'(h) -> written over h (groups [g, g+8)).  The stores wait for
+// `bar_w`: the weight-gradient MMAs of this stage, which read h through the async proxy.
+static __device__ __noinline__ bool epi_dgrad_mask_inplace(uint32_t tbase, uint32_t dcol, uint32_t warp, uint8_t* slab, uint32_t g, uint32_t t,
+                                                           uint64_t* bar_w, uint32_t phase_w) {
+    uint32_t r[4][16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tmem_ld16_nowait(tmem_addr(tbase, warp & 3, dcol + 16 * c), r[c]);
+    tmem_ld_wait();
+    uint4 o[8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[c][i]);
+        uint4 lo, hi;
+        pack16(v, lo, hi);
+        o[2 * c] = relu_mask8(lo, slab_load8(slab, g + 2 * c, t));
+        o[2 * c + 1] = relu_mask8(hi, slab_load8(slab, g + 2 * c + 1, t));
+    }
+    const bool ok = mbar_wait(bar_w, phase_w);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(slab + (size_t)(g + c) * GB + t * 16) = o[c];
+    return ok;
+}
+
+// MLP chain of group CG (128 threads, thread t = row t, tq = TMEM lane quarter = warp index inside the group)
+template <uint32_t CG>
+__device__ __forceinline__ void bwd2_chain(uint8_t* smem, uint32_t t, uint32_t tq, uint32_t n_live, uint32_t ntiles, const float* __restrict__ coords,
+                                           const __half* __restrict__ enc_save, const __half* __restrict__ dout, float* __restrict__ dwd,
+                                           float* __restrict__ dwr, int* __restrict__ err, uint32_t dbg, uint32_t tmem_base) {
+    using S = SmemBwd2G<CG>;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::bar);
+    uint64_t* bar = bars + 2 * CG;                               // dgrad / forward MMAs of this chain group are done
+    uint64_t* bar_w = bar + 1;                                   // the weight-gradient MMAs of the current stage are done
+    uint8_t* act = smem + S::act;
+    uint8_t* denc = act + 32 * GB;
+    constexpr uint32_t coords_off = S::coords + CG * 2 * 3584;
+    constexpr uint32_t B_CHAIN = 1 + 6 * CG, B_FULL = 2 + 6 * CG, B_EMPTY = 4 + 6 * CG;   // named barriers of this group
+    const uint32_t tbase = tmem_base + CG * 256;                 // this chain group's 256 columns
+    const uint32_t smem_s = smem_u32(smem), act_s = smem_s + S::act, denc_s = act_s + 32 * GB;
+    // TMEM columns (relative to the group's base): working tiles, then the five weight-gradient accumulators
+    // (W0d / W0r transposed: lane = output feature)
+    constexpr uint32_t D_H = 0, D_S = 64, A_W0D = 96, A_WOUTD = 128, A_W0R = 144, A_W1R = 176, A_WOUTR = 240;
+    const uint32_t tile0 = blockIdx.x * BW2_GROUPS + CG, tile_step = gridDim.x * BW2_GROUPS;   // tile stream of this group
+    uint32_t acc = 0;
+    Pipe pipe{bar, 0, err};
+    uint32_t phase_w = 0;
+    // software prefetch of the next tile's inputs (7 coordinate words, the 64 B encoded row, the 8 B output gradient)
+    float pf_c[7];
+    uint4 pf_e[4];
+    uint2 pf_d;
+    auto prefetch = [&](uint32_t tile_) {
+        const uint32_t r0 = tile_ * ROWS, r = r0 + t;
+        const bool ok = r < n_live;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            const uint32_t i = t + 128 * j;
+            pf_c[j] = (r0 + i / 7 < n_live) ? __ldg(coords + (size_t)r0 * 7 + i) : 0.f;
+        }
+        const uint4* es = reinterpret_cast<const uint4*>(enc_save + (size_t)r * 32);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) pf_e[g] = ok ? __ldg(es + g) : make_uint4(0, 0, 0, 0);
+        pf_d = ok ? __ldg(reinterpret_cast<const uint2*>(dout) + r) : make_uint2(0, 0);
+    };
+    auto wait_w = [&]() {
+        if (!mbar_wait(bar_w, phase_w)) atomicExch(err, 2);
+        phase_w ^= 1;
+    };
+    // one stage: the elected thread issues the dgrad MMAs (-> bar) and the weight-gradient MMAs that read the same operands (-> bar_w)
+#define BW2_ISSUE(DGRAD, WGRAD)                                                                                              \
+    if (tq == 0) {                                                                                                            \
+        if (elect_one()) { DGRAD; pipe.commit(); if (!(dbg & 4)) { WGRAD; } mma_commit(bar_w); }                              \
+        __syncwarp();                                                                                                         \
+    }
+    if (tile0 < ntiles) prefetch(tile0);
+    uint32_t it = 0;
+    for (uint32_t tile = tile0; tile < ntiles; tile += tile_step, acc = 1, ++it) {
+        const uint32_t buf = it & 1;
+        float* s_coords = reinterpret_cast<float*>(smem + coords_off + buf * 3584);
+        uint8_t* denc_b = denc + buf * 4 * GB;
+        if (it >= 2) named_bar_sync(B_EMPTY + buf, 256);        // the scatter of tile it-2 has released coords[buf] / d_enc[buf]
+#pragma unroll
+        for (int j = 0; j < 7; ++j) s_coords[t + 128 * j] = pf_c[j];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(act + (G_ENC + g) * GB + t * 16) = pf_e[g];
+        const uint32_t dsig = pf_d.y >> 16;
+        *reinterpret_cast<uint4*>(denc_b + t * 16) = make_uint4(pf_d.x, pf_d.y & 0xFFFFu, 0, 0);     // dYr: 3 colour gradients, K padded to 16
+        *reinterpret_cast<uint4*>(denc_b + GB + t * 16) = make_uint4(0, 0, 0, 0);
+        if (tile + tile_step < ntiles) prefetch(tile + tile_step);   // in flight during the whole chain
+        sync_chain(B_CHAIN);
+        forward_chain<S, G_H2B, true>(smem, G_ENC, s_coords, tbase, pipe, t, tq, false, B_CHAIN);
+        // B1: g_h2 = (dYr Woutr) . relu'(h2) over h2 ; wgrad Woutr (h2^T dYr).  dYr lives in the tile's dL/d(enc) buffer (alternates)
+        if (buf) { BW2_ISSUE((issue_dgrad<16, 64>(tbase + D_H, denc_s + 4 * GB, 0, smem_s + S::woutr)),
+                             (issue_wgrad<16>(tbase + A_WOUTR, act_s, G_H2B, denc_s + 4 * GB, 0, acc))) }
+        else     { BW2_ISSUE((issue_dgrad<16, 64>(tbase + D_H, denc_s, 0, smem_s + S::woutr)),
+                             (issue_wgrad<16>(tbase + A_WOUTR, act_s, G_H2B, denc_s, 0, acc))) }
+        pipe.wait();
+        if (!epi_dgrad_mask_inplace(tbase, D_H, tq, act, G_H2B, t, bar_w, phase_w)) atomicExch(err, 2);
+        phase_w ^= 1;
+        sync_chain(B_CHAIN);
+        // B2: g_h1 = (g_h2 W1r) . relu'(h1) over h1 ; wgrad W1r (h1^T g_h2)
+        BW2_ISSUE((issue_dgrad<64, 64>(tbase + D_H, act_s, G_H2B, smem_s + S::w1r)), (issue_wgrad<64>(tbase + A_W1R, act_s, G_H1, act_s, G_H2B, acc)))
+        pipe.wait();
+        if (!epi_dgrad_mask_inplace(tbase, D_H, tq, act, G_H1, t, bar_w, phase_w)) atomicExch(err, 2);
+        phase_w ^= 1;
+        sync_chain(B_CHAIN);
+        // B3: d_rin = g_h1 W0r (32 cols; the last 16 are dL/dSH, unused) -> dYd over the colour input ; wgrad W0r transposed (g_h1^T rin)
+        BW2_ISSUE((issue_dgrad<64, 32>(tbase + D_S, act_s, G_H1, smem_s + S::w0r)), (issue_wgrad<32>(tbase + A_W0R, act_s, G_H1, act_s, G_RIN, acc)))
+        pipe.wait();
+        {
+            float v[16];
+            tmem_ld16(tmem_addr(tbase, tq, D_S), v);
+            v[0] += __half2float(__ushort_as_half((unsigned short)dsig));   // + dL/dsigma (ngp_network.py:83)
+            uint4 lo, hi;
+            pack16(v, lo, hi);
+            wait_w();
+            slab_store16(act, G_RIN, t, lo, hi);
+        }
+        sync_chain(B_CHAIN);
+        // B4: g_hd = (dYd Woutd) . relu'(hd) over hd ; wgrad Woutd (hd^T dYd)
+        BW2_ISSUE((issue_dgrad<16, 64>(tbase + D_H, act_s, G_RIN, smem_s + S::woutd)), (issue_wgrad<16>(tbase + A_WOUTD, act_s, G_HD, act_s, G_RIN, acc)))
+        pipe.wait();
+        if (!epi_dgrad_mask_inplace(tbase, D_H, tq, act, G_HD, t, bar_w, phase_w)) atomicExch(err, 2);
+        phase_w ^= 1;
+        sync_chain(B_CHAIN);
+        // B5: d_enc = g_hd W0d -> dL/d(enc) buffer ; wgrad W0d transposed (g_hd^T enc)
+        BW2_ISSUE((issue_dgrad<64, 32>(tbase + D_S, act_s, G_HD, smem_s + S::w0d)), (issue_wgrad<32>(tbase + A_W0D, act_s, G_HD, act_s, G_ENC, acc)))
+        pipe.wait();
+        {
+            float v[16];
+            uint4 lo, hi;
+            tmem_ld16(tmem_addr(tbase, tq, D_S), v);
+            pack16(v, lo, hi);
+            slab_store16(denc_b, 0, t, lo, hi);
+            tmem_ld16(tmem_addr(tbase, tq, D_S + 16), v);
+            pack16(v, lo, hi);
+            slab_store16(denc_b, 2, t, lo, hi);
+        }
+        wait_w();                                                // enc / g_hd may be overwritten by the next tile from here on
+        tc_fence_before();
+        named_bar_arrive(B_FULL + buf, 256);                     // FULL[buf]: dL/d(enc) and coords of this tile are ready
+    }
+#undef BW2_ISSUE
+    // flush this group's weight gradients
+    if (acc) {
+        tc_fence_after();
+        float v[16];
+        const uint32_t f_col[5] = {A_W0D, A_WOUTD, A_W0R, A_W1R, A_WOUTR};
+        const uint32_t f_out[5] = {64, 16, 64, 64, 16}, f_valid[5] = {64, 16, 64, 64, 3};   // colour Wout rows >= 3 stay zero (fully_fused_mlp.py:136)
+        const uint32_t f_in[5] = {32, 64, 32, 64, 64};
+        const bool f_tr[5] = {true, false, true, false, false};                          // transposed: lane = output feature, column = input
+        float* const f_dst[5] = {dwd + WD_W0, dwd + WD_WOUT, dwr + WR_W0, dwr + WR_W1, dwr + WR_WOUT};
+#pragma unroll 1
+        for (int m = 0; m < 5; ++m) {
+            const uint32_t ncols = f_tr[m] ? f_in[m] : f_out[m], nlanes = f_tr[m] ? f_out[m] : f_in[m];
+#pragma unroll 1
+            for (uint32_t c = 0; c < ncols / 16; ++c) {
+                tmem_ld16(tmem_addr(tbase, tq, f_col[m] + 16 * c), v);
+                if (t < nlanes) {
+#pragma unroll
+                    for (int o = 0; o < 16; ++o) {
+                        const uint32_t out_f = f_tr[m] ? t : 16 * c + o, in_f = f_tr[m] ? 16 * c + o : t;
+                        if (out_f < f_valid[m]) red_add_f32(f_dst[m] + (size_t)out_f * f_in[m] + in_f, v[o]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// hash-grid scatter of group CG (128 threads): HashEncode.h:339-347 with run-length combining, as in the one-chain kernel
+template <uint32_t CG>
+__device__ __forceinline__ void bwd2_scatter(uint8_t* smem, uint32_t t, uint32_t n_live, uint32_t ntiles, __half* __restrict__ grid_grad, uint32_t dbg) {
+    using S = SmemBwd2G<CG>;
+    const NgpLevel* s_lv = reinterpret_cast<const NgpLevel*>(smem + S::levels);
+    const uint8_t* denc = smem + S::act + 32 * GB;
+    constexpr uint32_t coords_off = S::coords + CG * 2 * 3584;
+    constexpr uint32_t B_FULL = 2 + 6 * CG, B_EMPTY = 4 + 6 * CG;
+    const uint32_t tile0 = blockIdx.x * BW2_GROUPS + CG, tile_step = gridDim.x * BW2_GROUPS;
+    const uint32_t level = t & 15, sub = t >> 4;
+    const NgpLevel lv = s_lv[level];
+    __half2* gg = reinterpret_cast<__half2*>(grid_grad) + lv.offset;
+    uint32_t it = 0;
+    for (uint32_t tile = tile0; tile < ntiles; tile += tile_step, ++it) {
+        const uint32_t buf = it & 1, row0 = tile * ROWS;
+        const float* s_coords = reinterpret_cast<const float*>(smem + coords_off + buf * 3584);
+        const uint8_t* denc_b = denc + buf * 4 * GB;
+        named_bar_sync(B_FULL + buf, 256);                       // FULL[buf]
+        uint32_t cgx = 0xffffffffu, cgy = 0, cgz = 0, idx[8];
+        float2 accv[8];
+        bool dirty = false;
+#pragma unroll 1
+        for (int k = 0; k < 16; ++k) {
+            const uint32_t p = 16 * sub + k;
+            if (row0 + p >= n_live || (dbg & 2)) break;
+            const __half2 d = *reinterpret_cast<const __half2*>(denc_b + (size_t)(level >> 2) * GB + p * 16 + (level & 3) * 4);
+            const float2 df = __half22float2(d);
+            if (df.x == 0.f && df.y == 0.f) continue;
+            const HashCell hc = hash_cell(lv, s_coords[p * 7], s_coords[p * 7 + 1], s_coords[p * 7 + 2]);
+            if (hc.gx != cgx || hc.gy != cgy || hc.gz != cgz) {
+                if (dirty && !(dbg & 1)) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) red_add_h2(gg + idx[c], accv[c].x, accv[c].y);
+                }
+                cgx = hc.gx; cgy = hc.gy; cgz = hc.gz;
+                hash_cell_indices(lv, cgx, cgy, cgz, idx);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) accv[c] = make_float2(0.f, 0.f);
+                dirty = true;
+            }
+            float w[8];
+            hash_cell_weights(hc, w);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { accv[c].x = fmaf(df.x, w[c], accv[c].x); accv[c].y = fmaf(df.y, w[c], accv[c].y); }
+        }
+        if (dirty && !(dbg & 1)) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) red_add_h2(gg + idx[c], accv[c].x, accv[c].y);
+        }
+        if (tile + 2 * tile_step < ntiles) named_bar_arrive(B_EMPTY + buf, 256);   // EMPTY[buf] for the chain's tile it+2
+    }
+}
+
+__global__ void __launch_bounds__(512, 1)
+network_bwd2_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const float* __restrict__ coords, const __half* __restrict__ enc_save,
+                    const NgpLevel* __restrict__ levels, const __half* __restrict__ wd, const __half* __restrict__ wr,
+                    const __half* __restrict__ dout, __half* __restrict__ grid_grad, float* __restrict__ dwd, float* __restrict__ dwr,
+                    int* __restrict__ err, uint32_t dbg) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    using S = SmemBwd2;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t t = tid & 127, tq = warp & 3;               // row inside the tile, TMEM lane quarter
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::bar);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+    NgpLevel* s_lv = reinterpret_cast<NgpLevel*>(smem + S::levels);
+
+    stage_weights(smem + S::w0d, wd + WD_W0, 64, 32, tid, 512);
+    stage_weights(smem + S::woutd, wd + WD_WOUT, 16, 64, tid, 512);
+    stage_weights(smem + S::w0r, wr + WR_W0, 64, 32, tid, 512);
+    stage_weights(smem + S::w1r, wr + WR_W1, 64, 64, tid, 512);
+    stage_weights(smem + S::woutr, wr + WR_WOUT, 16, 64, tid, 512);
+    if (tid < N_LEVELS) s_lv[tid] = levels[tid];
+    // M = 128 weight-gradient operands run past their 8-group slab into whatever follows: keep it finite
+    for (uint32_t i = tid; i < BW2_GROUPS * S::act_stride / 16; i += 512) *reinterpret_cast<uint4*>(smem + S::act0 + i * 16) = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_ptr, 512);
+    sync_before_issue();
+    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t n_live = n_dev ? min(*n_dev, n_max) : n_max;
+    const uint32_t ntiles = (n_live + ROWS - 1) / ROWS;
+    if (warp < 4) bwd2_chain<0>(smem, t, tq, n_live, ntiles, coords, enc_save, dout, dwd, dwr, err, dbg, tmem_base);
+    else if (warp < 8) bwd2_chain<1>(smem, t, tq, n_live, ntiles, coords, enc_save, dout, dwd, dwr, err, dbg, tmem_base);
+    else if (warp < 12) bwd2_scatter<0>(smem, t, n_live, ntiles, grid_grad, dbg);
+    else bwd2_scatter<1>(smem, t, n_live, ntiles, grid_grad, dbg);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_free(tmem_base, 512);
+}
+
 }  // namespace
 
 extern "C" {
@@ -529,11 +830,20 @@ int ngp_network_bwd(void* stream, uint32_t n_max, const uint32_t* n_dev, const f
     const uint32_t ntiles = (n_max + ROWS - 1) / ROWS;
     // timing experiments only (results are wrong with any bit set): 1 = no atomics, 2 = no scatter, 4 = no weight-gradient MMAs
     static const uint32_t dbg = getenv("NGP_BWD_DEBUG") ? (uint32_t)atoi(getenv("NGP_BWD_DEBUG")) : 0u;
-    NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd::total));
-    const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms());
-    network_bwd_kernel<<<grid_dim, 128 + 32 * SW, SmemBwd::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
-                                                                     (const __half*)w_density, (const __half*)w_rgb, (const __half*)dout,
-                                                                     (__half*)grid_grad, dw_density, dw_rgb, ngp_err_flag(), dbg);
+    static const bool one_chain = getenv("NGP_BWD_ONE_CHAIN") != nullptr;     // A/B switch while both kernels exist
+    if (one_chain) {
+        NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd::total));
+        const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms());
+        network_bwd_kernel<<<grid_dim, 128 + 32 * SW, SmemBwd::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
+                                                                         (const __half*)w_density, (const __half*)w_rgb, (const __half*)dout,
+                                                                         (__half*)grid_grad, dw_density, dw_rgb, ngp_err_flag(), dbg);
+    } else {
+        NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd2::total));
+        const uint32_t grid_dim = min((ntiles + BW2_GROUPS - 1) / BW2_GROUPS, (uint32_t)ngp_num_sms());
+        network_bwd2_kernel<<<grid_dim, 512, SmemBwd2::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
+                                                                  (const __half*)w_density, (const __half*)w_rgb, (const __half*)dout,
+                                                                  (__half*)grid_grad, dw_density, dw_rgb, ngp_err_flag(), dbg);
+    }
     NGP_LAUNCH_CHECK();
     return 0;
 }

@@ -29,25 +29,24 @@ __host__ __device__ inline MarchCfg make_cfg(uint32_t cascades, int const_dt) {
 }
 __device__ __forceinline__ float calc_dt(const MarchCfg& c, float t, float cone) {
     if (c.const_dt) return c.min_cone * 0.5f;                                // density_grid_sampler.py:107-110
-    const float v = t * cone;                                                // :112-115
-    return v < c.min_cone ? c.min_cone : (c.max_cone < v ? c.max_cone : v);
+    // :112-115 clamp(t * cone, min, max), branch-free (identical for every non-NaN t; a NaN t ends the ray at its next bounds test anyway)
+    return fminf(fmaxf(t * cone, c.min_cone), c.max_cone);
 }
+// The exponent frexpf(x, &e) returns, for x >= 0 as the callers below use it: exponent field - 126 for every normal float, 0 for
+// x = 0; a denormal x (true exponent < -125) reads -126 here, which the callers clamp to the same result.
+__device__ __forceinline__ int frexp_exponent(float x) { return x == 0.f ? 0 : (int)((__float_as_uint(x) >> 23) & 0xffu) - 126; }
 __device__ __forceinline__ int mip_from_pos(const MarchCfg& c, float px, float py, float pz) {
-    int e;
     const float m = fmaxf(fmaxf(fabsf(px - 0.5f), fabsf(py - 0.5f)), fabsf(pz - 0.5f));
-    frexpf(m, &e);
-    return min((int)c.cascades - 1, max(0, e + 1));                          // ray_sampler_header.h:60-66
+    return min((int)c.cascades - 1, max(0, frexp_exponent(m) + 1));           // ray_sampler_header.h:60-66
 }
 __device__ __forceinline__ int mip_from_dt(const MarchCfg& c, float dt, float px, float py, float pz) {
     const int mip = mip_from_pos(c, px, py, pz);
     dt *= 2 * NERF_GRIDSIZE;
     if (dt < 1.f) return mip;
-    int e;
-    frexpf(dt, &e);
-    return min((int)c.cascades - 1, max(e, mip));                            // :68-77
+    return min((int)c.cascades - 1, max(frexp_exponent(dt), mip));            // :68-77
 }
 __device__ __forceinline__ uint32_t grid_idx_at(float px, float py, float pz, uint32_t mip) {
-    const float s = scalbnf(1.0f, -(int)mip);                                // :755-770
+    const float s = __uint_as_float((127u - mip) << 23);                     // scalbnf(1, -mip), :755-770
     float q[3] = {px, py, pz};
     int ix[3];
 #pragma unroll
@@ -283,10 +282,30 @@ march_count_kernel(uint32_t n_rays, float lo, float hi, const float* __restrict_
         // first half of a chunk: t values, positions, occupancy lookup issued (not consumed)
         auto stage1 = [&](ChunkState& st) {
             float t = tc;
+            bool closed = false;
+            if (c.const_dt) {
+                // t_{k+1} = fl(t_k + h) with a constant h: while the sequence stays inside one binade every t_k is a multiple of the
+                // binade's ulp, so every addition rounds h to the same multiple q of that ulp (unless h lies exactly half way between
+                // two multiples, where round-to-even looks at t_k) and t_k = t_0 + k q exactly.  Then lane k gets t_k from ONE fma
+                // (k q < 2^24 ulp: exact) instead of k dependent additions.  Any chunk that crosses a power of two, or a tie, takes the
+                // sequential path below.
+                const float h = c.min_cone * 0.5f;
+                const float q = (tc + h) - tc;                                    // exact (Sterbenz)
+                const float t_end = __fmaf_rn(32.0f, q, tc);
+                const uint32_t e0 = __float_as_uint(tc) >> 23, e1 = __float_as_uint(t_end) >> 23;
+                const float r = h * __uint_as_float((277u - e0) << 23);          // h / ulp(tc) = h * 2^(150 - e0), exact scaling
+                if (e0 == e1 && e0 >= 117u && e0 <= 140u && (r - floorf(r)) != 0.5f) {
+                    t = __fmaf_rn((float)lane, q, tc);
+                    tc = t_end;
+                    closed = true;
+                }
+            }
+            if (!closed) {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {                                        // t_k .. t_{k+31}: the reference's float additions, in order
-                if ((int)lane == k) t = tc;
-                tc += calc_dt(c, tc, cone);
+                for (int k = 0; k < 32; ++k) {                                    // t_k .. t_{k+31}: the reference's float additions, in order
+                    if ((int)lane == k) t = tc;
+                    tc += calc_dt(c, tc, cone);
+                }
             }
             st.t0_next = tc;
             st.t = t;
@@ -313,7 +332,8 @@ march_count_kernel(uint32_t n_rays, float lo, float hi, const float* __restrict_
                 const float tx = (floorf(q[0] + 0.5f + 0.5f * sgn(r.d[0])) - q[0]) * r.id[0];
                 const float ty = (floorf(q[1] + 0.5f + 0.5f * sgn(r.d[1])) - q[1]) * r.id[1];
                 const float tz = (floorf(q[2] + 0.5f + 0.5f * sgn(r.d[2])) - q[2]) * r.id[2];
-                tt = st.t + fmaxf(fminf(fminf(tx, ty), tz) / rs, 0.0f);
+                const float rs_inv = __uint_as_float((120u + st.mip) << 23);      // 1 / rs = 2^(mip - 7): x / rs == x * rs_inv bit for bit
+                tt = st.t + fmaxf(fminf(fminf(tx, ty), tz) * rs_inv, 0.0f);
             }
             // advance_to_next_voxel: do { t += dt } while (t < t_target) = the first later step with !(t < t_target); t increases
             // with the lane, so that step is found by bisection over the lanes (5 shuffles instead of a ballot per source lane)
