@@ -789,6 +789,292 @@ network_bwd2_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const fl
     if (warp == 0) tmem_free(tmem_base, 512);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Backward over 256 rows per stage (network_bwd256_kernel).
+//
+// The MLP chain is a strictly serial sequence of 10 stages per tile -- MMA -> commit -> TMEM load -> convert -> shared store ->
+// barrier, ~1.5 k cycles each of which the tensor pipe works 130 -- so the fixed latency of a stage is amortised over TWO 128-row
+// tiles that move through the chain in lock step: a dedicated issuer warp queues the MMAs of tile A and tile B back to back on one
+// commit, the eight epilogue warps (0-3: rows of tile A, 4-7: rows of tile B; two warps per scheduler hide each other's latencies)
+// drain both accumulators at once, and the weight gradients of both tiles accumulate into the same TMEM columns.  Two independent
+// chains per CTA (network_bwd2_kernel) did NOT pay: their in-place gradient slabs put every stage's weight-gradient MMAs on the
+// critical path (profiles/r02_call8: 112 vs 106 us).  Here gradients rotate through buffers that died one stage earlier instead:
+//     g_h2 -> GX (the one extra slab), g_h1 -> the h2 slab, dYd -> the dYr slab, g_hd -> the h1 slab,
+// whose last reader (a weight-gradient MMA) was queued before the dgrad MMA the writing epilogue waits for.
+// Warps: 0-7 epilogue, 8 MMA issuer, 9-12 hash-grid scatter of the previous pair of tiles.
+constexpr uint32_t B3_G_GX = 32, B3_G_DY = 40, B3_G_DENC = 42, B3_GROUPS = 46;   // slab groups of one tile after the 32 activation groups
+constexpr uint32_t B3_EPI_THREADS = 256, B3_SCATTER_WARPS = 4, B3_THREADS = 256 + 32 + 32 * B3_SCATTER_WARPS;
+struct SmemBwd3 {
+    static constexpr uint32_t coords = 0;                           // [tile][buf] 128 x 7 f32 (3584 B each)
+    static constexpr uint32_t tile0 = coords + 4 * 3584;
+    static constexpr uint32_t tile_stride = B3_GROUPS * GB;
+    static constexpr uint32_t w0d = tile0 + 2 * tile_stride;
+    static constexpr uint32_t woutd = w0d + 64 * 32 * 2;
+    static constexpr uint32_t w0r = woutd + 16 * 64 * 2;
+    static constexpr uint32_t w1r = w0r + 64 * 32 * 2;
+    static constexpr uint32_t woutr = w1r + 64 * 64 * 2;
+    static constexpr uint32_t levels = woutr + 16 * 64 * 2;
+    static constexpr uint32_t bar = levels + N_LEVELS * 32;         // 2 mbarriers, then the TMEM base word
+    static constexpr uint32_t total = bar + 64;
+};
+static_assert(SmemBwd3::total <= 227 * 1024, "backward CTA does not fit");
+constexpr uint32_t B3_READY = 1, B3_FULL = 2, B3_EMPTY = 3;         // named barriers
+
+__global__ void __launch_bounds__(B3_THREADS, 1)
+network_bwd256_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const float* __restrict__ coords, const __half* __restrict__ enc_save,
+                      const NgpLevel* __restrict__ levels, const __half* __restrict__ wd, const __half* __restrict__ wr,
+                      const __half* __restrict__ dout, __half* __restrict__ grid_grad, float* __restrict__ dwd, float* __restrict__ dwr,
+                      int* __restrict__ err, uint32_t dbg) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    using S = SmemBwd3;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    uint64_t* bar_d = reinterpret_cast<uint64_t*>(smem + S::bar);  // the forward / dgrad MMAs of the current stage are done
+    uint64_t* bar_w = bar_d + 1;                                   // all weight-gradient MMAs of the pair of tiles are done
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_d + 2);
+    NgpLevel* s_lv = reinterpret_cast<NgpLevel*>(smem + S::levels);
+
+    stage_weights(smem + S::w0d, wd + WD_W0, 64, 32, tid, B3_THREADS);
+    stage_weights(smem + S::woutd, wd + WD_WOUT, 16, 64, tid, B3_THREADS);
+    stage_weights(smem + S::w0r, wr + WR_W0, 64, 32, tid, B3_THREADS);
+    stage_weights(smem + S::w1r, wr + WR_W1, 64, 64, tid, B3_THREADS);
+    stage_weights(smem + S::woutr, wr + WR_WOUT, 16, 64, tid, B3_THREADS);
+    if (tid < N_LEVELS) s_lv[tid] = levels[tid];
+    // zero both tiles once: dYr columns 4..15 are never rewritten, and M = 128 weight-gradient operands run past their slab
+    for (uint32_t i = tid; i < 2 * S::tile_stride / 16; i += B3_THREADS) *reinterpret_cast<uint4*>(smem + S::tile0 + i * 16) = make_uint4(0, 0, 0, 0);
+    if (tid == 0) { mbar_init(bar_d, 1); mbar_init(bar_w, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc(tmem_ptr, 512);
+    sync_before_issue();
+    const uint32_t tbase = *tmem_ptr;
+    const uint32_t n_live = n_dev ? min(*n_dev, n_max) : n_max;
+    const uint32_t ntiles = (n_live + ROWS - 1) / ROWS, npairs = (ntiles + 1) / 2;
+    // TMEM columns: working accumulators of tile A / tile B, then the five weight-gradient accumulators (both tiles add into them)
+    constexpr uint32_t D_H = 0, D_S = 64, TB = 96 /* tile B's working columns */, A_W0D = 192, A_WOUTD = 256, A_W0R = 272, A_W1R = 336, A_WOUTR = 400;
+    static_assert(A_WOUTR + 16 <= 512, "TMEM columns");
+
+    if (warp < 8) {
+        // ------------------------------------------------------------------ epilogue threads: thread t = row t of tile T
+        const uint32_t T = warp >> 2, t = tid & 127, tq = warp & 3;
+        uint8_t* act = smem + S::tile0 + T * S::tile_stride;       // this tile's slabs
+        const uint32_t tb = tbase + T * TB;
+        uint32_t phase = 0;
+        auto wait_mma = [&]() {
+            if (!mbar_wait(bar_d, phase)) atomicExch(err, 1);
+            phase ^= 1;
+            tc_fence_after();
+        };
+        auto ready = [&]() {                                       // operands written, accumulators read: the issuer may queue the next stage
+            tc_fence_before();
+            fence_proxy_async_smem();
+            named_bar_arrive(B3_READY, B3_EPI_THREADS + 32);
+        };
+        float pf_c[7];
+        uint4 pf_e[4];
+        uint2 pf_d;
+        auto prefetch = [&](uint32_t pair) {
+            const uint32_t tile_ = 2 * pair + T, r0 = tile_ * ROWS, r = r0 + t;
+            const bool ok = r < n_live;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                const uint32_t i = t + 128 * j;
+                pf_c[j] = (r0 + i / 7 < n_live) ? __ldg(coords + (size_t)r0 * 7 + i) : 0.f;
+            }
+            const uint4* es = reinterpret_cast<const uint4*>(enc_save + (size_t)r * 32);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) pf_e[g] = ok ? __ldg(es + g) : make_uint4(0, 0, 0, 0);
+            pf_d = ok ? __ldg(reinterpret_cast<const uint2*>(dout) + r) : make_uint2(0, 0);
+        };
+        if (blockIdx.x < npairs) prefetch(blockIdx.x);
+        uint32_t it = 0;
+        for (uint32_t pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++it) {
+            const uint32_t buf = it & 1;
+            float* s_coords = reinterpret_cast<float*>(smem + S::coords + (2 * T + buf) * 3584);
+            if (it >= 1) { if (!mbar_wait(bar_w, (it - 1) & 1)) atomicExch(err, 2); }   // the previous pair's wgrad MMAs have read their slabs
+#pragma unroll
+            for (int j = 0; j < 7; ++j) s_coords[t + 128 * j] = pf_c[j];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(act + (G_ENC + g) * GB + t * 16) = pf_e[g];
+            const uint32_t dsig = pf_d.y >> 16;
+            *reinterpret_cast<uint4*>(act + B3_G_DY * GB + t * 16) = make_uint4(pf_d.x, pf_d.y & 0xFFFFu, 0, 0);   // dYr: 3 colour gradients, K padded to 16
+            *reinterpret_cast<uint4*>(act + (B3_G_DY + 1) * GB + t * 16) = make_uint4(0, 0, 0, 0);
+            if (pair + gridDim.x < npairs) prefetch(pair + gridDim.x);     // in flight during the whole chain
+            named_bar_sync(4 + T, 128);                                     // the SH epilogue reads other threads' coordinate words
+            ready();
+            // F1 density L0: enc -> hd
+            wait_mma();
+            epi_hidden_relu(tb, D_H, tq, act, G_HD, t, nullptr);
+            ready();
+            // F2 density L1: hd -> h (16), + SH(dir) -> colour-net input
+            wait_mma();
+            {
+                float v[16];
+                tmem_ld16(tmem_addr(tb, tq, D_S), v);
+                uint4 lo, hi;
+                pack16(v, lo, hi);
+                slab_store16(act, G_RIN, t, lo, hi);
+                float sh[16];
+                sh4(s_coords[t * 7 + 4], s_coords[t * 7 + 5], s_coords[t * 7 + 6], sh);
+                pack16(sh, lo, hi);
+                slab_store16(act, G_RIN + 2, t, lo, hi);
+            }
+            ready();
+            // F3 colour L0 -> h1 ; F4 colour L1 -> h2
+            wait_mma();
+            epi_hidden_relu(tb, D_H, tq, act, G_H1, t, nullptr);
+            ready();
+            wait_mma();
+            epi_hidden_relu(tb, D_H, tq, act, G_H2B, t, nullptr);
+            ready();
+            // B1: g_h2 = (dYr Woutr) . relu'(h2) -> GX
+            wait_mma();
+            epi_dgrad_mask(tb, D_H, tq, act, G_H2B, act, B3_G_GX, t, nullptr);
+            ready();
+            // B2: g_h1 = (g_h2 W1r) . relu'(h1) -> over h2 (dead: its last reader, the Woutr weight gradient, was queued before this stage's dgrad)
+            wait_mma();
+            epi_dgrad_mask(tb, D_H, tq, act, G_H1, act, G_H2B, t, nullptr);
+            ready();
+            // B3: d_rin = g_h1 W0r (the last 16 of its 32 columns are dL/dSH, unused) ; dYd = d_rin[0..16) + dL/dsigma -> over dYr
+            wait_mma();
+            {
+                float v[16];
+                tmem_ld16(tmem_addr(tb, tq, D_S), v);
+                v[0] += __half2float(__ushort_as_half((unsigned short)dsig));   // ngp_network.py:83
+                uint4 lo, hi;
+                pack16(v, lo, hi);
+                slab_store16(act, B3_G_DY, t, lo, hi);
+            }
+            ready();
+            // B4: g_hd = (dYd Woutd) . relu'(hd) -> over h1
+            wait_mma();
+            epi_dgrad_mask(tb, D_H, tq, act, G_HD, act, G_H1, t, nullptr);
+            ready();
+            // B5: d_enc = g_hd W0d -> DENC (the scatter warps still read the previous pair's until EMPTY)
+            wait_mma();
+            if (it >= 1) named_bar_sync(B3_EMPTY, B3_EPI_THREADS + 32 * B3_SCATTER_WARPS);
+            {
+                float v[16];
+                uint4 lo, hi;
+                tmem_ld16(tmem_addr(tb, tq, D_S), v);
+                pack16(v, lo, hi);
+                slab_store16(act, B3_G_DENC, t, lo, hi);
+                tmem_ld16(tmem_addr(tb, tq, D_S + 16), v);
+                pack16(v, lo, hi);
+                slab_store16(act, B3_G_DENC + 2, t, lo, hi);
+            }
+            tc_fence_before();
+            named_bar_arrive(B3_FULL, B3_EPI_THREADS + 32 * B3_SCATTER_WARPS);   // dL/d(enc) and coords of this pair are ready
+        }
+        // flush the weight gradients (lane = input feature, column = output feature): rows of tile A's threads
+        if (it && T == 0) {
+            if (!mbar_wait(bar_w, (it - 1) & 1)) atomicExch(err, 2);
+            tc_fence_after();
+            float v[16];
+            const uint32_t f_col[5] = {A_W0D, A_WOUTD, A_W0R, A_W1R, A_WOUTR};
+            const uint32_t f_nout[5] = {64, 16, 64, 64, 16}, f_valid[5] = {64, 16, 64, 64, 3};   // colour Wout rows >= 3 stay zero (fully_fused_mlp.py:136)
+            const uint32_t f_in[5] = {32, 64, 32, 64, 64};
+            float* const f_dst[5] = {dwd + WD_W0, dwd + WD_WOUT, dwr + WR_W0, dwr + WR_W1, dwr + WR_WOUT};
+#pragma unroll 1
+            for (int m = 0; m < 5; ++m) {
+#pragma unroll 1
+                for (uint32_t c = 0; c < f_nout[m] / 16; ++c) {
+                    tmem_ld16(tmem_addr(tbase, tq, f_col[m] + 16 * c), v);
+                    if (t < f_in[m]) {
+#pragma unroll
+                        for (int o = 0; o < 16; ++o)
+                            if (16 * c + o < f_valid[m]) red_add_f32(f_dst[m] + (size_t)(16 * c + o) * f_in[m] + t, v[o]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 8) {
+        // ------------------------------------------------------------------ MMA issuer
+        const uint32_t smem_s = smem_u32(smem), a0 = smem_s + S::tile0, a1 = a0 + S::tile_stride;
+        const uint32_t t0 = tbase, t1 = tbase + TB;
+        uint32_t acc = 0;
+        // one stage: wait until all 256 epilogue threads have written their operands, queue the stage's MMAs for both tiles, commit
+#define B3_STAGE(...)                                                                                  \
+        named_bar_sync(B3_READY, B3_EPI_THREADS + 32);                                                 \
+        tc_fence_after();                                                                              \
+        if (elect_one()) { __VA_ARGS__ }                                                               \
+        __syncwarp();
+        for (uint32_t pair = blockIdx.x; pair < npairs; pair += gridDim.x, acc = 1) {
+            const bool wg = !(dbg & 4);
+            B3_STAGE(issue_fwd<32, 64>(t0 + D_H, a0, G_ENC, smem_s + S::w0d); issue_fwd<32, 64>(t1 + D_H, a1, G_ENC, smem_s + S::w0d); mma_commit(bar_d);)
+            B3_STAGE(issue_fwd<64, 16>(t0 + D_S, a0, G_HD, smem_s + S::woutd); issue_fwd<64, 16>(t1 + D_S, a1, G_HD, smem_s + S::woutd); mma_commit(bar_d);)
+            B3_STAGE(issue_fwd<32, 64>(t0 + D_H, a0, G_RIN, smem_s + S::w0r); issue_fwd<32, 64>(t1 + D_H, a1, G_RIN, smem_s + S::w0r); mma_commit(bar_d);)
+            B3_STAGE(issue_fwd<64, 64>(t0 + D_H, a0, G_H1, smem_s + S::w1r); issue_fwd<64, 64>(t1 + D_H, a1, G_H1, smem_s + S::w1r); mma_commit(bar_d);)
+            // B1: dgrad through Woutr ; wgrad Woutr = h2^T dYr
+            B3_STAGE(issue_dgrad<16, 64>(t0 + D_H, a0, B3_G_DY, smem_s + S::woutr); issue_dgrad<16, 64>(t1 + D_H, a1, B3_G_DY, smem_s + S::woutr); mma_commit(bar_d);
+                     if (wg) { issue_wgrad<16>(tbase + A_WOUTR, a0, G_H2B, a0, B3_G_DY, acc); issue_wgrad<16>(tbase + A_WOUTR, a1, G_H2B, a1, B3_G_DY, 1); })
+            // B2: dgrad through W1r ; wgrad W1r = h1^T g_h2
+            B3_STAGE(issue_dgrad<64, 64>(t0 + D_H, a0, B3_G_GX, smem_s + S::w1r); issue_dgrad<64, 64>(t1 + D_H, a1, B3_G_GX, smem_s + S::w1r); mma_commit(bar_d);
+                     if (wg) { issue_wgrad<64>(tbase + A_W1R, a0, G_H1, a0, B3_G_GX, acc); issue_wgrad<64>(tbase + A_W1R, a1, G_H1, a1, B3_G_GX, 1); })
+            // B3: dgrad through W0r (g_h1 lives in the h2 slab) ; wgrad W0r = rin^T g_h1
+            B3_STAGE(issue_dgrad<64, 32>(t0 + D_S, a0, G_H2B, smem_s + S::w0r); issue_dgrad<64, 32>(t1 + D_S, a1, G_H2B, smem_s + S::w0r); mma_commit(bar_d);
+                     if (wg) { issue_wgrad<64>(tbase + A_W0R, a0, G_RIN, a0, G_H2B, acc); issue_wgrad<64>(tbase + A_W0R, a1, G_RIN, a1, G_H2B, 1); })
+            // B4: dgrad through Woutd (dYd lives in the dYr slab) ; wgrad Woutd = hd^T dYd
+            B3_STAGE(issue_dgrad<16, 64>(t0 + D_H, a0, B3_G_DY, smem_s + S::woutd); issue_dgrad<16, 64>(t1 + D_H, a1, B3_G_DY, smem_s + S::woutd); mma_commit(bar_d);
+                     if (wg) { issue_wgrad<16>(tbase + A_WOUTD, a0, G_HD, a0, B3_G_DY, acc); issue_wgrad<16>(tbase + A_WOUTD, a1, G_HD, a1, B3_G_DY, 1); })
+            // B5: dgrad through W0d (g_hd lives in the h1 slab) ; wgrad W0d = enc^T g_hd ; then everything of this pair is queued
+            B3_STAGE(issue_dgrad<64, 32>(t0 + D_S, a0, G_H1, smem_s + S::w0d); issue_dgrad<64, 32>(t1 + D_S, a1, G_H1, smem_s + S::w0d); mma_commit(bar_d);
+                     if (wg) { issue_wgrad<64>(tbase + A_W0D, a0, G_ENC, a0, G_H1, acc); issue_wgrad<64>(tbase + A_W0D, a1, G_ENC, a1, G_H1, 1); }
+                     mma_commit(bar_w);)
+        }
+#undef B3_STAGE
+    } else {
+        // ------------------------------------------------------------------ scatter (HashEncode.h:339-347), 128 threads: tile A then tile B
+        const uint32_t ts = tid - (B3_EPI_THREADS + 32), level = ts & 15, sub = ts >> 4;
+        const NgpLevel lv = s_lv[level];
+        __half2* gg = reinterpret_cast<__half2*>(grid_grad) + lv.offset;
+        uint32_t it = 0;
+        for (uint32_t pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++it) {
+            const uint32_t buf = it & 1;
+            named_bar_sync(B3_FULL, B3_EPI_THREADS + 32 * B3_SCATTER_WARPS);
+#pragma unroll 1
+            for (uint32_t T = 0; T < 2; ++T) {
+                const uint32_t row0 = (2 * pair + T) * ROWS;
+                const float* s_coords = reinterpret_cast<const float*>(smem + S::coords + (2 * T + buf) * 3584);
+                const uint8_t* denc = smem + S::tile0 + T * S::tile_stride + B3_G_DENC * GB;
+                uint32_t cgx = 0xffffffffu, cgy = 0, cgz = 0, idx[8];
+                float2 accv[8];
+                bool dirty = false;
+#pragma unroll 1
+                for (int k = 0; k < 16; ++k) {
+                    const uint32_t p = 16 * sub + k;
+                    if (row0 + p >= n_live || (dbg & 2)) break;
+                    const __half2 d = *reinterpret_cast<const __half2*>(denc + (size_t)(level >> 2) * GB + p * 16 + (level & 3) * 4);
+                    const float2 df = __half22float2(d);
+                    if (df.x == 0.f && df.y == 0.f) continue;
+                    const HashCell hc = hash_cell(lv, s_coords[p * 7], s_coords[p * 7 + 1], s_coords[p * 7 + 2]);
+                    if (hc.gx != cgx || hc.gy != cgy || hc.gz != cgz) {
+                        if (dirty && !(dbg & 1)) {
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) red_add_h2(gg + idx[c], accv[c].x, accv[c].y);
+                        }
+                        cgx = hc.gx; cgy = hc.gy; cgz = hc.gz;
+                        hash_cell_indices(lv, cgx, cgy, cgz, idx);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) accv[c] = make_float2(0.f, 0.f);
+                        dirty = true;
+                    }
+                    float w[8];
+                    hash_cell_weights(hc, w);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) { accv[c].x = fmaf(df.x, w[c], accv[c].x); accv[c].y = fmaf(df.y, w[c], accv[c].y); }
+                }
+                if (dirty && !(dbg & 1)) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) red_add_h2(gg + idx[c], accv[c].x, accv[c].y);
+                }
+            }
+            if (pair + gridDim.x < npairs) named_bar_arrive(B3_EMPTY, B3_EPI_THREADS + 32 * B3_SCATTER_WARPS);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_free(tbase, 512);
+}
+
 }  // namespace
 
 extern "C" {
@@ -830,8 +1116,15 @@ int ngp_network_bwd(void* stream, uint32_t n_max, const uint32_t* n_dev, const f
     const uint32_t ntiles = (n_max + ROWS - 1) / ROWS;
     // timing experiments only (results are wrong with any bit set): 1 = no atomics, 2 = no scatter, 4 = no weight-gradient MMAs
     static const uint32_t dbg = getenv("NGP_BWD_DEBUG") ? (uint32_t)atoi(getenv("NGP_BWD_DEBUG")) : 0u;
-    static const bool one_chain = getenv("NGP_BWD_ONE_CHAIN") != nullptr;     // A/B switch while both kernels exist
-    if (one_chain) {
+    static const bool one_chain = getenv("NGP_BWD_ONE_CHAIN") != nullptr;     // A/B switches while the kernels coexist
+    static const bool two_chain = getenv("NGP_BWD_TWO_CHAIN") != nullptr;
+    if (!one_chain && !two_chain) {
+        NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd3::total));
+        const uint32_t grid_dim = min((ntiles + 1) / 2, (uint32_t)ngp_num_sms());
+        network_bwd256_kernel<<<grid_dim, B3_THREADS, SmemBwd3::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
+                                                                           (const __half*)w_density, (const __half*)w_rgb, (const __half*)dout,
+                                                                           (__half*)grid_grad, dw_density, dw_rgb, ngp_err_flag(), dbg);
+    } else if (one_chain) {
         NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd::total));
         const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms());
         network_bwd_kernel<<<grid_dim, 128 + 32 * SW, SmemBwd::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
