@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libngp_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-EXTRA = os.environ.get("NGP_NVCC_FLAGS", "").split()          # e.g. -DNGP_TIMELINE for tools/dbg_timeline.py
+EXTRA = os.environ.get("NGP_NVCC_FLAGS", "").split()          # extra nvcc flags for experiments
 COMMON = EXTRA + ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-I", os.path.join(HERE, "..", "include")]
 # per-file extra flags: the sampler / grid code must not contract multiply-adds on its own (bit-exact sample indices)
 SOURCES = {

@@ -16,13 +16,6 @@
 
 int* ngp_err_flag();
 
-#ifdef NGP_TIMELINE
-__device__ long long g_dbg_bwd[64];
-#define DBGB(i) do { if (blockIdx.x == 0 && t == 0 && tile == blockIdx.x + gridDim.x) g_dbg_bwd[i] = clock64(); } while (0)
-#else
-#define DBGB(i) do { } while (0)
-#endif
-
 namespace {
 using namespace mlp;
 
@@ -46,22 +39,6 @@ struct SmemFwd {
     static constexpr uint32_t bar = levels + N_LEVELS * 32;
     static constexpr uint32_t total = bar + 64;
 };
-// gradient slab groups (backward)
-constexpr uint32_t Q_DYR = 0, Q_GH2 = 2, Q_GH1 = 10, Q_DYD = 18, Q_GHD = 22, Q_DENC = 30 /* two buffers of 4 groups */, Q_TOTAL = 38;
-struct SmemBwd {
-    static constexpr uint32_t coords = 0;                         // two buffers of 128 x 7 f32 (3584 B each)
-    static constexpr uint32_t act = 8192;                         // 32 groups
-    static constexpr uint32_t grd = act + 32 * GB;                // 34 groups
-    static constexpr uint32_t w0d = grd + Q_TOTAL * GB;
-    static constexpr uint32_t woutd = w0d + 64 * 32 * 2;
-    static constexpr uint32_t w0r = woutd + 16 * 64 * 2;
-    static constexpr uint32_t w1r = w0r + 64 * 32 * 2;
-    static constexpr uint32_t woutr = w1r + 64 * 64 * 2;
-    static constexpr uint32_t levels = woutr + 16 * 64 * 2;
-    static constexpr uint32_t bar = levels + N_LEVELS * 32;
-    static constexpr uint32_t total = bar + 64;
-};
-
 template <class S>
 __device__ __forceinline__ void stage_all_weights(uint8_t* smem, const __half* wd, const __half* wr, uint32_t t) {
     stage_weights(smem + S::w0d, wd + WD_W0, 64, 32, t, 128);
@@ -246,550 +223,6 @@ network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
     if (warp == 0) tmem_free(tbase, 128);
 }
 
-// Warp-specialised backward: warps 0-3 ("chain") run the tensor-core MLP chain of tile i while warps 4-7 ("scatter") push the
-// hash-grid gradient of tile i-1 from a double-buffered dL/d(enc) slab.  The scatter is bound by the L2 atomic rate, the chain
-// by its serial stage latency; neither keeps an SM busy alone (tools/dbg_timeline_bwd.py: 19 k vs 32 k cycles per tile), so
-// they overlap.  Hand-off through named barriers FULL[b] / EMPTY[b] (ids 2+b / 4+b, 256 threads: 128 arrive + 128 sync).
-// Scatter warps: 4 (16-sample runs).  Measured on the lego stand-in, us per backward: 2 warps x 32-sample runs 294, 4 x 16 177,
-// 8 x 8 209, 8 warps x 16-sample runs with the cell's corners split over two threads 250 -- longer runs save atomics, but more
-// scatter warps starve the MLP chain, which is the critical path of this kernel.
-constexpr int SW = 4;                             // scatter warps (16-sample runs per thread)
-__global__ void __launch_bounds__(128 + 32 * SW)
-network_bwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const float* __restrict__ coords, const __half* __restrict__ enc_save,
-                   const NgpLevel* __restrict__ levels, const __half* __restrict__ wd, const __half* __restrict__ wr,
-                   const __half* __restrict__ dout, __half* __restrict__ grid_grad, float* __restrict__ dwd, float* __restrict__ dwr,
-                   int* __restrict__ err, uint32_t dbg) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    using S = SmemBwd;
-    constexpr uint32_t NT = 128 + 32 * SW;                 // threads per CTA
-    const uint32_t t = threadIdx.x, warp = t >> 5;
-    const bool is_chain = warp < 4;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::bar);
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
-    NgpLevel* s_lv = reinterpret_cast<NgpLevel*>(smem + S::levels);
-    uint8_t* act = smem + S::act;
-    uint8_t* grd = smem + S::grd;
-
-    stage_weights(smem + S::w0d, wd + WD_W0, 64, 32, t, NT);
-    stage_weights(smem + S::woutd, wd + WD_WOUT, 16, 64, t, NT);
-    stage_weights(smem + S::w0r, wr + WR_W0, 64, 32, t, NT);
-    stage_weights(smem + S::w1r, wr + WR_W1, 64, 64, t, NT);
-    stage_weights(smem + S::woutr, wr + WR_WOUT, 16, 64, t, NT);
-    if (t < N_LEVELS) s_lv[t] = levels[t];
-    // dYr columns 4..15, the dYd pad groups: zero once (never rewritten)
-    for (uint32_t i = t; i < Q_TOTAL * GB / 16; i += NT) *reinterpret_cast<uint4*>(grd + i * 16) = make_uint4(0, 0, 0, 0);
-    uint64_t* bar_w = bar + 2;                                   // completes when the 5 wgrad batches of a tile are done
-    if (t == 0) { mbar_init(bar, 1); mbar_init(bar_w, 5); fence_mbar_init(); }
-    if (warp == 0) tmem_alloc(tmem_ptr, 512);
-    sync_before_issue();
-    const uint32_t tbase = *tmem_ptr;
-    const uint32_t smem_s = smem_u32(smem), act_s = smem_s + S::act, grd_s = smem_s + S::grd;
-    // TMEM columns
-    const uint32_t D_H = 0, D_S = 64, A_W0D = 96, A_WOUTD = 160, A_W0R = 176, A_W1R = 240, A_WOUTR = 304;
-    const uint32_t n_live = n_dev ? min(*n_dev, n_max) : n_max;
-    const uint32_t ntiles = (n_live + ROWS - 1) / ROWS;
-    uint32_t acc = 0;
-
-    if (is_chain) {
-        // ------------------------------------------------------------------ MLP chain (threads 0..127, thread t = row t)
-        Pipe pipe{bar, 0, err};
-        // software prefetch of the next tile's inputs (7 coordinate words, the 64 B encoded row, the 8 B output gradient)
-        float pf_c[7];
-        uint4 pf_e[4];
-        uint2 pf_d;
-        auto prefetch = [&](uint32_t tile_) {
-            const uint32_t r0 = tile_ * ROWS, r = r0 + t;
-            const bool ok = r < n_live;
-#pragma unroll
-            for (int j = 0; j < 7; ++j) {
-                const uint32_t i = t + 128 * j;
-                pf_c[j] = (r0 + i / 7 < n_live) ? __ldg(coords + (size_t)r0 * 7 + i) : 0.f;
-            }
-            const uint4* es = reinterpret_cast<const uint4*>(enc_save + (size_t)r * 32);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) pf_e[g] = ok ? __ldg(es + g) : make_uint4(0, 0, 0, 0);
-            pf_d = ok ? __ldg(reinterpret_cast<const uint2*>(dout) + r) : make_uint2(0, 0);
-        };
-        if (blockIdx.x < ntiles) prefetch(blockIdx.x);
-        uint32_t it = 0;
-        for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, acc = 1, ++it) {
-            const uint32_t buf = it & 1;
-            float* s_coords = reinterpret_cast<float*>(smem + S::coords + buf * 3584);
-            if (it >= 2) named_bar_sync(4 + buf, NT);          // the scatter of tile it-2 has released coords[buf] / d_enc[buf]
-            if (it >= 1) { if (!mbar_wait(bar_w, (it - 1) & 1)) atomicExch(err, 2); }   // the previous tile's wgrad MMAs have read their slabs
-            DBGB(0);
-#pragma unroll
-            for (int j = 0; j < 7; ++j) s_coords[t + 128 * j] = pf_c[j];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(act + (G_ENC + g) * GB + t * 16) = pf_e[g];
-            const uint32_t dsig = pf_d.y >> 16;
-            *reinterpret_cast<uint4*>(grd + Q_DYR * GB + t * 16) = make_uint4(pf_d.x, pf_d.y & 0xFFFFu, 0, 0);
-            if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x);   // in flight during the whole chain
-            DBGB(1);
-            sync_before_issue<true>();
-            DBGB(2);
-            forward_chain<S, G_H2B, true>(smem, G_ENC, s_coords, tbase, pipe, t, warp, false);
-            DBGB(3);
-            // B1: g_h2 = (dYr Woutr) . relu'(h2) ; wgrad Woutr
-            if (warp == 0) { if (elect_one()) { issue_dgrad<16, 64>(tbase + D_H, grd_s, Q_DYR, smem_s + S::woutr); DBGB(4); pipe.commit(); } __syncwarp(); }
-            if (warp == 1) { if (elect_one()) { if (!(dbg & 4)) issue_wgrad<16>(tbase + A_WOUTR, act_s, G_H2B, grd_s, Q_DYR, acc); mma_commit(bar_w); } __syncwarp(); }   // weight gradient: issued by a second thread, off the critical path
-            pipe.wait();
-            DBGB(5);
-            epi_dgrad_mask(tbase, D_H, warp, act, G_H2B, grd, Q_GH2, t, nullptr);
-            DBGB(6);
-            sync_before_issue<true>();
-            DBGB(7);
-            // B2: g_h1 = (g_h2 W1r) . relu'(h1) ; wgrad W1r
-            if (warp == 0) { if (elect_one()) { issue_dgrad<64, 64>(tbase + D_H, grd_s, Q_GH2, smem_s + S::w1r); DBGB(8); pipe.commit(); DBGB(21); } __syncwarp(); }
-            if (warp == 1) { if (elect_one()) { if (!(dbg & 4)) issue_wgrad<64>(tbase + A_W1R, act_s, G_H1, grd_s, Q_GH2, acc); mma_commit(bar_w); } __syncwarp(); }   // weight gradient: issued by a second thread, off the critical path
-            pipe.wait();
-            DBGB(9);
-#ifdef NGP_TIMELINE
-            {   // timeline builds only: epi_dgrad_mask + sync_before_issue of this stage spelled out, one stamp per step (16..20)
-                uint32_t r[4][16];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) tmem_ld16_nowait(tmem_addr(tbase, warp & 3, D_H + 16 * c), r[c]);
-                DBGB(16);
-                tmem_ld_wait();
-                DBGB(17);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float v[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[c][i]);
-                    uint4 lo, hi;
-                    pack16(v, lo, hi);
-                    lo = relu_mask8(lo, slab_load8(act, G_H1 + 2 * c, t));
-                    hi = relu_mask8(hi, slab_load8(act, G_H1 + 2 * c + 1, t));
-                    slab_store16(grd, Q_GH1 + 2 * c, t, lo, hi);
-                }
-                DBGB(18);
-                tc_fence_before();
-                fence_proxy_async_smem();
-                DBGB(19);
-                named_bar_sync(1, 128);
-                DBGB(20);
-                tc_fence_after();
-            }
-#else
-            epi_dgrad_mask(tbase, D_H, warp, act, G_H1, grd, Q_GH1, t, nullptr);
-            sync_before_issue<true>();
-#endif
-            DBGB(10);
-            // B3: d_rin = g_h1 W0r (32 cols; the last 16 are dL/dSH, unused) ; wgrad W0r
-            if (warp == 0) { if (elect_one()) { issue_dgrad<64, 32>(tbase + D_S, grd_s, Q_GH1, smem_s + S::w0r); pipe.commit(); } __syncwarp(); }
-            if (warp == 1) { if (elect_one()) { if (!(dbg & 4)) issue_wgrad<64>(tbase + A_W0R, act_s, G_RIN, grd_s, Q_GH1, acc); mma_commit(bar_w); } __syncwarp(); }   // weight gradient: issued by a second thread, off the critical path
-            pipe.wait();
-            {
-                float v[16];
-                tmem_ld16(tmem_addr(tbase, warp, D_S), v);
-                v[0] += __half2float(__ushort_as_half((unsigned short)dsig));   // + dL/dsigma (ngp_network.py:83)
-                uint4 lo, hi;
-                pack16(v, lo, hi);
-                slab_store16(grd, Q_DYD, t, lo, hi);
-            }
-            sync_before_issue<true>();
-            // B4: g_hd = (dYd Woutd) . relu'(hd) ; wgrad Woutd
-            if (warp == 0) { if (elect_one()) { issue_dgrad<16, 64>(tbase + D_H, grd_s, Q_DYD, smem_s + S::woutd); pipe.commit(); } __syncwarp(); }
-            if (warp == 1) { if (elect_one()) { if (!(dbg & 4)) issue_wgrad<16>(tbase + A_WOUTD, act_s, G_HD, grd_s, Q_DYD, acc); mma_commit(bar_w); } __syncwarp(); }   // weight gradient: issued by a second thread, off the critical path
-            pipe.wait();
-            epi_dgrad_mask(tbase, D_H, warp, act, G_HD, grd, Q_GHD, t, nullptr);
-            sync_before_issue<true>();
-            // B5: d_enc = g_hd W0d ; wgrad W0d
-            if (warp == 0) { if (elect_one()) { issue_dgrad<64, 32>(tbase + D_S, grd_s, Q_GHD, smem_s + S::w0d); pipe.commit(); } __syncwarp(); }
-            if (warp == 1) { if (elect_one()) { if (!(dbg & 4)) issue_wgrad<64>(tbase + A_W0D, act_s, G_ENC, grd_s, Q_GHD, acc); mma_commit(bar_w); } __syncwarp(); }   // weight gradient: issued by a second thread, off the critical path
-            pipe.wait();
-            {
-                float v[16];
-                uint4 lo, hi;
-                tmem_ld16(tmem_addr(tbase, warp, D_S), v);
-                pack16(v, lo, hi);
-                slab_store16(grd, Q_DENC + 4 * buf, t, lo, hi);
-                tmem_ld16(tmem_addr(tbase, warp, D_S + 16), v);
-                pack16(v, lo, hi);
-                slab_store16(grd, Q_DENC + 4 * buf + 2, t, lo, hi);
-            }
-            tc_fence_before();
-            named_bar_arrive(2 + buf, NT);                      // FULL[buf]: dL/d(enc) and coords of this tile are ready
-            DBGB(11);
-        }
-        // flush weight gradients (lane = input feature, column = output feature)
-        if (acc) {
-            if (!mbar_wait(bar_w, (it - 1) & 1)) atomicExch(err, 2);
-            tc_fence_after();
-            float v[16];
-            const uint32_t f_col[5] = {A_W0D, A_WOUTD, A_W0R, A_W1R, A_WOUTR};
-            const uint32_t f_nout[5] = {64, 16, 64, 64, 16}, f_valid[5] = {64, 16, 64, 64, 3};   // colour Wout rows >= 3 stay zero (fully_fused_mlp.py:136)
-            const uint32_t f_in[5] = {32, 64, 32, 64, 64};
-            float* const f_dst[5] = {dwd + WD_W0, dwd + WD_WOUT, dwr + WR_W0, dwr + WR_W1, dwr + WR_WOUT};
-#pragma unroll 1
-            for (int m = 0; m < 5; ++m) {
-#pragma unroll 1
-                for (uint32_t c = 0; c < f_nout[m] / 16; ++c) {
-                    tmem_ld16(tmem_addr(tbase, warp, f_col[m] + 16 * c), v);
-                    if (t < f_in[m]) {
-#pragma unroll
-                        for (int o = 0; o < 16; ++o)
-                            if (16 * c + o < f_valid[m]) red_add_f32(f_dst[m] + (size_t)(16 * c + o) * f_in[m] + t, v[o]);
-                    }
-                }
-            }
-        }
-    } else {
-        // ------------------------------------------------------------------ scatter (threads 128..255)
-        // HashEncode.h:339-347.  Thread (level, sub) walks its 16 consecutive samples, accumulates the 8 corner contributions in
-        // fp32 registers while the grid cell stays the same and issues the f16x2 reductions only when the cell changes.
-        const uint32_t ts = t - 128, level = ts & 15, sub = ts >> 4;
-        const NgpLevel lv = s_lv[level];
-        __half2* gg = reinterpret_cast<__half2*>(grid_grad) + lv.offset;
-        uint32_t it = 0;
-        for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            const uint32_t buf = it & 1, row0 = tile * ROWS;
-            const float* s_coords = reinterpret_cast<const float*>(smem + S::coords + buf * 3584);
-            named_bar_sync(2 + buf, NT);                        // FULL[buf]
-            uint32_t cgx = 0xffffffffu, cgy = 0, cgz = 0, idx[8];
-            float2 accv[8];
-            bool dirty = false;
-            constexpr int PTS = 64 / SW;                         // consecutive samples per scatter thread
-#pragma unroll 1
-            for (int k = 0; k < PTS; ++k) {
-                const uint32_t p = PTS * sub + k;
-                if (row0 + p >= n_live || (dbg & 2)) break;
-                const __half2 d = *reinterpret_cast<const __half2*>(grd + (size_t)(Q_DENC + 4 * buf + (level >> 2)) * GB + p * 16 + (level & 3) * 4);
-                const float2 df = __half22float2(d);
-                if (df.x == 0.f && df.y == 0.f) continue;
-                const HashCell hc = hash_cell(lv, s_coords[p * 7], s_coords[p * 7 + 1], s_coords[p * 7 + 2]);
-                if (hc.gx != cgx || hc.gy != cgy || hc.gz != cgz) {
-                    if (dirty && !(dbg & 1)) {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) red_add_h2(gg + idx[c], accv[c].x, accv[c].y);
-                    }
-                    cgx = hc.gx; cgy = hc.gy; cgz = hc.gz;
-                    hash_cell_indices(lv, cgx, cgy, cgz, idx);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) accv[c] = make_float2(0.f, 0.f);
-                    dirty = true;
-                }
-                float w[8];
-                hash_cell_weights(hc, w);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) { accv[c].x = fmaf(df.x, w[c], accv[c].x); accv[c].y = fmaf(df.y, w[c], accv[c].y); }
-            }
-            if (dirty && !(dbg & 1)) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) red_add_h2(gg + idx[c], accv[c].x, accv[c].y);
-            }
-            if (tile + 2 * gridDim.x < ntiles) named_bar_arrive(4 + buf, NT);   // EMPTY[buf] for the chain's tile it+2
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_free(tbase, 512);
-}
-
-
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Backward with TWO MLP chains per CTA (network_bwd2_kernel).
-//
-// One chain is a strictly serial sequence of 10 MMA -> commit -> TMEM load -> convert -> shared store -> barrier stages per
-// 128-sample tile (tools/dbg_timeline_bwd.py: ~1.6 k cycles a stage once the MMAs issue at the hardware rate), during which the
-// tensor pipe, the LSU and three quarters of the issue slots idle.  So the CTA runs two of them on independent tile streams:
-//     chain group 0 (warps 0-3) | chain group 1 (warps 4-7) | scatter group 0 (warps 8-11) | scatter group 1 (warps 12-15),
-// each chain group with its own activation slabs, TMEM columns, mbarriers and named barriers.  That fits because the per-chain
-// footprint is halved:
-//   * every gradient slab is written IN PLACE over the activation it is derived from: g_h2 over h2, g_h1 over h1, dYd over the
-//     colour net's input, g_hd over hd.  Safe because the only other reader of that activation is the weight-gradient MMA of the
-//     SAME stage (issued together with the dgrad MMA, tracked by its own mbarrier), and each thread reads and writes only its own row;
-//   * dYr (the 4-wide output gradient padded to K = 16) borrows the first two groups of the dL/d(enc) buffer of the tile, which is
-//     written only at the very end of the chain;
-//   * the W0 weight gradients (32 inputs x 64 outputs) are accumulated transposed (lane = output feature, 32 columns):
-//     160 accumulator + 96 working columns = 256 TMEM columns per chain, 512 per CTA.
-// Shared memory per chain: 7 KB coords + 64 KB activations + 16 KB dL/d(enc) (2 buffers); shared by both: 20 KB weights.
-// The group index is a template parameter so that every MMA descriptor stays a compile-time offset (see issue_fwd).
-constexpr uint32_t BW2_GROUPS = 2;
-struct SmemBwd2 {
-    static constexpr uint32_t coords = 0;                         // per chain group: two buffers of 128 x 7 f32 (3584 B each)
-    static constexpr uint32_t act0 = coords + BW2_GROUPS * 2 * 3584;  // per chain group: 32 activation groups + 8 dL/d(enc) groups (must follow: M=128 wgrad reads run into them)
-    static constexpr uint32_t act_stride = 40 * GB;
-    static constexpr uint32_t w0d = act0 + BW2_GROUPS * act_stride;
-    static constexpr uint32_t woutd = w0d + 64 * 32 * 2;
-    static constexpr uint32_t w0r = woutd + 16 * 64 * 2;
-    static constexpr uint32_t w1r = w0r + 64 * 32 * 2;
-    static constexpr uint32_t woutr = w1r + 64 * 64 * 2;
-    static constexpr uint32_t levels = woutr + 16 * 64 * 2;
-    static constexpr uint32_t bar = levels + N_LEVELS * 32;       // per chain group: 2 mbarriers; then the TMEM base word
-    static constexpr uint32_t total = bar + 64;
-};
-static_assert(SmemBwd2::total <= 227 * 1024, "backward CTA does not fit");
-template <uint32_t CG>
-struct SmemBwd2G : SmemBwd2 {                                     // the view forward_chain needs: this group's activation slabs
-    static constexpr uint32_t act = SmemBwd2::act0 + CG * SmemBwd2::act_stride;
-};
-
-// dgrad epilogue, in place: D[:, 0..64) -> fp16 -> masked by ReLU'(h) -> written over h (groups [g, g+8)).  The stores wait for
-// `bar_w`: the weight-gradient MMAs of this stage, which read h through the async proxy.
-static __device__ __noinline__ bool epi_dgrad_mask_inplace(uint32_t tbase, uint32_t dcol, uint32_t warp, uint8_t* slab, uint32_t g, uint32_t t,
-                                                           uint64_t* bar_w, uint32_t phase_w) {
-    uint32_t r[4][16];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) tmem_ld16_nowait(tmem_addr(tbase, warp & 3, dcol + 16 * c), r[c]);
-    tmem_ld_wait();
-    uint4 o[8];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[c][i]);
-        uint4 lo, hi;
-        pack16(v, lo, hi);
-        o[2 * c] = relu_mask8(lo, slab_load8(slab, g + 2 * c, t));
-        o[2 * c + 1] = relu_mask8(hi, slab_load8(slab, g + 2 * c + 1, t));
-    }
-    const bool ok = mbar_wait(bar_w, phase_w);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(slab + (size_t)(g + c) * GB + t * 16) = o[c];
-    return ok;
-}
-
-// MLP chain of group CG (128 threads, thread t = row t, tq = TMEM lane quarter = warp index inside the group)
-template <uint32_t CG>
-__device__ __forceinline__ void bwd2_chain(uint8_t* smem, uint32_t t, uint32_t tq, uint32_t n_live, uint32_t ntiles, const float* __restrict__ coords,
-                                           const __half* __restrict__ enc_save, const __half* __restrict__ dout, float* __restrict__ dwd,
-                                           float* __restrict__ dwr, int* __restrict__ err, uint32_t dbg, uint32_t tmem_base) {
-    using S = SmemBwd2G<CG>;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::bar);
-    uint64_t* bar = bars + 2 * CG;                               // dgrad / forward MMAs of this chain group are done
-    uint64_t* bar_w = bar + 1;                                   // the weight-gradient MMAs of the current stage are done
-    uint8_t* act = smem + S::act;
-    uint8_t* denc = act + 32 * GB;
-    constexpr uint32_t coords_off = S::coords + CG * 2 * 3584;
-    constexpr uint32_t B_CHAIN = 1 + 6 * CG, B_FULL = 2 + 6 * CG, B_EMPTY = 4 + 6 * CG;   // named barriers of this group
-    const uint32_t tbase = tmem_base + CG * 256;                 // this chain group's 256 columns
-    const uint32_t smem_s = smem_u32(smem), act_s = smem_s + S::act, denc_s = act_s + 32 * GB;
-    // TMEM columns (relative to the group's base): working tiles, then the five weight-gradient accumulators
-    // (W0d / W0r transposed: lane = output feature)
-    constexpr uint32_t D_H = 0, D_S = 64, A_W0D = 96, A_WOUTD = 128, A_W0R = 144, A_W1R = 176, A_WOUTR = 240;
-    const uint32_t tile0 = blockIdx.x * BW2_GROUPS + CG, tile_step = gridDim.x * BW2_GROUPS;   // tile stream of this group
-    uint32_t acc = 0;
-    Pipe pipe{bar, 0, err};
-    uint32_t phase_w = 0;
-    // software prefetch of the next tile's inputs (7 coordinate words, the 64 B encoded row, the 8 B output gradient)
-    float pf_c[7];
-    uint4 pf_e[4];
-    uint2 pf_d;
-    auto prefetch = [&](uint32_t tile_) {
-        const uint32_t r0 = tile_ * ROWS, r = r0 + t;
-        const bool ok = r < n_live;
-#pragma unroll
-        for (int j = 0; j < 7; ++j) {
-            const uint32_t i = t + 128 * j;
-            pf_c[j] = (r0 + i / 7 < n_live) ? __ldg(coords + (size_t)r0 * 7 + i) : 0.f;
-        }
-        const uint4* es = reinterpret_cast<const uint4*>(enc_save + (size_t)r * 32);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) pf_e[g] = ok ? __ldg(es + g) : make_uint4(0, 0, 0, 0);
-        pf_d = ok ? __ldg(reinterpret_cast<const uint2*>(dout) + r) : make_uint2(0, 0);
-    };
-    auto wait_w = [&]() {
-        if (!mbar_wait(bar_w, phase_w)) atomicExch(err, 2);
-        phase_w ^= 1;
-    };
-    // one stage: the elected thread issues the dgrad MMAs (-> bar) and the weight-gradient MMAs that read the same operands (-> bar_w)
-#define BW2_ISSUE(DGRAD, WGRAD)                                                                                              \
-    if (tq == 0) {                                                                                                            \
-        if (elect_one()) { DGRAD; pipe.commit(); if (!(dbg & 4)) { WGRAD; } mma_commit(bar_w); }                              \
-        __syncwarp();                                                                                                         \
-    }
-    if (tile0 < ntiles) prefetch(tile0);
-    uint32_t it = 0;
-    for (uint32_t tile = tile0; tile < ntiles; tile += tile_step, acc = 1, ++it) {
-        const uint32_t buf = it & 1;
-        float* s_coords = reinterpret_cast<float*>(smem + coords_off + buf * 3584);
-        uint8_t* denc_b = denc + buf * 4 * GB;
-        if (it >= 2) named_bar_sync(B_EMPTY + buf, 256);        // the scatter of tile it-2 has released coords[buf] / d_enc[buf]
-#pragma unroll
-        for (int j = 0; j < 7; ++j) s_coords[t + 128 * j] = pf_c[j];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(act + (G_ENC + g) * GB + t * 16) = pf_e[g];
-        const uint32_t dsig = pf_d.y >> 16;
-        *reinterpret_cast<uint4*>(denc_b + t * 16) = make_uint4(pf_d.x, pf_d.y & 0xFFFFu, 0, 0);     // dYr: 3 colour gradients, K padded to 16
-        *reinterpret_cast<uint4*>(denc_b + GB + t * 16) = make_uint4(0, 0, 0, 0);
-        if (tile + tile_step < ntiles) prefetch(tile + tile_step);   // in flight during the whole chain
-        sync_chain(B_CHAIN);
-        forward_chain<S, G_H2B, true>(smem, G_ENC, s_coords, tbase, pipe, t, tq, false, B_CHAIN);
-        // B1: g_h2 = (dYr Woutr) . relu'(h2) over h2 ; wgrad Woutr (h2^T dYr).  dYr lives in the tile's dL/d(enc) buffer (alternates)
-        if (buf) { BW2_ISSUE((issue_dgrad<16, 64>(tbase + D_H, denc_s + 4 * GB, 0, smem_s + S::woutr)),
-                             (issue_wgrad<16>(tbase + A_WOUTR, act_s, G_H2B, denc_s + 4 * GB, 0, acc))) }
-        else     { BW2_ISSUE((issue_dgrad<16, 64>(tbase + D_H, denc_s, 0, smem_s + S::woutr)),
-                             (issue_wgrad<16>(tbase + A_WOUTR, act_s, G_H2B, denc_s, 0, acc))) }
-        pipe.wait();
-        if (!epi_dgrad_mask_inplace(tbase, D_H, tq, act, G_H2B, t, bar_w, phase_w)) atomicExch(err, 2);
-        phase_w ^= 1;
-        sync_chain(B_CHAIN);
-        // B2: g_h1 = (g_h2 W1r) . relu'(h1) over h1 ; wgrad W1r (h1^T g_h2)
-        BW2_ISSUE((issue_dgrad<64, 64>(tbase + D_H, act_s, G_H2B, smem_s + S::w1r)), (issue_wgrad<64>(tbase + A_W1R, act_s, G_H1, act_s, G_H2B, acc)))
-        pipe.wait();
-        if (!epi_dgrad_mask_inplace(tbase, D_H, tq, act, G_H1, t, bar_w, phase_w)) atomicExch(err, 2);
-        phase_w ^= 1;
-        sync_chain(B_CHAIN);
-        // B3: d_rin = g_h1 W0r (32 cols; the last 16 are dL/dSH, unused) -> dYd over the colour input ; wgrad W0r transposed (g_h1^T rin)
-        BW2_ISSUE((issue_dgrad<64, 32>(tbase + D_S, act_s, G_H1, smem_s + S::w0r)), (issue_wgrad<32>(tbase + A_W0R, act_s, G_H1, act_s, G_RIN, acc)))
-        pipe.wait();
-        {
-            float v[16];
-            tmem_ld16(tmem_addr(tbase, tq, D_S), v);
-            v[0] += __half2float(__ushort_as_half((unsigned short)dsig));   // + dL/dsigma (ngp_network.py:83)
-            uint4 lo, hi;
-            pack16(v, lo, hi);
-            wait_w();
-            slab_store16(act, G_RIN, t, lo, hi);
-        }
-        sync_chain(B_CHAIN);
-        // B4: g_hd = (dYd Woutd) . relu'(hd) over hd ; wgrad Woutd (hd^T dYd)
-        BW2_ISSUE((issue_dgrad<16, 64>(tbase + D_H, act_s, G_RIN, smem_s + S::woutd)), (issue_wgrad<16>(tbase + A_WOUTD, act_s, G_HD, act_s, G_RIN, acc)))
-        pipe.wait();
-        if (!epi_dgrad_mask_inplace(tbase, D_H, tq, act, G_HD, t, bar_w, phase_w)) atomicExch(err, 2);
-        phase_w ^= 1;
-        sync_chain(B_CHAIN);
-        // B5: d_enc = g_hd W0d -> dL/d(enc) buffer ; wgrad W0d transposed (g_hd^T enc)
-        BW2_ISSUE((issue_dgrad<64, 32>(tbase + D_S, act_s, G_HD, smem_s + S::w0d)), (issue_wgrad<32>(tbase + A_W0D, act_s, G_HD, act_s, G_ENC, acc)))
-        pipe.wait();
-        {
-            float v[16];
-            uint4 lo, hi;
-            tmem_ld16(tmem_addr(tbase, tq, D_S), v);
-            pack16(v, lo, hi);
-            slab_store16(denc_b, 0, t, lo, hi);
-            tmem_ld16(tmem_addr(tbase, tq, D_S + 16), v);
-            pack16(v, lo, hi);
-            slab_store16(denc_b, 2, t, lo, hi);
-        }
-        wait_w();                                                // enc / g_hd may be overwritten by the next tile from here on
-        tc_fence_before();
-        named_bar_arrive(B_FULL + buf, 256);                     // FULL[buf]: dL/d(enc) and coords of this tile are ready
-    }
-#undef BW2_ISSUE
-    // flush this group's weight gradients
-    if (acc) {
-        tc_fence_after();
-        float v[16];
-        const uint32_t f_col[5] = {A_W0D, A_WOUTD, A_W0R, A_W1R, A_WOUTR};
-        const uint32_t f_out[5] = {64, 16, 64, 64, 16}, f_valid[5] = {64, 16, 64, 64, 3};   // colour Wout rows >= 3 stay zero (fully_fused_mlp.py:136)
-        const uint32_t f_in[5] = {32, 64, 32, 64, 64};
-        const bool f_tr[5] = {true, false, true, false, false};                          // transposed: lane = output feature, column = input
-        float* const f_dst[5] = {dwd + WD_W0, dwd + WD_WOUT, dwr + WR_W0, dwr + WR_W1, dwr + WR_WOUT};
-#pragma unroll 1
-        for (int m = 0; m < 5; ++m) {
-            const uint32_t ncols = f_tr[m] ? f_in[m] : f_out[m], nlanes = f_tr[m] ? f_out[m] : f_in[m];
-#pragma unroll 1
-            for (uint32_t c = 0; c < ncols / 16; ++c) {
-                tmem_ld16(tmem_addr(tbase, tq, f_col[m] + 16 * c), v);
-                if (t < nlanes) {
-#pragma unroll
-                    for (int o = 0; o < 16; ++o) {
-                        const uint32_t out_f = f_tr[m] ? t : 16 * c + o, in_f = f_tr[m] ? 16 * c + o : t;
-                        if (out_f < f_valid[m]) red_add_f32(f_dst[m] + (size_t)out_f * f_in[m] + in_f, v[o]);
-                    }
-                }
-            }
-        }
-    }
-}
-
-// hash-grid scatter of group CG (128 threads): HashEncode.h:339-347 with run-length combining, as in the one-chain kernel
-template <uint32_t CG>
-__device__ __forceinline__ void bwd2_scatter(uint8_t* smem, uint32_t t, uint32_t n_live, uint32_t ntiles, __half* __restrict__ grid_grad, uint32_t dbg) {
-    using S = SmemBwd2G<CG>;
-    const NgpLevel* s_lv = reinterpret_cast<const NgpLevel*>(smem + S::levels);
-    const uint8_t* denc = smem + S::act + 32 * GB;
-    constexpr uint32_t coords_off = S::coords + CG * 2 * 3584;
-    constexpr uint32_t B_FULL = 2 + 6 * CG, B_EMPTY = 4 + 6 * CG;
-    const uint32_t tile0 = blockIdx.x * BW2_GROUPS + CG, tile_step = gridDim.x * BW2_GROUPS;
-    const uint32_t level = t & 15, sub = t >> 4;
-    const NgpLevel lv = s_lv[level];
-    __half2* gg = reinterpret_cast<__half2*>(grid_grad) + lv.offset;
-    uint32_t it = 0;
-    for (uint32_t tile = tile0; tile < ntiles; tile += tile_step, ++it) {
-        const uint32_t buf = it & 1, row0 = tile * ROWS;
-        const float* s_coords = reinterpret_cast<const float*>(smem + coords_off + buf * 3584);
-        const uint8_t* denc_b = denc + buf * 4 * GB;
-        named_bar_sync(B_FULL + buf, 256);                       // FULL[buf]
-        uint32_t cgx = 0xffffffffu, cgy = 0, cgz = 0, idx[8];
-        float2 accv[8];
-        bool dirty = false;
-#pragma unroll 1
-        for (int k = 0; k < 16; ++k) {
-            const uint32_t p = 16 * sub + k;
-            if (row0 + p >= n_live || (dbg & 2)) break;
-            const __half2 d = *reinterpret_cast<const __half2*>(denc_b + (size_t)(level >> 2) * GB + p * 16 + (level & 3) * 4);
-            const float2 df = __half22float2(d);
-            if (df.x == 0.f && df.y == 0.f) continue;
-            const HashCell hc = hash_cell(lv, s_coords[p * 7], s_coords[p * 7 + 1], s_coords[p * 7 + 2]);
-            if (hc.gx != cgx || hc.gy != cgy || hc.gz != cgz) {
-                if (dirty && !(dbg & 1)) {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) red_add_h2(gg + idx[c], accv[c].x, accv[c].y);
-                }
-                cgx = hc.gx; cgy = hc.gy; cgz = hc.gz;
-                hash_cell_indices(lv, cgx, cgy, cgz, idx);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) accv[c] = make_float2(0.f, 0.f);
-                dirty = true;
-            }
-            float w[8];
-            hash_cell_weights(hc, w);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) { accv[c].x = fmaf(df.x, w[c], accv[c].x); accv[c].y = fmaf(df.y, w[c], accv[c].y); }
-        }
-        if (dirty && !(dbg & 1)) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) red_add_h2(gg + idx[c], accv[c].x, accv[c].y);
-        }
-        if (tile + 2 * tile_step < ntiles) named_bar_arrive(B_EMPTY + buf, 256);   // EMPTY[buf] for the chain's tile it+2
-    }
-}
-
-__global__ void __launch_bounds__(512, 1)
-network_bwd2_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const float* __restrict__ coords, const __half* __restrict__ enc_save,
-                    const NgpLevel* __restrict__ levels, const __half* __restrict__ wd, const __half* __restrict__ wr,
-                    const __half* __restrict__ dout, __half* __restrict__ grid_grad, float* __restrict__ dwd, float* __restrict__ dwr,
-                    int* __restrict__ err, uint32_t dbg) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    using S = SmemBwd2;
-    const uint32_t tid = threadIdx.x, warp = tid >> 5;
-    const uint32_t t = tid & 127, tq = warp & 3;               // row inside the tile, TMEM lane quarter
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::bar);
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
-    NgpLevel* s_lv = reinterpret_cast<NgpLevel*>(smem + S::levels);
-
-    stage_weights(smem + S::w0d, wd + WD_W0, 64, 32, tid, 512);
-    stage_weights(smem + S::woutd, wd + WD_WOUT, 16, 64, tid, 512);
-    stage_weights(smem + S::w0r, wr + WR_W0, 64, 32, tid, 512);
-    stage_weights(smem + S::w1r, wr + WR_W1, 64, 64, tid, 512);
-    stage_weights(smem + S::woutr, wr + WR_WOUT, 16, 64, tid, 512);
-    if (tid < N_LEVELS) s_lv[tid] = levels[tid];
-    // M = 128 weight-gradient operands run past their 8-group slab into whatever follows: keep it finite
-    for (uint32_t i = tid; i < BW2_GROUPS * S::act_stride / 16; i += 512) *reinterpret_cast<uint4*>(smem + S::act0 + i * 16) = make_uint4(0, 0, 0, 0);
-    if (tid == 0) {
-        for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);
-        fence_mbar_init();
-    }
-    if (warp == 0) tmem_alloc(tmem_ptr, 512);
-    sync_before_issue();
-    const uint32_t tmem_base = *tmem_ptr;
-    const uint32_t n_live = n_dev ? min(*n_dev, n_max) : n_max;
-    const uint32_t ntiles = (n_live + ROWS - 1) / ROWS;
-    if (warp < 4) bwd2_chain<0>(smem, t, tq, n_live, ntiles, coords, enc_save, dout, dwd, dwr, err, dbg, tmem_base);
-    else if (warp < 8) bwd2_chain<1>(smem, t, tq, n_live, ntiles, coords, enc_save, dout, dwd, dwr, err, dbg, tmem_base);
-    else if (warp < 12) bwd2_scatter<0>(smem, t, n_live, ntiles, grid_grad, dbg);
-    else bwd2_scatter<1>(smem, t, n_live, ntiles, grid_grad, dbg);
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_free(tmem_base, 512);
-}
-
-
 // ---------------------------------------------------------------------------------------------------------------------
 // Backward over 256 rows per stage (network_bwd256_kernel).
 //
@@ -798,8 +231,9 @@ network_bwd2_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const fl
 // tiles that move through the chain in lock step: a dedicated issuer warp queues the MMAs of tile A and tile B back to back on one
 // commit, the eight epilogue warps (0-3: rows of tile A, 4-7: rows of tile B; two warps per scheduler hide each other's latencies)
 // drain both accumulators at once, and the weight gradients of both tiles accumulate into the same TMEM columns.  Two independent
-// chains per CTA (network_bwd2_kernel) did NOT pay: their in-place gradient slabs put every stage's weight-gradient MMAs on the
-// critical path (profiles/r02_call8: 112 vs 106 us).  Here gradients rotate through buffers that died one stage earlier instead:
+// chains per CTA with in-place gradient slabs did NOT pay (every stage's weight-gradient MMAs sat on the critical path: 112 us against
+// 106 us for one chain of 128 rows, profiles/r02_call8; this kernel: 101 us, profiles/r02_call9).  Here gradients rotate through
+// buffers that died one stage earlier instead:
 //     g_h2 -> GX (the one extra slab), g_h1 -> the h2 slab, dYd -> the dYr slab, g_hd -> the h1 slab,
 // whose last reader (a weight-gradient MMA) was queued before the dgrad MMA the writing epilogue waits for.
 // Warps: 0-7 epilogue, 8 MMA issuer, 9-12 hash-grid scatter of the previous pair of tiles.
@@ -1079,10 +513,6 @@ network_bwd256_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const 
 
 extern "C" {
 
-#ifdef NGP_TIMELINE
-int ngp_debug_read_timeline_bwd(long long* host64) { return (int)cudaMemcpyFromSymbol(host64, g_dbg_bwd, sizeof(long long) * 64); }
-#endif
-
 int ngp_network_fwd(void* stream, uint32_t n_max, const uint32_t* n_dev, const float* coords, const void* grid, const void* levels_dev,
                     const void* w_density, const void* w_rgb, void* out, void* enc_save) {
     if (n_max == 0) return 0;
@@ -1116,27 +546,11 @@ int ngp_network_bwd(void* stream, uint32_t n_max, const uint32_t* n_dev, const f
     const uint32_t ntiles = (n_max + ROWS - 1) / ROWS;
     // timing experiments only (results are wrong with any bit set): 1 = no atomics, 2 = no scatter, 4 = no weight-gradient MMAs
     static const uint32_t dbg = getenv("NGP_BWD_DEBUG") ? (uint32_t)atoi(getenv("NGP_BWD_DEBUG")) : 0u;
-    static const bool one_chain = getenv("NGP_BWD_ONE_CHAIN") != nullptr;     // A/B switches while the kernels coexist
-    static const bool two_chain = getenv("NGP_BWD_TWO_CHAIN") != nullptr;
-    if (!one_chain && !two_chain) {
-        NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd3::total));
-        const uint32_t grid_dim = min((ntiles + 1) / 2, (uint32_t)ngp_num_sms());
-        network_bwd256_kernel<<<grid_dim, B3_THREADS, SmemBwd3::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
-                                                                           (const __half*)w_density, (const __half*)w_rgb, (const __half*)dout,
-                                                                           (__half*)grid_grad, dw_density, dw_rgb, ngp_err_flag(), dbg);
-    } else if (one_chain) {
-        NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd::total));
-        const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms());
-        network_bwd_kernel<<<grid_dim, 128 + 32 * SW, SmemBwd::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
-                                                                         (const __half*)w_density, (const __half*)w_rgb, (const __half*)dout,
-                                                                         (__half*)grid_grad, dw_density, dw_rgb, ngp_err_flag(), dbg);
-    } else {
-        NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd2::total));
-        const uint32_t grid_dim = min((ntiles + BW2_GROUPS - 1) / BW2_GROUPS, (uint32_t)ngp_num_sms());
-        network_bwd2_kernel<<<grid_dim, 512, SmemBwd2::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
-                                                                  (const __half*)w_density, (const __half*)w_rgb, (const __half*)dout,
-                                                                  (__half*)grid_grad, dw_density, dw_rgb, ngp_err_flag(), dbg);
-    }
+    NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd3::total));
+    const uint32_t grid_dim = min((ntiles + 1) / 2, (uint32_t)ngp_num_sms());
+    network_bwd256_kernel<<<grid_dim, B3_THREADS, SmemBwd3::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
+                                                                       (const __half*)w_density, (const __half*)w_rgb, (const __half*)dout,
+                                                                       (__half*)grid_grad, dw_density, dw_rgb, ngp_err_flag(), dbg);
     NGP_LAUNCH_CHECK();
     return 0;
 }

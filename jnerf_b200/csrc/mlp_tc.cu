@@ -19,12 +19,6 @@ using namespace mlp;
 constexpr int IN = 32, WIDTH = 64, OUTP = 16;
 constexpr int MAX_HM = 3;
 
-__device__ long long g_dbg[64];
-#ifdef NGP_TIMELINE   // per-stage clock64 timeline of CTA 0's second tile (tools/dbg_timeline.py)
-#define DBG(i) do { if (blockIdx.x == 0 && t == 0 && tile == blockIdx.x + gridDim.x) g_dbg[i] = clock64(); } while (0)
-#else
-#define DBG(i) do { } while (0)
-#endif
 
 struct FwdSmem {
     // slab ping-pong: 2 x 8 groups
@@ -60,7 +54,6 @@ mlp_fwd_kernel(const __half* __restrict__ W, const __half* __restrict__ X, __hal
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint32_t row = tile * ROWS + t;
         const bool valid = row < n;
-        DBG(0);
         // input row -> slab0 groups 0..3
         {
             const uint4* src = reinterpret_cast<const uint4*>(X + (size_t)row * IN);
@@ -70,18 +63,13 @@ mlp_fwd_kernel(const __half* __restrict__ W, const __half* __restrict__ X, __hal
                 *reinterpret_cast<uint4*>(smem + FwdSmem::slab0 + g * GB + t * 16) = v;
             }
         }
-        DBG(1);
         sync_before_issue();
-        DBG(2);
         uint32_t cur = FwdSmem::slab0, nxt = FwdSmem::slab1;
         // layer 0
         if (warp == 0) { if (elect_one()) { issue_fwd<IN, WIDTH>(tbase + D_H, smem_s + cur, 0, smem_s + FwdSmem::w0); pipe.commit(); } __syncwarp(); }
         pipe.wait();
-        DBG(4);
         epi_hidden_relu(tbase, D_H, warp, smem + nxt, 0, t, (inter && valid) ? inter + ((size_t)0 * n + row) * WIDTH : nullptr);
-        DBG(5);
         sync_before_issue();
-        DBG(6);
         { uint32_t s = cur; cur = nxt; nxt = s; }
         for (uint32_t j = 0; j < nhm; ++j) {
             if (warp == 0) { if (elect_one()) { issue_fwd<WIDTH, WIDTH>(tbase + D_H, smem_s + cur, 0, smem_s + FwdSmem::wh + j * WIDTH * WIDTH * 2); pipe.commit(); } __syncwarp(); }
@@ -90,10 +78,8 @@ mlp_fwd_kernel(const __half* __restrict__ W, const __half* __restrict__ X, __hal
             sync_before_issue();
             { uint32_t s = cur; cur = nxt; nxt = s; }
         }
-        DBG(7);
         if (warp == 0) { if (elect_one()) { issue_fwd<WIDTH, OUTP>(tbase + D_O, smem_s + cur, 0, smem_s + FwdSmem::wout(nhm)); pipe.commit(); } __syncwarp(); }
         pipe.wait();
-        DBG(8);
         {
             float v[16];
             tmem_ld16(tmem_addr(tbase, warp, D_O), v);
@@ -104,7 +90,6 @@ mlp_fwd_kernel(const __half* __restrict__ W, const __half* __restrict__ X, __hal
                 dst[0] = lo; dst[1] = hi;
             }
         }
-        DBG(9);
         // the next tile's sync_before_issue orders these TMEM reads before the next MMA
     }
     tc_fence_before();
@@ -292,7 +277,6 @@ int* ngp_err_flag() { return err_flag(); }
 
 extern "C" {
 
-int ngp_debug_read_timeline(long long* host64) { return (int)cudaMemcpyFromSymbol(host64, g_dbg, sizeof(long long) * 64); }
 
 // Debug aid: 1 if any tcgen05 pipeline wait timed out since the last call (synchronises the device).
 int ngp_debug_timeout_flag(void) {

@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# One GPU call: layout probe, the full GPU suite, bench (lego, fox, timing-only knobs), microbench, backward timeline.  usage: gpu_check.sh [tag]
+# One GPU call: layout probe, the full GPU suite, bench (lego, fox, timing-only knobs), microbench.  usage: gpu_check.sh [tag]
 set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out/${1:-check}
@@ -21,8 +21,4 @@ bench bwd_no_scatter_TIMING_ONLY NGP_BWD_DEBUG=2 --
 bench fox -- --workload fox
 run microbench 300 python tools/microbench.py
 run ref_gpu_compare 400 python tools/ref_gpu_compare.py
-if NGP_NVCC_FLAGS=-DNGP_TIMELINE python jnerf_b200/build.py --force > "$OUT/build_timeline.log" 2>&1; then
-    run timeline_bwd 120 python tools/dbg_timeline_bwd.py
-fi
-python jnerf_b200/build.py --force > "$OUT/build_restore.log" 2>&1 || echo "RESTORING THE DEFAULT BUILD FAILED" >> "$SUM"
 cat "$SUM"
