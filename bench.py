@@ -273,13 +273,12 @@ def run_ours(args):
         b = runner.next_batch()
         host_batches.append(tuple(t.cpu().pin_memory() for t in b))
     h2d = sum(t.numel() * t.element_size() for t in host_batches[0])
-    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
 
     def host_step(k):
+        # the user-facing call for host-fed batches: this step's batch and (for overlap) the next one, both in pinned host memory;
+        # the H2D copies and the D2H of the mean loss run on the Runner's copy stream inside the timed region
         hb = host_batches[k % len(host_batches)]
-        dev = tuple(t.cuda(non_blocking=True) for t in hb)
-        loss = runner.train_step(dev)
-        loss_host.copy_(loss.mean().reshape(1), non_blocking=True)
+        loss_host = runner.train_step_host(hb, host_batches[(k + 1) % len(host_batches)])
         return hb[1].shape[0]
 
     for k in range(max(args.warmup, 3)):

@@ -177,6 +177,9 @@ int ngp_prepare_batch(void* stream, uint32_t n, const uint32_t* pix_index, uint3
                       const float* focal, const float* principal, const void* images_rgba, int image_is_u8, const float* bg,
                       uint32_t* img_id_out, float* rays_o, float* rays_d, float* target);
 
+/* target = rgb*a + bg*(1-a) (runner/runner.py:68) for a batch whose RGBA (n,4) f32 is already gathered (host-fed ray batches) */
+int ngp_blend_target(void* stream, uint32_t n, const float* rgba, const float* bg, float* target);
+
 /* pcg32 helpers (ops/op_include/pcg32/pcg32.h): host-side, pure integer */
 void ngp_pcg32_seed(uint64_t initstate, uint64_t initseq, uint64_t* state_inc);
 void ngp_pcg32_advance(uint64_t* state_inc, int64_t delta);

@@ -139,6 +139,16 @@ __global__ void prepare_batch_kernel(uint32_t n, const uint32_t* __restrict__ pi
     target[3 * (size_t)i + 2] = c.z * c.w + bg[3 * (size_t)i + 2] * ia;
 }
 
+// target = rgb*a + bg*(1-a) (runner.py:68) for a ray batch that arrives with its RGBA already gathered (host-fed batches)
+__global__ void blend_target_kernel(uint32_t n, const float4* __restrict__ rgba, const float* __restrict__ bg, float* __restrict__ target) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 c = rgba[i];
+    const float ia = 1.0f - c.w;
+    target[3 * (size_t)i] = c.x * c.w + bg[3 * (size_t)i] * ia;
+    target[3 * (size_t)i + 1] = c.y * c.w + bg[3 * (size_t)i + 1] * ia;
+    target[3 * (size_t)i + 2] = c.z * c.w + bg[3 * (size_t)i + 2] * ia;
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // 8e: data-parallel gradient exchange + optimizer in ONE kernel over NVLink peer memory.
@@ -382,6 +392,13 @@ int ngp_prepare_batch(void* stream, uint32_t n, const uint32_t* pix_index, uint3
     cudaStream_t s = (cudaStream_t)stream;
     if (image_is_u8) prepare_batch_kernel<uint8_t><<<(n + 127) / 128, 128, 0, s>>>(n, pix_index, W, H, xforms, focal, principal, (const uint8_t*)images_rgba, bg, img_id_out, rays_o, rays_d, target);
     else prepare_batch_kernel<float><<<(n + 127) / 128, 128, 0, s>>>(n, pix_index, W, H, xforms, focal, principal, (const float*)images_rgba, bg, img_id_out, rays_o, rays_d, target);
+    NGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int ngp_blend_target(void* stream, uint32_t n, const float* rgba, const float* bg, float* target) {
+    if (n == 0) return 0;
+    blend_target_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, reinterpret_cast<const float4*>(rgba), bg, target);
     NGP_LAUNCH_CHECK();
     return 0;
 }

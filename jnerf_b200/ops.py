@@ -225,6 +225,15 @@ def prepare_batch(pix, W, H, xforms, focal, principal, images, bg):
     return img, o, d, target
 
 
+def blend_target(rgba, bg, target=None):
+    """target = rgb*a + bg*(1-a) (runner.py:68) for an (n,4) f32 RGBA batch."""
+    n = rgba.shape[0]
+    if target is None:
+        target = torch.empty((n, 3), dtype=torch.float32, device=rgba.device)
+    lib.call("ngp_blend_target", _stream(), n, _p(rgba), _p(bg), _p(target))
+    return target
+
+
 def pcg32_seed(seed=1337, seq=1):
     si = np.zeros(2, np.uint64)
     lib.load().ngp_pcg32_seed(seed, seq, si.ctypes.data)

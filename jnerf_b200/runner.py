@@ -49,6 +49,7 @@ class Runner:
         self.fast = bool(getattr(self.model, "fused", False))
         # state the evaluation / checkpoint code reads on EVERY kind of model (fused or the nn.Linear fallback)
         self._table_work, self._pending_epoch = None, None
+        self._host_stage = None
         self._st = {id(s.p): s for s in self.optimizer._nested_optimizer.state}
         if world_size > 1 and not self.fast:
             raise ValueError("data-parallel training needs the fused model (fp16=True, use_fully=True): the per-operator autograd step "
@@ -189,7 +190,7 @@ class Runner:
             bg = torch.rand((R * self.world_size, 3), device="cuda", generator=self._bg_gen)
             if self.world_size > 1:
                 bg = bg[self.rank * R:(self.rank + 1) * R].contiguous()
-            target = rgba[:, :3] * rgba[:, 3:] + bg * (1 - rgba[:, 3:])                     # runner.py:68
+            target = ops.blend_target(rgba.contiguous(), bg.contiguous())                  # runner.py:68
         if i % s.update_den_freq == 0:
             self._table_ready()                                      # the occupancy-grid update evaluates the density network
         s.sample(img_ids, rays_o, rays_d, is_training=True, ray_index_offset=dp.shard_range(R, self.rank)[0])  # grid update /16, march, bookkeeping
@@ -208,6 +209,54 @@ class Runner:
         self.last_loss, self.last_rgb = loss, rgb
         cfg.m_training_step = i + 1
         return loss
+
+    # ------------------------------------------------------------------------------------------ host-fed batches
+    def train_step_host(self, batch, next_batch=None):
+        """One training step on a ray batch that lives in PINNED HOST memory -- (img_ids int32 (R,), rays_o (R,3), rays_d (R,3),
+        rgba (R,4) f32), what the reference's dataset yields (dataset.py:172-188).  The batch is copied on a side stream into one of
+        two device staging slots; passing `next_batch` starts the copy of the following step's batch before this step's kernels are
+        enqueued, so that the copy runs under them.  The mean loss goes back to the host on the side stream as well: the returned
+        pinned 1-element tensor holds it once that stream has caught up (read it a step later, or synchronise)."""
+        st = self._host_stage
+        if st is None:
+            st = self._host_stage = dict(stream=torch.cuda.Stream(), slots=[None, None], ready=[torch.cuda.Event(), torch.cuda.Event()],
+                                         free=[torch.cuda.Event(), torch.cuda.Event()], staged=[None, None], k=0,
+                                         loss_host=torch.zeros(1, dtype=torch.float32).pin_memory(), done=torch.cuda.Event())
+            for e in st["free"]:
+                e.record()
+        main = torch.cuda.current_stream()
+
+        def put(b, slot):
+            R = b[1].shape[0]
+            if st["slots"][slot] is None or st["slots"][slot][1].shape[0] < R:
+                cap = max(2 * R, 4096)
+                st["slots"][slot] = (torch.empty(cap, dtype=torch.int32, device="cuda"), torch.empty((cap, 3), device="cuda"),
+                                     torch.empty((cap, 3), device="cuda"), torch.empty((cap, 4), device="cuda"))
+            with torch.cuda.stream(st["stream"]):
+                st["stream"].wait_event(st["free"][slot])              # the step that read this slot has finished with it
+                for dst, src in zip(st["slots"][slot], b):
+                    dst[:R].copy_(src, non_blocking=True)
+                st["ready"][slot].record()
+            st["staged"][slot] = (b, R)
+
+        slot = st["k"] % 2
+        if st["staged"][slot] is None or st["staged"][slot][0] is not batch:
+            put(batch, slot)
+        if next_batch is not None:
+            put(next_batch, 1 - slot)
+        R = st["staged"][slot][1]
+        main.wait_event(st["ready"][slot])
+        dev = tuple(t[:R] for t in st["slots"][slot])
+        loss = self.train_step(dev)
+        st["free"][slot].record(main)
+        st["staged"][slot] = None
+        st["k"] += 1
+        st["done"].record(main)
+        with torch.cuda.stream(st["stream"]):
+            st["stream"].wait_event(st["done"])
+            loss.record_stream(st["stream"])
+            st["loss_host"].copy_(loss.mean().reshape(1), non_blocking=True)
+        return st["loss_host"]
 
     def net_forward(self, coords, n_dev):
         """Fused hash encode + SH + both MLPs on the sampler's coordinate rows -> self.net_out (+ self.enc)."""

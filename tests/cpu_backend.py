@@ -243,6 +243,14 @@ class OracleOps:
         target = rgba[:, :3] * rgba[:, 3:] + bg * (1 - rgba[:, 3:])            # runner.py:68
         return img, o, d, target.contiguous()
 
+    def blend_target(self, rgba, bg, target=None):
+        self._log("blend_target")
+        t = (rgba[:, :3] * rgba[:, 3:] + bg * (1 - rgba[:, 3:])).contiguous()   # runner.py:68
+        if target is not None:
+            target.copy_(t)
+            return target
+        return t
+
     def pcg32_seed(self, seed=1337, seq=1):
         return ol.pcg32_seed(seed, seq)
 
@@ -284,7 +292,35 @@ def install(monkeypatch):
     load = torch.load
     monkeypatch.setattr(torch, "load", lambda f, *a, **k: load(f, *a, **dict(k, map_location="cpu")))
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
-    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: types.SimpleNamespace(cuda_stream=0))
+
+    class _FakeStream:                                             # the host-batch pipeline's copy stream: everything is synchronous here
+        cuda_stream = 0
+
+        def wait_event(self, ev):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    class _FakeEvent:
+        def __init__(self, *a, **k):
+            pass
+
+        def record(self, *a, **k):
+            pass
+
+        def elapsed_time(self, other):
+            return 1.0
+    one = _FakeStream()
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: one)
+    monkeypatch.setattr(torch.cuda, "Stream", _FakeStream)
+    monkeypatch.setattr(torch.cuda, "stream", lambda st: st)
+    monkeypatch.setattr(torch.cuda, "Event", _FakeEvent)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, *a, **k: None)
     from jnerf_b200.plugin import dataset as D
     monkeypatch.setattr(D, "DEVICE", "cpu")
     return fake

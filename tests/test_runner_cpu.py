@@ -315,3 +315,22 @@ def test_runner_on_the_linear_fallback_model_renders_and_saves(monkeypatch, tmp_
     cfg.dataset.val = None
     with pytest.raises(ValueError, match="data-parallel"):
         R.Runner(rank=0, world_size=2, process_group=None)
+
+
+def test_host_fed_batches_equal_device_batches(monkeypatch):
+    """Runner.train_step_host (pinned host batch -> staging slot on the copy stream -> train_step) gives the same step as train_step on
+    the same batch, alternates its two staging slots, and does not copy a batch twice when it was announced as `next_batch`."""
+    ra, fa = make_runner(monkeypatch, seed=8)
+    rb, fb = make_runner(monkeypatch, seed=8)
+    batches = [tuple(t.clone() for t in ra.next_batch()) for _ in range(3)]
+    for b in batches:
+        rb.next_batch()                                            # keep the two datasets' pixel streams aligned
+    fb.calls.clear()                                               # (the second install replaced the operator layer for both runners)
+    for k, b in enumerate(batches):
+        la = ra.train_step(tuple(t.clone() for t in b))
+        lh = rb.train_step_host(b, batches[k + 1] if k + 1 < len(batches) else None)
+        assert abs(float(lh) - float(la.mean())) <= 1e-6 * max(1.0, abs(float(la.mean())))
+    assert fb.calls.count("blend_target") == 6 and "prepare_batch" not in fb.calls
+    assert torch.equal(ra.model.pos_encoder.m_grid.detach(), rb.model.pos_encoder.m_grid.detach())
+    st = rb._host_stage
+    assert st["k"] == 3 and st["slots"][0] is not None and st["slots"][1] is not None and st["staged"] == [None, None]
