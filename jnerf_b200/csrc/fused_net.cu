@@ -70,8 +70,7 @@ __device__ __forceinline__ void gather_tile(const float* __restrict__ s_pos /* s
             cgx = hc.gx; cgy = hc.gy; cgz = hc.gz;
             uint32_t idx[8];
             hash_cell_indices(lv, cgx, cgy, cgz, idx);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) v[c] = __ldg(g + idx[c]);
+            load_corners(g, idx, v);
         }
         float w[8];
         hash_cell_weights(hc, w);
@@ -481,10 +480,7 @@ network_bwd256_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const 
                     if (df.x == 0.f && df.y == 0.f) continue;
                     const HashCell hc = hash_cell(lv, s_coords[p * 7], s_coords[p * 7 + 1], s_coords[p * 7 + 2]);
                     if (hc.gx != cgx || hc.gy != cgy || hc.gz != cgz) {
-                        if (dirty && !(dbg & 1)) {
-#pragma unroll
-                            for (int c = 0; c < 8; ++c) red_add_h2(gg + idx[c], accv[c].x, accv[c].y);
-                        }
+                        if (dirty && !(dbg & 1)) red_add_corners(gg, idx, accv);
                         cgx = hc.gx; cgy = hc.gy; cgz = hc.gz;
                         hash_cell_indices(lv, cgx, cgy, cgz, idx);
 #pragma unroll
@@ -496,10 +492,7 @@ network_bwd256_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const 
 #pragma unroll
                     for (int c = 0; c < 8; ++c) { accv[c].x = fmaf(df.x, w[c], accv[c].x); accv[c].y = fmaf(df.y, w[c], accv[c].y); }
                 }
-                if (dirty && !(dbg & 1)) {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) red_add_h2(gg + idx[c], accv[c].x, accv[c].y);
-                }
+                if (dirty && !(dbg & 1)) red_add_corners(gg, idx, accv);
             }
             if (pair + gridDim.x < npairs) named_bar_arrive(B3_EMPTY, B3_EPI_THREADS + 32 * B3_SCATTER_WARPS);
         }

@@ -78,8 +78,15 @@ hash_fwd_kernel(uint32_t n, const float* __restrict__ x, const T* __restrict__ g
             cgx = hc.gx; cgy = hc.gy; cgz = hc.gz;
             uint32_t idx[8];
             hash_cell_indices(lv, cgx, cgy, cgz, idx);
+            if constexpr (sizeof(T) == 2) {
+                __half2 hv[8];
+                load_corners(g, idx, hv);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) v[c] = to_f2(__ldg(g + idx[c]));
+                for (int c = 0; c < 8; ++c) v[c] = __half22float2(hv[c]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[c] = to_f2(__ldg(g + idx[c]));
+            }
         }
         float w[8];
         hash_cell_weights(hc, w);
@@ -116,8 +123,11 @@ hash_bwd_kernel(uint32_t n, const float* __restrict__ x, const T* __restrict__ d
         const HashCell hc = hash_cell(lv, __ldg(x + 3 * (size_t)i), __ldg(x + 3 * (size_t)i + 1), __ldg(x + 3 * (size_t)i + 2));
         if (hc.gx != cgx || hc.gy != cgy || hc.gz != cgz) {
             if (dirty) {
+                if constexpr (sizeof(T) == 2) red_add_corners(g, idx, acc);
+                else {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) red_add(g + idx[c], acc[c].x, acc[c].y);
+                    for (int c = 0; c < 8; ++c) red_add(g + idx[c], acc[c].x, acc[c].y);
+                }
             }
             cgx = hc.gx; cgy = hc.gy; cgz = hc.gz;
             hash_cell_indices(lv, cgx, cgy, cgz, idx);
@@ -131,8 +141,11 @@ hash_bwd_kernel(uint32_t n, const float* __restrict__ x, const T* __restrict__ d
         for (int c = 0; c < 8; ++c) { acc[c].x = fmaf(d.x, w[c], acc[c].x); acc[c].y = fmaf(d.y, w[c], acc[c].y); }
     }
     if (dirty) {
+        if constexpr (sizeof(T) == 2) red_add_corners(g, idx, acc);
+        else {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) red_add(g + idx[c], acc[c].x, acc[c].y);
+            for (int c = 0; c < 8; ++c) red_add(g + idx[c], acc[c].x, acc[c].y);
+        }
     }
 }
 
