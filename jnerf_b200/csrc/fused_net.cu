@@ -70,7 +70,8 @@ __device__ __forceinline__ void gather_tile(const float* __restrict__ s_pos /* s
             cgx = hc.gx; cgy = hc.gy; cgz = hc.gz;
             uint32_t idx[8];
             hash_cell_indices(lv, cgx, cgy, cgz, idx);
-            load_corners(g, idx, v);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[c] = __ldg(g + idx[c]);      // (pairing x-neighbours into 64-bit loads costs more issue slots than it saves here)
         }
         float w[8];
         hash_cell_weights(hc, w);
@@ -235,9 +236,9 @@ network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
 // buffers that died one stage earlier instead:
 //     g_h2 -> GX (the one extra slab), g_h1 -> the h2 slab, dYd -> the dYr slab, g_hd -> the h1 slab,
 // whose last reader (a weight-gradient MMA) was queued before the dgrad MMA the writing epilogue waits for.
-// Warps: 0-7 epilogue, 8 MMA issuer, 9-12 hash-grid scatter of the previous pair of tiles.
+// Warps: 0-7 epilogue, 8 MMA issuer, 9-16 hash-grid scatter of the previous pair of tiles (four warps per tile).
 constexpr uint32_t B3_G_GX = 32, B3_G_DY = 40, B3_G_DENC = 42, B3_GROUPS = 46;   // slab groups of one tile after the 32 activation groups
-constexpr uint32_t B3_EPI_THREADS = 256, B3_SCATTER_WARPS = 4, B3_THREADS = 256 + 32 + 32 * B3_SCATTER_WARPS;
+constexpr uint32_t B3_EPI_THREADS = 256, B3_SCATTER_WARPS = 8, B3_THREADS = 256 + 32 + 32 * B3_SCATTER_WARPS;
 struct SmemBwd3 {
     static constexpr uint32_t coords = 0;                           // [tile][buf] 128 x 7 f32 (3584 B each)
     static constexpr uint32_t tile0 = coords + 4 * 3584;
@@ -254,7 +255,7 @@ struct SmemBwd3 {
 static_assert(SmemBwd3::total <= 227 * 1024, "backward CTA does not fit");
 constexpr uint32_t B3_READY = 1, B3_FULL = 2, B3_EMPTY = 3;         // named barriers
 
-__global__ void __launch_bounds__(B3_THREADS, 1)
+__global__ void __maxnreg__(120)
 network_bwd256_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const float* __restrict__ coords, const __half* __restrict__ enc_save,
                       const NgpLevel* __restrict__ levels, const __half* __restrict__ wd, const __half* __restrict__ wr,
                       const __half* __restrict__ dout, __half* __restrict__ grid_grad, float* __restrict__ dwd, float* __restrict__ dwr,
@@ -455,44 +456,52 @@ network_bwd256_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const 
         }
 #undef B3_STAGE
     } else {
-        // ------------------------------------------------------------------ scatter (HashEncode.h:339-347), 128 threads: tile A then tile B
-        const uint32_t ts = tid - (B3_EPI_THREADS + 32), level = ts & 15, sub = ts >> 4;
+        // ------------------------------------------------------------------ scatter (HashEncode.h:339-347): 128 threads per tile
+        // Thread (level, sub) walks its 16 consecutive samples, accumulates the 8 corner contributions in fp32 registers while the grid
+        // cell stays the same and issues the f16x2 reductions only when the cell changes.  The scatter warps are latency-bound (one
+        // dependent instruction stream per scheduler), not request-bound: measured, 4 warps for both tiles took 100 us against a
+        // 70 us chain, and pairing x-neighbour corners into REDG.F16x4 -- which wins 17 % in the full-occupancy standalone
+        // ngp_hash_bwd -- LOST 33 % here (more instructions on the critical warps).
+        const uint32_t ts = tid - (B3_EPI_THREADS + 32), T = ts >> 7, level = ts & 15, sub = (ts & 127) >> 4;
         const NgpLevel lv = s_lv[level];
         __half2* gg = reinterpret_cast<__half2*>(grid_grad) + lv.offset;
+        const uint8_t* denc = smem + S::tile0 + T * S::tile_stride + B3_G_DENC * GB;
         uint32_t it = 0;
         for (uint32_t pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++it) {
             const uint32_t buf = it & 1;
             named_bar_sync(B3_FULL, B3_EPI_THREADS + 32 * B3_SCATTER_WARPS);
+            const uint32_t row0 = (2 * pair + T) * ROWS;
+            const float* s_coords = reinterpret_cast<const float*>(smem + S::coords + (2 * T + buf) * 3584);
+            uint32_t cgx = 0xffffffffu, cgy = 0, cgz = 0, idx[8];
+            float2 accv[8];
+            bool dirty = false;
 #pragma unroll 1
-            for (uint32_t T = 0; T < 2; ++T) {
-                const uint32_t row0 = (2 * pair + T) * ROWS;
-                const float* s_coords = reinterpret_cast<const float*>(smem + S::coords + (2 * T + buf) * 3584);
-                const uint8_t* denc = smem + S::tile0 + T * S::tile_stride + B3_G_DENC * GB;
-                uint32_t cgx = 0xffffffffu, cgy = 0, cgz = 0, idx[8];
-                float2 accv[8];
-                bool dirty = false;
-#pragma unroll 1
-                for (int k = 0; k < 16; ++k) {
-                    const uint32_t p = 16 * sub + k;
-                    if (row0 + p >= n_live || (dbg & 2)) break;
-                    const __half2 d = *reinterpret_cast<const __half2*>(denc + (size_t)(level >> 2) * GB + p * 16 + (level & 3) * 4);
-                    const float2 df = __half22float2(d);
-                    if (df.x == 0.f && df.y == 0.f) continue;
-                    const HashCell hc = hash_cell(lv, s_coords[p * 7], s_coords[p * 7 + 1], s_coords[p * 7 + 2]);
-                    if (hc.gx != cgx || hc.gy != cgy || hc.gz != cgz) {
-                        if (dirty && !(dbg & 1)) red_add_corners(gg, idx, accv);
-                        cgx = hc.gx; cgy = hc.gy; cgz = hc.gz;
-                        hash_cell_indices(lv, cgx, cgy, cgz, idx);
+            for (int k = 0; k < 16; ++k) {
+                const uint32_t p = 16 * sub + k;
+                if (row0 + p >= n_live || (dbg & 2)) break;
+                const __half2 d = *reinterpret_cast<const __half2*>(denc + (size_t)(level >> 2) * GB + p * 16 + (level & 3) * 4);
+                const float2 df = __half22float2(d);
+                if (df.x == 0.f && df.y == 0.f) continue;
+                const HashCell hc = hash_cell(lv, s_coords[p * 7], s_coords[p * 7 + 1], s_coords[p * 7 + 2]);
+                if (hc.gx != cgx || hc.gy != cgy || hc.gz != cgz) {
+                    if (dirty && !(dbg & 1)) {
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) accv[c] = make_float2(0.f, 0.f);
-                        dirty = true;
+                        for (int c = 0; c < 8; ++c) red_add_h2(gg + idx[c], accv[c].x, accv[c].y);
                     }
-                    float w[8];
-                    hash_cell_weights(hc, w);
+                    cgx = hc.gx; cgy = hc.gy; cgz = hc.gz;
+                    hash_cell_indices(lv, cgx, cgy, cgz, idx);
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) { accv[c].x = fmaf(df.x, w[c], accv[c].x); accv[c].y = fmaf(df.y, w[c], accv[c].y); }
+                    for (int c = 0; c < 8; ++c) accv[c] = make_float2(0.f, 0.f);
+                    dirty = true;
                 }
-                if (dirty && !(dbg & 1)) red_add_corners(gg, idx, accv);
+                float w[8];
+                hash_cell_weights(hc, w);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { accv[c].x = fmaf(df.x, w[c], accv[c].x); accv[c].y = fmaf(df.y, w[c], accv[c].y); }
+            }
+            if (dirty && !(dbg & 1)) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) red_add_h2(gg + idx[c], accv[c].x, accv[c].y);
             }
             if (pair + gridDim.x < npairs) named_bar_arrive(B3_EMPTY, B3_EPI_THREADS + 32 * B3_SCATTER_WARPS);
         }

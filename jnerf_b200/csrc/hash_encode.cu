@@ -78,15 +78,8 @@ hash_fwd_kernel(uint32_t n, const float* __restrict__ x, const T* __restrict__ g
             cgx = hc.gx; cgy = hc.gy; cgz = hc.gz;
             uint32_t idx[8];
             hash_cell_indices(lv, cgx, cgy, cgz, idx);
-            if constexpr (sizeof(T) == 2) {
-                __half2 hv[8];
-                load_corners(g, idx, hv);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) v[c] = __half22float2(hv[c]);
-            } else {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) v[c] = to_f2(__ldg(g + idx[c]));
-            }
+            for (int c = 0; c < 8; ++c) v[c] = to_f2(__ldg(g + idx[c]));   // (64-bit loads for x-neighbour pairs: 49 -> 52 us, not kept)
         }
         float w[8];
         hash_cell_weights(hc, w);

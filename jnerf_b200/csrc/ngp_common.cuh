@@ -124,25 +124,11 @@ __device__ __forceinline__ void hash_cell_indices(const NgpLevel& lv, uint32_t g
         }
     }
 }
-// The gather and the scatter are bound by the number of L1 / L2 REQUESTS (one per lane and instruction), not by bytes.  Corners c and
+// A full-occupancy scatter is bound by the number of L2 reduction REQUESTS (one per lane and instruction), not by bytes.  Corners c and
 // c+1 of a cell are x-neighbours: whenever their entries share an aligned 8-byte word -- dense levels: even index; hashed levels:
-// even x, because (x+1) ^ h = (x ^ h) ^ 1 then -- one 64-bit load / one REDG.F16x4 serves both.  Half of all cells qualify, i.e. 6
-// requests per cell instead of 8 on average.  The values read and the sums formed are exactly the same.
-__device__ __forceinline__ void load_corners(const __half2* __restrict__ g, const uint32_t idx[8], __half2 v[8]) {
-#pragma unroll
-    for (int c = 0; c < 8; c += 2) {
-        if ((idx[c] ^ idx[c + 1]) == 1u) {
-            const uint2 u = __ldg(reinterpret_cast<const uint2*>(g + (idx[c] & ~1u)));
-            const bool lo = (idx[c] & 1u) == 0u;
-            const uint32_t a = lo ? u.x : u.y, b = lo ? u.y : u.x;
-            v[c] = *reinterpret_cast<const __half2*>(&a);
-            v[c + 1] = *reinterpret_cast<const __half2*>(&b);
-        } else {
-            v[c] = __ldg(g + idx[c]);
-            v[c + 1] = __ldg(g + idx[c + 1]);
-        }
-    }
-}
+// even x, because (x+1) ^ h = (x ^ h) ^ 1 then -- one REDG.F16x4 serves both.  Half of all cells qualify, i.e. 6 requests per cell
+// instead of 8 on average; the sums formed are exactly the same.  Measured (profiles/r02_kernels/call12): standalone ngp_hash_bwd
+// 99 -> 83 us.  The same idea for the gather (64-bit loads) and inside the fused kernels did not pay and is not used there.
 __device__ __forceinline__ void red_add_corners(__half2* __restrict__ g, const uint32_t idx[8], const float2 acc[8]) {
 #pragma unroll
     for (int c = 0; c < 8; c += 2) {
