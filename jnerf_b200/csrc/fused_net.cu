@@ -255,7 +255,7 @@ struct SmemBwd3 {
 static_assert(SmemBwd3::total <= 227 * 1024, "backward CTA does not fit");
 constexpr uint32_t B3_READY = 1, B3_FULL = 2, B3_EMPTY = 3;         // named barriers
 
-__global__ void __maxnreg__(120)
+__global__ void __maxnreg__(112)   // 17 warps x 112 registers (allocated per warp in units of 512) fit the 64 K register file; 120 do not
 network_bwd256_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const float* __restrict__ coords, const __half* __restrict__ enc_save,
                       const NgpLevel* __restrict__ levels, const __half* __restrict__ wd, const __half* __restrict__ wr,
                       const __half* __restrict__ dout, __half* __restrict__ grid_grad, float* __restrict__ dwd, float* __restrict__ dwr,
