@@ -1,5 +1,7 @@
 // Error state, version and small host-side helpers of the C ABI (include/ngp_b200.h).
 #include "ngp_common.cuh"
+#include <vector>
+#include <utility>
 #include <mutex>
 
 namespace {
@@ -10,15 +12,26 @@ thread_local std::string g_err;
 void ngp_set_error(const std::string& msg) { g_err = msg; }
 
 int ngp_num_sms() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        cudaDeviceProp p;
-        if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
-        sms = p.multiProcessorCount;
+    static int sms[64] = {0};                                     // per device: a process may drive several GPUs
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (sms[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+        sms[dev] = n;
     }
-    return sms;
+    return sms[dev];
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of on every launch
+bool ngp_first_use(const void* kernel) {
+    static std::vector<std::pair<const void*, int>> seen;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (const auto& e : seen)
+        if (e.first == kernel && e.second == dev) return false;
+    seen.emplace_back(kernel, dev);
+    return true;
 }
 
 extern "C" {

@@ -236,9 +236,12 @@ network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
 // buffers that died one stage earlier instead:
 //     g_h2 -> GX (the one extra slab), g_h1 -> the h2 slab, dYd -> the dYr slab, g_hd -> the h1 slab,
 // whose last reader (a weight-gradient MMA) was queued before the dgrad MMA the writing epilogue waits for.
-// Warps: 0-7 epilogue, 8 MMA issuer, 9-16 hash-grid scatter of the previous pair of tiles (four warps per tile).
+// Warps: 0-7 epilogue, 8 MMA issuer, 9-14 hash-grid scatter of the previous pair of tiles.
 constexpr uint32_t B3_G_GX = 32, B3_G_DY = 40, B3_G_DENC = 42, B3_GROUPS = 46;   // slab groups of one tile after the 32 activation groups
-constexpr uint32_t B3_EPI_THREADS = 256, B3_SCATTER_WARPS = 8, B3_THREADS = 256 + 32 + 32 * B3_SCATTER_WARPS;
+// 8 epilogue + 1 issuer + 6 scatter = 15 warps: registers are allocated for warps in groups of four, so 16 warps x 128 registers
+// is what fits (17 warps -- four scatter warps per tile -- would be charged as 20)
+constexpr uint32_t B3_EPI_THREADS = 256, B3_SCATTER_WARPS = 6, B3_THREADS = 256 + 32 + 32 * B3_SCATTER_WARPS;
+constexpr uint32_t B3_RUN = (2 * 128 * 16 + 32 * B3_SCATTER_WARPS - 1) / (32 * B3_SCATTER_WARPS);   // consecutive rows per scatter thread (22)
 struct SmemBwd3 {
     static constexpr uint32_t coords = 0;                           // [tile][buf] 128 x 7 f32 (3584 B each)
     static constexpr uint32_t tile0 = coords + 4 * 3584;
@@ -255,7 +258,7 @@ struct SmemBwd3 {
 static_assert(SmemBwd3::total <= 227 * 1024, "backward CTA does not fit");
 constexpr uint32_t B3_READY = 1, B3_FULL = 2, B3_EMPTY = 3;         // named barriers
 
-__global__ void __maxnreg__(112)   // 17 warps x 112 registers (allocated per warp in units of 512) fit the 64 K register file; 120 do not
+__global__ void __launch_bounds__(B3_THREADS, 1)
 network_bwd256_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const float* __restrict__ coords, const __half* __restrict__ enc_save,
                       const NgpLevel* __restrict__ levels, const __half* __restrict__ wd, const __half* __restrict__ wr,
                       const __half* __restrict__ dout, __half* __restrict__ grid_grad, float* __restrict__ dwd, float* __restrict__ dwr,
@@ -456,29 +459,30 @@ network_bwd256_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const 
         }
 #undef B3_STAGE
     } else {
-        // ------------------------------------------------------------------ scatter (HashEncode.h:339-347): 128 threads per tile
-        // Thread (level, sub) walks its 16 consecutive samples, accumulates the 8 corner contributions in fp32 registers while the grid
+        // ------------------------------------------------------------------ scatter (HashEncode.h:339-347): 192 threads over the pair's 256 rows
+        // Thread (level, sub) walks its B3_RUN consecutive samples, accumulates the 8 corner contributions in fp32 registers while the grid
         // cell stays the same and issues the f16x2 reductions only when the cell changes.  The scatter warps are latency-bound (one
         // dependent instruction stream per scheduler), not request-bound: measured, 4 warps for both tiles took 100 us against a
         // 70 us chain, and pairing x-neighbour corners into REDG.F16x4 -- which wins 17 % in the full-occupancy standalone
         // ngp_hash_bwd -- LOST 33 % here (more instructions on the critical warps).
-        const uint32_t ts = tid - (B3_EPI_THREADS + 32), T = ts >> 7, level = ts & 15, sub = (ts & 127) >> 4;
+        const uint32_t ts = tid - (B3_EPI_THREADS + 32), level = ts & 15, sub = ts >> 4;   // 12 row ranges of B3_RUN rows over the 256 rows of the pair
         const NgpLevel lv = s_lv[level];
         __half2* gg = reinterpret_cast<__half2*>(grid_grad) + lv.offset;
-        const uint8_t* denc = smem + S::tile0 + T * S::tile_stride + B3_G_DENC * GB;
         uint32_t it = 0;
         for (uint32_t pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++it) {
             const uint32_t buf = it & 1;
             named_bar_sync(B3_FULL, B3_EPI_THREADS + 32 * B3_SCATTER_WARPS);
-            const uint32_t row0 = (2 * pair + T) * ROWS;
-            const float* s_coords = reinterpret_cast<const float*>(smem + S::coords + (2 * T + buf) * 3584);
             uint32_t cgx = 0xffffffffu, cgy = 0, cgz = 0, idx[8];
             float2 accv[8];
             bool dirty = false;
 #pragma unroll 1
-            for (int k = 0; k < 16; ++k) {
-                const uint32_t p = 16 * sub + k;
-                if (row0 + p >= n_live || (dbg & 2)) break;
+            for (uint32_t k = 0; k < B3_RUN; ++k) {
+                const uint32_t r = B3_RUN * sub + k;                                   // row of the pair: tile r >> 7, row r & 127
+                if (r >= 2 * ROWS || (dbg & 2)) break;
+                const uint32_t T = r >> 7, p = r & 127;
+                if ((2 * pair + T) * ROWS + p >= n_live) break;
+                const uint8_t* denc = smem + S::tile0 + T * S::tile_stride + B3_G_DENC * GB;
+                const float* s_coords = reinterpret_cast<const float*>(smem + S::coords + (2 * T + buf) * 3584);
                 const __half2 d = *reinterpret_cast<const __half2*>(denc + (size_t)(level >> 2) * GB + p * 16 + (level & 3) * 4);
                 const float2 df = __half22float2(d);
                 if (df.x == 0.f && df.y == 0.f) continue;
@@ -519,7 +523,7 @@ int ngp_network_fwd(void* stream, uint32_t n_max, const uint32_t* n_dev, const f
                     const void* w_density, const void* w_rgb, void* out, void* enc_save) {
     if (n_max == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    NGP_CHECK_CUDA(cudaFuncSetAttribute(network_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemFwd::total));
+    if (ngp_first_use((const void*)network_fwd_kernel<false>)) NGP_CHECK_CUDA(cudaFuncSetAttribute(network_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemFwd::total));
     const uint32_t ntiles = (n_max + ROWS - 1) / ROWS;
     const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms() * 2u);
     network_fwd_kernel<false><<<grid_dim, FWD_THREADS, SmemFwd::total, s>>>(n_max, n_dev, coords, (const __half*)grid, (const NgpLevel*)levels_dev,
@@ -532,7 +536,7 @@ int ngp_network_fwd(void* stream, uint32_t n_max, const uint32_t* n_dev, const f
 int ngp_density_fwd(void* stream, uint32_t n, const float* pos, const void* grid, const void* levels_dev, const void* w_density, void* sigma_out) {
     if (n == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    NGP_CHECK_CUDA(cudaFuncSetAttribute(network_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemFwd::total));
+    if (ngp_first_use((const void*)network_fwd_kernel<true>)) NGP_CHECK_CUDA(cudaFuncSetAttribute(network_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemFwd::total));
     const uint32_t ntiles = (n + ROWS - 1) / ROWS;
     const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms() * 2u);
     network_fwd_kernel<true><<<grid_dim, FWD_THREADS, SmemFwd::total, s>>>(n, nullptr, pos, (const __half*)grid, (const NgpLevel*)levels_dev,
@@ -548,7 +552,7 @@ int ngp_network_bwd(void* stream, uint32_t n_max, const uint32_t* n_dev, const f
     const uint32_t ntiles = (n_max + ROWS - 1) / ROWS;
     // timing experiments only (results are wrong with any bit set): 1 = no atomics, 2 = no scatter, 4 = no weight-gradient MMAs
     static const uint32_t dbg = getenv("NGP_BWD_DEBUG") ? (uint32_t)atoi(getenv("NGP_BWD_DEBUG")) : 0u;
-    NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd3::total));
+    if (ngp_first_use((const void*)network_bwd256_kernel)) NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd3::total));
     const uint32_t grid_dim = min((ntiles + 1) / 2, (uint32_t)ngp_num_sms());
     network_bwd256_kernel<<<grid_dim, B3_THREADS, SmemBwd3::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
                                                                        (const __half*)w_density, (const __half*)w_rgb, (const __half*)dout,

@@ -295,7 +295,7 @@ int ngp_mlp_fwd(void* stream, const void* weights, const void* input, void* inte
     if (n == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t smem = FwdSmem::total(nhm);
-    NGP_CHECK_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (ngp_first_use((const void*)mlp_fwd_kernel)) NGP_CHECK_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdSmem::total(MAX_HM)));
     const uint32_t ntiles = (n + ROWS - 1) / ROWS;
     uint32_t per_sm = 4u;
     if (const char* e = getenv("NGP_MLP_CTAS_PER_SM")) per_sm = (uint32_t)atoi(e);   // experiment knob
@@ -311,7 +311,7 @@ static int mlp_bwd_launch(void* stream, const void* weights, const void* input, 
     if (dW) NGP_CHECK_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * ngp_mlp_param_count(nhm), s));
     if (n == 0) return 0;
     const BwdLayout L{nhm};
-    NGP_CHECK_CUDA(cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total()));
+    if (ngp_first_use((const void*)mlp_bwd_kernel)) NGP_CHECK_CUDA(cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdLayout{MAX_HM}.total()));
     const uint32_t ntiles = (n + ROWS - 1) / ROWS;
     const uint32_t per_sm = L.tmem_cols() <= 256 && L.total() <= 110 * 1024 ? 2u : 1u;
     const uint32_t grid = min(ntiles, (uint32_t)ngp_num_sms() * per_sm);

@@ -97,14 +97,17 @@ __device__ __forceinline__ float ray_tmin(float lo, float hi, const float o[3], 
 struct RayState {
     float o[3], d[3], id[3], startt;
 };
+// rng: the kernel arguments, or -- ngp_march_dev -- the device-resident step state (ngp_common.cuh); `ray_offset` = index of ray 0 in
+// the global ray batch (data-parallel shards draw the jitter of the global ray id)
+struct MarchRng { uint64_t state, inc; const NgpStepState* st; uint32_t ray_offset; };
 __device__ __forceinline__ RayState ray_setup(uint32_t i, const float* __restrict__ rays_o, const float* __restrict__ rays_d, float lo,
-                                              float hi, float near_distance, float cone, const MarchCfg& c, uint64_t rng_state,
-                                              uint64_t rng_inc) {
+                                              float hi, float near_distance, float cone, const MarchCfg& c, const MarchRng& mr) {
+    const uint64_t rng_state = mr.st ? mr.st->rng_state : mr.state, rng_inc = mr.st ? mr.st->rng_inc : mr.inc;
     RayState r;
 #pragma unroll
     for (int k = 0; k < 3; ++k) { r.o[k] = rays_o[3 * (size_t)i + k]; r.d[k] = rays_d[3 * (size_t)i + k]; r.id[k] = 1.0f / r.d[k]; }
     Pcg32 rng{rng_state, rng_inc};
-    rng.advance((int64_t)(uint32_t)(i * 8u));                                // ray_sampler.h:30, N_MAX_RANDOM_SAMPLES_PER_RAY = 8
+    rng.advance((int64_t)(uint32_t)((i + mr.ray_offset) * 8u));               // ray_sampler.h:30, N_MAX_RANDOM_SAMPLES_PER_RAY = 8
     float tmin = fmaxf(ray_tmin(lo, hi, r.o, r.d), near_distance);           // :41-44
     r.startt = __fmaf_rn(calc_dt(c, tmin, cone), rng.next_float(), tmin);    // :48
     return r;
@@ -261,7 +264,7 @@ struct ChunkState {           // per lane: one step of a chunk between the two h
 constexpr int MARCH_RAYS_PER_CTA = 4;
 __global__ void __launch_bounds__(64 * MARCH_RAYS_PER_CTA)
 march_count_kernel(uint32_t n_rays, float lo, float hi, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                   const uint8_t* __restrict__ bits, float cone, float near_distance, MarchCfg c, uint64_t rng_state, uint64_t rng_inc,
+                   const uint8_t* __restrict__ bits, float cone, float near_distance, MarchCfg c, MarchRng mr,
                    uint8_t* __restrict__ ws, uint32_t* __restrict__ counts, uint32_t* __restrict__ n_emit, int* __restrict__ err) {
     __shared__ RayRing s_ring[MARCH_RAYS_PER_CTA];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -277,7 +280,7 @@ march_count_kernel(uint32_t n_rays, float lo, float hi, const float* __restrict_
     const unsigned FULL = 0xffffffffu;
 
     if (producer) {
-        const RayState r = ray_setup(i, rays_o, rays_d, lo, hi, near_distance, cone, c, rng_state, rng_inc);
+        const RayState r = ray_setup(i, rays_o, rays_d, lo, hi, near_distance, cone, c, mr);
         float tc = r.startt;                 // running t of the sequence (identical in all lanes)
         // first half of a chunk: t values, positions, occupancy lookup issued (not consumed)
         auto stage1 = [&](ChunkState& st) {
@@ -485,7 +488,7 @@ __global__ void __launch_bounds__(1024) march_scan_kernel(uint32_t n_rays, uint3
 // one coalesced block of n x 7 floats instead of 7 strided 4-byte stores per lane.  A ray whose list overflowed is re-marched.
 __global__ void __launch_bounds__(128) march_emit_kernel(uint32_t n_rays, float lo, float hi, const float* __restrict__ rays_o,
                                                          const float* __restrict__ rays_d, const uint8_t* __restrict__ bits, float cone,
-                                                         float near_distance, MarchCfg c, uint64_t rng_state, uint64_t rng_inc,
+                                                         float near_distance, MarchCfg c, MarchRng mr,
                                                          const uint32_t* __restrict__ numsteps, float* __restrict__ coords,
                                                          const uint8_t* __restrict__ ws, const uint32_t* __restrict__ n_emit) {
     __shared__ float s_rows[4][32 * 7];
@@ -496,7 +499,7 @@ __global__ void __launch_bounds__(128) march_emit_kernel(uint32_t n_rays, float 
     const uint32_t ne = n_emit[i];
     if (ne > MARCH_EMIT_CAP) {
         if (warp == 0) {
-            const RayState r = ray_setup(i, rays_o, rays_d, lo, hi, near_distance, cone, c, rng_state, rng_inc);
+            const RayState r = ray_setup(i, rays_o, rays_d, lo, hi, near_distance, cone, c, mr);
             march_ray_warp<true>(r, lo, hi, cone, c, bits, n, out);
         }
         return;
@@ -786,9 +789,9 @@ uint64_t ngp_march_workspace_bytes(uint32_t n_rays) {
     return (uint64_t)n_rays * (8 + MARCH_RAY_BYTES) + 1024;
 }
 
-int ngp_march(void* stream, uint32_t n_rays, float aabb_lo, float aabb_hi, uint32_t max_samples, const float* rays_o, const float* rays_d,
-              const uint8_t* bitfield, float cone_angle, float near_distance, uint32_t cascades, int const_dt, uint64_t rng_state,
-              uint64_t rng_inc, uint32_t* counters, uint32_t* ray_indices, uint32_t* numsteps, float* coords, void* workspace) {
+static int march_launch(void* stream, uint32_t n_rays, float aabb_lo, float aabb_hi, uint32_t max_samples, const float* rays_o, const float* rays_d,
+                        const uint8_t* bitfield, float cone_angle, float near_distance, uint32_t cascades, int const_dt, MarchRng mr,
+                        uint32_t* counters, uint32_t* ray_indices, uint32_t* numsteps, float* coords, void* workspace) {
     cudaStream_t s = (cudaStream_t)stream;
     NGP_REQUIRE(cascades >= 1 && cascades <= 8, "ngp_march: cascades out of range");
     NGP_CHECK_CUDA(cudaMemsetAsync(counters, 0, 8, s));                                     // ray_sampler.py:29
@@ -798,15 +801,30 @@ int ngp_march(void* stream, uint32_t n_rays, float aabb_lo, float aabb_hi, uint3
     uint32_t* n_emit = counts + n_rays;
     uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(n_emit + n_rays) + 255) & ~(uintptr_t)255);
     const uint32_t blocks = (n_rays + MARCH_RAYS_PER_CTA - 1) / MARCH_RAYS_PER_CTA;   // two warps (producer, consumer) per ray
-    march_count_kernel<<<blocks, 64 * MARCH_RAYS_PER_CTA, 0, s>>>(n_rays, aabb_lo, aabb_hi, rays_o, rays_d, bitfield, cone_angle, near_distance, c,
-                                                                 rng_state, rng_inc, ws, counts, n_emit, ngp_err_flag());
+    march_count_kernel<<<blocks, 64 * MARCH_RAYS_PER_CTA, 0, s>>>(n_rays, aabb_lo, aabb_hi, rays_o, rays_d, bitfield, cone_angle, near_distance, c, mr,
+                                                                 ws, counts, n_emit, ngp_err_flag());
     NGP_LAUNCH_CHECK();
     march_scan_kernel<<<1, 1024, 0, s>>>(n_rays, max_samples, counts, numsteps, ray_indices, counters);
     NGP_LAUNCH_CHECK();
-    march_emit_kernel<<<n_rays, 128, 0, s>>>(n_rays, aabb_lo, aabb_hi, rays_o, rays_d, bitfield, cone_angle, near_distance, c, rng_state,
-                                             rng_inc, numsteps, coords, ws, n_emit);
+    march_emit_kernel<<<n_rays, 128, 0, s>>>(n_rays, aabb_lo, aabb_hi, rays_o, rays_d, bitfield, cone_angle, near_distance, c, mr, numsteps, coords,
+                                             ws, n_emit);
     NGP_LAUNCH_CHECK();
     return 0;
+}
+
+int ngp_march(void* stream, uint32_t n_rays, float aabb_lo, float aabb_hi, uint32_t max_samples, const float* rays_o, const float* rays_d,
+              const uint8_t* bitfield, float cone_angle, float near_distance, uint32_t cascades, int const_dt, uint64_t rng_state,
+              uint64_t rng_inc, uint32_t* counters, uint32_t* ray_indices, uint32_t* numsteps, float* coords, void* workspace) {
+    return march_launch(stream, n_rays, aabb_lo, aabb_hi, max_samples, rays_o, rays_d, bitfield, cone_angle, near_distance, cascades, const_dt,
+                        MarchRng{rng_state, rng_inc, nullptr, 0u}, counters, ray_indices, numsteps, coords, workspace);
+}
+
+int ngp_march_dev(void* stream, uint32_t n_rays, float aabb_lo, float aabb_hi, uint32_t max_samples, const float* rays_o, const float* rays_d,
+                  const uint8_t* bitfield, float cone_angle, float near_distance, uint32_t cascades, int const_dt, const void* state_dev,
+                  uint32_t ray_offset, uint32_t* counters, uint32_t* ray_indices, uint32_t* numsteps, float* coords, void* workspace) {
+    NGP_REQUIRE(state_dev != nullptr, "ngp_march_dev: state_dev is required");
+    return march_launch(stream, n_rays, aabb_lo, aabb_hi, max_samples, rays_o, rays_d, bitfield, cone_angle, near_distance, cascades, const_dt,
+                        MarchRng{0, 0, (const NgpStepState*)state_dev, ray_offset}, counters, ray_indices, numsteps, coords, workspace);
 }
 
 int ngp_compact(void* stream, uint32_t n_rays, uint32_t max_compacted, const float* coords_in, const uint32_t* numsteps_in, float* coords_out,
