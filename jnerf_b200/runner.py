@@ -50,6 +50,7 @@ class Runner:
         # state the evaluation / checkpoint code reads on EVERY kind of model (fused or the nn.Linear fallback)
         self._table_work, self._pending_epoch = None, None
         self._host_stage = None
+        self._dev_state = None                                       # device-resident step state + CUDA graphs (single-GPU fast path)
         self._st = {id(s.p): s for s in self.optimizer._nested_optimizer.state}
         if world_size > 1 and not self.fast:
             raise ValueError("data-parallel training needs the fused model (fp16=True, use_fully=True): the per-operator autograd step "
@@ -74,6 +75,15 @@ class Runner:
         self.dnet = torch.zeros((cap, 4), dtype=torch.float16, device=dev)
         self.last_loss = None
         self.last_rgb = None
+        if self.world_size == 1:
+            # Device-resident step state (include/ngp_b200.h: ngp_step_state_*): the sampler rng, the pixel cursor and Adam's step
+            # factors live on the device, so every launch of a training step has the same arguments and the step can be captured in
+            # a CUDA graph per ray-batch size (NGP_GRAPHS=0 keeps the eager launches).
+            self._dev_state = ops.step_state_new()
+            self._dev_expect = None
+            self._graphs, self._graph_seen, self._graph_pool = {}, {}, None
+            self._graphs_enabled = os.environ.get("NGP_GRAPHS", "1") == "1" and torch.cuda.is_available() and hasattr(torch.cuda, "CUDAGraph")
+            self.graph_replays = 0
         if self.world_size > 1:
             self._init_sharded_table()
 
@@ -171,7 +181,96 @@ class Runner:
         img_ids, rays_o, rays_d = ds.rays_for(pix)
         return img_ids, rays_o, rays_d, ds.rgba_for(pix)
 
+    # ------------------------------------------------------------------------------------------ device-state / CUDA-graph step
+    def _lr_for_step(self, k):
+        """ExpDecay's learning rate for its k-th call (optims/expdecay.py:20-25), without advancing it."""
+        dec = self.optimizer
+        f = dec.m_learning_rate_factor
+        for q in range(dec.steps, k + 1):
+            if q >= dec.decay_start and (q - dec.decay_start) % dec.decay_interval == 0 and q <= dec.decay_end:
+                f *= dec.decay_base
+        return dec.base_lr * f
+
+    def _step_body(self, R, lr_next):
+        """Every launch of one training step on R device-generated rays, with nothing step-dependent among the launch arguments (the
+        rng, the pixel cursor and Adam's factors come from the device step state): run eagerly or captured into a CUDA graph."""
+        s, m, ds, st = self.sampler, self.model, self.dataset["train"], self._dev_state
+        adam = self.optimizer._nested_optimizer
+        bg = torch.rand((R, 3), device="cuda", generator=self._bg_gen)                               # runner.py:66
+        img_ids, rays_o, rays_d, target = ops.prepare_batch_dev(R, ds.shuffle_index, st, 0, ds.W, ds.H, ds.transforms_gpu, ds.focal_lengths,
+                                                                ds.principal, ds.image_data, bg)      # dataset.py:172-188 + runner.py:68
+        s.sample_dev(rays_o, rays_d, st)                                                              # march, compaction bookkeeping
+        coords, n_dev = s.coords_compacted, s.n_samples_dev
+        self.net_forward(coords, n_dev)
+        rgb, loss, _ = ops.composite_loss_bwd(self.net_out, coords, s._rays_numsteps, s._rays_numsteps_compacted, bg, target,
+                                              s.density_grid_mean, delta=self.loss_func.delta, cascades=s.NERF_CASCADES, dnet=self.dnet)
+        self.net_backward(coords, n_dev)
+        for p, g in ((m.pos_encoder.m_grid, self.grid_grad), (m.density_mlp.con_weights, self.dwd), (m.rgb_mlp.con_weights, self.dwr)):
+            stp = self._st[id(p)]
+            ops.adam_ema_dev(p.data, g, stp.m, stp.v, stp.master, st, zero_grad=True)
+        ops.step_state_tick(st, R, lr_next, adam.betas[0], adam.betas[1], adam.eps, self.ema_optimizer.decay, 1.0)
+        self.last_loss, self.last_rgb = loss, rgb
+        return loss
+
+    def _train_step_dev(self):
+        cfg, s, ds = self.cfg, self.sampler, self.dataset["train"]
+        adam, dec = self.optimizer._nested_optimizer, self.optimizer
+        i = cfg.m_training_step
+        R = s.n_rays_per_batch
+        edge = i % s.update_den_freq == 0 or i % s.update_den_freq == s.update_den_freq - 1
+        if i % s.update_den_freq == 0:
+            s.update_density_grid()                                  # evaluates the density network, advances the sampler rng
+        if R > s._march_ws_rays:
+            s._ensure_march_ws(2 * R)
+        start = ds.reserve_pixels(R)
+        lr, lr_next = self._lr_for_step(dec.steps), self._lr_for_step(dec.steps + 1)
+        want = (int(s.rng[0]), int(s.rng[1]), start, adam.n_step, lr)
+        if self._dev_expect != want:                                 # first step, or the host changed something outside a step
+            ops.step_state_set(self._dev_state, s.rng, start, adam.n_step, lr, adam.betas[0], adam.betas[1], adam.eps, self.ema_optimizer.decay, 1.0)
+        key = (R, lr_next)
+        g = self._graphs.get(key) if self._graphs_enabled and not edge else None
+        if g is not None:
+            g[0].replay()
+            ops.lib.launch_count += g[1]
+            self.graph_replays += 1
+            loss = g[2]
+            self.last_loss, self.last_rgb = g[2], g[3]
+            s._rays_numsteps, s._rays_numsteps_compacted, s._counters_compacted, s._coords = g[4]
+        else:
+            seen = self._graph_seen.get(key, 0) + 1
+            self._graph_seen[key] = seen
+            if self._graphs_enabled and not edge and seen >= 2 and i >= 2 * s.update_den_freq and len(self._graphs) < 64:
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                if hasattr(graph, "register_generator_state"):
+                    graph.register_generator_state(self._bg_gen)
+                n0 = ops.lib.launch_count
+                with torch.cuda.graph(graph, pool=self._graph_pool):
+                    loss = self._step_body(R, lr_next)
+                if self._graph_pool is None:
+                    self._graph_pool = graph.pool()
+                self._graphs[key] = (graph, ops.lib.launch_count - n0, loss, self.last_rgb,
+                                     (s._rays_numsteps, s._rays_numsteps_compacted, s._counters_compacted, s._coords))
+                ops.lib.launch_count = n0
+                graph.replay()                                       # capture records the launches, the replay performs the step
+                ops.lib.launch_count += self._graphs[key][1]
+                self.graph_replays += 1
+            else:
+                loss = self._step_body(R, lr_next)
+        # host mirrors of what the step advanced on the device
+        ops.pcg32_advance(s.rng)                                     # rng.advance(), ray_sampler.py:61
+        dec.advance_lr()
+        adam.n_step += 1
+        self.ema_optimizer.steps += 1
+        self._dev_expect = (int(s.rng[0]), int(s.rng[1]), start + R, adam.n_step, lr_next)
+        if i % s.update_den_freq == s.update_den_freq - 1:
+            s.update_batch_rays()
+        cfg.m_training_step = i + 1
+        return loss
+
     def train_step(self, batch=None):
+        if batch is None and self._dev_state is not None:
+            return self._train_step_dev()
         cfg, s, m = self.cfg, self.sampler, self.model
         i = cfg.m_training_step
         if batch is None:

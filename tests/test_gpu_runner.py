@@ -132,3 +132,30 @@ def test_dp_shards_reproduce_single_rank_gradients():
     w_sum = (parts[0][1] + parts[1][1]) * 0.5
     assert (w_sum - w_full).abs().max() <= 2e-2 * w_full.abs().max()
     assert (g_sum - g_full).abs().max() <= 5e-2 * g_full.abs().max() and (g_sum - g_full).abs().mean() <= 2e-3 * g_full.abs().max()
+
+
+def test_cuda_graph_replay_equals_eager_steps(monkeypatch):
+    """The single-GPU fast path replays a training step as a CUDA graph once a ray-batch size has been seen twice (device-resident rng /
+    pixel cursor / Adam factors, include/ngp_b200.h ngp_step_state_*).  Same seeds with and without graphs: the same pixels, the same
+    samples (march counters bit-identical), losses equal up to the order of the gradient atomics, and the host mirrors stay in step."""
+    import numpy as np
+    monkeypatch.setenv("NGP_GRAPHS", "1")
+    ra = make_runner(seed=21)
+    monkeypatch.setenv("NGP_GRAPHS", "0")
+    rb = make_runner(seed=21)
+    assert ra._graphs_enabled and not rb._graphs_enabled
+    la, lb = [], []
+    for k in range(112):
+        la.append(float(ra.train_step().mean()))
+        lb.append(float(rb.train_step().mean()))
+        if k in (40, 111):
+            assert torch.equal(ra.sampler._counters_compacted, rb.sampler._counters_compacted)       # identical sample counts
+            assert torch.equal(ra.sampler._rays_numsteps, rb.sampler._rays_numsteps)
+    assert ra.graph_replays >= 40 and rb.graph_replays == 0, (ra.graph_replays, len(ra._graphs))
+    assert np.array_equal(ra.sampler.rng, rb.sampler.rng) and ra.dataset["train"].idx_now == rb.dataset["train"].idx_now
+    assert ra.optimizer._nested_optimizer.n_step == rb.optimizer._nested_optimizer.n_step == 112
+    la, lb = np.array(la), np.array(lb)
+    assert np.all(np.isfinite(la)) and np.abs(la - lb).max() <= 5e-2 * np.abs(lb).max() and abs(la[-8:].mean() - lb[-8:].mean()) <= 2e-2 * lb[-8:].mean()
+    # a checkpoint written from the graph-replayed run restores into an eager run that continues identically in its bookkeeping
+    from jnerf_b200 import ops
+    assert ops.lib.load().ngp_debug_timeout_flag() == 0

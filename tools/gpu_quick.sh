@@ -14,8 +14,7 @@ bench() { local name=$1; shift; local envs=(); while [ "$1" != "--" ]; do envs+=
 python -c "import __graft_entry__ as g; g.build()" > "$OUT/build.log" 2>&1 || echo "build failed" >> "$SUM"
 if [ -n "${2:-}" ]; then run pytest_gpu 1200 python -m pytest tests -m gpu -q -p no:cacheprovider -k "$2"; else run pytest_gpu 1200 python -m pytest tests -m gpu -q -p no:cacheprovider; fi
 bench default --
-bench bwd_no_scatter_TIMING_ONLY NGP_BWD_DEBUG=2 --
-bench bwd_no_wgrad_TIMING_ONLY NGP_BWD_DEBUG=4 --
+bench no_graphs NGP_GRAPHS=0 --
 bench fox -- --workload fox
 run ref_gpu_compare 400 python tools/ref_gpu_compare.py
 cat "$SUM"
