@@ -81,7 +81,7 @@ class Runner:
             # a CUDA graph per ray-batch size (NGP_GRAPHS=0 keeps the eager launches).
             self._dev_state = ops.step_state_new()
             self._dev_expect = None
-            self._graphs, self._graph_seen, self._graph_pool = {}, {}, None
+            self._graphs, self._graph_seen, self._graph_pool, self._cap_stream = {}, {}, None, None
             self._graphs_enabled = os.environ.get("NGP_GRAPHS", "1") == "1" and torch.cuda.is_available() and hasattr(torch.cuda, "CUDAGraph")
             self.graph_replays = 0
         if self.world_size > 1:
@@ -222,6 +222,7 @@ class Runner:
             s.update_density_grid()                                  # evaluates the density network, advances the sampler rng
         if R > s._march_ws_rays:
             s._ensure_march_ws(2 * R)
+            self._graphs.clear()                                     # the captured launches hold the old workspace's address
         start = ds.reserve_pixels(R)
         lr, lr_next = self._lr_for_step(dec.steps), self._lr_for_step(dec.steps + 1)
         want = (int(s.rng[0]), int(s.rng[1]), start, adam.n_step, lr)
@@ -240,13 +241,24 @@ class Runner:
             seen = self._graph_seen.get(key, 0) + 1
             self._graph_seen[key] = seen
             if self._graphs_enabled and not edge and seen >= 2 and i >= 2 * s.update_den_freq and len(self._graphs) < 64:
-                torch.cuda.synchronize()
+                # capture on a side stream with the raw begin / end calls: torch.cuda.graph() would synchronise the device, run the
+                # Python garbage collector and empty the allocator cache on every capture (~10 ms each)
                 graph = torch.cuda.CUDAGraph()
                 if hasattr(graph, "register_generator_state"):
                     graph.register_generator_state(self._bg_gen)
                 n0 = ops.lib.launch_count
-                with torch.cuda.graph(graph, pool=self._graph_pool):
+                if self._cap_stream is None:
+                    self._cap_stream = torch.cuda.Stream()
+                main = torch.cuda.current_stream()
+                self._cap_stream.wait_stream(main)
+                with torch.cuda.stream(self._cap_stream):
+                    if self._graph_pool is None:
+                        graph.capture_begin(capture_error_mode="thread_local")
+                    else:
+                        graph.capture_begin(pool=self._graph_pool, capture_error_mode="thread_local")
                     loss = self._step_body(R, lr_next)
+                    graph.capture_end()
+                main.wait_stream(self._cap_stream)
                 if self._graph_pool is None:
                     self._graph_pool = graph.pool()
                 self._graphs[key] = (graph, ops.lib.launch_count - n0, loss, self.last_rgb,
