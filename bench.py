@@ -14,7 +14,8 @@ is also the state the reference's published tqdm reading (133 it/s) refers to.
 
 value  = rays/s over all ranks, inputs resident in HBM (pixels shuffled and rays generated on the device, as the
          reference does);  e2e = the same metric with every step's ray batch (origins, directions, RGBA targets)
-         copied from pinned host memory and the loss read back, through Runner.train_step(batch).
+         copied from pinned host memory and the loss read back, through Runner.train_step_host(batch, next_batch): the
+         copies run on the Runner's copy stream inside the timed region, the next batch's under the current step.
 Prints ONE JSON line on rank 0."""
 import argparse
 import json
@@ -45,8 +46,8 @@ def peaks():
 def measured_traffic(stage):
     """DRAM bytes per launch (read + write) of the stage's kernel from the committed ncu --set full capture, or None."""
     try:
-        k = json.load(open(os.path.join(ROOT, "profiles", "r01b_traffic.json")))["kernels"]
-        e = k[{"network_bwd": "network_bwd_kernel", "network_fwd": "network_fwd_kernel<0>"}[stage]]
+        k = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["kernels"]
+        e = k[{"network_bwd": "network_bwd256_kernel", "network_fwd": "network_fwd_kernel<0>"}[stage]]
         return e["dram_bytes_read"] + e["dram_bytes_write"]
     except Exception:
         return None
@@ -307,7 +308,7 @@ def run_ours(args):
     t_dom = stage[dom] * 1e-3
     gbs = n_samples * algo["bytes"] / t_dom / 1e9
     roofline = {"kernel": dom, "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": measured_traffic(dom),
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01b_traffic.json (gradient atomics resolve in L2, "
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r02_traffic.json (gradient atomics resolve in L2, "
                                 "so DRAM traffic is well below the algorithmic bytes)",
                 "peak_source": f"{src} (MEASURED_PEAKS.json hbm_gbs)", "launch_ms": stage[dom], "samples_per_launch": n_samples,
                 "algorithmic_bytes_per_sample": algo["bytes"],
@@ -325,7 +326,9 @@ def run_ours(args):
                                f"{' (2^18)' if args.target_batch == 1 << 18 else ''}, adaptive ray batch "
                                f"({runner.sampler.n_rays_per_batch} rays/iter/GPU at measurement), pretrain {args.pretrain} steps",
                    "parallelism": f"dp{world}", "target_batch_size": args.target_batch,
-                   "l2": "per-step working set (24 MB table + 171 MB optimizer state + 7 MB samples) exceeds the 126 MB L2; no explicit flush"},
+                   "l2": "per-step working set (24 MB table + 171 MB optimizer state + 7 MB samples) exceeds the 126 MB L2; no explicit flush",
+                   "cuda_graphs": {"enabled": bool(getattr(runner, "_graphs_enabled", False)), "graphs": len(getattr(runner, "_graphs", {}) or {}),
+                                   "replays": int(getattr(runner, "graph_replays", 0))}},
         "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline,
     }
     if rank == 0:

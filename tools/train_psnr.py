@@ -27,26 +27,36 @@ def main():
                     help="BASELINE metric 'PSNR@5min': keep training after --steps until this much device time has been spent on training "
                          "steps or the configuration's tot_train_steps (40 000, ngp_base.py) is reached, then evaluate once more")
     ap.add_argument("--data-dir", default=None, help="a real capture in the reference's dataset layout (train/val splits) instead of the stand-in")
+    ap.add_argument("--workload", default="lego", choices=["lego", "fox"],
+                    help="fox = projects/ngp/configs/ngp_fox.py (aabb_scale from the capture, cone stepping); PSNR on training views (the capture has no val split)")
     args = ap.parse_args()
 
     import torch
     from jnerf_b200 import lib, plugin  # noqa: F401
-    from jnerf_b200.runner import Runner, lego_cfg
+    from jnerf_b200.runner import Runner, fox_cfg, lego_cfg
     from jnerf_b200.utils.config import get_cfg, update_cfg
 
     lib.load()
     get_cfg().clear()
-    update_cfg(**lego_cfg(fp16=True, synthetic=True, seed=1))
-    cfg = get_cfg()
-    for split in ("train", "val"):
-        d = cfg.dataset[split]
-        d.n_images = args.images
-        d.H = d.W = args.res
-        d.pop("root_dir", None)
-    cfg.dataset.test = None
-    if args.data_dir:
+    if args.workload == "fox":
+        update_cfg(**fox_cfg(fp16=True, synthetic=args.data_dir is None, seed=1))
+        cfg = get_cfg()
+        if args.data_dir:
+            cfg.dataset.train.root_dir = args.data_dir
+            cfg.dataset.test.root_dir = args.data_dir
+        cfg.dataset.val = None                                      # Runner evaluates on the training views then
+    else:
+        update_cfg(**lego_cfg(fp16=True, synthetic=True, seed=1))
+        cfg = get_cfg()
         for split in ("train", "val"):
-            cfg.dataset[split] = dict(type="NerfDataset", root_dir=args.data_dir, batch_size=4096, mode=split, preload_shuffle=split == "train")
+            d = cfg.dataset[split]
+            d.n_images = args.images
+            d.H = d.W = args.res
+            d.pop("root_dir", None)
+        cfg.dataset.test = None
+        if args.data_dir:
+            for split in ("train", "val"):
+                cfg.dataset[split] = dict(type="NerfDataset", root_dir=args.data_dir, batch_size=4096, mode=split, preload_shuffle=split == "train")
     runner = Runner()
     evals = sorted({int(x) for x in args.evals.split(",") if int(x) <= args.steps} | {args.steps})
     rows, train_ms, done = [], 0.0, 0
@@ -70,6 +80,9 @@ def main():
     res = {"config": f"ngp_base + fp16, {args.images} synthetic {args.res}x{args.res} views, {args.val_images} held-out views", "curve": rows}
     if args.data_dir:
         res["config"] = f"ngp_base + fp16 on {args.data_dir}, {args.val_images} validation views"
+    if args.workload == "fox":
+        res["config"] = (f"ngp_fox.py (fp16, cone stepping) on {args.data_dir or 'the synthetic fox stand-in'}, PSNR on {args.val_images} training views "
+                         f"(the capture has no validation split)")
     if args.budget_seconds > 0:
         tot = int(cfg.tot_train_steps or 40000)
         while train_ms * 1e-3 < args.budget_seconds and done < tot:
