@@ -45,6 +45,10 @@ int ngp_hash_offsets(double aabb_scale, int n_levels, int base_resolution, int l
  * levels_dev: NGP_N_LEVELS * NGP_LEVEL_BYTES bytes. */
 int ngp_hash_level_table(void* stream, const uint32_t* offsets_host, int n_levels, uint32_t base_resolution,
                          float log2_per_level_scale, void* levels_dev);
+/* the same with the three multipliers of cfg.hash_func, get_index(p0,p1,p2) = p0*prime0 ^ p1*prime1 ^ p2*prime2
+ * (HE/hash_encoder.py:13-16 pastes the config string into the kernel source; the configs use 1, 19349663, 83492791) */
+int ngp_hash_level_table_primes(void* stream, const uint32_t* offsets_host, int n_levels, uint32_t base_resolution,
+                                float log2_per_level_scale, void* levels_dev, uint32_t prime0, uint32_t prime1, uint32_t prime2);
 
 /* ---- R2/R3  hash-grid encode -------------------------------------------------------------------------
  * Replaces extract_position + kernel_grid + transpose_encoded_position (HashEncode.h:36-50,117-252,254-268;

@@ -15,7 +15,7 @@
 namespace {
 
 __global__ void level_table_kernel(const uint32_t* __restrict__ offsets, int n_levels, uint32_t base_res, float log2_pls,
-                                   NgpLevel* __restrict__ out) {
+                                   NgpLevel* __restrict__ out, uint32_t p0, uint32_t p1, uint32_t p2) {
     const uint32_t level = threadIdx.x;
     if ((int)level >= n_levels) return;
     NgpLevel lv;
@@ -26,7 +26,7 @@ __global__ void level_table_kernel(const uint32_t* __restrict__ offsets, int n_l
     uint32_t stride = 1;                                            // grid_index loop, :80-91
     for (uint32_t dim = 0; dim < 3 && stride <= lv.size; ++dim) stride *= lv.resolution;
     lv.hashed = lv.size < stride ? 1u : 0u;
-    lv.pad[0] = lv.pad[1] = lv.pad[2] = 0;
+    lv.prime[0] = p0; lv.prime[1] = p1; lv.prime[2] = p2;
     out[level] = lv;
 }
 
@@ -189,18 +189,24 @@ int ngp_hash_offsets(double aabb_scale, int n_levels, int base_resolution, int l
     return 0;
 }
 
-int ngp_hash_level_table(void* stream, const uint32_t* offsets_host, int n_levels, uint32_t base_resolution,
-                         float log2_per_level_scale, void* levels_dev) {
+int ngp_hash_level_table_primes(void* stream, const uint32_t* offsets_host, int n_levels, uint32_t base_resolution,
+                                float log2_per_level_scale, void* levels_dev, uint32_t prime0, uint32_t prime1, uint32_t prime2) {
     NGP_REQUIRE(n_levels == N_LEVELS, "ngp_hash_level_table: the encoder is fixed at 16 levels (HE/hash_encoder.py:17-18)");
     cudaStream_t s = (cudaStream_t)stream;
     uint32_t* d_off = nullptr;
     NGP_CHECK_CUDA(cudaMallocAsync(&d_off, sizeof(uint32_t) * (n_levels + 1), s));   // init-time only
     NGP_CHECK_CUDA(cudaMemcpyAsync(d_off, offsets_host, sizeof(uint32_t) * (n_levels + 1), cudaMemcpyHostToDevice, s));
-    level_table_kernel<<<1, 32, 0, s>>>(d_off, n_levels, base_resolution, log2_per_level_scale, (NgpLevel*)levels_dev);
+    level_table_kernel<<<1, 32, 0, s>>>(d_off, n_levels, base_resolution, log2_per_level_scale, (NgpLevel*)levels_dev, prime0, prime1, prime2);
     NGP_LAUNCH_CHECK();
     NGP_CHECK_CUDA(cudaFreeAsync(d_off, s));
     NGP_CHECK_CUDA(cudaStreamSynchronize(s));
     return 0;
+}
+
+int ngp_hash_level_table(void* stream, const uint32_t* offsets_host, int n_levels, uint32_t base_resolution,
+                         float log2_per_level_scale, void* levels_dev) {
+    // the configs' hash_func: p0 ^ p1 * 19349663 ^ p2 * 83492791 (projects/ngp/configs/ngp_base.py:66)
+    return ngp_hash_level_table_primes(stream, offsets_host, n_levels, base_resolution, log2_per_level_scale, levels_dev, 1u, 19349663u, 83492791u);
 }
 
 int ngp_hash_fwd(void* stream, uint32_t n, const float* x, const void* grid, int dtype, const void* levels_dev, void* out) {

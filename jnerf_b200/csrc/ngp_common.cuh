@@ -55,7 +55,7 @@ struct __align__(32) NgpLevel {
     uint32_t offset;      // first entry of the level
     uint32_t size;        // entries in the level (hashmap_size)
     uint32_t hashed;      // 1: prime-XOR hash, 0: dense stride index (HashEncode.h:74-94)
-    uint32_t pad[3];
+    uint32_t prime[3];    // get_index(p0,p1,p2) = p0*prime[0] ^ p1*prime[1] ^ p2*prime[2]  (cfg.hash_func, HE/hash_encoder.py:13-16)
 };
 static_assert(sizeof(NgpLevel) == 32, "NgpLevel must be 32 bytes");
 constexpr int N_LEVELS = 16;
@@ -71,11 +71,12 @@ __device__ __forceinline__ void hash_corners(const NgpLevel& lv, float x, float 
     const float wx[2] = {1.0f - px, px}, wy[2] = {1.0f - py, py}, wz[2] = {1.0f - pz, pz};
     if (lv.hashed) {
         const uint32_t mask = lv.size - 1;  // hashed levels always have size == 2^log2_hashmap_size
-        const uint32_t hy0 = gy * 19349663u, hy1 = (gy + 1) * 19349663u;
-        const uint32_t hz0 = gz * 83492791u, hz1 = (gz + 1) * 83492791u;
+        const uint32_t hx0 = gx * lv.prime[0], hx1 = (gx + 1) * lv.prime[0];
+        const uint32_t hy0 = gy * lv.prime[1], hy1 = (gy + 1) * lv.prime[1];
+        const uint32_t hz0 = gz * lv.prime[2], hz1 = (gz + 1) * lv.prime[2];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const uint32_t hx = gx + (c & 1);
+            const uint32_t hx = (c & 1) ? hx1 : hx0;
             const uint32_t hy = (c & 2) ? hy1 : hy0;
             const uint32_t hz = (c & 4) ? hz1 : hz0;
             idx[c] = (hx ^ hy ^ hz) & mask;
@@ -110,10 +111,11 @@ __device__ __forceinline__ HashCell hash_cell(const NgpLevel& lv, float x, float
 __device__ __forceinline__ void hash_cell_indices(const NgpLevel& lv, uint32_t gx, uint32_t gy, uint32_t gz, uint32_t idx[8]) {
     if (lv.hashed) {
         const uint32_t mask = lv.size - 1;
-        const uint32_t hy0 = gy * 19349663u, hy1 = (gy + 1) * 19349663u;
-        const uint32_t hz0 = gz * 83492791u, hz1 = (gz + 1) * 83492791u;
+        const uint32_t hx0 = gx * lv.prime[0], hx1 = (gx + 1) * lv.prime[0];
+        const uint32_t hy0 = gy * lv.prime[1], hy1 = (gy + 1) * lv.prime[1];
+        const uint32_t hz0 = gz * lv.prime[2], hz1 = (gz + 1) * lv.prime[2];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) idx[c] = ((gx + (c & 1)) ^ ((c & 2) ? hy1 : hy0) ^ ((c & 4) ? hz1 : hz0)) & mask;
+        for (int c = 0; c < 8; ++c) idx[c] = (((c & 1) ? hx1 : hx0) ^ ((c & 2) ? hy1 : hy0) ^ ((c & 4) ? hz1 : hz0)) & mask;
     } else {
         const uint32_t res = lv.resolution, res2 = res * res;
         const uint32_t b = (gx + gy * res + gz * res2) % lv.size;

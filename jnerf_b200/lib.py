@@ -16,6 +16,7 @@ SIGNATURES = {
     "ngp_debug_timeout_flag": (_i32, []),
     "ngp_hash_offsets": (_i32, [_f64, _i32, _i32, _i32, _vp, _vp]),
     "ngp_hash_level_table": (_i32, [_vp, _vp, _i32, _u32, _f32, _vp]),
+    "ngp_hash_level_table_primes": (_i32, [_vp, _vp, _i32, _u32, _f32, _vp, _u32, _u32, _u32]),
     "ngp_hash_fwd": (_i32, [_vp, _u32, _vp, _vp, _i32, _vp, _vp]),
     "ngp_hash_bwd": (_i32, [_vp, _u32, _vp, _vp, _i32, _vp, _vp, _u64]),
     "ngp_sh_fwd": (_i32, [_vp, _u32, _vp, _i32, _vp]),
@@ -60,7 +61,7 @@ SIGNATURES = {
 
 # kernels launched by each entry point (our own __global__ functions; memsets not counted) -- bench.py's gpu_launches
 KERNELS_PER_CALL = {
-    "ngp_hash_level_table": 1, "ngp_hash_fwd": 1, "ngp_hash_bwd": 1, "ngp_sh_fwd": 1, "ngp_mlp_fwd": 1, "ngp_mlp_bwd": 1, "ngp_mlp_bwd_dgrad": 1,
+    "ngp_hash_level_table": 1, "ngp_hash_level_table_primes": 1, "ngp_hash_fwd": 1, "ngp_hash_bwd": 1, "ngp_sh_fwd": 1, "ngp_mlp_fwd": 1, "ngp_mlp_bwd": 1, "ngp_mlp_bwd_dgrad": 1,
     "ngp_network_fwd": 1, "ngp_network_bwd": 1, "ngp_density_fwd": 1, "ngp_march": 3, "ngp_compact": 1, "ngp_composite_fwd": 1,
     "ngp_composite_bwd": 1, "ngp_composite_infer": 1, "ngp_composite_loss_bwd": 1, "ngp_grid_mark_untrained": 1,
     "ngp_grid_generate_samples": 1, "ngp_grid_splat": 1, "ngp_grid_ema": 1, "ngp_grid_update_bitfield": 7, "ngp_adam_ema": 1, "ngp_dp_exchange_step": 1, "ngp_dp_exchange_wait": 1, "ngp_raygen": 1, "ngp_prepare_batch": 1,

@@ -30,8 +30,9 @@ def _stream():
 class HashLevels:
     """R1: offsets (host, HE/grid_encode.py:17-39) + the device level table the kernels stage in shared memory."""
 
-    def __init__(self, aabb_scale=1, n_levels=16, base_resolution=16, log2_hashmap_size=19, device="cuda"):
+    def __init__(self, aabb_scale=1, n_levels=16, base_resolution=16, log2_hashmap_size=19, device="cuda", primes=(1, 19349663, 83492791)):
         import ctypes as C
+        self.primes = tuple(int(p) & 0xFFFFFFFF for p in primes)
         self.n_levels, self.base_resolution = n_levels, base_resolution
         self.offsets = np.zeros(n_levels + 1, np.uint32)
         pls = C.c_double()
@@ -41,7 +42,8 @@ class HashLevels:
         self.n_entries = int(self.offsets[-1])
         self.n_params = 2 * self.n_entries
         self.table = torch.empty(n_levels * 32, dtype=torch.uint8, device=device)
-        lib.call("ngp_hash_level_table", _stream(), self.offsets.ctypes.data, n_levels, base_resolution, self.log2_per_level_scale, _p(self.table))
+        lib.call("ngp_hash_level_table_primes", _stream(), self.offsets.ctypes.data, n_levels, base_resolution, self.log2_per_level_scale,
+                 _p(self.table), *self.primes)
 
 
 def hash_fwd(x, grid, levels):

@@ -12,6 +12,25 @@ from .module import Module
 DEFAULT_HASH = "p0 ^ p1 * 19349663 ^ p2 * 83492791"
 
 
+def parse_hash_func(expr):
+    """cfg.hash_func -> (prime0, prime1, prime2).  The reference pastes the string into its kernel source as
+    `#define get_index(p0,p1,p2) <hash_func>` (HE/hash_encoder.py:13-16); the kernels here take the XOR-of-products family the NGP
+    configs use -- `p0 [* a] ^ p1 [* b] ^ p2 [* c]` in any order, unsigned 32-bit arithmetic -- as three multipliers in the level table."""
+    import re
+    primes = {}
+    for term in "".join(str(expr).split()).split("^"):
+        m = re.fullmatch(r"p([012])(?:\*(\d+)[uU]?)?|(\d+)[uU]?\*p([012])", term)
+        if not m:
+            raise NotImplementedError(f"hash_func {expr!r}: term {term!r} is not of the form pK or pK * N")
+        k, n = (int(m.group(1)), m.group(2)) if m.group(1) is not None else (int(m.group(4)), m.group(3))
+        if k in primes:
+            raise NotImplementedError(f"hash_func {expr!r}: p{k} appears twice")
+        primes[k] = int(n) & 0xFFFFFFFF if n is not None else 1
+    if sorted(primes) != [0, 1, 2]:
+        raise NotImplementedError(f"hash_func {expr!r}: every one of p0, p1, p2 must appear exactly once")
+    return primes[0], primes[1], primes[2]
+
+
 class _GridEncodeFn(torch.autograd.Function):
     """GridEncode.execute / .grad (HE/grid_encode.py:66-190): returns (None, grid_gradient) -- no dL/dx."""
 
@@ -35,7 +54,9 @@ class GridEncode:
     def __init__(self, hash_func_header, aabb_scale=1, n_pos_dims=3, n_features_per_level=2, n_levels=16, base_resolution=16,
                  log2_hashmap_size=19, n_rays_per_batch=4096, MAX_STEP=1024, using_fp16=False):
         assert n_pos_dims == 3 and n_features_per_level == 2 and n_levels == 16, "kernels are specialised for 3D, F=2, L=16"
-        self.levels = ops.HashLevels(aabb_scale, n_levels, base_resolution, log2_hashmap_size)
+        # hash_func_header: the reference's "#define get_index(p0,p1,p2) <expr>" (or just <expr>, or empty for the default)
+        expr = hash_func_header.split(")", 1)[1] if "get_index" in hash_func_header else hash_func_header
+        self.levels = ops.HashLevels(aabb_scale, n_levels, base_resolution, log2_hashmap_size, primes=parse_hash_func(expr.strip() or DEFAULT_HASH))
         self.m_n_params = self.levels.n_params
         self.m_per_level_scale = self.levels.per_level_scale
         self.m_n_levels = n_levels
@@ -57,9 +78,8 @@ class HashEncoder(Module):
         using_fp16 = bool(self.cfg.fp16)
         aabb_scale = self.cfg.dataset_obj.aabb_scale if self.cfg.dataset_obj is not None else 1
         self.hash_func = self.cfg.hash_func or DEFAULT_HASH
-        if "".join(self.hash_func.split()) != "".join(DEFAULT_HASH.split()):
-            raise NotImplementedError(f"hash_func {self.hash_func!r}: only the Instant-NGP prime-XOR hash is compiled in")
-        self.encoder = GridEncode("", aabb_scale=aabb_scale, n_pos_dims=3, n_features_per_level=2, n_levels=16, base_resolution=16,
+        self.hash_func_header = f"#define get_index(p0,p1,p2) {self.hash_func}"
+        self.encoder = GridEncode(self.hash_func_header, aabb_scale=aabb_scale, n_pos_dims=3, n_features_per_level=2, n_levels=16, base_resolution=16,
                                   log2_hashmap_size=19, using_fp16=using_fp16)
         self.grad_type = torch.float16 if using_fp16 else torch.float32
         g = torch.Generator(device="cuda").manual_seed(int(self.cfg.seed or 1))

@@ -102,10 +102,14 @@ double orc_hash_offsets(double aabb_scale, int n_levels, int base_resolution, in
  * R2: hash-grid forward  (HE/op_header/HashEncode.h:68-115 hash/index/fract, :117-203 kernel_grid;
  *     launch + layout HE/grid_encode.py:86-124).  x (n,3) f32 in [0,1]; out (n, 2*L), feature 2*level+f.
  * ---------------------------------------------------------------------------------------------- */
+/* cfg.hash_func is pasted into the reference's kernel source as get_index(p0,p1,p2) (HE/hash_encoder.py:13-16); both NGP configs
+ * use p0 ^ p1 * 19349663 ^ p2 * 83492791 (ngp_base.py:66).  orc_set_hash_primes selects another member of that XOR-of-products family. */
+static uint32_t g_hash_prime[3] = {1u, 19349663u, 83492791u};
+void orc_set_hash_primes(uint32_t p0, uint32_t p1, uint32_t p2) { g_hash_prime[0] = p0; g_hash_prime[1] = p1; g_hash_prime[2] = p2; }
 static inline uint32_t grid_index(uint32_t hashmap_size, uint32_t res, const uint32_t g[3]) {
     uint32_t stride = 1, index = 0;
     for (uint32_t dim = 0; dim < 3 && stride <= hashmap_size; ++dim) { index += g[dim] * stride; stride *= res; }
-    if (hashmap_size < stride) index = g[0] ^ g[1] * 19349663u ^ g[2] * 83492791u; /* cfg hash_func, ngp_base.py:66 */
+    if (hashmap_size < stride) index = g[0] * g_hash_prime[0] ^ g[1] * g_hash_prime[1] ^ g[2] * g_hash_prime[2];
     return (index % hashmap_size) * 2;
 }
 /* The reference evaluates exp2f on the GPU (MUFU.EX2, <= 2 ulp), libm's exp2f is correctly rounded: the two can

@@ -39,7 +39,9 @@ def _u32view(t):
 class CpuHashLevels:
     """ops.HashLevels without the device table: the offsets come from the real host entry point (ngp_hash_offsets)."""
 
-    def __init__(self, aabb_scale=1, n_levels=16, base_resolution=16, log2_hashmap_size=19, device="cpu"):
+    def __init__(self, aabb_scale=1, n_levels=16, base_resolution=16, log2_hashmap_size=19, device="cpu", primes=(1, 19349663, 83492791)):
+        assert tuple(primes) == (1, 19349663, 83492791), "the CPU stand-in evaluates the configs' hash only"
+        self.primes = tuple(primes)
         self.cfg = ol.HashCfg(aabb_scale, n_levels, base_resolution, log2_hashmap_size)
         self.n_levels, self.base_resolution = n_levels, base_resolution
         self.offsets = self.cfg.offsets

@@ -43,6 +43,8 @@ def oracle():
         _oracle.orc_morton3D.restype = _u32
         _oracle.orc_morton3D_invert.restype = _u32
         _oracle.orc_set_level_scales.argtypes = [_p]
+        _oracle.orc_set_hash_primes.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+        _oracle.orc_set_hash_primes.restype = None
     return _oracle
 
 

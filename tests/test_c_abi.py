@@ -143,3 +143,13 @@ def test_reference_config_files_load_unchanged():
         assert cfg.dataset.train.root_dir == ds and cfg.fp16 == fp16 and cfg.const_dt == const_dt
         assert cfg.target_batch_size == 1 << 18 and cfg.optim.betas == (0.9, 0.99) and cfg.hash_func == "p0 ^ p1 * 19349663 ^ p2 * 83492791"
         cfg.clear()
+
+
+def test_hash_func_parsing():
+    """cfg.hash_func -> the three multipliers of the level table (HE/hash_encoder.py:13-16)."""
+    from jnerf_b200.plugin.encoders import DEFAULT_HASH, parse_hash_func
+    assert parse_hash_func(DEFAULT_HASH) == (1, 19349663, 83492791)
+    assert parse_hash_func("p2*7u ^ 3*p0 ^ p1") == (3, 1, 7)
+    for bad in ("p0 + p1 ^ p2", "p0 ^ p1", "p0 ^ p0 ^ p1 ^ p2", "hash(p0, p1, p2)"):
+        with pytest.raises(NotImplementedError):
+            parse_hash_func(bad)

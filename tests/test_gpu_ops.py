@@ -93,6 +93,32 @@ def test_hash_fwd_config1(ops, log2T):
         assert np.abs(out[:256] - G["hash_fwd_f32_head"]).max() <= 1e-7
 
 
+def test_hash_func_from_config(ops):
+    """cfg.hash_func (HE/hash_encoder.py:13-16): another member of the XOR-of-products family, parsed into the level table's three
+    multipliers -- forward and backward against the oracle evaluating the same expression."""
+    from jnerf_b200.plugin.encoders import parse_hash_func
+    primes = parse_hash_func("p1 * 2654435761 ^ p0 * 3 ^ 805459861 * p2")
+    assert primes == (3, 2654435761, 805459861)
+    cfg = ol.HashCfg(1, log2_hashmap_size=14)
+    lv = ops.HashLevels(1, log2_hashmap_size=14, primes=primes)
+    x = INP["x"]
+    grid = table(cfg, np.float16)
+    dy = INP["dy"].astype(np.float16)
+    ol.oracle().orc_set_hash_primes(*primes)
+    try:
+        with device_scales(lv):
+            ref = ol.hash_fwd(cfg, x, grid, acc32=True)
+            gref = ol.hash_bwd(cfg, x, dy, acc32=True).astype(np.float64)
+    finally:
+        ol.oracle().orc_set_hash_primes(1, 19349663, 83492791)
+    out = npy(ops.hash_fwd(cu(x), cu(grid), lv))
+    assert np.abs(out.astype(np.float64) - ref.astype(np.float64)).max() <= 2.0 ** -11 * 2e-4
+    default = npy(ops.hash_fwd(cu(x), cu(grid), ops.HashLevels(1, log2_hashmap_size=14)))
+    assert np.abs(out.astype(np.float32) - default.astype(np.float32)).max() > 0          # the hashed levels really changed
+    g = npy(ops.hash_bwd(cu(x), cu(dy), lv)).astype(np.float64)
+    assert np.abs(g - gref).max() <= 2e-2 * np.abs(gref).max()
+
+
 def test_hash_bwd(ops):
     cfg = ol.HashCfg(1, log2_hashmap_size=14)
     lv = ops.HashLevels(1, log2_hashmap_size=14)
