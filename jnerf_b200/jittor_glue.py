@@ -51,10 +51,10 @@ SRC = {
     "grid_generate_samples": ("NGP_OK(ngp_grid_generate_samples(0, out1_shape0, rng.state, rng.inc, (uint32_t*)in1_p, {aabb0}, {aabb1}, in0_p, out0_p, "
                               "(uint32_t*)out1_p, {n_cascades}, {thresh})); rng.advance();"),
     "grid_splat": "NGP_OK(ngp_grid_splat(0, in0_shape0, (uint32_t*)in0_p, in1_p, {dtype}, out0_p));",
-    "grid_ema": "NGP_OK(ngp_grid_ema(0, out0_shape0, {decay}f, out0_p, in0_p));",
+    "grid_ema": "NGP_OK(ngp_grid_ema(0, out0_shape0, (float){decay}, out0_p, in0_p));",
     "grid_update_bitfield": "NGP_OK(ngp_grid_update_bitfield(0, in0_p, out1_p, (uint8_t*)out0_p, NERF_CASCADES()));",
     # optims/adam.py + optims/ema.py in one sweep per parameter tensor
-    "adam_ema": "NGP_OK(ngp_adam_ema(0, in0_shape0, in0_p, NGP_F16, in1_p, NGP_F16, 1.0f, in2_p, in3_p, in4_p, {lr}f, 0.9f, 0.99f, 1e-15f, {step}, 0.95f, 1));",
+    "adam_ema": "NGP_OK(ngp_adam_ema(0, in0_shape0, in0_p, NGP_F16, in1_p, NGP_F16, 1.0f, in2_p, in3_p, in4_p, (float){lr}, 0.9f, 0.99f, 1e-15f, {step}, 0.95f, 1));",
 }
 
 

@@ -43,7 +43,7 @@ def _type_check(calls, declared, tmp_path, name):
         c = re.sub(r"\{[^{}]*\}", "1", c)                       # python f-string fields become literals
         ids = set(re.findall(r"[A-Za-z_][A-Za-z_0-9]*", re.sub(r"/\*.*?\*/", "", c)))
         ids -= {"NGP_OK", "NGP_F16", "NGP_F32", "NERF_CASCADES", "nullptr", "sizeof", "const", "uint32_t", "uint8_t", "in1_type", "out_type",
-                "state", "inc", "num", "f", "e"} | declared
+                "state", "inc", "num", "f", "e", "float"} | declared
         decl = []
         for v in sorted(ids):
             if v == "rng":
@@ -98,7 +98,7 @@ def test_jittor_glue_module_imports_and_its_cuda_bodies_type_check(tmp_path):
     hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ngp_b200.h")).read(), flags=re.S)
     declared = set(re.findall(r"\b(ngp_[a-z0-9_]+)\s*\(", hdr))
     calls = extract_calls("\n".join(glue.SRC.values()))
-    assert len(calls) == len(glue.SRC) >= 20
+    assert len(calls) == len(glue.SRC) >= 19
     _type_check(calls, declared, tmp_path, "glue.cpp")
     assert "-Xlinker" in next(iter(glue.ngp_options())) and glue.NGP_LIB.endswith("libngp_b200.so")
     import pytest
