@@ -133,6 +133,7 @@ class GridEncode:
 
 def sh_encode(x, grad_type="float16"):
     """models/position_encoders/sh_encoder/sh_encoder.py:26-53."""
+    _jt()
     return _code((x.shape[0], 16), grad_type, [x], SRC["sh_fwd"])
 
 
@@ -168,6 +169,7 @@ class FullyFusedMlp_weight:
 
 def network_fwd(coords, m_grid, levels, wd, wr):
     """models/networks/ngp_network.py:77-84 fused: (N,7) NerfCoordinate rows -> ((N,4) fp16 {r,g,b,sigma_raw}, (N,32) encoded features)."""
+    _jt()
     N = coords.shape[0]
     return _code([(N, 4), (N, 32)], ["float16", "float16"], [coords, m_grid, levels, wd, wr], SRC["network_fwd"])
 
