@@ -1,5 +1,6 @@
 // Error state, version and small host-side helpers of the C ABI (include/ngp_b200.h).
 #include "ngp_common.cuh"
+#include <cuda.h>
 #include <vector>
 #include <utility>
 #include <mutex>
@@ -21,6 +22,28 @@ int ngp_num_sms() {
         sms[dev] = n;
     }
     return sms[dev];
+}
+
+// Tensor map for the encoded-feature matrix (rows, 32) fp16: box = 8 columns (one slab feature group) x 128 rows (one tile).
+// cuTensorMapEncodeTiled is a driver entry point; the library links the runtime only, so it is looked up through the runtime.
+bool ngp_make_rows32_tensormap(NgpTensorMap* out, const void* base, unsigned long long n_rows) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeFn)p;
+    }
+    if (!fn || n_rows == 0 || (reinterpret_cast<uintptr_t>(base) & 15)) return false;
+    static_assert(sizeof(NgpTensorMap) == sizeof(CUtensorMap), "tensor map size");
+    const cuuint64_t dims[2] = {32, n_rows};
+    const cuuint64_t strides[1] = {64};                          // bytes between rows
+    const cuuint32_t box[2] = {8, 128}, estr[2] = {1, 1};
+    return fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of on every launch

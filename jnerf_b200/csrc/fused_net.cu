@@ -147,7 +147,11 @@ template <bool DENSITY_ONLY>
 __global__ void __launch_bounds__(FWD_THREADS, 2)   // two CTAs per SM (128 TMEM columns each): <= 85 registers per thread
 network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const float* __restrict__ coords, const __half* __restrict__ grid,
                    const NgpLevel* __restrict__ levels, const __half* __restrict__ wd, const __half* __restrict__ wr,
-                   __half* __restrict__ out, __half* __restrict__ enc_save, int* __restrict__ err) {
+                   __half* __restrict__ out, __half* __restrict__ enc_save, int* __restrict__ err,
+                   const __grid_constant__ NgpTensorMap enc_map, uint32_t enc_tma) {
+    // enc_tma: the encoded-feature rows kept for the backward pass leave the SM as four TMA tensor stores per tile, straight from the
+    // slab the gather warps fill (one 8-column x 128-row box per feature group), instead of 16 four-byte global stores per row from the
+    // gather warps -- which are the LSU-bound side of this kernel.  enc_save is then only the base address the tensor map was built for.
     extern __shared__ __align__(1024) uint8_t smem[];
     using S = SmemFwd;
     constexpr int CS = DENSITY_ONLY ? 3 : 7;
@@ -180,9 +184,22 @@ network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             const float* s_coords = reinterpret_cast<const float*>(smem + S::coords + buf * 3584);
             named_bar_sync(2 + buf, FWD_THREADS);                       // FULL[buf]: enc slab + coordinates of this tile are in smem
             tc_fence_after();
+            if (!DENSITY_ONLY && enc_tma && warp == 0) {                 // the gather threads fenced their slab writes for the async proxy
+                if (elect_one()) {
+#pragma unroll
+                    for (uint32_t g4 = 0; g4 < 4; ++g4)
+                        tma_store_2d(&enc_map, 8 * g4, tile * ROWS, smem_u32(smem) + S::act + ((buf ? G_ENC1 : G_ENC) + g4) * GB);
+                    tma_store_commit();
+                }
+                __syncwarp();
+            }
             // forward_chain releases nothing itself: the enc slab is dead after layer 0, the coordinates after the SH epilogue;
             // both are handed back together right after the chain (the gather runs a full tile ahead, so this is not on its path)
             const uint32_t sig = forward_chain<S, G_H2F, true>(smem, buf ? G_ENC1 : G_ENC, s_coords, tbase, pipe, t, warp, DENSITY_ONLY);
+            if (!DENSITY_ONLY && enc_tma && warp == 0) {                 // the tensor stores have read the slab before it is handed back
+                if (elect_one()) tma_store_wait_read();
+                __syncwarp();
+            }
             if (tile + 2 * gridDim.x < ntiles) named_bar_arrive(4 + buf, FWD_THREADS);   // EMPTY[buf]
             if constexpr (DENSITY_ONLY) {
                 if (row < n_live) reinterpret_cast<uint16_t*>(out)[row] = (uint16_t)sig;
@@ -213,10 +230,15 @@ network_fwd_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const flo
             for (uint32_t i = tg; i < ROWS * CS; i += 32 * FWD_GW)       // stage the coordinate tile (coalesced)
                 s_coords[i] = (row0 + i / CS < n_live) ? __ldg(coords + (size_t)row0 * CS + i) : 0.f;
             named_bar_sync(6, 32 * FWD_GW);
-            gather_tile<CS, 64 / FWD_GW>(s_coords, lv, g, smem + S::act, buf ? G_ENC1 : G_ENC, level, sub, DENSITY_ONLY ? nullptr : enc_save, row0, n_live);
+            gather_tile<CS, 64 / FWD_GW>(s_coords, lv, g, smem + S::act, buf ? G_ENC1 : G_ENC, level, sub, (DENSITY_ONLY || enc_tma) ? nullptr : enc_save, row0,
+                                         n_live);
             fence_proxy_async_smem();                           // the enc slab is read by the tensor core (async proxy)
             named_bar_arrive(2 + buf, FWD_THREADS);                     // FULL[buf]
         }
+    }
+    if (!DENSITY_ONLY && enc_tma && warp == 0) {                         // shared memory must outlive the last tensor store
+        if (elect_one()) tma_store_wait_all();
+        __syncwarp();
     }
     tc_fence_before();
     __syncthreads();
@@ -262,13 +284,14 @@ __global__ void __launch_bounds__(B3_THREADS, 1)
 network_bwd256_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const float* __restrict__ coords, const __half* __restrict__ enc_save,
                       const NgpLevel* __restrict__ levels, const __half* __restrict__ wd, const __half* __restrict__ wr,
                       const __half* __restrict__ dout, __half* __restrict__ grid_grad, float* __restrict__ dwd, float* __restrict__ dwr,
-                      int* __restrict__ err, uint32_t dbg) {
+                      int* __restrict__ err, uint32_t dbg, const __grid_constant__ NgpTensorMap enc_map, uint32_t enc_tma) {
     extern __shared__ __align__(1024) uint8_t smem[];
     using S = SmemBwd3;
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     uint64_t* bar_d = reinterpret_cast<uint64_t*>(smem + S::bar);  // the forward / dgrad MMAs of the current stage are done
     uint64_t* bar_w = bar_d + 1;                                   // all weight-gradient MMAs of the pair of tiles are done
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_d + 2);
+    uint64_t* bar_t = bar_d + 2;                                   // [2]: the TMA loads of a tile's encoded-feature rows have landed
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_d + 4);
     NgpLevel* s_lv = reinterpret_cast<NgpLevel*>(smem + S::levels);
 
     stage_weights(smem + S::w0d, wd + WD_W0, 64, 32, tid, B3_THREADS);
@@ -279,7 +302,7 @@ network_bwd256_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const 
     if (tid < N_LEVELS) s_lv[tid] = levels[tid];
     // zero both tiles once: dYr columns 4..15 are never rewritten, and M = 128 weight-gradient operands run past their slab
     for (uint32_t i = tid; i < 2 * S::tile_stride / 16; i += B3_THREADS) *reinterpret_cast<uint4*>(smem + S::tile0 + i * 16) = make_uint4(0, 0, 0, 0);
-    if (tid == 0) { mbar_init(bar_d, 1); mbar_init(bar_w, 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(bar_d, 1); mbar_init(bar_w, 1); mbar_init(bar_t, 1); mbar_init(bar_t + 1, 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(tmem_ptr, 512);
     sync_before_issue();
     const uint32_t tbase = *tmem_ptr;
@@ -316,9 +339,11 @@ network_bwd256_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const 
                 const uint32_t i = t + 128 * j;
                 pf_c[j] = (r0 + i / 7 < n_live) ? __ldg(coords + (size_t)r0 * 7 + i) : 0.f;
             }
-            const uint4* es = reinterpret_cast<const uint4*>(enc_save + (size_t)r * 32);
+            if (!enc_tma) {
+                const uint4* es = reinterpret_cast<const uint4*>(enc_save + (size_t)r * 32);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) pf_e[g] = ok ? __ldg(es + g) : make_uint4(0, 0, 0, 0);
+                for (int g = 0; g < 4; ++g) pf_e[g] = ok ? __ldg(es + g) : make_uint4(0, 0, 0, 0);
+            }
             pf_d = ok ? __ldg(reinterpret_cast<const uint2*>(dout) + r) : make_uint2(0, 0);
         };
         if (blockIdx.x < npairs) prefetch(blockIdx.x);
@@ -329,12 +354,32 @@ network_bwd256_kernel(uint32_t n_max, const uint32_t* __restrict__ n_dev, const 
             if (it >= 1) { if (!mbar_wait(bar_w, (it - 1) & 1)) atomicExch(err, 2); }   // the previous pair's wgrad MMAs have read their slabs
 #pragma unroll
             for (int j = 0; j < 7; ++j) s_coords[t + 128 * j] = pf_c[j];
+            if (enc_tma) {
+                // encoded-feature rows of this tile: four tensor loads (8-column x 128-row boxes = the four slab groups) by one thread
+                if (tq == 0) {
+                    if (elect_one()) {
+                        mbar_expect_tx(bar_t + T, ROWS * 64);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(act + (G_ENC + g) * GB + t * 16) = pf_e[g];
+                        for (uint32_t g4 = 0; g4 < 4; ++g4)
+                            tma_load_2d(smem_u32(act) + (G_ENC + g4) * GB, &enc_map, 8 * g4, (2 * pair + T) * ROWS, bar_t + T);
+                    }
+                    __syncwarp();
+                }
+            } else {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(act + (G_ENC + g) * GB + t * 16) = pf_e[g];
+            }
             const uint32_t dsig = pf_d.y >> 16;
             *reinterpret_cast<uint4*>(act + B3_G_DY * GB + t * 16) = make_uint4(pf_d.x, pf_d.y & 0xFFFFu, 0, 0);   // dYr: 3 colour gradients, K padded to 16
             *reinterpret_cast<uint4*>(act + (B3_G_DY + 1) * GB + t * 16) = make_uint4(0, 0, 0, 0);
             if (pair + gridDim.x < npairs) prefetch(pair + gridDim.x);     // in flight during the whole chain
+            if (enc_tma) {
+                if (!mbar_wait(bar_t + T, it & 1)) atomicExch(err, 4);
+                if ((2 * pair + T) * ROWS + t >= n_live) {                  // rows past the live samples hold whatever an earlier step left: zero them
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(act + (G_ENC + g) * GB + t * 16) = make_uint4(0, 0, 0, 0);
+                }
+            }
             named_bar_sync(4 + T, 128);                                     // the SH epilogue reads other threads' coordinate words
             ready();
             // F1 density L0: enc -> hd
@@ -526,9 +571,12 @@ int ngp_network_fwd(void* stream, uint32_t n_max, const uint32_t* n_dev, const f
     if (ngp_first_use((const void*)network_fwd_kernel<false>)) NGP_CHECK_CUDA(cudaFuncSetAttribute(network_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemFwd::total));
     const uint32_t ntiles = (n_max + ROWS - 1) / ROWS;
     const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms() * 2u);
+    NgpTensorMap enc_map{};
+    static const bool no_tma = getenv("NGP_NO_TMA") != nullptr;           // A/B switch
+    const uint32_t enc_tma = (!no_tma && enc_save && ngp_make_rows32_tensormap(&enc_map, enc_save, n_max)) ? 1u : 0u;
     network_fwd_kernel<false><<<grid_dim, FWD_THREADS, SmemFwd::total, s>>>(n_max, n_dev, coords, (const __half*)grid, (const NgpLevel*)levels_dev,
                                                                    (const __half*)w_density, (const __half*)w_rgb, (__half*)out,
-                                                                   (__half*)enc_save, ngp_err_flag());
+                                                                   (__half*)enc_save, ngp_err_flag(), enc_map, enc_tma);
     NGP_LAUNCH_CHECK();
     return 0;
 }
@@ -540,7 +588,7 @@ int ngp_density_fwd(void* stream, uint32_t n, const float* pos, const void* grid
     const uint32_t ntiles = (n + ROWS - 1) / ROWS;
     const uint32_t grid_dim = min(ntiles, (uint32_t)ngp_num_sms() * 2u);
     network_fwd_kernel<true><<<grid_dim, FWD_THREADS, SmemFwd::total, s>>>(n, nullptr, pos, (const __half*)grid, (const NgpLevel*)levels_dev,
-                                                                  (const __half*)w_density, nullptr, (__half*)sigma_out, nullptr, ngp_err_flag());
+                                                                  (const __half*)w_density, nullptr, (__half*)sigma_out, nullptr, ngp_err_flag(), NgpTensorMap{}, 0u);
     NGP_LAUNCH_CHECK();
     return 0;
 }
@@ -554,9 +602,12 @@ int ngp_network_bwd(void* stream, uint32_t n_max, const uint32_t* n_dev, const f
     static const uint32_t dbg = getenv("NGP_BWD_DEBUG") ? (uint32_t)atoi(getenv("NGP_BWD_DEBUG")) : 0u;
     if (ngp_first_use((const void*)network_bwd256_kernel)) NGP_CHECK_CUDA(cudaFuncSetAttribute(network_bwd256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemBwd3::total));
     const uint32_t grid_dim = min((ntiles + 1) / 2, (uint32_t)ngp_num_sms());
+    NgpTensorMap enc_map{};
+    static const bool no_tma = getenv("NGP_NO_TMA") != nullptr;           // A/B switch
+    const uint32_t enc_tma = (!no_tma && ngp_make_rows32_tensormap(&enc_map, enc_save, n_max)) ? 1u : 0u;
     network_bwd256_kernel<<<grid_dim, B3_THREADS, SmemBwd3::total, s>>>(n_max, n_dev, coords, (const __half*)enc_save, (const NgpLevel*)levels_dev,
                                                                        (const __half*)w_density, (const __half*)w_rgb, (const __half*)dout,
-                                                                       (__half*)grid_grad, dw_density, dw_rgb, ngp_err_flag(), dbg);
+                                                                       (__half*)grid_grad, dw_density, dw_rgb, ngp_err_flag(), dbg, enc_map, enc_tma);
     NGP_LAUNCH_CHECK();
     return 0;
 }

@@ -25,6 +25,9 @@ void ngp_set_error(const std::string& msg);
 #define NGP_LAUNCH_CHECK() NGP_CHECK_CUDA(cudaGetLastError())
 
 int ngp_num_sms();
+// 128-byte TMA descriptor (CUtensorMap) of a row-major (n_rows, 32) fp16 matrix with an 8-column x 128-row box; false = no driver support
+struct alignas(64) NgpTensorMap { unsigned long long opaque[16]; };
+bool ngp_make_rows32_tensormap(NgpTensorMap* out, const void* base, unsigned long long n_rows);
 bool ngp_first_use(const void* kernel);      // true the first time a kernel is seen on the current device (one-time attribute setup)
 
 // ---- fire-and-forget reductions --------------------------------------------------------------------
