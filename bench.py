@@ -289,11 +289,15 @@ def run_ours(args):
         host_batches.append(tuple(t.cpu().pin_memory() for t in b))
     h2d = sum(t.numel() * t.element_size() for t in host_batches[0])
 
+    R_e2e, ds_e2e = runner.sampler.n_rays_per_batch, runner.dataset["train"]
+
     def host_step(k):
         # the user-facing call for host-fed batches: this step's batch and (for overlap) the next one, both in pinned host memory;
         # the H2D copies and the D2H of the mean loss run on the Runner's copy stream inside the timed region
         hb = host_batches[k % len(host_batches)]
         loss_host = runner.train_step_host(hb, host_batches[(k + 1) % len(host_batches)])
+        # the pre-generated batches keep their size: do not let the 16-step adaptation run away from them
+        runner.sampler.n_rays_per_batch = ds_e2e.batch_size = R_e2e
         return hb[1].shape[0]
 
     for k in range(max(args.warmup, 3)):

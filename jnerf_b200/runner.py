@@ -223,6 +223,7 @@ class Runner:
         if R > s._march_ws_rays:
             s._ensure_march_ws(2 * R)
             self._graphs.clear()                                     # the captured launches hold the old workspace's address
+            self._graph_pool = None                                  # (the allocator drops a pool together with its last graph)
         start = ds.reserve_pixels(R)
         lr, lr_next = self._lr_for_step(dec.steps), self._lr_for_step(dec.steps + 1)
         want = (int(s.rng[0]), int(s.rng[1]), start, adam.n_step, lr)
@@ -240,7 +241,9 @@ class Runner:
         else:
             seen = self._graph_seen.get(key, 0) + 1
             self._graph_seen[key] = seen
-            if self._graphs_enabled and not edge and seen >= 2 and i >= 2 * s.update_den_freq and len(self._graphs) < 64:
+            # a capture costs about as much as 200 replays save: only ray-batch sizes that keep coming back (a second 16-step window)
+            # get a graph
+            if self._graphs_enabled and not edge and seen >= 20 and len(self._graphs) < 64:
                 # capture on a side stream with the raw begin / end calls: torch.cuda.graph() would synchronise the device, run the
                 # Python garbage collector and empty the allocator cache on every capture (~10 ms each)
                 graph = torch.cuda.CUDAGraph()

@@ -10,7 +10,7 @@ WANT = {"gpu__time_duration.sum": "duration_ns", "dram__bytes_read.sum": "dram_b
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pipe_pct", "smsp__inst_executed.sum": "warp_instructions",
         "launch__registers_per_thread": "registers", "lts__t_sector_hit_rate.pct": "l2_hit_pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_throughput_pct",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_throughput_pct"}
-UNIT = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "usecond": 1e3, "msecond": 1e6, "nsecond": 1.0, "second": 1e9}
+UNIT = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "usecond": 1e3, "msecond": 1e6, "nsecond": 1.0, "second": 1e9, "us": 1e3, "ms": 1e6, "ns": 1.0, "s": 1e9}
 
 
 def main():
