@@ -84,6 +84,7 @@ class Runner:
             self._graphs, self._graph_seen, self._graph_pool, self._cap_stream = {}, {}, None, None
             self._graphs_enabled = os.environ.get("NGP_GRAPHS", "1") == "1" and torch.cuda.is_available() and hasattr(torch.cuda, "CUDAGraph")
             self.graph_replays = 0
+            self._graph_after = int(os.environ.get("NGP_GRAPH_AFTER", "20"))     # occurrences of a ray-batch size before it gets a graph
         if self.world_size > 1:
             self._init_sharded_table()
 
@@ -243,7 +244,7 @@ class Runner:
             self._graph_seen[key] = seen
             # a capture costs about as much as 200 replays save: only ray-batch sizes that keep coming back (a second 16-step window)
             # get a graph
-            if self._graphs_enabled and not edge and seen >= 20 and len(self._graphs) < 64:
+            if self._graphs_enabled and not edge and seen >= self._graph_after and len(self._graphs) < 64:
                 # capture on a side stream with the raw begin / end calls: torch.cuda.graph() would synchronise the device, run the
                 # Python garbage collector and empty the allocator cache on every capture (~10 ms each)
                 graph = torch.cuda.CUDAGraph()

@@ -144,6 +144,7 @@ def test_cuda_graph_replay_equals_eager_steps(monkeypatch):
     runs = {}
     for graphs in ("1", "0"):
         monkeypatch.setenv("NGP_GRAPHS", graphs)
+        monkeypatch.setenv("NGP_GRAPH_AFTER", "2")                 # capture at the second step of a ray-batch size (default: its second window)
         r = make_runner(seed=21)
         assert r._graphs_enabled == (graphs == "1")
         losses, marks = [], []
