@@ -335,7 +335,7 @@ def run_ours(args):
                 "stage_ms": stage}
     out = {
         "metric": f"ngp_{args.workload}_train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f16",
         "data": f"real: {args.data_dir}" if args.data_dir else "synthetic",
         "iters_per_s": args.steps / (ms * 1e-3), "published_iters_per_s_rtx3090": 133.0, "samples_per_s": None,
         "config": {"workload": ("Instant-NGP fox: projects/ngp/configs/ngp_fox.py (BASELINE config #3: aabb_scale 4, cone stepping, fp16 fully-fused MLP), "
@@ -416,7 +416,13 @@ def main():
     ap.add_argument("--data-dir", default=None, help="train on a real capture in the reference's dataset layout instead of the synthetic stand-in")
     ap.add_argument("--target-batch", type=int, default=1 << 18,
                     help="target_batch_size, samples per iteration per GPU (ngp_base.py:75); BASELINE config #5 sweeps 2^16 .. 2^22 (tools/sweep.py)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --target-batch samples per iteration PER GPU (the contract's default); strong: --target-batch is the GLOBAL "
+                         "sample budget of an iteration, split evenly over the GPUs")
     args = ap.parse_args()
+    if args.scaling == "strong":
+        args.target_batch_global = args.target_batch
+        args.target_batch = max(1 << 12, args.target_batch // max(1, int(os.environ.get("WORLD_SIZE", "1"))))
     if args.steps is None:
         args.steps = 32 if args.impl == "reference" else 1000
     if args.impl == "reference":

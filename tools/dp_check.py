@@ -54,6 +54,16 @@ def main():
     r1 = make_runner(0, 1, None, R * world)
     loss_single = float(r1.train_step().float().mean().item())
     del r1
+    # equal global batch, equal iterations on ONE GPU (SURVEY 8e's criterion), twice: the second run measures how far two runs of the
+    # very same single-GPU configuration drift apart (gradient atomics are summed in a different order every time)
+    psnr_single = []
+    for _ in range(2):
+        r1 = make_runner(0, 1, None, R * world)
+        for _ in range(K):
+            r1.train_step()
+        img, tar = r1.render_img("train", 0)
+        psnr_single.append(float(-10.0 * torch.log10(((img - tar) ** 2).mean()).item()))
+        del r1
 
     tables, losses = {}, {}
     for mode in ("p2p", "nccl"):
@@ -87,6 +97,10 @@ def main():
         ok[f"{mode}_ckpt_roundtrip"] = bool(torch.equal(st.m, m0) and torch.equal(st.v, v0) and torch.equal(st.master, ms0))
         tables[mode], losses[mode] = table.float().clone(), ls
         del rw
+    ok["world_size"] = world
+    ok["single_gpu_global_batch_train_view_psnr_db"] = psnr_single
+    ok["dp_minus_single_psnr_db"] = {m: ok[f"{m}_train_view_psnr_db"] - sum(psnr_single) / 2 for m in ("p2p", "nccl")}
+    ok["single_gpu_run_to_run_psnr_db"] = abs(psnr_single[0] - psnr_single[1])
     ok["loss_step0_single_gpu_global_batch"] = loss_single
     ok["loss_step0_dp"] = {m: losses[m][0] for m in losses}
     ok["loss_first8"] = {m: [round(x, 5) for x in losses[m][:8]] for m in losses}
@@ -96,13 +110,15 @@ def main():
     good = good and all(abs(v - loss_single) <= 1e-3 * loss_single for v in ok["loss_step0_dp"].values())
     good = good and ok["p2p_vs_nccl_first8_max_rel_diff"] < 0.02
     good = good and all(ok[f"{m}_train_view_psnr_db"] > 20.0 for m in ("p2p", "nccl")) and all(v < 0.5 * loss_single for v in ok["loss_last"].values())
+    # PSNR at equal global batch and iterations: within 0.05 dB of the single-GPU run, or within twice that run's own run-to-run spread
+    good = good and all(abs(v) <= max(0.05, 2 * ok["single_gpu_run_to_run_psnr_db"]) for v in ok["dp_minus_single_psnr_db"].values())
     flag = torch.tensor([int(good)], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     ok["pass"] = bool(flag.item())
     if rank == 0:
         print(json.dumps(ok), flush=True)
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        json.dump(ok, open(os.path.join(ROOT, "gpurun_out", "dp_check.json"), "w"), indent=1)
+        json.dump(ok, open(os.path.join(ROOT, "gpurun_out", f"dp_check_{world}gpu.json"), "w"), indent=1)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok["pass"] else 1)
