@@ -78,11 +78,13 @@ class Runner:
         if self.world_size == 1:
             # Device-resident step state (include/ngp_b200.h: ngp_step_state_*): the sampler rng, the pixel cursor and Adam's step
             # factors live on the device, so every launch of a training step has the same arguments and the step can be captured in
-            # a CUDA graph per ray-batch size (NGP_GRAPHS=0 keeps the eager launches).
+            # a CUDA graph per ray-batch size.  Opt-in (NGP_GRAPHS=1): measured +2.5 % at 2^18 samples per iteration once every
+            # ray-batch size of the run has its graph, nothing over 1 000 steps of a still-converging scene (17 sizes, 17 captures),
+            # and -4 % at 2^20 where a capture allocates hundreds of MB (profiles/r02_kernels/call17, r02_final).
             self._dev_state = ops.step_state_new()
             self._dev_expect = None
             self._graphs, self._graph_seen, self._graph_pool, self._cap_stream = {}, {}, None, None
-            self._graphs_enabled = os.environ.get("NGP_GRAPHS", "1") == "1" and torch.cuda.is_available() and hasattr(torch.cuda, "CUDAGraph")
+            self._graphs_enabled = os.environ.get("NGP_GRAPHS", "0") == "1" and torch.cuda.is_available() and hasattr(torch.cuda, "CUDAGraph")
             self.graph_replays = 0
             self._graph_after = int(os.environ.get("NGP_GRAPH_AFTER", "20"))     # occurrences of a ray-batch size before it gets a graph
         if self.world_size > 1:
