@@ -25,11 +25,11 @@ import torch
 import torch.distributed as dist
 
 
-def make_runner(rank, world, pg, rays):
+def make_runner(rank, world, pg, rays, target_batch=1 << 18):
     from jnerf_b200.runner import Runner, lego_cfg
     from jnerf_b200.utils.config import get_cfg, update_cfg
     get_cfg().clear()
-    update_cfg(**lego_cfg(fp16=True, synthetic=True, seed=1))
+    update_cfg(**lego_cfg(fp16=True, synthetic=True, seed=1, target_batch_size=target_batch))
     cfg = get_cfg()
     cfg.dataset.train.n_images = 12
     cfg.dataset.train.H = cfg.dataset.train.W = 200
@@ -58,7 +58,7 @@ def main():
     # very same single-GPU configuration drift apart (gradient atomics are summed in a different order every time)
     psnr_single = []
     for _ in range(2):
-        r1 = make_runner(0, 1, None, R * world)
+        r1 = make_runner(0, 1, None, R * world, target_batch=world << 18)     # the ray batch adapts to the GLOBAL sample budget, as the W ranks' does
         for _ in range(K):
             r1.train_step()
         img, tar = r1.render_img("train", 0)
