@@ -129,11 +129,13 @@ int ngp_composite_bwd(void* stream, uint32_t n_rays, uint32_t n_elements, const 
 int ngp_composite_infer(void* stream, uint32_t n_rays, const void* net_out, int dtype, const float* coords,
                         const uint32_t* numsteps, uint32_t cascades, float* rgb_out, float* alpha_out);
 /* Fused training tail: composite fwd (calc_rgb.h:10-74) + Huber(delta) gradient (models/losses/huber_loss.py:11-14)
- * + composite bwd (calc_rgb.h:76-148) in one pass per ray; also returns rgb and the per-ray summed loss. */
+ * + composite bwd (calc_rgb.h:76-148) in one pass per ray; also returns rgb and the per-ray summed loss.
+ * reg_scale multiplies the density regulariser of calc_rgb.h:112,139 (1 on one GPU; the world size under data parallelism, where
+ * the summed shard gradients are scaled by 1 / world but the regulariser is an absolute per-sample term). */
 int ngp_composite_loss_bwd(void* stream, uint32_t n_rays, uint32_t n_elements, const void* net_out, const float* coords,
                            const uint32_t* numsteps_in, const uint32_t* numsteps_compacted, const float* bg,
                            const float* target, float huber_delta, const float* density_grid_mean, uint32_t cascades,
-                           float* rgb_out, float* loss_out, void* dnet_out);
+                           float* rgb_out, float* loss_out, void* dnet_out, float reg_scale);
 
 /* ---- R10 occupancy-grid maintenance (DGS/density_grid_sampler.py:204-264 + five headers) ------------- */
 int ngp_grid_mark_untrained(void* stream, uint32_t n_elements, float* grid, uint32_t n_images, const float* focal_lengths,

@@ -753,7 +753,7 @@ __global__ void __launch_bounds__(256) composite_loss_bwd_kernel(uint32_t n_rays
                                                                  const uint32_t* __restrict__ numsteps_in, const uint32_t* __restrict__ numsteps_c,
                                                                  const float* __restrict__ bg, const float* __restrict__ target, float delta,
                                                                  const float* __restrict__ mean, uint32_t cascades, float* __restrict__ rgb_out,
-                                                                 float* __restrict__ loss_out, __half* __restrict__ dnet) {
+                                                                 float* __restrict__ loss_out, __half* __restrict__ dnet, float reg_scale) {
     const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= n_rays) return;
     const uint32_t n = numsteps_c[2 * i], base = numsteps_c[2 * i + 1];
@@ -776,7 +776,10 @@ __global__ void __launch_bounds__(256) composite_loss_bwd_kernel(uint32_t n_rays
     if (loss_out && lane == 0) loss_out[i] = loss;
     float loss_scale = 128;
     loss_scale /= n_rays;
-    const float l1 = *mean < 0.01f ? 1e-4f : 0.0f;
+    // calc_rgb.h:112: the density regulariser is an absolute per-sample term, NOT scaled by 128 / n_rays.  Data-parallel shards
+    // normalise by their local ray count and the exchange applies 1 / W: reg_scale = W keeps the regulariser what one GPU with the
+    // global batch would add (without it a W-GPU run trains with 1/W of the sparsity pressure: -1.8 dB after 300 steps at W = 2)
+    const float l1 = (*mean < 0.01f ? 1e-4f : 0.0f) * reg_scale;
     composite_ray_bwd<__half>(n, base, net, coords, lg, r, loss_scale, l1, cascades, lane, dnet);
 }
 
@@ -885,12 +888,13 @@ int ngp_composite_bwd(void* stream, uint32_t n_rays, uint32_t n_elements, const 
 
 int ngp_composite_loss_bwd(void* stream, uint32_t n_rays, uint32_t n_elements, const void* net_out, const float* coords,
                            const uint32_t* numsteps_in, const uint32_t* numsteps_compacted, const float* bg, const float* target,
-                           float huber_delta, const float* density_grid_mean, uint32_t cascades, float* rgb_out, float* loss_out, void* dnet_out) {
+                           float huber_delta, const float* density_grid_mean, uint32_t cascades, float* rgb_out, float* loss_out, void* dnet_out,
+                           float reg_scale) {
     (void)n_elements;   // rows not covered by a ray are never read downstream (the network backward is count-limited)
     if (n_rays == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     composite_loss_bwd_kernel<<<(n_rays + 7) / 8, 256, 0, s>>>(n_rays, (const __half*)net_out, coords, numsteps_in, numsteps_compacted, bg, target,
-                                                               huber_delta, density_grid_mean, cascades, rgb_out, loss_out, (__half*)dnet_out);
+                                                               huber_delta, density_grid_mean, cascades, rgb_out, loss_out, (__half*)dnet_out, reg_scale);
     NGP_LAUNCH_CHECK();
     return 0;
 }

@@ -162,7 +162,7 @@ def composite_infer(net, coords, numsteps, cascades=5):
     return rgb, alpha
 
 
-def composite_loss_bwd(net, coords, numsteps_in, numsteps_c, bg, target, mean, delta=0.1, cascades=5, dnet=None, rgb=None, loss=None):
+def composite_loss_bwd(net, coords, numsteps_in, numsteps_c, bg, target, mean, delta=0.1, cascades=5, dnet=None, rgb=None, loss=None, reg_scale=1.0):
     R = numsteps_c.shape[0]
     dev = net.device
     if dnet is None:
@@ -172,7 +172,7 @@ def composite_loss_bwd(net, coords, numsteps_in, numsteps_c, bg, target, mean, d
     if loss is None:
         loss = torch.empty(R, dtype=torch.float32, device=dev)
     lib.call("ngp_composite_loss_bwd", _stream(), R, net.shape[0], _p(net), _p(coords), _p(numsteps_in), _p(numsteps_c), _p(bg), _p(target),
-             float(delta), _p(mean), cascades, _p(rgb), _p(loss), _p(dnet))
+             float(delta), _p(mean), cascades, _p(rgb), _p(loss), _p(dnet), float(reg_scale))
     return rgb, loss, dnet
 
 

@@ -315,7 +315,8 @@ class Runner:
         coords, n_dev = s.coords_compacted, s.n_samples_dev
         self.net_forward(coords, n_dev)
         rgb, loss, _ = ops.composite_loss_bwd(self.net_out, coords, s._rays_numsteps, s._rays_numsteps_compacted, bg, target.contiguous(),
-                                              s.density_grid_mean, delta=self.loss_func.delta, cascades=s.NERF_CASCADES, dnet=self.dnet)
+                                              s.density_grid_mean, delta=self.loss_func.delta, cascades=s.NERF_CASCADES, dnet=self.dnet,
+                                              reg_scale=float(self.world_size))    # the exchange applies 1 / W to the summed gradients
         self.net_backward(coords, n_dev)
         # local loss_scale is 128/R_local (calc_rgb.h:100-101): the all-reduced sum is W x the global-batch gradient
         lr = self.optimizer.advance_lr()

@@ -105,6 +105,8 @@ double orc_hash_offsets(double aabb_scale, int n_levels, int base_resolution, in
 /* cfg.hash_func is pasted into the reference's kernel source as get_index(p0,p1,p2) (HE/hash_encoder.py:13-16); both NGP configs
  * use p0 ^ p1 * 19349663 ^ p2 * 83492791 (ngp_base.py:66).  orc_set_hash_primes selects another member of that XOR-of-products family. */
 static uint32_t g_hash_prime[3] = {1u, 19349663u, 83492791u};
+static float g_reg_scale = 1.0f;       /* data-parallel shards: ngp_composite_loss_bwd's reg_scale (test infrastructure mirrors the product's knob) */
+void orc_set_reg_scale(float s) { g_reg_scale = s; }
 void orc_set_hash_primes(uint32_t p0, uint32_t p1, uint32_t p2) { g_hash_prime[0] = p0; g_hash_prime[1] = p1; g_hash_prime[2] = p2; }
 static inline uint32_t grid_index(uint32_t hashmap_size, uint32_t res, const uint32_t g[3]) {
     uint32_t stride = 1, index = 0;
@@ -699,7 +701,7 @@ void orc_composite_bwd(uint32_t n_rays, uint32_t n_elements, const void* net, in
     march_cfg c = make_cfg(cascades, 1);
     memset(dnet, 0, (size_t)n_elements * 4 * (is_half ? 2 : 4));
     float loss_scale = 128; loss_scale /= n_rays;
-    const float l1 = density_grid_mean < 0.01f ? 1e-4f : 0.0f;
+    const float l1 = (density_grid_mean < 0.01f ? 1e-4f : 0.0f) * g_reg_scale;
     for (uint32_t i = 0; i < n_rays; ++i) {
         uint32_t n = numsteps_compacted[2 * i], base = numsteps_compacted[2 * i + 1];
         const float* lg = loss_grad + 3 * i; const float* rr = rgb_ray + 3 * i;

@@ -175,13 +175,16 @@ class OracleOps:
         rgb, alpha = ol.composite_infer(_np(net), _np(coords, np.float32), _u32view(numsteps), cascades)
         return torch.from_numpy(rgb), torch.from_numpy(alpha)
 
-    def composite_loss_bwd(self, net, coords, numsteps_in, numsteps_c, bg, target, mean, delta=0.1, cascades=5, dnet=None, rgb=None, loss=None):
+    def composite_loss_bwd(self, net, coords, numsteps_in, numsteps_c, bg, target, mean, delta=0.1, cascades=5, dnet=None, rgb=None, loss=None,
+                           reg_scale=1.0):
         self._log("composite_loss_bwd")
+        ol.oracle().orc_set_reg_scale(float(reg_scale))
         R = numsteps_c.shape[0]
         n, c, ns_in, ns_c = _np(net), _np(coords, np.float32), _u32view(numsteps_in), _u32view(numsteps_c)
         r = ol.composite_fwd(n, c, ns_in, ns_c, _np(bg), cascades)
         g, l = ol.huber_grad(r, _np(target), delta)
         d = ol.composite_bwd(n, c, ns_c, g.reshape(R, 3), r, float(mean.reshape(-1)[0]), cascades)
+        ol.oracle().orc_set_reg_scale(1.0)
         rows = int((ns_c[:, 0].astype(np.int64)).sum())
         if dnet is None:
             dnet = torch.zeros_like(net)

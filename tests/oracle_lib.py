@@ -45,6 +45,8 @@ def oracle():
         _oracle.orc_set_level_scales.argtypes = [_p]
         _oracle.orc_set_hash_primes.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
         _oracle.orc_set_hash_primes.restype = None
+        _oracle.orc_set_reg_scale.argtypes = [C.c_float]
+        _oracle.orc_set_reg_scale.restype = None
     return _oracle
 
 
