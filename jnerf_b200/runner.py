@@ -5,6 +5,9 @@ reference's own batch-size adaptation every 16 steps), one C-ABI call per stage:
     [grid update /16] -> raygen -> march -> (compaction bookkeeping) -> fused network fwd ->
     fused composite + Huber + composite bwd -> fused network bwd -> [NCCL all-reduce] -> fused Adam+EMA
 
+On one GPU the steps are software-pipelined: raygen + march of step i+1 run on a second stream under step i's Adam+EMA sweep
+(`_train_step_pipe`; NGP_PIPELINE=0 restores the strictly sequential step, NGP_GRAPHS=1 the CUDA-graph replay of it).
+
 `train_step_autograd` runs the same step through the per-operator plugin classes and torch autograd, exactly as
 JNeRF's Runner.train does with Jittor; tests check that both give the same parameters."""
 import os
@@ -51,6 +54,7 @@ class Runner:
         self._table_work, self._pending_epoch = None, None
         self._host_stage = None
         self._dev_state = None                                       # device-resident step state + CUDA graphs (single-GPU fast path)
+        self._pipe = None                                            # march of step i+1 under the optimizer sweep of step i (single GPU)
         self._st = {id(s.p): s for s in self.optimizer._nested_optimizer.state}
         if world_size > 1 and not self.fast:
             raise ValueError("data-parallel training needs the fused model (fp16=True, use_fully=True): the per-operator autograd step "
@@ -87,6 +91,16 @@ class Runner:
             self._graphs_enabled = os.environ.get("NGP_GRAPHS", "0") == "1" and torch.cuda.is_available() and hasattr(torch.cuda, "CUDAGraph")
             self.graph_replays = 0
             self._graph_after = int(os.environ.get("NGP_GRAPH_AFTER", "20"))     # occurrences of a ray-batch size before it gets a graph
+            # Software pipeline over steps (default): nothing the march reads is written by the network kernels -- rays, jitter and the
+            # occupancy bitfield only -- so the "front" of step i+1 (background colours, ray generation, march, compaction) is enqueued
+            # on a second stream while step i's backward / Adam+EMA sweep still run.  The sweep is HBM-bound and the march is
+            # latency-bound: side by side they share the SMs instead of queueing.  NGP_PIPE_AT picks the point of
+            # step i the front of step i+1 may start at: after its network forward ("fwd"), backward ("bwd") or at once ("front").
+            if os.environ.get("NGP_PIPELINE", "1") == "1" and not self._graphs_enabled:
+                at = os.environ.get("NGP_PIPE_AT", "bwd")
+                assert at in ("front", "fwd", "bwd")
+                self._pipe = dict(stream=torch.cuda.Stream(), coords=[None, None], made=0, pending=None, at=at, mid=torch.cuda.Event(),
+                                  back_done=[torch.cuda.Event(), torch.cuda.Event()], prefetched=0)
         if self.world_size > 1:
             self._init_sharded_table()
 
@@ -286,7 +300,95 @@ class Runner:
         cfg.m_training_step = i + 1
         return loss
 
-    def train_step(self, batch=None):
+    # ------------------------------------------------------------------------------------------ software pipeline over steps
+    def _front(self, step, batch, prefetch):
+        """The part of training step `step` that does not read a network parameter: background colours, ray generation + target
+        lookup (or the blend of a fed batch), march, compaction.  prefetch=True runs it on the side stream, behind the point of the
+        step in flight that NGP_PIPE_AT names; otherwise on the current stream (first step, and every step that starts with an
+        occupancy-grid update: the update evaluates the density network, so it needs the finished optimizer sweep)."""
+        P, s, ds = self._pipe, self.sampler, self.dataset["train"]
+        slot = P["made"] & 1
+        if P["coords"][slot] is None:
+            P["coords"][slot] = torch.zeros_like(s._coords_raw)
+        main = torch.cuda.current_stream()
+        side = P["stream"]
+        if prefetch:
+            side.wait_event(P["mid"])                                # recorded on the main stream inside the step in flight
+        # the step that read this slot's coordinate rows two fronts ago must be through (it is, unless the host runs far ahead)
+        (side if prefetch else main).wait_event(P["back_done"][slot])
+        with torch.cuda.stream(side if prefetch else main):
+            rng_before = s.rng.copy()
+            if step % s.update_den_freq == 0:
+                assert not prefetch
+                s.update_density_grid()
+            if batch is None:
+                R = s.n_rays_per_batch
+                pix = ds.next_pixels(R)
+                bg = torch.rand((R, 3), device="cuda", generator=self._bg_gen)                         # runner.py:66
+                img_ids, rays_o, rays_d, target = ops.prepare_batch(pix.contiguous(), ds.W, ds.H, ds.transforms_gpu, ds.focal_lengths,
+                                                                    ds.principal, ds.image_data, bg)    # dataset.py:172-188 + runner.py:68
+            else:
+                img_ids, rays_o, rays_d, rgba = batch
+                R = rays_o.shape[0]
+                bg = torch.rand((R, 3), device="cuda", generator=self._bg_gen)
+                target = ops.blend_target(rgba.contiguous(), bg)                                       # runner.py:68
+            numsteps, ns_c, cnt_c, coords = s.sample_front(rays_o, rays_d, P["coords"][slot])
+            done = torch.cuda.Event()
+            done.record()
+        P["made"] += 1
+        P["prefetched"] += int(prefetch)
+        return dict(step=step, src=batch, slot=slot, bg=bg, target=target, numsteps=numsteps, ns_c=ns_c, cnt_c=cnt_c, coords=coords, done=done,
+                    rng_before=rng_before, rays=(img_ids, rays_o, rays_d), side=prefetch)
+
+    def _sync_front(self):
+        """Evaluation and checkpoint code shares the march workspace with a prefetched front: order the current stream behind it."""
+        P = self._pipe
+        if P is not None and P["pending"] is not None:
+            torch.cuda.current_stream().wait_event(P["pending"]["done"])
+
+    def _train_step_pipe(self, batch=None, next_batch=None):
+        cfg, s, P = self.cfg, self.sampler, self._pipe
+        i = cfg.m_training_step
+        main = torch.cuda.current_stream()
+        F, P["pending"] = P["pending"], None
+        if F is not None and (F["step"] != i or F["src"] is not batch):
+            F = None                                                 # the caller changed course (checkpoint loaded, other batch): drop it
+        if F is None:
+            F = self._front(i, batch, prefetch=False)
+        elif F["side"]:
+            main.wait_event(F["done"])
+        if i % s.update_den_freq == s.update_den_freq - 1:
+            s.update_batch_rays()                                    # the one host sync per 16 steps; after this step's march, as in sample()
+        if P["at"] == "front":
+            P["mid"].record(main)
+        s._rays_numsteps, s._rays_numsteps_compacted, s._counters_compacted, s._coords = F["numsteps"], F["ns_c"], F["cnt_c"], F["coords"]
+        coords, n_dev = F["coords"], F["cnt_c"][0:1]
+        self.net_forward(coords, n_dev)
+        if P["at"] == "fwd":
+            P["mid"].record(main)
+        rgb, loss, _ = ops.composite_loss_bwd(self.net_out, coords, F["numsteps"], F["ns_c"], F["bg"], F["target"], s.density_grid_mean,
+                                              delta=self.loss_func.delta, cascades=s.NERF_CASCADES, dnet=self.dnet)
+        self.net_backward(coords, n_dev)
+        if P["at"] == "bwd":
+            P["mid"].record(main)
+        lr = self.optimizer.advance_lr()
+        adam = self.optimizer._nested_optimizer
+        adam.n_step += 1
+        self.ema_optimizer.steps += 1
+        self._optimizer_step(lr, adam.n_step)
+        P["back_done"][F["slot"]].record(main)
+        self.last_loss, self.last_rgb = loss, rgb
+        cfg.m_training_step = i + 1
+        self._pipe_last = F                                          # keeps the front's tensors alive until the next step replaces them
+        # the front of step i+1, unless that step opens with an occupancy-grid update (needs the sweep above) or the caller feeds
+        # batches and has not said which one comes next
+        if (i + 1) % s.update_den_freq != 0 and (batch is None or next_batch is not None):
+            P["pending"] = self._front(i + 1, next_batch if batch is not None else None, prefetch=True)
+        return loss
+
+    def train_step(self, batch=None, next_batch=None):
+        if self._pipe is not None:
+            return self._train_step_pipe(batch, next_batch)
         if batch is None and self._dev_state is not None:
             return self._train_step_dev()
         cfg, s, m = self.cfg, self.sampler, self.model
@@ -338,7 +440,7 @@ class Runner:
         st = self._host_stage
         if st is None:
             st = self._host_stage = dict(stream=torch.cuda.Stream(), slots=[None, None], ready=[torch.cuda.Event(), torch.cuda.Event()],
-                                         free=[torch.cuda.Event(), torch.cuda.Event()], staged=[None, None], k=0,
+                                         free=[torch.cuda.Event(), torch.cuda.Event()], staged=[None, None], dev=[None, None], k=0,
                                          loss_host=torch.zeros(1, dtype=torch.float32).pin_memory(), done=torch.cuda.Event())
             for e in st["free"]:
                 e.record()
@@ -356,16 +458,19 @@ class Runner:
                     dst[:R].copy_(src, non_blocking=True)
                 st["ready"][slot].record()
             st["staged"][slot] = (b, R)
+            st["dev"][slot] = tuple(t[:R] for t in st["slots"][slot])
 
         slot = st["k"] % 2
         if st["staged"][slot] is None or st["staged"][slot][0] is not batch:
             put(batch, slot)
         if next_batch is not None:
             put(next_batch, 1 - slot)
-        R = st["staged"][slot][1]
         main.wait_event(st["ready"][slot])
-        dev = tuple(t[:R] for t in st["slots"][slot])
-        loss = self.train_step(dev)
+        dev, nxt = st["dev"][slot], None
+        if next_batch is not None and self._pipe is not None:
+            nxt = st["dev"][1 - slot]                                # its front (blend, march) is enqueued under this step's kernels
+            self._pipe["stream"].wait_event(st["ready"][1 - slot])
+        loss = self.train_step(dev, nxt)
         st["free"][slot].record(main)
         st["staged"][slot] = None
         st["k"] += 1
@@ -447,6 +552,7 @@ class Runner:
     def render_img(self, dataset_mode="train", img_id=0):
         """runner.py:197-236: tile the image in n_rays_per_batch chunks; returns (img HxWx3, target HxWx3)."""
         self._table_ready()
+        self._sync_front()
         ds = self.dataset[dataset_mode]
         W, H = ds.resolution
         rays_o, rays_d = ds.generate_rays_total_test(img_id)
@@ -484,6 +590,7 @@ class Runner:
         before the caller uses the result.  Same kernels, same RNG consumption, same pixels as render_img."""
         assert self.fast, "render_img_nosync drives the fused network kernel"
         self._table_ready()
+        self._sync_front()
         ds = self.dataset[dataset_mode]
         W, H = ds.resolution
         rays_o, rays_d = ds.generate_rays_total_test(img_id)
@@ -539,7 +646,11 @@ class Runner:
                 nested[key][k] = t
             if self.rank != 0:
                 return
-        ck = {"global_step": self.cfg.m_training_step, "model": self.model.state_dict(), "sampler": self.sampler.state_dict(),
+        sampler_state = self.sampler.state_dict()
+        if self._pipe is not None and self._pipe["pending"] is not None:
+            # a prefetched front has drawn the next step's jitter already: the checkpoint holds the stream position of global_step
+            sampler_state["rng"] = torch.from_numpy(self._pipe["pending"]["rng_before"].astype(np.int64))
+        ck = {"global_step": self.cfg.m_training_step, "model": self.model.state_dict(), "sampler": sampler_state,
               "optimizer": self.optimizer.state_dict(), "nested_optimizer": nested, "ema_optimizer": self.ema_optimizer.state_dict()}
         if str(path).endswith(".pkl") and not hasattr(self.model.density_mlp, "con_weights"):
             raise NotImplementedError("the .pkl interchange format is written for the fused-MLP parameter layout (con_weights); "
@@ -559,6 +670,9 @@ class Runner:
 
     def load_ckpt(self, path):
         self._table_ready()                                          # an exchange of the previous step may still be writing the table
+        if self._pipe is not None:
+            self._sync_front()
+            self._pipe["pending"] = None                             # marched against the occupancy grid that is about to be replaced
         if self.world_size > 1:
             import torch.distributed as dist
             dist.barrier(group=self.pg)                              # no peer may still push into this rank's table while it is overwritten

@@ -300,6 +300,8 @@ class OracleOps:
 
 
 def install(monkeypatch):
+    # the sequential step by default (tests count one step's calls); tests of the software pipeline over steps switch it back on
+    monkeypatch.setenv("NGP_PIPELINE", "0")
     """Route jnerf_b200.ops to the oracle and torch's "cuda" device to the CPU for the duration of one test."""
     import jnerf_b200.ops as real_ops
     fake = OracleOps()

@@ -11,8 +11,10 @@ import cpu_backend
 import oracle_lib as ol
 
 
-def make_runner(monkeypatch, cfg_fn="lego_cfg", images=4, H=24, W=24, rays=64, target=32768, seed=1, start_step=1, **over):
+def make_runner(monkeypatch, cfg_fn="lego_cfg", images=4, H=24, W=24, rays=64, target=32768, seed=1, start_step=1, pipeline=False, **over):
     fake = cpu_backend.install(monkeypatch)
+    # pipeline=False: the strictly sequential step (one step's calls, then the next's); the software pipeline over steps has its own tests
+    monkeypatch.setenv("NGP_PIPELINE", "1" if pipeline else "0")
     from jnerf_b200 import plugin  # noqa: F401
     from jnerf_b200 import runner as R
     from jnerf_b200.utils.config import get_cfg, update_cfg
@@ -339,3 +341,92 @@ def test_host_fed_batches_equal_device_batches(monkeypatch):
     assert torch.equal(ra.model.pos_encoder.m_grid.detach(), rb.model.pos_encoder.m_grid.detach())
     st = rb._host_stage
     assert st["k"] == 3 and st["slots"][0] is not None and st["slots"][1] is not None and st["staged"] == [None, None]
+
+
+FRONT_OPS = ["prepare_batch", "march", "compact"]
+BACK_OPS = ["network_fwd", "composite_loss_bwd", "network_bwd", "adam_ema", "adam_ema", "adam_ema"]
+
+
+def test_pipelined_steps_equal_sequential_steps(monkeypatch):
+    """The software pipeline (front of step i+1 enqueued under step i) reorders launches, not arithmetic: same losses, parameters, ray
+    batch adaptation and rng position as the sequential step, across a 16-step window edge (no prefetch into a step that opens with
+    an occupancy-grid update; the ray batch adapts after the 16th march, before the next front)."""
+    out = {}
+    for pipe in (False, True):
+        r, fake = make_runner(monkeypatch, seed=11, start_step=12, pipeline=pipe)
+        assert (r._pipe is not None) == pipe
+        # the grid update at step 16 evaluates 2 M densities in the scalar oracle: stand-in that only counts (its own test covers it)
+        upd = []
+        monkeypatch.setattr(r.sampler, "update_density_grid", lambda: upd.append(r.cfg.m_training_step))
+        fake.calls.clear()
+        losses, rays = [], []
+        for k in range(7):                                          # steps 12 .. 18
+            rays.append(r.sampler.n_rays_per_batch)
+            n0 = len(fake.calls)
+            losses.append(r.train_step().clone())
+            if pipe:
+                step = 12 + k
+                first = k == 0 or step == 16                        # nothing was prefetched for these
+                expect = (FRONT_OPS if first else []) + BACK_OPS + (FRONT_OPS if (step + 1) % 16 else [])
+                assert fake.calls[n0:] == expect, (step, fake.calls[n0:])
+        assert upd == [16]
+        if pipe:
+            assert r._pipe["pending"] is not None and r._pipe["pending"]["step"] == 19 and r._pipe["prefetched"] == 6
+            r._pipe["pending"] = None
+        out[pipe] = dict(losses=torch.stack([l.float().mean() for l in losses]), rays=rays, grid=r.model.pos_encoder.m_grid.detach().clone(),
+                         w=r.model.rgb_mlp.con_weights.detach().clone(), n_step=r.optimizer._nested_optimizer.n_step, rng=r.sampler.rng.copy())
+    a, b = out[False], out[True]
+    assert a["rays"] == b["rays"] and a["rays"][4] != a["rays"][3]               # adapted after step 15's march, in both
+    assert torch.equal(a["losses"], b["losses"]) and torch.equal(a["grid"], b["grid"]) and torch.equal(a["w"], b["w"])
+    assert a["n_step"] == b["n_step"] == 7
+    assert np.array_equal(ol.pcg32_advance(a["rng"].copy()), b["rng"])           # the pipelined run has marched step 19 already
+
+
+def test_pipelined_checkpoint_and_evaluation_between_steps(monkeypatch, tmp_path):
+    """With a prefetched front pending: a checkpoint stores the jitter-stream position of its global_step (not the prefetched one),
+    loading a checkpoint drops the front, and the evaluation renderer leaves it intact for the next step."""
+    r, fake = make_runner(monkeypatch, seed=13, pipeline=True)
+    rng0 = r.sampler.rng.copy()
+    for _ in range(3):
+        r.train_step()
+    assert r._pipe["pending"]["step"] == 4
+    assert np.array_equal(r.sampler.rng, ol.pcg32_advance(rng0.copy(), 4 << 32))   # four marches done
+    p = str(tmp_path / "ckpt.pt")
+    r.save_ckpt(p)
+    ck = torch.load(p, weights_only=True)
+    assert np.array_equal(ck["sampler"]["rng"].numpy().astype(np.uint64), ol.pcg32_advance(rng0.copy(), 3 << 32)) and ck["global_step"] == 4
+    pend = r._pipe["pending"]
+    img, _ = r.render_img_nosync("train", 0)
+    assert r._pipe["pending"] is pend and torch.isfinite(img).all()
+    fake.calls.clear()
+    r.train_step()
+    assert fake.calls[:len(BACK_OPS)] == BACK_OPS                                  # consumed the prefetched front
+    r.load_ckpt(p)
+    assert r._pipe["pending"] is None and r.cfg.m_training_step == 4
+    fake.calls.clear()
+    r.train_step()
+    assert fake.calls[:len(FRONT_OPS)] == FRONT_OPS
+
+
+def test_pipelined_host_fed_batches(monkeypatch):
+    """train_step_host with next_batch: the next batch's blend + march are enqueued under the current step; same result as feeding the
+    batches one by one without announcing the next."""
+    out = {}
+    for announce in (False, True):
+        r, fake = make_runner(monkeypatch, seed=17, pipeline=True)
+        ds = r.dataset["train"]
+        batches = []
+        for k in range(4):
+            pix = ds.next_pixels(64)
+            img_ids, o, d = ds.rays_for(pix)
+            batches.append((img_ids.clone(), o.clone(), d.clone(), ds.rgba_for(pix).clone()))
+        fake.calls.clear()
+        ls = []
+        for k in range(4):
+            n0 = len(fake.calls)
+            ls.append(float(r.train_step_host(batches[k], batches[k + 1] if announce and k < 3 else None).item()))
+            if announce:
+                front = ["blend_target", "march", "compact"]
+                assert fake.calls[n0:] == (front if k == 0 else []) + BACK_OPS + (front if k < 3 else []), fake.calls[n0:]
+        out[announce] = (ls, r.model.pos_encoder.m_grid.detach().clone())
+    assert out[False][0] == out[True][0] and torch.equal(out[False][1], out[True][1])

@@ -56,11 +56,14 @@ def main():
     del r1
     # equal global batch, equal iterations on ONE GPU (SURVEY 8e's criterion), twice: the second run measures how far two runs of the
     # very same single-GPU configuration drift apart (gradient atomics are summed in a different order every time)
-    psnr_single = []
+    psnr_single, loss_single_traj, rays_single = [], [], []
     for _ in range(2):
         r1 = make_runner(0, 1, None, R * world, target_batch=world << 18)     # the ray batch adapts to the GLOBAL sample budget, as the W ranks' does
+        tr = []
         for _ in range(K):
-            r1.train_step()
+            rays_single.append(r1.sampler.n_rays_per_batch)
+            tr.append(r1.train_step().float().mean().reshape(1))
+        loss_single_traj.append([float(x) for x in torch.cat(tr).tolist()])
         img, tar = r1.render_img("train", 0)
         psnr_single.append(float(-10.0 * torch.log10(((img - tar) ** 2).mean()).item()))
         del r1
@@ -70,8 +73,9 @@ def main():
         os.environ["NGP_DP_EXCHANGE"] = mode
         rw = make_runner(rank, world, pg, R)
         assert rw.dp_mode == mode
-        ls = []
+        ls, rays_dp = [], []
         for _ in range(K):
+            rays_dp.append(rw.sampler.n_rays_per_batch * world)
             l = rw.train_step().float().mean().reshape(1)
             dist.all_reduce(l)
             ls.append(float(l.item()) / world)
@@ -96,6 +100,7 @@ def main():
         rw.load_ckpt(path)
         ok[f"{mode}_ckpt_roundtrip"] = bool(torch.equal(st.m, m0) and torch.equal(st.v, v0) and torch.equal(st.master, ms0))
         tables[mode], losses[mode] = table.float().clone(), ls
+        ok[f"{mode}_global_rays_every_16"] = rays_dp[::16]
         del rw
     ok["world_size"] = world
     ok["single_gpu_global_batch_train_view_psnr_db"] = psnr_single
@@ -103,6 +108,14 @@ def main():
     ok["single_gpu_run_to_run_psnr_db"] = abs(psnr_single[0] - psnr_single[1])
     ok["loss_step0_single_gpu_global_batch"] = loss_single
     ok["loss_step0_dp"] = {m: losses[m][0] for m in losses}
+    ok["single_gpu_rays_every_16"] = rays_single[:K:16]
+    # where the trajectories part: relative loss difference against the first single-GPU run, per step (the second single-GPU run
+    # gives the floor: two runs of the same configuration)
+    rel = lambda a, b: [abs(x - y) / abs(y) for x, y in zip(a, b)]
+    for name, tr in (("single_rerun", loss_single_traj[1]), ("p2p", losses["p2p"]), ("nccl", losses["nccl"])):
+        d = rel(tr, loss_single_traj[0])
+        ok[f"loss_rel_diff_vs_single_{name}"] = {"steps_0_15": max(d[:16]), "steps_16_63": max(d[16:64]), "steps_64_299": max(d[64:]),
+                                                  "first_step_over_1e-3": next((i for i, x in enumerate(d) if x > 1e-3), None)}
     ok["loss_first8"] = {m: [round(x, 5) for x in losses[m][:8]] for m in losses}
     ok["loss_last"] = {m: sum(losses[m][-20:]) / 20 for m in losses}
     ok["p2p_vs_nccl_first8_max_rel_diff"] = max(abs(a - b) / abs(a) for a, b in zip(losses["p2p"][:8], losses["nccl"][:8]))
