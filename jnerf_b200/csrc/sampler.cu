@@ -617,13 +617,38 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// A ray with many samples is one warp's serial loop over 32-sample chunks, and the kernel lasts as long as its longest ray: the loads
-// of chunk j+1 are issued before chunk j is evaluated, so every iteration but the first finds its operands in registers (measured
-// 42 -> 36 us for the fused training tail, profiles/r02_first_call).
+// A ray is one warp's loop over its samples, and the kernel lasts as long as its longest ray (all rays of a batch are resident at
+// once; ncu: 7 % of the warp slots active on average), i.e. as long as that ray's chain of warp scans.  Each lane therefore owns
+// COMP_K CONSECUTIVE samples of a 32 x COMP_K chunk: the products / sums over its own samples are plain register arithmetic, and
+// one warp scan over the lane totals serves COMP_K x 32 samples -- a 1024-sample ray is 8 scan rounds instead of 32.  The loads of
+// the next chunk are issued before the current one is evaluated (raw rows in a register set of their own).
+constexpr int COMP_K = 4;
+template <typename T> struct NetRow;
+template <> struct NetRow<float> { float4 v; };
+template <> struct NetRow<__half> { uint2 v; };
+__device__ __forceinline__ void load_row(const float* net, size_t k, NetRow<float>* r) { r->v = __ldg(reinterpret_cast<const float4*>(net) + k); }
+__device__ __forceinline__ void load_row(const __half* net, size_t k, NetRow<__half>* r) { r->v = __ldg(reinterpret_cast<const uint2*>(net) + k); }
+__device__ __forceinline__ float4 row_f4(const NetRow<float>& r) { return r.v; }
+__device__ __forceinline__ float4 row_f4(const NetRow<__half>& r) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&r.v.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T> struct ChunkRaw {
+    NetRow<T> row[COMP_K];
+    float dtw[COMP_K];
+};
+// lane's COMP_K rows of the chunk that starts at sample j0 (rows past the ray's end are not touched and never used)
 template <typename T>
-__device__ __forceinline__ void load_sample_raw(const T* __restrict__ net, const float* __restrict__ coords, size_t k, float4* raw, float* dt_warped) {
-    *raw = load_net<T>(net, k);
-    *dt_warped = __ldg(coords + k * 7 + 3);
+__device__ __forceinline__ void load_chunk(const T* __restrict__ net, const float* __restrict__ coords, uint32_t base, uint32_t j0, uint32_t n,
+                                           uint32_t lane, ChunkRaw<T>* c) {
+#pragma unroll
+    for (int q = 0; q < COMP_K; ++q) {
+        const uint32_t j = j0 + COMP_K * lane + q;
+        if (j < n) {
+            load_row(net, (size_t)base + j, &c->row[q]);
+            c->dtw[q] = __ldg(coords + ((size_t)base + j) * 7 + 3);
+        }
+    }
 }
 __device__ __forceinline__ Sample make_sample(const float4& o, float dt_warped, uint32_t cascades) {   // network_to_rgb (Logistic), network_to_density (Exponential)
     Sample s;
@@ -640,26 +665,30 @@ template <typename T>
 __device__ __forceinline__ void composite_ray_fwd(uint32_t n, uint32_t base, const T* __restrict__ net, const float* __restrict__ coords,
                                                   uint32_t cascades, uint32_t lane, float rgb[3], float* T_final) {
     float carry = 1.f, acc[3] = {0.f, 0.f, 0.f};
-    float4 nraw = make_float4(0.f, 0.f, 0.f, 0.f);
-    float ndt = 0.f;
-    if (lane < n) load_sample_raw<T>(net, coords, (size_t)base + lane, &nraw, &ndt);
-    for (uint32_t j0 = 0; j0 < n; j0 += 32) {
-        const uint32_t j = j0 + lane;
-        float a = 0.f, c[3] = {0.f, 0.f, 0.f};
-        {
-            const float4 raw = nraw;
-            const float dtw = ndt;
-            if (j + 32 < n) load_sample_raw<T>(net, coords, (size_t)base + j + 32, &nraw, &ndt);
-            if (j < n) {
-                const Sample s = make_sample(raw, dtw, cascades);
-                a = s.alpha; c[0] = s.rgb[0]; c[1] = s.rgb[1]; c[2] = s.rgb[2];
+    ChunkRaw<T> nxt;
+    load_chunk<T>(net, coords, base, 0, n, lane, &nxt);
+    for (uint32_t j0 = 0; j0 < n; j0 += 32 * COMP_K) {
+        const ChunkRaw<T> cur = nxt;
+        if (j0 + 32 * COMP_K < n) load_chunk<T>(net, coords, base, j0 + 32 * COMP_K, n, lane, &nxt);
+        float a[COMP_K], c[COMP_K][3], p[COMP_K];                               // p[q] = prod_{r <= q} (1 - a[r]) over the lane's own samples
+#pragma unroll
+        for (int q = 0; q < COMP_K; ++q) {
+            a[q] = 0.f; c[q][0] = c[q][1] = c[q][2] = 0.f;
+            if (j0 + COMP_K * lane + q < n) {
+                const Sample s = make_sample(row_f4(cur.row[q]), cur.dtw[q], cascades);
+                a[q] = s.alpha; c[q][0] = s.rgb[0]; c[q][1] = s.rgb[1]; c[q][2] = s.rgb[2];
             }
+            p[q] = q == 0 ? 1.f - a[q] : p[q - 1] * (1.f - a[q]);
         }
-        const float incl = warp_incl_prod(1.f - a, lane);
+        const float incl = warp_incl_prod(p[COMP_K - 1], lane);
         float excl = __shfl_up_sync(0xffffffffu, incl, 1);
         if (lane == 0) excl = 1.f;
-        const float w = a * (carry * excl);
-        acc[0] = __fmaf_rn(w, c[0], acc[0]); acc[1] = __fmaf_rn(w, c[1], acc[1]); acc[2] = __fmaf_rn(w, c[2], acc[2]);
+        const float T_lane = carry * excl;                                      // transmittance in front of the lane's first sample
+#pragma unroll
+        for (int q = 0; q < COMP_K; ++q) {
+            const float w = a[q] * (q == 0 ? T_lane : T_lane * p[q - 1]);
+            acc[0] = __fmaf_rn(w, c[q][0], acc[0]); acc[1] = __fmaf_rn(w, c[q][1], acc[1]); acc[2] = __fmaf_rn(w, c[q][2], acc[2]);
+        }
         carry *= __shfl_sync(0xffffffffu, incl, 31);
     }
     rgb[0] = warp_sum(acc[0]); rgb[1] = warp_sum(acc[1]); rgb[2] = warp_sum(acc[2]);
@@ -671,44 +700,62 @@ __device__ __forceinline__ void composite_ray_bwd(uint32_t n, uint32_t base, con
                                                   const float lg[3], const float rr[3], float loss_scale, float l1, uint32_t cascades,
                                                   uint32_t lane, T* __restrict__ dnet) {
     float carry_T = 1.f, carry_S[3] = {0.f, 0.f, 0.f};
-    float4 nraw = make_float4(0.f, 0.f, 0.f, 0.f);
-    float ndt = 0.f;
-    if (lane < n) load_sample_raw<T>(net, coords, (size_t)base + lane, &nraw, &ndt);
-    for (uint32_t j0 = 0; j0 < n; j0 += 32) {
-        const uint32_t j = j0 + lane;
-        float a = 0.f, c[3] = {0.f, 0.f, 0.f}, dt = 0.f;
-        float4 raw = make_float4(0.f, 0.f, 0.f, 0.f);
-        {
-            const float dtw = ndt;
-            if (j < n) raw = nraw;
-            if (j + 32 < n) load_sample_raw<T>(net, coords, (size_t)base + j + 32, &nraw, &ndt);
-            if (j < n) {
-                const Sample s = make_sample(raw, dtw, cascades);
-                a = s.alpha; c[0] = s.rgb[0]; c[1] = s.rgb[1]; c[2] = s.rgb[2]; dt = s.dt;
+    for (uint32_t j0 = 0; j0 < n; j0 += 32 * COMP_K) {
+        // no look-ahead here: the rows were read by the forward pass a moment ago (L1 / L2 hits, at most 8 rounds a ray), and the
+        // 12 registers of a second chunk are what keeps a whole 4096-ray batch resident (<= 72 registers a thread)
+        ChunkRaw<T> cur;
+        load_chunk<T>(net, coords, base, j0, n, lane, &cur);
+        float a[COMP_K], c[COMP_K][3], p[COMP_K], dt[COMP_K], sig[COMP_K];
+#pragma unroll
+        for (int q = 0; q < COMP_K; ++q) {
+            a[q] = 0.f; c[q][0] = c[q][1] = c[q][2] = 0.f; dt[q] = 0.f; sig[q] = 0.f;
+            if (j0 + COMP_K * lane + q < n) {
+                const Sample s = make_sample(row_f4(cur.row[q]), cur.dtw[q], cascades);
+                a[q] = s.alpha; c[q][0] = s.rgb[0]; c[q][1] = s.rgb[1]; c[q][2] = s.rgb[2]; dt[q] = s.dt; sig[q] = s.sigma_raw;
             }
+            p[q] = q == 0 ? 1.f - a[q] : p[q - 1] * (1.f - a[q]);
         }
-        const float incl = warp_incl_prod(1.f - a, lane);
+        const float incl = warp_incl_prod(p[COMP_K - 1], lane);
         float excl = __shfl_up_sync(0xffffffffu, incl, 1);
         if (lane == 0) excl = 1.f;
-        const float w = a * (carry_T * excl);
-        const float T_after = carry_T * incl;                                 // T after this sample (calc_rgb.h:125)
-        float S[3];
+        const float T_lane = carry_T * excl;
+        float w[COMP_K], tot[3] = {0.f, 0.f, 0.f};                              // tot = colour accumulated over the lane's own samples
 #pragma unroll
-        for (int q = 0; q < 3; ++q) S[q] = carry_S[q] + warp_incl_sum(w * c[q], lane);   // rgb_ray2 including this sample
-        if (j < n) {
-            const float suffix[3] = {rr[0] - S[0], rr[1] - S[1], rr[2] - S[2]};
-            float4 dl;
-            dl.x = loss_scale * ((w * lg[0]) * (c[0] * (1 - c[0])));                        // calc_rgb.h:133-135 (l2 reg is 0 for Logistic)
-            dl.y = loss_scale * ((w * lg[1]) * (c[1] * (1 - c[1])));
-            dl.z = loss_scale * ((w * lg[2]) * (c[2] * (1 - c[2])));
-            const float dd = __expf(fminf(fmaxf(raw.w, -15.0f), 15.0f));                    // network_to_density_derivative
-            const float dot = lg[0] * (T_after * c[0] - suffix[0]) + (lg[1] * (T_after * c[1] - suffix[1]) + lg[2] * (T_after * c[2] - suffix[2]));
-            dl.w = loss_scale * (dd * (dt * dot)) + (raw.w < 0 ? -l1 : 0.0f);               // :137-139
-            store_net<T>(dnet, (size_t)base + j, dl);
+        for (int q = 0; q < COMP_K; ++q) {
+            w[q] = a[q] * (q == 0 ? T_lane : T_lane * p[q - 1]);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) tot[k] = __fmaf_rn(w[q], c[q][k], tot[k]);
+        }
+        float run[3], incl_S[3];                                                // run = colour accumulated up to (and then including) sample q
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            incl_S[k] = warp_incl_sum(tot[k], lane);
+            float e = __shfl_up_sync(0xffffffffu, incl_S[k], 1);
+            if (lane == 0) e = 0.f;
+            run[k] = carry_S[k] + e;
+        }
+#pragma unroll
+        for (int q = 0; q < COMP_K; ++q) {
+            const uint32_t j = j0 + COMP_K * lane + q;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) run[k] = __fmaf_rn(w[q], c[q][k], run[k]);         // rgb_ray2 including this sample
+            if (j < n) {
+                const float T_after = T_lane * p[q];                                        // T after this sample (calc_rgb.h:125)
+                const float suffix[3] = {rr[0] - run[0], rr[1] - run[1], rr[2] - run[2]};
+                float4 dl;
+                dl.x = loss_scale * ((w[q] * lg[0]) * (c[q][0] * (1 - c[q][0])));           // calc_rgb.h:133-135 (l2 reg is 0 for Logistic)
+                dl.y = loss_scale * ((w[q] * lg[1]) * (c[q][1] * (1 - c[q][1])));
+                dl.z = loss_scale * ((w[q] * lg[2]) * (c[q][2] * (1 - c[q][2])));
+                const float dd = __expf(fminf(fmaxf(sig[q], -15.0f), 15.0f));               // network_to_density_derivative
+                const float dot = lg[0] * (T_after * c[q][0] - suffix[0]) +
+                                  (lg[1] * (T_after * c[q][1] - suffix[1]) + lg[2] * (T_after * c[q][2] - suffix[2]));
+                dl.w = loss_scale * (dd * (dt[q] * dot)) + (sig[q] < 0 ? -l1 : 0.0f);       // :137-139
+                store_net<T>(dnet, (size_t)base + j, dl);
+            }
         }
         carry_T *= __shfl_sync(0xffffffffu, incl, 31);
 #pragma unroll
-        for (int q = 0; q < 3; ++q) carry_S[q] = __shfl_sync(0xffffffffu, S[q], 31);
+        for (int k = 0; k < 3; ++k) carry_S[k] += __shfl_sync(0xffffffffu, incl_S[k], 31);
     }
 }
 
@@ -749,7 +796,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(uint32_t n_rays, con
 }
 
 // Fused training tail: composite forward, Huber gradient, composite backward -- one warp per ray.
-__global__ void __launch_bounds__(256) composite_loss_bwd_kernel(uint32_t n_rays, const __half* __restrict__ net, const float* __restrict__ coords,
+__global__ void __launch_bounds__(128, 7) composite_loss_bwd_kernel(uint32_t n_rays, const __half* __restrict__ net, const float* __restrict__ coords,
                                                                  const uint32_t* __restrict__ numsteps_in, const uint32_t* __restrict__ numsteps_c,
                                                                  const float* __restrict__ bg, const float* __restrict__ target, float delta,
                                                                  const float* __restrict__ mean, uint32_t cascades, float* __restrict__ rgb_out,
@@ -893,7 +940,7 @@ int ngp_composite_loss_bwd(void* stream, uint32_t n_rays, uint32_t n_elements, c
     (void)n_elements;   // rows not covered by a ray are never read downstream (the network backward is count-limited)
     if (n_rays == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    composite_loss_bwd_kernel<<<(n_rays + 7) / 8, 256, 0, s>>>(n_rays, (const __half*)net_out, coords, numsteps_in, numsteps_compacted, bg, target,
+    composite_loss_bwd_kernel<<<(n_rays + 3) / 4, 128, 0, s>>>(n_rays, (const __half*)net_out, coords, numsteps_in, numsteps_compacted, bg, target,
                                                                huber_delta, density_grid_mean, cascades, rgb_out, loss_out, (__half*)dnet_out, reg_scale);
     NGP_LAUNCH_CHECK();
     return 0;

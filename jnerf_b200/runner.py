@@ -97,10 +97,11 @@ class Runner:
             # latency-bound: side by side they share the SMs instead of queueing.  NGP_PIPE_AT picks the point of
             # step i the front of step i+1 may start at: after its network forward ("fwd"), backward ("bwd") or at once ("front").
             if os.environ.get("NGP_PIPELINE", "1") == "1" and not self._graphs_enabled:
-                at = os.environ.get("NGP_PIPE_AT", "bwd")
+                at = os.environ.get("NGP_PIPE_AT", "fwd")
                 assert at in ("front", "fwd", "bwd")
                 self._pipe = dict(stream=torch.cuda.Stream(), coords=[None, None], made=0, pending=None, at=at, mid=torch.cuda.Event(),
-                                  back_done=[torch.cuda.Event(), torch.cuda.Event()], prefetched=0)
+                                  back_done=[torch.cuda.Event(), torch.cuda.Event()], prefetched=0, aux=torch.cuda.Stream(),
+                                  bwd_done=torch.cuda.Event(), aux_done=torch.cuda.Event())
         if self.world_size > 1:
             self._init_sharded_table()
 
@@ -375,7 +376,20 @@ class Runner:
         adam = self.optimizer._nested_optimizer
         adam.n_step += 1
         self.ema_optimizer.steps += 1
-        self._optimizer_step(lr, adam.n_step)
+        # fused Adam+EMA sweeps (optims/adam.py + ema.py; runner.py:75-76): the two MLP weight vectors are single-CTA launches that
+        # cost a launch latency each -- on a third stream they run beside the table's sweep instead of after it
+        m = self.model
+        hyper = (lr, adam.n_step, adam.betas[0], adam.betas[1], adam.eps, self.ema_optimizer.decay)
+        P["bwd_done"].record(main)
+        P["aux"].wait_event(P["bwd_done"])
+        with torch.cuda.stream(P["aux"]):
+            for p_, g_ in ((m.density_mlp.con_weights, self.dwd), (m.rgb_mlp.con_weights, self.dwr)):
+                st = self._st[id(p_)]
+                ops.adam_ema(p_.data, g_, st.m, st.v, st.master, *hyper, grad_scale=1.0, zero_grad=True)
+            P["aux_done"].record()
+        st = self._st[id(m.pos_encoder.m_grid)]
+        ops.adam_ema(m.pos_encoder.m_grid.data, self.grid_grad, st.m, st.v, st.master, *hyper, grad_scale=1.0, zero_grad=True)
+        main.wait_event(P["aux_done"])
         P["back_done"][F["slot"]].record(main)
         self.last_loss, self.last_rgb = loss, rgb
         cfg.m_training_step = i + 1

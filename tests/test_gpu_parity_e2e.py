@@ -88,13 +88,15 @@ def test_identical_ray_batch_to_radiance(kind):
     err = np.abs(rgb - rgb_ref)
     bright = rgb_ref > 0.1
     stats = dict(samples=S, frac_bit_identical=float((d_out == 0).mean()), frac_within_2ulp=float((d_out <= 2 * ulp).mean()),
+                 worst_excess=float((d_out - np.maximum(1e-2, 2 * ulp)).max()),
                  out_max_abs=float(d_out.max()), out_absmax_ref=float(np.abs(out_ref).max()), rgb_max_abs=float(err.max()), rgb_mean_abs=float(err.mean()),
                  rgb_max_rel_bright=float((err[bright] / rgb_ref[bright]).max()) if bright.any() else 0.0,
                  infer_rgb_max_abs=float(np.abs(npy(rgb_i) - ri_ref).max()), infer_alpha_max_abs=float(np.abs(npy(alpha_i) - ai_ref).max()))
     print("parity", kind, stats)
     # per sample: bit-identical for the bulk, within 2 fp16 ulp for 99.9 %; the tail is a hidden activation that rounded the other way
     # (1 ulp of an O(1..8) activation times an O(0.3) weight), bounded absolutely
-    assert stats["frac_bit_identical"] > 0.80 and stats["frac_within_2ulp"] > 0.999 and stats["out_max_abs"] <= 1e-2, stats
+    # (1e-2, or 2 ulp where the output itself is large: the fox scene's raw densities reach +-25, where one fp16 ulp is 0.0156)
+    assert stats["frac_bit_identical"] > 0.80 and stats["frac_within_2ulp"] > 0.999 and stats["worst_excess"] <= 0, stats
     # radiance: north_star's bar is 1e-3 (absolute on [0,1] radiance, and relative to the pixel for pixels brighter than 0.1);
     # measured on a B200 (profiles/r02_parity_e2e.json): 1.1e-5 absolute / 7.3e-5 relative on lego, 7.2e-6 / 1.4e-5 on fox -- asserted
     # at 2e-4 so that a regression shows long before the contract is at risk

@@ -144,6 +144,7 @@ def test_cuda_graph_replay_equals_eager_steps(monkeypatch):
     runs = {}
     for graphs in ("1", "0"):
         monkeypatch.setenv("NGP_GRAPHS", graphs)
+        monkeypatch.setenv("NGP_PIPELINE", "0")                    # eager = the same sequential device-state step the graph captures
         monkeypatch.setenv("NGP_GRAPH_AFTER", "2")                 # capture at the second step of a ray-batch size (default: its second window)
         r = make_runner(seed=21)
         assert r._graphs_enabled == (graphs == "1")
@@ -167,3 +168,39 @@ def test_cuda_graph_replay_equals_eager_steps(monkeypatch):
     la, lb = a["losses"], b["losses"]
     assert np.all(np.isfinite(la)) and np.abs(la[:41] - lb[:41]).max() <= 5e-2 * np.abs(lb).max()
     assert abs(la[-8:].mean() - lb[-8:].mean()) <= 0.1 * lb[-8:].mean()
+
+
+@pytest.mark.gpu
+def test_pipelined_steps_match_sequential_steps(monkeypatch):
+    """The software pipeline over steps (march of step i+1 on a second stream under step i's backward / optimizer sweep) against the
+    strictly sequential step with the same seeds: the same pixels, the same rays and samples until the first occupancy-grid rebuild
+    (bit for bit: the march reads nothing the network kernels write), losses equal up to the order of the gradient atomics, and the
+    same training progress afterwards.  Exact equality of the two orders is tests/test_runner_cpu.py's (deterministic oracle)."""
+    import numpy as np
+    from jnerf_b200 import ops
+    runs = {}
+    for pipe in ("1", "0"):
+        monkeypatch.setenv("NGP_PIPELINE", pipe)
+        monkeypatch.setenv("NGP_GRAPHS", "0")
+        r = make_runner(seed=23)
+        assert (r._pipe is not None) == (pipe == "1")
+        losses, marks = [], []
+        for k in range(120):
+            losses.append(float(r.train_step().mean()))
+            if k in (7, 40):
+                marks.append((r.sampler._counters_compacted.clone(), r.sampler._rays_numsteps.clone()))
+        runs[pipe] = dict(losses=np.array(losses), marks=marks, n_step=r.optimizer._nested_optimizer.n_step, rays=r.sampler.n_rays_per_batch,
+                          prefetched=r._pipe["prefetched"] if r._pipe is not None else 0)
+        img, tar = r.render_img_nosync("train", 0)
+        runs[pipe]["psnr"] = float(-10.0 * torch.log10(((img - tar) ** 2).mean()))
+        assert ops.lib.load().ngp_debug_timeout_flag() == 0
+    a, b = runs["1"], runs["0"]
+    assert a["prefetched"] == 120 - 8 and a["n_step"] == b["n_step"] == 120       # every step but the 8 that open with a grid update
+    (cnt_a, ns_a), (cnt_b, ns_b) = a["marks"][0], b["marks"][0]
+    assert torch.equal(cnt_a, cnt_b) and torch.equal(ns_a, ns_b)                  # step 7: same occupancy grid, same jitter -> same samples
+    (cnt_a, ns_a), (cnt_b, ns_b) = a["marks"][1], b["marks"][1]
+    assert int(cnt_a[1]) == int(cnt_b[1]) and abs(int(cnt_a[0]) - int(cnt_b[0])) <= 0.02 * int(cnt_b[0])
+    la, lb = a["losses"], b["losses"]
+    assert np.all(np.isfinite(la)) and np.abs(la[:16] - lb[:16]).max() <= 2e-3 * np.abs(lb[:16]).max()
+    assert np.abs(la[:41] - lb[:41]).max() <= 5e-2 * np.abs(lb).max() and abs(la[-8:].mean() - lb[-8:].mean()) <= 0.1 * lb[-8:].mean()
+    assert abs(a["psnr"] - b["psnr"]) < 0.5 and a["psnr"] > 18.0, (a["psnr"], b["psnr"])

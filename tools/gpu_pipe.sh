@@ -12,11 +12,11 @@ bench() { local name=$1; shift; local envs=(); while [ "$1" != "--" ]; do envs+=
           run "bench_$name" 300 env "${envs[@]}" python bench.py --steps 300 --warmup 5 --no-cpu-baseline "$@"
           python tools/bench_line_summary.py "$OUT/bench_$name.log" "$name" >> "$SUM"; }
 python -c "import __graft_entry__ as g; g.build()" > "$OUT/build.log" 2>&1 || echo "build failed" >> "$SUM"
+run pytest_gpu 1200 python -m pytest tests -m gpu -q -p no:cacheprovider
 bench seq NGP_PIPELINE=0 --
-bench pipe_bwd NGP_PIPE_AT=bwd --
 bench pipe_fwd NGP_PIPE_AT=fwd --
 bench pipe_front NGP_PIPE_AT=front --
-bench seq_again NGP_PIPELINE=0 --
-bench pipe_bwd_fox NGP_PIPE_AT=bwd -- --workload fox
-run pytest_runner 900 python -m pytest tests/test_gpu_runner.py tests/test_gpu_parity_e2e.py -m gpu -q -p no:cacheprovider -x
+bench fox_fwd NGP_PIPE_AT=fwd -- --workload fox
+bench fox_front NGP_PIPE_AT=front -- --workload fox
+run psnr_lego 300 python tools/train_psnr.py --steps 3000 --evals 1000,3000 --out $OUT/psnr_lego.json
 cat "$SUM"
