@@ -97,7 +97,7 @@ class Runner:
             # latency-bound: side by side they share the SMs instead of queueing.  NGP_PIPE_AT picks the point of
             # step i the front of step i+1 may start at: after its network forward ("fwd"), backward ("bwd") or at once ("front").
             if os.environ.get("NGP_PIPELINE", "1") == "1" and not self._graphs_enabled:
-                at = os.environ.get("NGP_PIPE_AT", "fwd")
+                at = os.environ.get("NGP_PIPE_AT", "front")
                 assert at in ("front", "fwd", "bwd")
                 self._pipe = dict(stream=torch.cuda.Stream(), coords=[None, None], made=0, pending=None, at=at, mid=torch.cuda.Event(),
                                   back_done=[torch.cuda.Event(), torch.cuda.Event()], prefetched=0, aux=torch.cuda.Stream(),
