@@ -126,7 +126,7 @@ class DensityGridSampler(Module):
         self._counters_compacted = cnt_c
         return self._coords[:, :3], self._coords[:, 4:]
 
-    def sample_front(self, rays_o, rays_d, coords_raw):
+    def sample_front(self, rays_o, rays_d, coords_raw, ray_index_offset=0):
         """Training-mode march + compaction into a caller-owned coordinate buffer, returning the step's bookkeeping instead of
         keeping it on the sampler: the runner's software pipeline runs this for step i+1 (on a second stream) while step i still
         reads its own rows.  The caller runs the occupancy-grid update and the ray-batch adaptation around it."""
@@ -134,7 +134,9 @@ class DensityGridSampler(Module):
             self._ensure_march_ws(2 * rays_o.shape[0])
         coords, _, rays_numsteps, _ = ops.march(rays_o.contiguous(), rays_d.contiguous(), self.density_grid_bitfield, self.aabb_range,
                                                 self.max_samples, self.cone_angle_constant, self.near_distance, self.NERF_CASCADES,
-                                                self.const_dt, self.rng, coords=coords_raw, workspace=self._march_ws)
+                                                self.const_dt,
+                                                ops.pcg32_advance(self.rng.copy(), ray_index_offset * 8) if ray_index_offset else self.rng,
+                                                coords=coords_raw, workspace=self._march_ws)
         ops.pcg32_advance(self.rng)                                    # rng.advance(), ray_sampler.py:61
         cap = self.target_batch_size
         _, ns_c, cnt_c = ops.compact(coords, rays_numsteps, cap, alias=True)

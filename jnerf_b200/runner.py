@@ -91,17 +91,18 @@ class Runner:
             self._graphs_enabled = os.environ.get("NGP_GRAPHS", "0") == "1" and torch.cuda.is_available() and hasattr(torch.cuda, "CUDAGraph")
             self.graph_replays = 0
             self._graph_after = int(os.environ.get("NGP_GRAPH_AFTER", "20"))     # occurrences of a ray-batch size before it gets a graph
-            # Software pipeline over steps (default): nothing the march reads is written by the network kernels -- rays, jitter and the
-            # occupancy bitfield only -- so the "front" of step i+1 (background colours, ray generation, march, compaction) is enqueued
-            # on a second stream while step i's backward / Adam+EMA sweep still run.  The sweep is HBM-bound and the march is
-            # latency-bound: side by side they share the SMs instead of queueing.  NGP_PIPE_AT picks the point of
-            # step i the front of step i+1 may start at: after its network forward ("fwd"), backward ("bwd") or at once ("front").
-            if os.environ.get("NGP_PIPELINE", "1") == "1" and not self._graphs_enabled:
-                at = os.environ.get("NGP_PIPE_AT", "front")
-                assert at in ("front", "fwd", "bwd")
-                self._pipe = dict(stream=torch.cuda.Stream(), coords=[None, None], made=0, pending=None, at=at, mid=torch.cuda.Event(),
-                                  back_done=[torch.cuda.Event(), torch.cuda.Event()], prefetched=0, aux=torch.cuda.Stream(),
-                                  bwd_done=torch.cuda.Event(), aux_done=torch.cuda.Event())
+        # Software pipeline over steps (default): nothing the march reads is written by the network kernels -- rays, jitter and the
+        # occupancy bitfield only -- so the "front" of step i+1 (background colours, ray generation, march, compaction) is enqueued
+        # on a second stream while step i's backward / Adam+EMA sweep still run.  The sweep is HBM-bound and the march is
+        # latency-bound: side by side they share the SMs instead of queueing.  NGP_PIPE_AT picks the point of
+        # step i the front of step i+1 may start at: after its network forward ("fwd"), backward ("bwd") or at once ("front").
+        if os.environ.get("NGP_PIPELINE", "1") == "1" and not getattr(self, "_graphs_enabled", False):
+            at = os.environ.get("NGP_PIPE_AT", "front")
+            assert at in ("front", "fwd", "bwd")
+            self._pipe = dict(stream=torch.cuda.Stream(), coords=[None, None], made=0, pending=None, at=at, mid=torch.cuda.Event(),
+                              back_done=[torch.cuda.Event(), torch.cuda.Event()], prefetched=0, aux=torch.cuda.Stream(),
+                              bwd_done=torch.cuda.Event(), aux_done=torch.cuda.Event(),
+                              hi=torch.cuda.Stream(priority=-1) if os.environ.get("NGP_PIPE_PRIO", "0") == "1" else None)
         if self.world_size > 1:
             self._init_sharded_table()
 
@@ -319,21 +320,30 @@ class Runner:
         (side if prefetch else main).wait_event(P["back_done"][slot])
         with torch.cuda.stream(side if prefetch else main):
             rng_before = s.rng.copy()
+            W = self.world_size
             if step % s.update_den_freq == 0:
                 assert not prefetch
+                self._table_ready()                                  # the update evaluates the density network on the exchanged table
                 s.update_density_grid()
             if batch is None:
-                R = s.n_rays_per_batch
-                pix = ds.next_pixels(R)
-                bg = torch.rand((R, 3), device="cuda", generator=self._bg_gen)                         # runner.py:66
+                R = s.n_rays_per_batch                               # per-rank rays; the global batch is W x R (weak scaling)
+                pix = ds.next_pixels(R * W)
+                bg = torch.rand((R * W, 3), device="cuda", generator=self._bg_gen)                     # runner.py:66 (global batch, then this rank's rows)
+                if W > 1:
+                    lo, hi = dp.shard_range(R, self.rank)
+                    pix, bg = pix[lo:hi], bg[lo:hi]
+                bg = bg.contiguous()
                 img_ids, rays_o, rays_d, target = ops.prepare_batch(pix.contiguous(), ds.W, ds.H, ds.transforms_gpu, ds.focal_lengths,
                                                                     ds.principal, ds.image_data, bg)    # dataset.py:172-188 + runner.py:68
             else:
                 img_ids, rays_o, rays_d, rgba = batch
                 R = rays_o.shape[0]
-                bg = torch.rand((R, 3), device="cuda", generator=self._bg_gen)
+                bg = torch.rand((R * W, 3), device="cuda", generator=self._bg_gen)
+                if W > 1:
+                    bg = bg[self.rank * R:(self.rank + 1) * R]
+                bg = bg.contiguous()
                 target = ops.blend_target(rgba.contiguous(), bg)                                       # runner.py:68
-            numsteps, ns_c, cnt_c, coords = s.sample_front(rays_o, rays_d, P["coords"][slot])
+            numsteps, ns_c, cnt_c, coords = s.sample_front(rays_o, rays_d, P["coords"][slot], ray_index_offset=dp.shard_range(R, self.rank)[0])
             done = torch.cuda.Event()
             done.record()
         P["made"] += 1
@@ -348,6 +358,17 @@ class Runner:
             torch.cuda.current_stream().wait_event(P["pending"]["done"])
 
     def _train_step_pipe(self, batch=None, next_batch=None):
+        hi = self._pipe["hi"]
+        if hi is None:
+            return self._pipe_body(batch, next_batch)
+        cur = torch.cuda.current_stream()
+        hi.wait_stream(cur)
+        with torch.cuda.stream(hi):
+            loss = self._pipe_body(batch, next_batch)
+        cur.wait_stream(hi)
+        return loss
+
+    def _pipe_body(self, batch, next_batch):
         cfg, s, P = self.cfg, self.sampler, self._pipe
         i = cfg.m_training_step
         main = torch.cuda.current_stream()
@@ -364,11 +385,13 @@ class Runner:
             P["mid"].record(main)
         s._rays_numsteps, s._rays_numsteps_compacted, s._counters_compacted, s._coords = F["numsteps"], F["ns_c"], F["cnt_c"], F["coords"]
         coords, n_dev = F["coords"], F["cnt_c"][0:1]
+        self._table_ready()                                          # data parallel: the exchange of step i-1 has delivered the table
         self.net_forward(coords, n_dev)
         if P["at"] == "fwd":
             P["mid"].record(main)
         rgb, loss, _ = ops.composite_loss_bwd(self.net_out, coords, F["numsteps"], F["ns_c"], F["bg"], F["target"], s.density_grid_mean,
-                                              delta=self.loss_func.delta, cascades=s.NERF_CASCADES, dnet=self.dnet)
+                                              delta=self.loss_func.delta, cascades=s.NERF_CASCADES, dnet=self.dnet,
+                                              reg_scale=float(self.world_size))    # the exchange applies 1 / W to the summed gradients
         self.net_backward(coords, n_dev)
         if P["at"] == "bwd":
             P["mid"].record(main)
@@ -380,6 +403,9 @@ class Runner:
         # cost a launch latency each -- on a third stream they run beside the table's sweep instead of after it
         m = self.model
         hyper = (lr, adam.n_step, adam.betas[0], adam.betas[1], adam.eps, self.ema_optimizer.decay)
+        if self.world_size > 1:
+            self._optimizer_step(lr, adam.n_step)                    # gradient exchange fused with the sliced sweep (section 6)
+            return self._pipe_finish(F, loss, rgb, batch, next_batch)
         P["bwd_done"].record(main)
         P["aux"].wait_event(P["bwd_done"])
         with torch.cuda.stream(P["aux"]):
@@ -390,7 +416,12 @@ class Runner:
         st = self._st[id(m.pos_encoder.m_grid)]
         ops.adam_ema(m.pos_encoder.m_grid.data, self.grid_grad, st.m, st.v, st.master, *hyper, grad_scale=1.0, zero_grad=True)
         main.wait_event(P["aux_done"])
-        P["back_done"][F["slot"]].record(main)
+        return self._pipe_finish(F, loss, rgb, batch, next_batch)
+
+    def _pipe_finish(self, F, loss, rgb, batch, next_batch):
+        cfg, s, P = self.cfg, self.sampler, self._pipe
+        i = cfg.m_training_step
+        P["back_done"][F["slot"]].record(torch.cuda.current_stream())
         self.last_loss, self.last_rgb = loss, rgb
         cfg.m_training_step = i + 1
         self._pipe_last = F                                          # keeps the front's tensors alive until the next step replaces them

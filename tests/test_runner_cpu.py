@@ -173,7 +173,7 @@ def test_occupancy_grid_update_glue(monkeypatch):
 
 
 # ------------------------------------------------------------------------------------------------ data parallel (gloo, 2 ranks)
-def _dp_worker(rank, world, port, tmp, ret):
+def _dp_worker(rank, world, port, tmp, ret, pipeline=False):
     import os
     import sys
     import torch.distributed as dist
@@ -184,6 +184,7 @@ def _dp_worker(rank, world, port, tmp, ret):
     mp_ = pytest.MonkeyPatch()
     try:
         fake = cpu_backend.install(mp_)
+        mp_.setenv("NGP_PIPELINE", "1" if pipeline else "0")
         from jnerf_b200 import plugin  # noqa: F401
         from jnerf_b200 import runner as R
         from jnerf_b200.utils.config import get_cfg, update_cfg
@@ -199,6 +200,7 @@ def _dp_worker(rank, world, port, tmp, ret):
         assert r.dp_mode == "nccl" and r._hi - r._lo == r._table.numel() // world
         losses = [float(r.train_step().mean()) for _ in range(3)]
         r._table_ready()
+        assert (r._pipe is not None) == pipeline
         g = r.model.pos_encoder.m_grid.detach().float()
         st = r.optimizer._nested_optimizer.state[0]
         r.save_ckpt(os.path.join(tmp, "dp.pt"))                                  # every rank calls; rank 0 writes the gathered state
@@ -226,6 +228,13 @@ def test_two_rank_runner_sharded_optimizer_keeps_replicas_identical(tmp_path):
     assert a["calls"] == ["prepare_batch", "march", "compact", "network_fwd", "composite_loss_bwd", "network_bwd", "adam_ema", "adam_ema", "adam_ema"]
     ck = torch.load(str(tmp_path / "dp.pt"), map_location="cpu", weights_only=False)
     assert ck["nested_optimizer"]["m"][0].numel() == 12196240 and ck["global_step"] == 4
+    # the same two ranks with the software pipeline over steps (march of step i+1 enqueued under step i, the exchange of step i-1
+    # awaited right before the network forward): the same losses and the same table, to the last bit
+    ret2 = mp.Manager().dict()
+    mp.spawn(_dp_worker, args=(world, 29713 + os.getpid() % 1000, str(tmp_path), ret2, True), nprocs=world, join=True)
+    for k in (0, 1):
+        assert ret2[k]["losses"] == ret[k]["losses"] and ret2[k]["table_sum"] == ret[k]["table_sum"] and np.array_equal(ret2[k]["w"], ret[k]["w"])
+    assert ret2[0]["calls"][-3:] == ["prepare_batch", "march", "compact"]          # the prefetched front of the next step
 
 
 def test_real_capture_through_the_runner(monkeypatch, tmp_path):
