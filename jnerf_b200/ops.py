@@ -23,7 +23,14 @@ def _p(t):
     return t.data_ptr()
 
 
+# The raw handle of torch's current stream.  torch.cuda.current_stream() builds a Stream object and re-checks the device on every call
+# (~3 us; 16 calls a training step were a sixth of the step's host time, tools/host_probe.py): the two C getters are what it wraps.
+_raw_stream, _raw_device = getattr(torch._C, "_cuda_getCurrentRawStream", None), getattr(torch._C, "_cuda_getDevice", None)
+
+
 def _stream():
+    if _raw_stream is not None and _raw_device is not None:
+        return _raw_stream(_raw_device())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -10,6 +10,7 @@ On one GPU the steps are software-pipelined: raygen + march of step i+1 run on a
 
 `train_step_autograd` runs the same step through the per-operator plugin classes and torch autograd, exactly as
 JNeRF's Runner.train does with Jittor; tests check that both give the same parameters."""
+import contextlib
 import os
 
 import numpy as np
@@ -101,8 +102,7 @@ class Runner:
             assert at in ("front", "fwd", "bwd")
             self._pipe = dict(stream=torch.cuda.Stream(), coords=[None, None], made=0, pending=None, at=at, mid=torch.cuda.Event(),
                               back_done=[torch.cuda.Event(), torch.cuda.Event()], prefetched=0, aux=torch.cuda.Stream(),
-                              bwd_done=torch.cuda.Event(), aux_done=torch.cuda.Event(),
-                              hi=torch.cuda.Stream(priority=-1) if os.environ.get("NGP_PIPE_PRIO", "0") == "1" else None)
+                              bwd_done=torch.cuda.Event(), aux_done=torch.cuda.Event(), main=None)
         if self.world_size > 1:
             self._init_sharded_table()
 
@@ -312,13 +312,13 @@ class Runner:
         slot = P["made"] & 1
         if P["coords"][slot] is None:
             P["coords"][slot] = torch.zeros_like(s._coords_raw)
-        main = torch.cuda.current_stream()
+        main = P["main"] if P["main"] is not None else torch.cuda.current_stream()
         side = P["stream"]
         if prefetch:
             side.wait_event(P["mid"])                                # recorded on the main stream inside the step in flight
         # the step that read this slot's coordinate rows two fronts ago must be through (it is, unless the host runs far ahead)
         (side if prefetch else main).wait_event(P["back_done"][slot])
-        with torch.cuda.stream(side if prefetch else main):
+        with (torch.cuda.stream(side) if prefetch else contextlib.nullcontext()):
             rng_before = s.rng.copy()
             W = self.world_size
             if step % s.update_den_freq == 0:
@@ -345,7 +345,7 @@ class Runner:
                 target = ops.blend_target(rgba.contiguous(), bg)                                       # runner.py:68
             numsteps, ns_c, cnt_c, coords = s.sample_front(rays_o, rays_d, P["coords"][slot], ray_index_offset=dp.shard_range(R, self.rank)[0])
             done = torch.cuda.Event()
-            done.record()
+            done.record(side if prefetch else main)
         P["made"] += 1
         P["prefetched"] += int(prefetch)
         return dict(step=step, src=batch, slot=slot, bg=bg, target=target, numsteps=numsteps, ns_c=ns_c, cnt_c=cnt_c, coords=coords, done=done,
@@ -358,20 +358,9 @@ class Runner:
             torch.cuda.current_stream().wait_event(P["pending"]["done"])
 
     def _train_step_pipe(self, batch=None, next_batch=None):
-        hi = self._pipe["hi"]
-        if hi is None:
-            return self._pipe_body(batch, next_batch)
-        cur = torch.cuda.current_stream()
-        hi.wait_stream(cur)
-        with torch.cuda.stream(hi):
-            loss = self._pipe_body(batch, next_batch)
-        cur.wait_stream(hi)
-        return loss
-
-    def _pipe_body(self, batch, next_batch):
         cfg, s, P = self.cfg, self.sampler, self._pipe
         i = cfg.m_training_step
-        main = torch.cuda.current_stream()
+        main = P["main"] = torch.cuda.current_stream()
         F, P["pending"] = P["pending"], None
         if F is not None and (F["step"] != i or F["src"] is not batch):
             F = None                                                 # the caller changed course (checkpoint loaded, other batch): drop it
@@ -383,7 +372,8 @@ class Runner:
             s.update_batch_rays()                                    # the one host sync per 16 steps; after this step's march, as in sample()
         if P["at"] == "front":
             P["mid"].record(main)
-        s._rays_numsteps, s._rays_numsteps_compacted, s._counters_compacted, s._coords = F["numsteps"], F["ns_c"], F["cnt_c"], F["coords"]
+        # (the sampler is an nn.Module: plain attribute assignment goes through Module.__setattr__, ~2 us apiece)
+        s.__dict__.update(_rays_numsteps=F["numsteps"], _rays_numsteps_compacted=F["ns_c"], _counters_compacted=F["cnt_c"], _coords=F["coords"])
         coords, n_dev = F["coords"], F["cnt_c"][0:1]
         self._table_ready()                                          # data parallel: the exchange of step i-1 has delivered the table
         self.net_forward(coords, n_dev)
@@ -412,7 +402,7 @@ class Runner:
             for p_, g_ in ((m.density_mlp.con_weights, self.dwd), (m.rgb_mlp.con_weights, self.dwr)):
                 st = self._st[id(p_)]
                 ops.adam_ema(p_.data, g_, st.m, st.v, st.master, *hyper, grad_scale=1.0, zero_grad=True)
-            P["aux_done"].record()
+            P["aux_done"].record(P["aux"])
         st = self._st[id(m.pos_encoder.m_grid)]
         ops.adam_ema(m.pos_encoder.m_grid.data, self.grid_grad, st.m, st.v, st.master, *hyper, grad_scale=1.0, zero_grad=True)
         main.wait_event(P["aux_done"])
@@ -421,7 +411,7 @@ class Runner:
     def _pipe_finish(self, F, loss, rgb, batch, next_batch):
         cfg, s, P = self.cfg, self.sampler, self._pipe
         i = cfg.m_training_step
-        P["back_done"][F["slot"]].record(torch.cuda.current_stream())
+        P["back_done"][F["slot"]].record(P["main"])
         self.last_loss, self.last_rgb = loss, rgb
         cfg.m_training_step = i + 1
         self._pipe_last = F                                          # keeps the front's tensors alive until the next step replaces them
