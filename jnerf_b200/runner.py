@@ -100,7 +100,10 @@ class Runner:
         if os.environ.get("NGP_PIPELINE", "1") == "1" and not getattr(self, "_graphs_enabled", False):
             at = os.environ.get("NGP_PIPE_AT", "front")
             assert at in ("front", "fwd", "bwd")
-            self._pipe = dict(stream=torch.cuda.Stream(), coords=[None, None], made=0, pending=None, at=at, mid=torch.cuda.Event(),
+            # both coordinate buffers are allocated (and zero-filled) HERE, on the constructor's stream: a fill enqueued lazily from inside
+            # a step would land on the main stream behind that step's kernels and wipe what the side stream's march had just written
+            raw = self.sampler._coords_raw
+            self._pipe = dict(stream=torch.cuda.Stream(), coords=[torch.zeros_like(raw), torch.zeros_like(raw)], made=0, pending=None, at=at, mid=torch.cuda.Event(),
                               back_done=[torch.cuda.Event(), torch.cuda.Event()], prefetched=0, aux=torch.cuda.Stream(),
                               bwd_done=torch.cuda.Event(), aux_done=torch.cuda.Event(), main=None)
         if self.world_size > 1:
@@ -310,8 +313,6 @@ class Runner:
         occupancy-grid update: the update evaluates the density network, so it needs the finished optimizer sweep)."""
         P, s, ds = self._pipe, self.sampler, self.dataset["train"]
         slot = P["made"] & 1
-        if P["coords"][slot] is None:
-            P["coords"][slot] = torch.zeros_like(s._coords_raw)
         main = P["main"] if P["main"] is not None else torch.cuda.current_stream()
         side = P["stream"]
         if prefetch:
