@@ -77,6 +77,13 @@ def global_mean_count(counter, group, world_size):
     return counter
 
 
+def global_sum_count(counter, group, world_size):
+    """All-reduce an integer sample counter in place (the sum over ranks, identical on every rank)."""
+    if world_size > 1:
+        dist.all_reduce(counter, op=dist.ReduceOp.SUM, group=group)
+    return counter
+
+
 def adapt_rays_per_batch(n_rays_per_batch, measured_per_step, target_batch_size):
     """DensityGridSampler.update_batch_rays (density_grid_sampler.py:266-271) as a pure function."""
     measured = max(measured_per_step, 1)

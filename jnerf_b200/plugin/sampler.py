@@ -215,10 +215,15 @@ class DensityGridSampler(Module):
 
     def update_batch_rays(self):
         from .. import dp
-        if self.dp_group is not None:                                  # data parallel: every rank adapts to the global mean
-            dp.global_mean_count(self.measured_batch_size, self.dp_group[0], self.dp_group[1])
+        W = 1
+        if self.dp_group is not None:
+            # data parallel: the GLOBAL ray batch adapts to the GLOBAL sample budget, exactly as one GPU training on the global batch
+            # would (same rounding to 128 rays), and every rank takes 1/W of it -- adapting each rank's shard on its own rounds to
+            # 128 rays PER RANK and the two runs part ways at the first adaptation (tools/dp_check.py)
+            W = self.dp_group[1]
+            dp.global_sum_count(self.measured_batch_size, self.dp_group[0], W)
         measured = self.measured_batch_size.item() / 16                # the one host sync per 16 steps (density_grid_sampler.py:266-271)
-        self.n_rays_per_batch = dp.adapt_rays_per_batch(self.n_rays_per_batch, measured, self.target_batch_size)
+        self.n_rays_per_batch = max(dp.adapt_rays_per_batch(self.n_rays_per_batch * W, measured, self.target_batch_size * W) // W, 1)
         self.measured_batch_size.zero_()
         self.dataset.batch_size = self.n_rays_per_batch
 
