@@ -60,7 +60,7 @@ def main():
     ok = {}
 
     # single-GPU forward of the global batch: the data-parallel shards must see the same rays, jitter and background
-    r1 = make_runner(0, 1, None, R * world)
+    r1 = make_runner(0, 1, None, R * world, target_batch=world << 18)   # the global batch must not be truncated to ONE rank's capacity
     loss_single = float(r1.train_step().float().mean().item())
     del r1
     # equal global batch, equal iterations on ONE GPU (SURVEY 8e's criterion), twice: the second run measures how far two runs of the
