@@ -110,9 +110,17 @@ def main():
         ok[f"{mode}_global_rays_every_16"] = rays_dp[::16]
         del rw
     ok["world_size"] = world
-    ok["single_gpu_global_batch_train_view_psnr_db"] = psnr_single
-    ok["dp_minus_single_psnr_db"] = {m: ok[f"{m}_train_view_psnr_db"] - sum(psnr_single) / 2 for m in ("p2p", "nccl")}
-    ok["single_gpu_run_to_run_psnr_db"] = abs(psnr_single[0] - psnr_single[1])
+    # every rank has trained the same single-GPU configuration twice: 2 W samples of the single-GPU result (the runs differ only in the
+    # order the gradient atomics were summed in), i.e. its mean and its spread
+    every = [None] * world
+    dist.all_gather_object(every, psnr_single)
+    every = [x for pair in every for x in pair]
+    mean_single = sum(every) / len(every)
+    ok["single_gpu_global_batch_train_view_psnr_db"] = every
+    ok["single_gpu_psnr_mean_db"] = mean_single
+    ok["single_gpu_psnr_std_db"] = (sum((x - mean_single) ** 2 for x in every) / (len(every) - 1)) ** 0.5
+    ok["dp_minus_single_psnr_db"] = {m: ok[f"{m}_train_view_psnr_db"] - mean_single for m in ("p2p", "nccl")}
+    ok["single_gpu_run_to_run_psnr_db"] = max(every) - min(every)
     ok["loss_step0_single_gpu_global_batch"] = loss_single
     ok["loss_step0_dp"] = {m: losses[m][0] for m in losses}
     ok["single_gpu_rays_every_16"] = rays_single[:K:16]
@@ -130,10 +138,10 @@ def main():
     good = good and all(abs(v - loss_single) <= 1e-3 * loss_single for v in ok["loss_step0_dp"].values())
     good = good and ok["p2p_vs_nccl_first8_max_rel_diff"] < 0.02
     good = good and all(ok[f"{m}_train_view_psnr_db"] > 20.0 for m in ("p2p", "nccl")) and all(v < 0.5 * loss_single for v in ok["loss_last"].values())
-    # PSNR at equal global batch and iterations: within 0.1 dB of the single-GPU run, or within three times that run's own
-    # run-to-run spread.  Training is chaotic at the level of the gradient atomics' summation order: two identical single-GPU runs end
+    # PSNR at equal global batch and iterations: within 0.1 dB of the mean of the 2 W single-GPU runs, or within three
+    # of their standard deviations.  Training is chaotic at the level of the gradient atomics' summation order: two identical single-GPU runs end
     # 0.004-0.05 dB apart after 300 steps, the p2p and the NCCL exchange (same arithmetic, different order) up to 0.1 dB.
-    good = good and all(abs(v) <= max(0.1, 3 * ok["single_gpu_run_to_run_psnr_db"]) for v in ok["dp_minus_single_psnr_db"].values())
+    good = good and all(abs(v) <= max(0.1, 3 * ok["single_gpu_psnr_std_db"]) for v in ok["dp_minus_single_psnr_db"].values())
     flag = torch.tensor([int(good)], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     ok["pass"] = bool(flag.item())
