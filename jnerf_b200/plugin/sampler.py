@@ -213,9 +213,16 @@ class DensityGridSampler(Module):
         else:
             self.update_density_grid_nerf(self.density_grid_decay, G3 * n_cascades // 4, G3 * n_cascades // 4)
 
-    def update_batch_rays(self):
+    def update_batch_rays(self, measured_total=None):
+        """measured_total: the (global) sample count of the 16 steps when the caller has read the counter back itself (the runner's
+        software pipeline does, on its side stream, so that the host does not wait for the step in flight)."""
         from .. import dp
         W = 1
+        if measured_total is not None:
+            W = self.dp_group[1] if self.dp_group is not None else 1
+            self.n_rays_per_batch = max(dp.adapt_rays_per_batch(self.n_rays_per_batch * W, measured_total / 16, self.target_batch_size * W) // W, 1)
+            self.dataset.batch_size = self.n_rays_per_batch
+            return
         if self.dp_group is not None:
             # data parallel: the GLOBAL ray batch adapts to the GLOBAL sample budget, exactly as one GPU training on the global batch
             # would (same rounding to 128 rays), and every rank takes 1/W of it -- adapting each rank's shard on its own rounds to

@@ -352,6 +352,27 @@ class Runner:
         return dict(step=step, src=batch, slot=slot, bg=bg, target=target, numsteps=numsteps, ns_c=ns_c, cnt_c=cnt_c, coords=coords, done=done,
                     rng_before=rng_before, rays=(img_ids, rays_o, rays_d), side=prefetch)
 
+    def _adapt_ray_batch(self, F):
+        """DensityGridSampler.update_batch_rays (density_grid_sampler.py:266-271) without stalling the pipeline: the 16-step sample
+        counter is read back on the SIDE stream (all-reduced there first under data parallelism), behind the last march that added
+        to it -- the host waits for that march only, not for the network kernels of the step it has just enqueued, and keeps its
+        lead over the device (a `.item()` on the main stream drained the queue every 16 steps: the device then idled while the host
+        enqueued the next step from scratch)."""
+        P, s = self._pipe, self.sampler
+        side = P["stream"]
+        if P.get("count_host") is None:
+            P["count_host"], P["count_ev"] = torch.zeros(1, dtype=torch.int32).pin_memory(), torch.cuda.Event()
+        side.wait_event(F["done"])
+        with torch.cuda.stream(side):
+            if self.world_size > 1:
+                dp.global_sum_count(s.measured_batch_size, self.pg, self.world_size)
+            P["count_host"].copy_(s.measured_batch_size, non_blocking=True)
+            s.measured_batch_size.zero_()
+            P["count_ev"].record(side)
+        P["count_ev"].synchronize()
+        P["main"].wait_event(P["count_ev"])                          # the next front (a grid-update step: main stream) adds to the counter
+        s.update_batch_rays(measured_total=int(P["count_host"][0]))
+
     def _sync_front(self):
         """Evaluation and checkpoint code shares the march workspace with a prefetched front: order the current stream behind it."""
         P = self._pipe
@@ -369,8 +390,6 @@ class Runner:
             F = self._front(i, batch, prefetch=False)
         elif F["side"]:
             main.wait_event(F["done"])
-        if i % s.update_den_freq == s.update_den_freq - 1:
-            s.update_batch_rays()                                    # the one host sync per 16 steps; after this step's march, as in sample()
         if P["at"] == "front":
             P["mid"].record(main)
         # (the sampler is an nn.Module: plain attribute assignment goes through Module.__setattr__, ~2 us apiece)
@@ -416,6 +435,8 @@ class Runner:
         self.last_loss, self.last_rgb = loss, rgb
         cfg.m_training_step = i + 1
         self._pipe_last = F                                          # keeps the front's tensors alive until the next step replaces them
+        if i % s.update_den_freq == s.update_den_freq - 1:
+            self._adapt_ray_batch(F)                                 # after this step's march, before the next front, as in sample()
         # the front of step i+1, unless that step opens with an occupancy-grid update (needs the sweep above) or the caller feeds
         # batches and has not said which one comes next
         if (i + 1) % s.update_den_freq != 0 and (batch is None or next_batch is not None):

@@ -357,6 +357,9 @@ def install(monkeypatch):
 
         def elapsed_time(self, other):
             return 1.0
+
+        def synchronize(self):
+            pass
     one = _FakeStream()
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: one)
     monkeypatch.setattr(torch.cuda, "Stream", _FakeStream)
