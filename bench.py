@@ -7,6 +7,9 @@
 A step = one full training iteration of projects/ngp/configs/ngp_base.py + fp16 (BASELINE config #2):
 [density-grid update every 16] -> ray gen -> march -> fused hash+MLP forward -> composite + Huber + composite
 backward -> fused MLP/hash backward -> [grad all-reduce] -> fused Adam+EMA over all 12.2 M parameters.
+On the device the steps are software-pipelined (jnerf_b200/runner.py: ray gen + march of step i+1 run on a second stream under step
+i's network kernels and optimizer sweep; NGP_PIPELINE=0 gives the strictly sequential step): the timed region holds K complete
+steps either way, nothing is skipped or cached.
 Data is synthetic (lego is downloaded at run time by the reference and is not available offline): 100 procedurally
 ray-traced 800x800 RGBA views with lego's intrinsics; weights are random-init.  Before the W warm-up steps the model is
 trained for --pretrain steps (untimed) so that the occupancy grid and the adaptive ray batch are in steady state, which
@@ -345,6 +348,10 @@ def run_ours(args):
                                f"({runner.sampler.n_rays_per_batch} rays/iter/GPU at measurement), pretrain {args.pretrain} steps",
                    "parallelism": f"dp{world}", "target_batch_size": args.target_batch,
                    "l2": "per-step working set (24 MB table + 171 MB optimizer state + 7 MB samples) exceeds the 126 MB L2; no explicit flush",
+                   "step_pipeline": ({"enabled": True, "front_starts_at": runner._pipe["at"], "fronts_prefetched": int(runner._pipe["prefetched"]),
+                                      "note": "ray generation + march of step i+1 on a second stream under step i's network kernels / optimizer sweep; "
+                                              "every timed step contains one front and one back"}
+                                     if getattr(runner, "_pipe", None) is not None else {"enabled": False}),
                    "cuda_graphs": {"enabled": bool(getattr(runner, "_graphs_enabled", False)), "graphs": len(getattr(runner, "_graphs", {}) or {}),
                                    "replays": int(getattr(runner, "graph_replays", 0))}},
         "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline,
