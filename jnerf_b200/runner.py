@@ -164,15 +164,29 @@ class Runner:
         st.m = torch.zeros(self._hi - self._lo, dtype=torch.float32, device=g.device)
         st.v = torch.zeros_like(st.m)
 
-    def _table_ready(self):
-        """Make the current stream wait for the in-flight all-gather of the updated table (no-op on one GPU)."""
+    def _table_ready(self, zero_on=None):
+        """Make the current stream wait for the in-flight all-gather of the updated table (no-op on one GPU).
+        zero_on: (stream, event) -- clear the gradient buffers on that stream instead of the current one and record the event; the
+        caller waits for it before its backward.  The 25 MB memset then runs beside the network forward (which does not touch the
+        gradients) instead of in front of it."""
         if self._table_work is not None:
             self._table_work.wait()
             self._table_work = None
         if getattr(self, "_pending_epoch", None) is not None:
             ops.dp_exchange_wait(self.world_size, self._arena.flags, self._pending_epoch)
-            self._arena.grads.zero_()                                # peers no longer read them: clear table + MLP gradients in one memset
             self._pending_epoch = None
+            # peers no longer read the gradients: clear table + MLP gradients in one memset
+            if zero_on is None:
+                self._arena.grads.zero_()
+                return False
+            stream, ev = zero_on
+            ev.record(torch.cuda.current_stream())                   # behind the wait kernel
+            stream.wait_event(ev)
+            with torch.cuda.stream(stream):
+                self._arena.grads.zero_()
+                ev.record(stream)
+            return True
+        return False
 
     def _gather_table_state(self):
         """Full-length (m, v, master) of the hash table for checkpoints: all-gather of the per-rank slices."""
@@ -395,13 +409,16 @@ class Runner:
         # (the sampler is an nn.Module: plain attribute assignment goes through Module.__setattr__, ~2 us apiece)
         s.__dict__.update(_rays_numsteps=F["numsteps"], _rays_numsteps_compacted=F["ns_c"], _counters_compacted=F["cnt_c"], _coords=F["coords"])
         coords, n_dev = F["coords"], F["cnt_c"][0:1]
-        self._table_ready()                                          # data parallel: the exchange of step i-1 has delivered the table
+        # data parallel: the exchange of step i-1 has delivered the table; its gradient buffers are cleared beside the forward
+        zeroing = self._table_ready(zero_on=(P["aux"], P["aux_done"]))
         self.net_forward(coords, n_dev)
         if P["at"] == "fwd":
             P["mid"].record(main)
         rgb, loss, _ = ops.composite_loss_bwd(self.net_out, coords, F["numsteps"], F["ns_c"], F["bg"], F["target"], s.density_grid_mean,
                                               delta=self.loss_func.delta, cascades=s.NERF_CASCADES, dnet=self.dnet,
                                               reg_scale=float(self.world_size))    # the exchange applies 1 / W to the summed gradients
+        if zeroing:
+            main.wait_event(P["aux_done"])
         self.net_backward(coords, n_dev)
         if P["at"] == "bwd":
             P["mid"].record(main)

@@ -13,5 +13,5 @@ run bench_weak_$N 200 $TR --nproc-per-node $N --master-port $((29540 + N)) bench
 run bench_weak_1 120 python bench.py --gpus 1 --steps 300 --warmup 5 --no-cpu-baseline
 run dp_check_$N 300 $TR --nproc-per-node $N --master-port 29533 tools/dp_check.py
 cp gpurun_out/dp_check_${N}gpu.json "$OUT/" 2>/dev/null
-run bench_strong_$N 200 $TR --nproc-per-node $N --master-port $((29560 + N)) bench.py --gpus $N --steps 300 --warmup 5 --no-cpu-baseline --scaling strong
+if [ "${3:-}" = "strong" ]; then run bench_strong_$N 200 $TR --nproc-per-node $N --master-port $((29560 + N)) bench.py --gpus $N --steps 300 --warmup 5 --no-cpu-baseline --scaling strong; fi
 cat "$SUM"
