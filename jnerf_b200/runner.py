@@ -399,7 +399,8 @@ class Runner:
         main = P["main"] = torch.cuda.current_stream()
         F, P["pending"] = P["pending"], None
         if F is not None and (F["step"] != i or F["src"] is not batch):
-            F = None                                                 # the caller changed course (checkpoint loaded, other batch): drop it
+            main.wait_event(F["done"])                               # it may still be marching: the workspace is shared with the new front
+            F = None                                                 # the caller changed course (other batch, other step): drop it
         if F is None:
             F = self._front(i, batch, prefetch=False)
         elif F["side"]:

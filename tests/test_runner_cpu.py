@@ -439,3 +439,22 @@ def test_pipelined_host_fed_batches(monkeypatch):
                 assert fake.calls[n0:] == (front if k == 0 else []) + BACK_OPS + (front if k < 3 else []), fake.calls[n0:]
         out[announce] = (ls, r.model.pos_encoder.m_grid.detach().clone())
     assert out[False][0] == out[True][0] and torch.equal(out[False][1], out[True][1])
+
+
+def test_pipelined_front_is_dropped_when_the_caller_changes_course(monkeypatch):
+    """A prefetched front that no longer matches the next call (another batch is fed, or the step counter was moved) is discarded and a
+    fresh one is made on the spot; training goes on."""
+    r, fake = make_runner(monkeypatch, seed=19, pipeline=True)
+    ds = r.dataset["train"]
+    r.train_step()
+    assert r._pipe["pending"] is not None and r._pipe["pending"]["src"] is None
+    pix = ds.next_pixels(64)
+    img_ids, o, d = ds.rays_for(pix)
+    fake.calls.clear()
+    loss = r.train_step((img_ids, o, d, ds.rgba_for(pix)))           # a fed batch instead of the device-generated one that was prefetched
+    assert fake.calls[:3] == ["blend_target", "march", "compact"] and torch.isfinite(loss).all()
+    assert r._pipe["pending"] is None                                # the caller did not say which batch comes next
+    r.train_step()
+    r.cfg.m_training_step += 5                                       # e.g. a resumed schedule
+    fake.calls.clear()
+    assert torch.isfinite(r.train_step()).all() and fake.calls[:3] == FRONT_OPS
