@@ -375,6 +375,8 @@ def stage_times(runner, iters):
     names = ["prepare_batch", "march", "network_fwd", "composite_loss_bwd", "network_bwd", "adam_ema"]
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)] for _ in range(iters)]
     n_dev = None
+    if hasattr(runner, "_sync_front"):
+        runner._sync_front()                             # a prefetched front of the step pipeline shares the march workspace with s.sample()
     for ev in evs:
         while runner.cfg.m_training_step % 16 in (0, 15):    # keep grid updates and the ray-batch adaptation (.item() sync) out of the split
             runner.cfg.m_training_step += 1
