@@ -578,13 +578,6 @@ __global__ void zero_tail_kernel(float* __restrict__ coords_out, const uint32_t*
 }
 
 // ---- composite -------------------------------------------------------------------------------------------
-template <typename T> __device__ __forceinline__ float4 load_net(const T* net, size_t k);
-template <> __device__ __forceinline__ float4 load_net<float>(const float* net, size_t k) { return __ldg(reinterpret_cast<const float4*>(net) + k); }
-template <> __device__ __forceinline__ float4 load_net<__half>(const __half* net, size_t k) {
-    const uint2 u = __ldg(reinterpret_cast<const uint2*>(net) + k);
-    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-    return make_float4(a.x, a.y, b.x, b.y);
-}
 template <typename T> __device__ __forceinline__ void store_net(T* dst, size_t k, float4 v);
 template <> __device__ __forceinline__ void store_net<float>(float* dst, size_t k, float4 v) { reinterpret_cast<float4*>(dst)[k] = v; }
 template <> __device__ __forceinline__ void store_net<__half>(__half* dst, size_t k, float4 v) {
