@@ -173,7 +173,7 @@ def test_occupancy_grid_update_glue(monkeypatch):
 
 
 # ------------------------------------------------------------------------------------------------ data parallel (gloo, 2 ranks)
-def _dp_worker(rank, world, port, tmp, ret, pipeline=False):
+def _dp_worker(rank, world, port, tmp, ret, pipeline=False, start_step=1, steps=3):
     import os
     import sys
     import torch.distributed as dist
@@ -196,16 +196,21 @@ def _dp_worker(rank, world, port, tmp, ret, pipeline=False):
         r = R.Runner(rank=rank, world_size=world, process_group=dist.group.WORLD)
         bits, _ = ol.sphere_bitfield(0.35)
         r.sampler.density_grid_bitfield.copy_(torch.from_numpy(bits))
-        cfg.m_training_step = 1
+        cfg.m_training_step = start_step
+        r.sampler.update_density_grid = lambda: None               # 2 M density evaluations in the scalar oracle; it has its own test
         assert r.dp_mode == "nccl" and r._hi - r._lo == r._table.numel() // world
-        losses = [float(r.train_step().mean()) for _ in range(3)]
+        losses, rays = [], []
+        for _ in range(steps):
+            rays.append(r.sampler.n_rays_per_batch)
+            losses.append(float(r.train_step().mean()))
+        rays.append(r.sampler.n_rays_per_batch)
         r._table_ready()
         assert (r._pipe is not None) == pipeline
         g = r.model.pos_encoder.m_grid.detach().float()
         st = r.optimizer._nested_optimizer.state[0]
         r.save_ckpt(os.path.join(tmp, "dp.pt"))                                  # every rank calls; rank 0 writes the gathered state
         ret[rank] = dict(losses=losses, table_sum=float(g.double().sum()), table_head=g[:4096].clone().numpy(), w=r.model.rgb_mlp.con_weights.detach().float().numpy(),
-                         slice_len=int(st.m.numel()), calls=list(fake.calls[-9:]), n_samples=int(r.sampler.n_samples_dev.item()))
+                         slice_len=int(st.m.numel()), calls=list(fake.calls[-9:]), n_samples=int(r.sampler.n_samples_dev.item()), rays=rays)
     finally:
         mp_.undo()
         dist.destroy_process_group()
@@ -458,3 +463,22 @@ def test_pipelined_front_is_dropped_when_the_caller_changes_course(monkeypatch):
     r.cfg.m_training_step += 5                                       # e.g. a resumed schedule
     fake.calls.clear()
     assert torch.isfinite(r.train_step()).all() and fake.calls[:3] == FRONT_OPS
+
+
+def test_two_rank_ray_batch_adapts_globally_across_a_window_edge(tmp_path):
+    """Steps 12 .. 17 on two gloo ranks, sequential and pipelined: at the end of step 15 the GLOBAL ray batch (2 x 32 rays) is adapted to
+    the global 16-step sample count against the global budget with the reference's formula (rounded to 128 rays), and every rank takes
+    half of it -- identically on both ranks and in both step orders (the pipelined runner all-reduces and reads the counter back on
+    its side stream); the replicas stay identical across the edge."""
+    import os
+    import torch.multiprocessing as mp
+    out = {}
+    for pipe in (False, True):
+        ret = mp.Manager().dict()
+        mp.spawn(_dp_worker, args=(2, 29715 + int(pipe) + os.getpid() % 1000, str(tmp_path), ret, pipe, 12, 6), nprocs=2, join=True)
+        a, b = ret[0], ret[1]
+        assert a["rays"] == b["rays"] and a["rays"][:4] == [32] * 4 and a["rays"][4] != 32          # adapted after step 15's march
+        assert (2 * a["rays"][4]) % 128 == 0                                                          # the GLOBAL batch is rounded, not the shard
+        assert a["table_sum"] == b["table_sum"] and np.array_equal(a["w"], b["w"])
+        out[pipe] = (a["rays"], a["losses"], a["table_sum"])
+    assert out[False] == out[True]
